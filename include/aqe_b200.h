@@ -1,0 +1,318 @@
+/*
+ * aqe_b200.h -- C-ABI of libaqe_b200.so, the B200 (sm_100a) aggregation engine that sits behind
+ * ApproximateQueryEngine's `aqe_backend` pybind11 module.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes / PODs, returns an `aqe_status`
+ * (0 = OK) and never throws.  `aqe_last_error()` returns a thread-local message for the last non-OK
+ * status.  A handle (`aqe_db`) is one contiguous shard of the record table resident in the HBM of ONE
+ * GPU (one process per GPU; shards of several processes are merged by the host layer, see
+ * approximatequeryengine_b200/sharded.py).  Handles are thread-compatible (one caller at a time).
+ *
+ * Reference interfaces replaced (paths relative to the reference repo, file:line):
+ *   Record                                   src/aqe_backend/core/custom_bplus_db.hpp:17-27
+ *   CustomBPlusDB (37 bound methods)         src/aqe_backend/bindings/bindings.cpp:42-101
+ *                                            src/aqe_backend/core/custom_bplus_db.hpp:57-146
+ *   CustomApproximateScheduler               src/aqe_backend/bindings/bindings.cpp:103-123
+ *   file format                              src/aqe_backend/core/custom_bplus_db.cpp:665-711
+ *   CLI estimators (E1/E2)                   enhanced_aqe_cli.py:188-200, 257-291
+ * Each declaration below cites the reference code it stands in for.
+ */
+#ifndef AQE_B200_H
+#define AQE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AQE_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------------
+ * Types
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Fixed-width row, 32 bytes, natural alignment -- custom_bplus_db.hpp:17-27 (struct Record). */
+typedef struct aqe_record {
+    int64_t id;
+    double  amount;
+    int32_t region;
+    int32_t product_id;
+    int64_t timestamp;
+} aqe_record;
+
+typedef struct aqe_db aqe_db; /* opaque: one shard, columnar, HBM resident */
+
+typedef enum aqe_status {
+    AQE_OK = 0,
+    AQE_ERR_INVALID = 1,     /* bad argument (the reference would hit UB / div-by-zero) */
+    AQE_ERR_IO = 2,          /* file cannot be opened / short read (reference: returns false) */
+    AQE_ERR_CUDA = 3,        /* CUDA runtime error, no device, kernel fault */
+    AQE_ERR_NOMEM = 4,
+    AQE_ERR_STATE = 5,       /* e.g. query on a closed handle */
+    AQE_ERR_UNSUPPORTED = 6
+} aqe_status;
+
+/* Column ids of the columnar copy. */
+typedef enum aqe_column {
+    AQE_COL_ID = 0,          /* i64 */
+    AQE_COL_AMOUNT = 1,      /* f64 */
+    AQE_COL_REGION = 2,      /* i32 */
+    AQE_COL_PRODUCT_ID = 3,  /* i32 */
+    AQE_COL_TIMESTAMP = 4,   /* i64 */
+    AQE_COL_NONE = -1
+} aqe_column;
+
+/* Full-scan aggregate request.  Predicate is the closed interval lo <= pred_col <= hi evaluated in
+ * double (custom_bplus_db.cpp:269); pred_col = AQE_COL_NONE scans everything. */
+typedef struct aqe_scan_spec {
+    int32_t agg_col;   /* column summed */
+    int32_t pred_col;  /* predicate column or AQE_COL_NONE */
+    double  lo, hi;
+} aqe_scan_spec;
+
+/* Result of a full scan over one shard; also the 64-byte unit exchanged between ranks.
+ * f64 aggregate: sum + comp is the double-double (error-free transformed) sum, `sum` alone is the
+ * rounded result.  Integer aggregate: (isum_hi:isum_lo) is the exact two's-complement 128-bit sum. */
+typedef struct aqe_partial {
+    uint64_t count;    /* rows that passed the predicate */
+    double   sum;
+    double   comp;
+    uint64_t isum_lo;
+    int64_t  isum_hi;
+    double   sumsq;    /* sum of squares (f64 aggregate), for exact variance */
+    double   minv, maxv;
+} aqe_partial;
+
+/* Sample moments of a gathered sample (K3).  m2 = sum (x - mean)^2. */
+typedef struct aqe_stats {
+    uint64_t n;
+    double   mean;
+    double   m2;
+    double   sum;
+} aqe_stats;
+
+/* Sampler ids: the list-returning methods of CustomBPlusDB (bindings.cpp:49-101).  Line numbers are
+ * src/aqe_backend/core/custom_bplus_db.cpp. */
+typedef enum aqe_method {
+    AQE_M_SLOW_POINTER = 0,                 /* :759  */
+    AQE_M_FAST_POINTER = 1,                 /* :737   step_size */
+    AQE_M_DUAL_POINTER = 2,                 /* :780  */
+    AQE_M_PARALLEL_POINTER = 3,             /* :814   num_threads */
+    AQE_M_RANDOM_POINTER = 4,               /* :856   seed (mt19937) */
+    AQE_M_MEMORY_STRIDE = 5,                /* :1526  block_size = stride_bytes */
+    AQE_M_OPT_ADDRESS_ARITHMETIC = 6,       /* :1667 */
+    AQE_M_INDEX_BASED = 7,                  /* :444  */
+    AQE_M_BYTE_OFFSET = 8,                  /* :1461 */
+    AQE_M_OPTIMIZED_CLT = 9,                /* :1046  num_threads */
+    AQE_M_BLOCK = 10,                       /* :1151  block_size */
+    AQE_M_PAGE = 11,                        /* :1183  block_size = page_size bytes */
+    AQE_M_PARALLEL_BLOCK = 12,              /* :1218  block_size, num_threads */
+    AQE_M_NODE_SKIP = 13,                   /* :489   step_size = skip_factor */
+    AQE_M_BALANCED_TREE = 14,               /* :534  */
+    AQE_M_DIRECT_ACCESS = 15,               /* :584  */
+    AQE_M_ADAPTIVE_BLOCK = 16,              /* :1273  block_size = min, block_size_max = max */
+    AQE_M_STRATIFIED_BLOCK = 17,            /* :1331  block_size, block_size_max = strata_count */
+    AQE_M_SAMPLE_RECORDS = 18,              /* :345   seeded SRSWOR (reference: random_device) */
+    AQE_M_OPTIMIZED_SEQUENTIAL = 19,        /* :366   seeded */
+    AQE_M_RANDOM_START_NTH = 20,            /* :1483  step_size = nth, seeded */
+    AQE_M_ADDRESS_ARITHMETIC = 21,          /* :1605  seeded */
+    AQE_M_RANDOM_START_MEMORY_STRIDE = 22,  /* :1838  seeded */
+    AQE_M_MULTITHREADED_MEMORY_STRIDE = 23, /* :1880  num_threads, seeded */
+    AQE_M_CLT_VALIDATED_DUAL_POINTER = 24,  /* :885   lock-step deterministic schedule */
+    AQE_M_SIGNAL_BASED_CLT = 25,            /* :1705  lock-step deterministic schedule */
+    AQE_M__COUNT = 26
+} aqe_method;
+
+/* Arguments of a sampler call; defaults are the pybind defaults (bindings.cpp:56-101). */
+typedef struct aqe_sample_params {
+    double   sample_percent;
+    int64_t  step_size;         /* fast_pointer step_size=2 | node_skip skip_factor=2 | random_start_nth nth=10 */
+    int64_t  num_threads;       /* 4 */
+    int64_t  block_size;        /* block 1000 | page_size 4096 | adaptive min 500 | stride_bytes 0 */
+    int64_t  block_size_max;    /* adaptive max 2000 | stratified strata_count 4 */
+    int64_t  check_interval;    /* clt_validated 10 | optimized_clt 20 | signal_based 10 */
+    double   confidence_level;  /* 0.95 */
+    double   max_error_percent; /* 2.0 */
+    uint64_t seed;              /* random_pointer 42; elsewhere replaces std::random_device */
+} aqe_sample_params;
+
+/* One affine run of sample positions:  for k in [0,count):
+ *   kind 0:  idx = base + (k / inner_len) * outer_step + (k % inner_len)
+ *   kind 1:  idx = (int64) ((double) k * scale)              (index_based_sample, :462-470)        */
+typedef struct aqe_segment {
+    int64_t base;
+    int64_t outer_step;
+    int64_t inner_len;
+    int64_t count;
+    double  scale;
+    int32_t kind;
+    int32_t _pad;
+} aqe_segment;
+
+typedef struct aqe_plan aqe_plan; /* opaque: a sample position list (segments or explicit indices) */
+
+/* Aggregates for the fused estimators. */
+typedef enum aqe_agg { AQE_AGG_SUM = 0, AQE_AGG_AVG = 1, AQE_AGG_COUNT = 2 } aqe_agg;
+
+/* Draw designs of the persistent CLT kernel (K4). */
+typedef enum aqe_design {
+    AQE_DESIGN_SRS = 0,    /* Philox simple random sampling with replacement over the shard */
+    AQE_DESIGN_BLOCK = 1   /* Philox-chosen contiguous tiles of block_size rows (cluster sample) */
+} aqe_design;
+
+typedef struct aqe_approx_spec {
+    int32_t  agg;                /* aqe_agg */
+    int32_t  design;             /* aqe_design */
+    int32_t  agg_col;            /* AQE_COL_AMOUNT (f64) */
+    int32_t  pred_col;           /* AQE_COL_NONE or predicate column (ratio estimator) */
+    double   lo, hi;
+    double   error_percent;      /* stop when z*SE/|estimate| * 100 <= error_percent */
+    double   confidence_level;   /* 0.90 / 0.95 / 0.99 or any in (0,1) */
+    uint64_t seed;
+    uint64_t min_samples;        /* first look; 0 = default */
+    uint64_t max_samples;        /* budget; 0 = default (N) */
+    uint32_t block_size;         /* AQE_DESIGN_BLOCK tile rows; 0 = 1000 (block_sample default) */
+    uint32_t _pad;
+} aqe_approx_spec;
+
+/* status values follow CustomApproximationStatus (custom_scheduler.hpp:8-13). */
+typedef enum aqe_approx_status {
+    AQE_STABLE = 0, AQE_DRIFTING = 1, AQE_INSUFFICIENT_DATA = 2, AQE_ERROR = 3
+} aqe_approx_status;
+
+/* Result fields = the reference's CustomValidationResult + QueryResult
+ * (custom_scheduler.hpp:15-22, executor.h:8-12) with the correct SUM interval. */
+typedef struct aqe_approx_result {
+    double   estimate;
+    double   ci_lower, ci_upper;
+    double   error_margin;       /* achieved relative half width z*SE/|estimate| */
+    double   confidence_level;
+    uint64_t n_samples;          /* rows gathered */
+    uint64_t n_units;            /* sampling units (rows for SRS, tiles for BLOCK) */
+    uint64_t population;         /* N of the shard */
+    double   mean, m2;           /* unit-level moments (merge across shards with Chan's formula) */
+    uint32_t rounds;
+    int32_t  status;             /* aqe_approx_status */
+    double   elapsed_us;         /* device time of the persistent kernel (CUDA events) */
+} aqe_approx_result;
+
+/* Synthetic "sales-shaped" generator distributions. */
+typedef enum aqe_synth { AQE_SYNTH_UNIFORM = 0, AQE_SYNTH_LOGNORMAL = 1 } aqe_synth;
+
+/* ------------------------------------------------------------------------------------------------
+ * Library
+ * ---------------------------------------------------------------------------------------------- */
+int         aqe_abi_version(void);
+const char* aqe_last_error(void);          /* thread-local, never NULL */
+int         aqe_device_count(int* out);    /* AQE_ERR_CUDA when no driver / device */
+/* Number of this library's kernels launched since load (bench.py gpu_launches). */
+uint64_t    aqe_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Lifecycle / ingest  (create_database :135, open_database :153, load_from_file :685,
+ * save_to_file :665, insert_record :164, insert_batch :196, close_database :157)
+ * ---------------------------------------------------------------------------------------------- */
+/* Empty table bound to CUDA device `device` (no CUDA call is made until rows are needed on device). */
+int aqe_create(int device, aqe_db** out);
+/* create + load_file of the whole file. */
+int aqe_open(const char* path, int device, aqe_db** out);
+/* Replace contents with rows [first_row, first_row + n_rows) of the record file (n_rows = UINT64_MAX:
+ * to the end).  Rows are (stably) ordered by id, as load_from_file's insert_batch does (:198-200). */
+int aqe_load_file(aqe_db* db, const char* path, uint64_t first_row, uint64_t n_rows);
+/* Write header (total, height, count) + rows in ascending id (:665-683). */
+int aqe_save_file(aqe_db* db, const char* path);
+/* Append host rows (insert_record / insert_batch); the device copy is rebuilt lazily. */
+int aqe_append_records(aqe_db* db, const aqe_record* rows, size_t n);
+/* Replace contents with n host rows (AoS, pageable or pinned), chunked H2D + AoS->SoA on device. */
+int aqe_from_host_records(aqe_db* db, const aqe_record* rows, size_t n);
+/* Borrow device-resident columns (Torch hand-off through data_ptr()); any pointer may be NULL if the
+ * column is never queried.  The caller keeps ownership and must keep them alive. */
+int aqe_attach_device_columns(aqe_db* db, const int64_t* id, const double* amount, const int32_t* region,
+                              const int32_t* product_id, const int64_t* timestamp, uint64_t n);
+/* Fill the shard on the device with rows [first_row, first_row+n_rows) of the synthetic table
+ * (Philox4x32-10, key = seed, counter = global row).  columns_mask bit c = materialise column c. */
+int aqe_generate_synthetic(aqe_db* db, uint64_t seed, uint64_t first_row, uint64_t n_rows, int dist,
+                           uint32_t columns_mask);
+/* Host twin of the generator (same bits), for files / oracles.  rows[i] = global row first_row+i. */
+int aqe_synth_rows_host(uint64_t seed, uint64_t first_row, uint64_t n_rows, int dist, aqe_record* rows);
+int aqe_close(aqe_db* db); /* frees device + host memory; db invalid afterwards */
+
+uint64_t aqe_count(const aqe_db* db);                 /* get_total_records :646 */
+uint64_t aqe_node_count(const aqe_db* db);            /* get_node_count :654 (N/255+1) */
+uint64_t aqe_tree_height(const aqe_db* db);           /* get_tree_height :650 (bulk-load shape) */
+int      aqe_device(const aqe_db* db);
+/* Device pointer of a column (NULL if absent) -- zero-copy export to torch / cupy. */
+const void* aqe_column_device_ptr(aqe_db* db, int col);
+/* Copy rows [first,first+n) back to host AoS (collect_all_records :660). */
+int aqe_read_records(aqe_db* db, uint64_t first, uint64_t n, aqe_record* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Exact full scans (K1/K2)  -- sum_amount :242, avg_amount :253, count_records :259,
+ * sum_amount_where :263
+ * ---------------------------------------------------------------------------------------------- */
+int aqe_scan(aqe_db* db, const aqe_scan_spec* spec, aqe_partial* out);
+/* Asynchronous form: launches on `stream` (a cudaStream_t, 0 = the handle's own stream) and leaves
+ * the 64-byte partial in device memory at `partial_dev` (e.g. a torch tensor's data_ptr()). */
+int aqe_scan_async(aqe_db* db, const aqe_scan_spec* spec, void* partial_dev, void* stream);
+/* Scan host-resident column data through the device: chunked, double-buffered H2D from `host_col`
+ * (n elements of agg column type; pinned recommended) overlapped with the reduction.  This is the
+ * end-to-end (host buffers in, scalar out) form of sum_amount / sum_amount_where. */
+int aqe_scan_host_column(int device, const void* host_col, int col_kind, uint64_t n, double lo, double hi,
+                         int use_pred, aqe_partial* out);
+/* Fixed-order merge of per-shard partials (rank order) -- pure host code. */
+int aqe_merge_partials(const aqe_partial* parts, int n, int is_integer, aqe_partial* out);
+/* Conveniences over aqe_scan: */
+int aqe_sum_f64(aqe_db* db, int col, double* out);                                   /* :242 */
+int aqe_sum_where_f64(aqe_db* db, int col, double lo, double hi, double* sum, uint64_t* count); /* :263 */
+int aqe_sum_i128(aqe_db* db, int col, uint64_t* lo64, int64_t* hi64);                /* new */
+
+/* ------------------------------------------------------------------------------------------------
+ * Sample plans (Appendix A index generators) -- host arithmetic only, no device needed
+ * ---------------------------------------------------------------------------------------------- */
+void aqe_sample_params_default(aqe_sample_params* p, int method); /* pybind defaults */
+/* Build the position list of `method` for a table of n_rows rows.  Methods that depend on data
+ * (ADAPTIVE_BLOCK, STRATIFIED_BLOCK, CLT_VALIDATED_DUAL_POINTER) need `db` (may be NULL otherwise). */
+int  aqe_plan_build(aqe_db* db, uint64_t n_rows, int method, const aqe_sample_params* p, aqe_plan** out);
+int  aqe_plan_from_indices(const int64_t* idx, uint64_t n, aqe_plan** out);
+uint64_t aqe_plan_count(const aqe_plan* plan);
+uint32_t aqe_plan_num_segments(const aqe_plan* plan);  /* 0 => explicit index list */
+int  aqe_plan_segments(const aqe_plan* plan, aqe_segment* out, uint32_t cap);
+int  aqe_plan_indices(const aqe_plan* plan, int64_t* out, uint64_t cap); /* expand on host */
+int  aqe_plan_sorted_by_amount(const aqe_plan* plan);  /* 1: positions index the amount-sorted order */
+void aqe_plan_free(aqe_plan* plan);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampled aggregates (K3/K5/K6)
+ * ---------------------------------------------------------------------------------------------- */
+/* Moments of column `col` (as double) over the plan's positions. */
+int aqe_stats_from_plan(aqe_db* db, const aqe_plan* plan, int col, aqe_stats* out);
+/* Same for a caller-supplied host index list ("same sample index list" parity, E1/E2). */
+int aqe_stats_from_indices(aqe_db* db, const int64_t* idx, uint64_t n, int col, aqe_stats* out);
+/* Rows at the plan's positions, AoS, in plan order (the legacy list[Record] return path). */
+int aqe_gather_plan(aqe_db* db, const aqe_plan* plan, aqe_record* out, uint64_t cap);
+int aqe_gather_records(aqe_db* db, const int64_t* idx, uint64_t n, aqe_record* out);
+/* fast_aggregated_memory_stride_sum :1962 -- raw (unscaled) sample sum, plus the sample count. */
+int aqe_fast_aggregated_sum(aqe_db* db, const aqe_sample_params* p, double* sum, uint64_t* n);
+
+/* CLI estimators (enhanced_aqe_cli.py:188-200 random, 257-291 clt) from sample moments.
+ * legacy_ci != 0 reproduces the reference's SUM interval (margin * N/n). */
+int aqe_estimate(const aqe_stats* s, uint64_t population, int agg, double z, int legacy_ci,
+                 double* estimate, double* ci_lower, double* ci_upper);
+
+/* ------------------------------------------------------------------------------------------------
+ * Persistent CLT kernel (K4): Philox draws, Welford partials, in-kernel stop rule
+ * ---------------------------------------------------------------------------------------------- */
+int aqe_approx(aqe_db* db, const aqe_approx_spec* spec, aqe_approx_result* out);
+/* Merge per-shard results (stratified by shard, rank order) into the table-level estimate. */
+int aqe_approx_merge(const aqe_approx_result* parts, int n, int agg, double confidence_level,
+                     aqe_approx_result* out);
+/* z for a two-sided confidence level: the reference's table 2.576/1.96/1.645 (:911-912) when
+ * exact == 0, else the inverse normal CDF. */
+double aqe_z_score(double confidence_level, int exact);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AQE_B200_H */
