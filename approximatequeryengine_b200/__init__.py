@@ -1,0 +1,407 @@
+"""approximatequeryengine_b200 -- B200-native aggregation engine behind ApproximateQueryEngine's
+``aqe_backend`` API.
+
+Two native artefacts live in ``_lib/`` (built in-tree by ``python -m approximatequeryengine_b200.build``):
+
+* ``libaqe_b200.so``  -- the C-ABI engine (include/aqe_b200.h): hand-written sm_100a kernels + host code;
+* ``aqe_backend*.so`` -- the pybind11 module with the reference's Python surface
+  (reference: src/aqe_backend/bindings/bindings.cpp).
+
+This package is the host-side mirror: ``backend()`` returns the drop-in module, ``Engine`` is a ctypes
+view of the C-ABI for tests/bench, ``sharded`` merges per-rank partials (one process per GPU).
+There is no CPU fallback: without the built libraries or without a CUDA device, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import importlib
+import os
+import sys
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(PKG_DIR, "_lib")
+LIB_PATH = os.path.join(LIB_DIR, "libaqe_b200.so")
+
+RECORD_DTYPE = np.dtype(
+    [("id", "<i8"), ("amount", "<f8"), ("region", "<i4"), ("product_id", "<i4"), ("timestamp", "<i8")]
+)
+
+COLS = {"id": 0, "amount": 1, "region": 2, "product_id": 3, "timestamp": 4, None: -1}
+COL_KIND = {"amount": 0, "id": 1, "timestamp": 1, "region": 2, "product_id": 2}  # 0 f64, 1 i64, 2 i32
+AGG = {"sum": 0, "avg": 1, "count": 2}
+DESIGN = {"srs": 0, "block": 1}
+METHODS = {
+    "slow_pointer": 0, "fast_pointer": 1, "dual_pointer": 2, "parallel_pointer": 3, "random_pointer": 4,
+    "memory_stride": 5, "optimized_address_arithmetic": 6, "index_based": 7, "byte_offset": 8,
+    "optimized_clt": 9, "block": 10, "page": 11, "parallel_block": 12, "node_skip": 13, "balanced_tree": 14,
+    "direct_access": 15, "adaptive_block": 16, "stratified_block": 17, "sample_records": 18,
+    "optimized_sequential": 19, "random_start_nth": 20, "address_arithmetic": 21,
+    "random_start_memory_stride": 22, "multithreaded_memory_stride": 23, "clt_validated_dual_pointer": 24,
+    "signal_based_clt": 25,
+}
+STATUS = {0: "STABLE", 1: "DRIFTING", 2: "INSUFFICIENT_DATA", 3: "ERROR"}
+
+
+class AqeError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[aqe status {code}] {msg}")
+        self.code = code
+
+
+class SampleParams(C.Structure):
+    _fields_ = [
+        ("sample_percent", C.c_double), ("step_size", C.c_int64), ("num_threads", C.c_int64),
+        ("block_size", C.c_int64), ("block_size_max", C.c_int64), ("check_interval", C.c_int64),
+        ("confidence_level", C.c_double), ("max_error_percent", C.c_double), ("seed", C.c_uint64),
+    ]
+
+
+class ScanSpec(C.Structure):
+    _fields_ = [("agg_col", C.c_int32), ("pred_col", C.c_int32), ("lo", C.c_double), ("hi", C.c_double)]
+
+
+class Partial(C.Structure):
+    _fields_ = [
+        ("count", C.c_uint64), ("sum", C.c_double), ("comp", C.c_double), ("isum_lo", C.c_uint64),
+        ("isum_hi", C.c_int64), ("sumsq", C.c_double), ("minv", C.c_double), ("maxv", C.c_double),
+    ]
+
+    @property
+    def isum(self) -> int:
+        return (int(self.isum_hi) << 64) + int(self.isum_lo)
+
+
+class Stats(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("mean", C.c_double), ("m2", C.c_double), ("sum", C.c_double)]
+
+
+class Segment(C.Structure):
+    _fields_ = [("base", C.c_int64), ("outer_step", C.c_int64), ("inner_len", C.c_int64), ("count", C.c_int64),
+                ("scale", C.c_double), ("kind", C.c_int32), ("_pad", C.c_int32)]
+
+
+class ApproxSpec(C.Structure):
+    _fields_ = [
+        ("agg", C.c_int32), ("design", C.c_int32), ("agg_col", C.c_int32), ("pred_col", C.c_int32),
+        ("lo", C.c_double), ("hi", C.c_double), ("error_percent", C.c_double), ("confidence_level", C.c_double),
+        ("seed", C.c_uint64), ("min_samples", C.c_uint64), ("max_samples", C.c_uint64),
+        ("block_size", C.c_uint32), ("_pad", C.c_uint32),
+    ]
+
+
+class ApproxResult(C.Structure):
+    _fields_ = [
+        ("estimate", C.c_double), ("ci_lower", C.c_double), ("ci_upper", C.c_double), ("error_margin", C.c_double),
+        ("confidence_level", C.c_double), ("n_samples", C.c_uint64), ("n_units", C.c_uint64),
+        ("population", C.c_uint64), ("mean", C.c_double), ("m2", C.c_double), ("rounds", C.c_uint32),
+        ("status", C.c_int32), ("elapsed_us", C.c_double),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The C-ABI library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -m approximatequeryengine_b200.build` (needs nvcc)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, i32, dbl = C.c_void_p, C.c_uint64, C.c_int, C.c_double
+    sig = {
+        "aqe_abi_version": (i32, []),
+        "aqe_last_error": (C.c_char_p, []),
+        "aqe_device_count": (i32, [C.POINTER(C.c_int)]),
+        "aqe_launch_count": (u64, []),
+        "aqe_host_alloc": (i32, [C.c_size_t, C.POINTER(vp)]),
+        "aqe_host_free": (i32, [vp]),
+        "aqe_create": (i32, [i32, C.POINTER(vp)]),
+        "aqe_open": (i32, [C.c_char_p, i32, C.POINTER(vp)]),
+        "aqe_load_file": (i32, [vp, C.c_char_p, u64, u64]),
+        "aqe_save_file": (i32, [vp, C.c_char_p]),
+        "aqe_append_records": (i32, [vp, vp, C.c_size_t]),
+        "aqe_from_host_records": (i32, [vp, vp, C.c_size_t]),
+        "aqe_attach_device_columns": (i32, [vp, vp, vp, vp, vp, vp, u64]),
+        "aqe_generate_synthetic": (i32, [vp, u64, u64, u64, i32, C.c_uint32]),
+        "aqe_synth_rows_host": (i32, [u64, u64, u64, i32, vp]),
+        "aqe_close": (i32, [vp]),
+        "aqe_count": (u64, [vp]),
+        "aqe_node_count": (u64, [vp]),
+        "aqe_tree_height": (u64, [vp]),
+        "aqe_device": (i32, [vp]),
+        "aqe_column_device_ptr": (vp, [vp, i32]),
+        "aqe_read_records": (i32, [vp, u64, u64, vp]),
+        "aqe_scan": (i32, [vp, C.POINTER(ScanSpec), C.POINTER(Partial)]),
+        "aqe_scan_async": (i32, [vp, C.POINTER(ScanSpec), vp, vp]),
+        "aqe_scan_host_column": (i32, [i32, vp, i32, u64, dbl, dbl, i32, C.POINTER(Partial)]),
+        "aqe_merge_partials": (i32, [C.POINTER(Partial), i32, i32, C.POINTER(Partial)]),
+        "aqe_sum_f64": (i32, [vp, i32, C.POINTER(dbl)]),
+        "aqe_sum_where_f64": (i32, [vp, i32, dbl, dbl, C.POINTER(dbl), C.POINTER(u64)]),
+        "aqe_sum_i128": (i32, [vp, i32, C.POINTER(u64), C.POINTER(C.c_int64)]),
+        "aqe_sample_params_default": (None, [C.POINTER(SampleParams), i32]),
+        "aqe_plan_build": (i32, [vp, u64, i32, C.POINTER(SampleParams), C.POINTER(vp)]),
+        "aqe_plan_from_indices": (i32, [vp, u64, C.POINTER(vp)]),
+        "aqe_plan_count": (u64, [vp]),
+        "aqe_plan_num_segments": (C.c_uint32, [vp]),
+        "aqe_plan_segments": (i32, [vp, C.POINTER(Segment), C.c_uint32]),
+        "aqe_plan_indices": (i32, [vp, vp, u64]),
+        "aqe_plan_sorted_by_amount": (i32, [vp]),
+        "aqe_plan_free": (None, [vp]),
+        "aqe_stats_from_plan": (i32, [vp, vp, i32, C.POINTER(Stats)]),
+        "aqe_stats_from_plan_where": (i32, [vp, vp, i32, i32, dbl, dbl, C.POINTER(Stats)]),
+        "aqe_stats_from_indices": (i32, [vp, vp, u64, i32, C.POINTER(Stats)]),
+        "aqe_gather_plan": (i32, [vp, vp, vp, u64]),
+        "aqe_gather_records": (i32, [vp, vp, u64, vp]),
+        "aqe_fast_aggregated_sum": (i32, [vp, C.POINTER(SampleParams), C.POINTER(dbl), C.POINTER(u64)]),
+        "aqe_estimate": (i32, [C.POINTER(Stats), u64, i32, dbl, i32, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)]),
+        "aqe_approx": (i32, [vp, C.POINTER(ApproxSpec), C.POINTER(ApproxResult)]),
+        "aqe_approx_merge": (i32, [C.POINTER(ApproxResult), i32, i32, dbl, C.POINTER(ApproxResult)]),
+        "aqe_z_score": (dbl, [dbl, i32]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    L._signatures = sig
+    _lib = L
+    return L
+
+
+def backend():
+    """The drop-in ``aqe_backend`` module (same surface as the reference's pybind11 module)."""
+    if LIB_DIR not in sys.path:
+        sys.path.insert(0, LIB_DIR)
+    try:
+        return importlib.import_module("aqe_backend")
+    except ImportError as e:  # loud, never a fallback
+        raise ImportError(f"aqe_backend extension not built in {LIB_DIR}: run `python -m approximatequeryengine_b200.build`") from e
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise AqeError(rc, lib().aqe_last_error().decode(errors="replace"))
+
+
+def make_params(method: str, sample_percent: float, **kw) -> SampleParams:
+    p = SampleParams()
+    lib().aqe_sample_params_default(C.byref(p), METHODS[method])
+    p.sample_percent = sample_percent
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Plan:
+    """A sample position list (affine segments or explicit indices)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().aqe_plan_free(self.h)
+            self.h = None
+
+    @property
+    def count(self) -> int:
+        return lib().aqe_plan_count(self.h)
+
+    @property
+    def num_segments(self) -> int:
+        return lib().aqe_plan_num_segments(self.h)
+
+    @property
+    def by_amount_order(self) -> bool:
+        return bool(lib().aqe_plan_sorted_by_amount(self.h))
+
+    def segments(self):
+        n = self.num_segments
+        arr = (Segment * max(n, 1))()
+        check(lib().aqe_plan_segments(self.h, arr, n))
+        return list(arr[:n])
+
+    def indices(self) -> np.ndarray:
+        out = np.empty(self.count, dtype=np.int64)
+        check(lib().aqe_plan_indices(self.h, _ptr(out), len(out)))
+        return out
+
+
+def build_plan(n_rows: int, method: str, params: SampleParams, engine: "Engine | None" = None) -> Plan:
+    h = C.c_void_p()
+    check(lib().aqe_plan_build(engine.h if engine else None, n_rows, METHODS[method], C.byref(params), C.byref(h)))
+    return Plan(h)
+
+
+def host_scan_column(col: np.ndarray, lo: float = 0.0, hi: float = 0.0, use_pred: bool = False, device: int = 0,
+                     ptr: int | None = None, n: int | None = None, kind: int | None = None) -> Partial:
+    """End-to-end form: a host-resident column in, a scalar partial out (chunked H2D overlapped with the scan)."""
+    out = Partial()
+    if ptr is None:
+        kind = {np.dtype("float64"): 0, np.dtype("int64"): 1, np.dtype("int32"): 2}[col.dtype]
+        ptr, n = col.ctypes.data, len(col)
+    check(lib().aqe_scan_host_column(device, C.c_void_p(ptr), kind, n, lo, hi, int(use_pred), C.byref(out)))
+    return out
+
+
+def merge_partials(parts, is_integer: bool = False) -> Partial:
+    arr = (Partial * len(parts))(*parts)
+    out = Partial()
+    check(lib().aqe_merge_partials(arr, len(parts), int(is_integer), C.byref(out)))
+    return out
+
+
+class Engine:
+    """ctypes view of one ``aqe_db`` handle (one shard on one GPU)."""
+
+    def __init__(self, device: int | None = None):
+        if device is None:
+            device = int(os.environ.get("AQE_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        self.L = lib()
+        self.h = C.c_void_p()
+        check(self.L.aqe_create(device, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.aqe_close(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # ---- ingest ----
+    def load_file(self, path: str, first_row: int = 0, n_rows: int | None = None):
+        check(self.L.aqe_load_file(self.h, path.encode(), first_row, (1 << 64) - 1 if n_rows is None else n_rows))
+        return self
+
+    def save_file(self, path: str):
+        check(self.L.aqe_save_file(self.h, path.encode()))
+
+    def from_rows(self, rows: np.ndarray):
+        rows = np.ascontiguousarray(rows, dtype=RECORD_DTYPE)
+        check(self.L.aqe_from_host_records(self.h, _ptr(rows), len(rows)))
+        return self
+
+    def append(self, rows: np.ndarray):
+        rows = np.ascontiguousarray(rows, dtype=RECORD_DTYPE)
+        check(self.L.aqe_append_records(self.h, _ptr(rows), len(rows)))
+        return self
+
+    def generate(self, n_rows: int, seed: int = 7, first_row: int = 0, dist: int = 0, columns=("id", "amount", "region", "product_id", "timestamp")):
+        mask = 0
+        for c in columns:
+            mask |= 1 << COLS[c]
+        check(self.L.aqe_generate_synthetic(self.h, seed, first_row, n_rows, dist, mask))
+        return self
+
+    def attach(self, n: int, id=0, amount=0, region=0, product_id=0, timestamp=0):
+        check(self.L.aqe_attach_device_columns(self.h, id or None, amount or None, region or None, product_id or None, timestamp or None, n))
+        return self
+
+    def read_rows(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        n = self.count - first if n is None else n
+        out = np.empty(n, dtype=RECORD_DTYPE)
+        check(self.L.aqe_read_records(self.h, first, n, _ptr(out)))
+        return out
+
+    @property
+    def count(self) -> int:
+        return self.L.aqe_count(self.h)
+
+    def column_ptr(self, col: str) -> int:
+        return self.L.aqe_column_device_ptr(self.h, COLS[col]) or 0
+
+    # ---- exact ----
+    def scan(self, agg_col="amount", pred_col=None, lo=0.0, hi=0.0) -> Partial:
+        sp = ScanSpec(COLS[agg_col], COLS[pred_col], lo, hi)
+        out = Partial()
+        check(self.L.aqe_scan(self.h, C.byref(sp), C.byref(out)))
+        return out
+
+    def scan_async(self, partial_dev_ptr: int, agg_col="amount", pred_col=None, lo=0.0, hi=0.0, stream: int = 0):
+        sp = ScanSpec(COLS[agg_col], COLS[pred_col], lo, hi)
+        check(self.L.aqe_scan_async(self.h, C.byref(sp), C.c_void_p(partial_dev_ptr), C.c_void_p(stream)))
+
+    def sum_amount(self) -> float:
+        v = C.c_double()
+        check(self.L.aqe_sum_f64(self.h, COLS["amount"], C.byref(v)))
+        return v.value
+
+    def sum_amount_where(self, lo: float, hi: float):
+        v, c = C.c_double(), C.c_uint64()
+        check(self.L.aqe_sum_where_f64(self.h, COLS["amount"], lo, hi, C.byref(v), C.byref(c)))
+        return v.value, c.value
+
+    def sum_int(self, col: str) -> int:
+        lo, hi = C.c_uint64(), C.c_int64()
+        check(self.L.aqe_sum_i128(self.h, COLS[col], C.byref(lo), C.byref(hi)))
+        return (hi.value << 64) + lo.value
+
+    # ---- sampled ----
+    def plan(self, method: str, params: SampleParams) -> Plan:
+        return build_plan(self.count, method, params, self)
+
+    def plan_from_indices(self, idx) -> Plan:
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        h = C.c_void_p()
+        check(self.L.aqe_plan_from_indices(_ptr(idx), len(idx), C.byref(h)))
+        return Plan(h)
+
+    def stats(self, plan: Plan, col="amount", where=None, where_col="amount") -> Stats:
+        s = Stats()
+        if where is None:
+            check(self.L.aqe_stats_from_plan(self.h, plan.h, COLS[col], C.byref(s)))
+        else:
+            check(self.L.aqe_stats_from_plan_where(self.h, plan.h, COLS[col], COLS[where_col], where[0], where[1], C.byref(s)))
+        return s
+
+    def stats_from_indices(self, idx, col="amount") -> Stats:
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        s = Stats()
+        check(self.L.aqe_stats_from_indices(self.h, _ptr(idx), len(idx), COLS[col], C.byref(s)))
+        return s
+
+    def gather(self, plan: Plan) -> np.ndarray:
+        out = np.empty(plan.count, dtype=RECORD_DTYPE)
+        check(self.L.aqe_gather_plan(self.h, plan.h, _ptr(out), len(out)))
+        return out
+
+    def gather_indices(self, idx) -> np.ndarray:
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        out = np.empty(len(idx), dtype=RECORD_DTYPE)
+        check(self.L.aqe_gather_records(self.h, _ptr(idx), len(idx), _ptr(out)))
+        return out
+
+    def fast_aggregated(self, params: SampleParams):
+        s, n = C.c_double(), C.c_uint64()
+        check(self.L.aqe_fast_aggregated_sum(self.h, C.byref(params), C.byref(s), C.byref(n)))
+        return s.value, n.value
+
+    def approx(self, agg="sum", error_percent=1.0, confidence_level=0.95, design="srs", seed=0, where=None,
+               where_col="amount", agg_col="amount", block_size=0, min_samples=0, max_samples=0) -> ApproxResult:
+        sp = ApproxSpec(AGG[agg], DESIGN[design], COLS[agg_col], COLS[where_col] if where else -1,
+                        where[0] if where else 0.0, where[1] if where else 0.0, error_percent, confidence_level, seed,
+                        min_samples, max_samples, block_size, 0)
+        out = ApproxResult()
+        check(self.L.aqe_approx(self.h, C.byref(sp), C.byref(out)))
+        return out
+
+
+def estimate(stats: Stats, population: int, agg: str, z: float = 1.96, legacy_ci: bool = False):
+    e, lo, hi = C.c_double(), C.c_double(), C.c_double()
+    check(lib().aqe_estimate(C.byref(stats), population, AGG[agg], z, int(legacy_ci), C.byref(e), C.byref(lo), C.byref(hi)))
+    return e.value, lo.value, hi.value
+
+
+def synth_rows_host(n: int, seed: int = 7, first_row: int = 0, dist: int = 0) -> np.ndarray:
+    rows = np.empty(n, dtype=RECORD_DTYPE)
+    check(lib().aqe_synth_rows_host(seed, first_row, n, dist, _ptr(rows)))
+    return rows

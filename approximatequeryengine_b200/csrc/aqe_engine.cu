@@ -1,0 +1,1333 @@
+// aqe_engine.cu -- host side of libaqe_b200.so: the C-ABI of include/aqe_b200.h over the kernels in
+// aqe_kernels.cuh.  One handle = one shard of the record table as five HBM-resident columns on one GPU.
+//
+// What it replaces in the reference (src/aqe_backend/core/custom_bplus_db.cpp): the B+ tree
+// (insert_record :164, insert_batch :196), the "mmap" cache cached_records_ (:186-191), the per-query
+// O(N) copies collect_all_records :660 / collect_leaf_records :715, the serial scans sum_amount :242 /
+// sum_amount_where :263 and the std::async sampler fan-outs.  No CPU fallback exists: without a CUDA
+// device every data-path entry point returns AQE_ERR_CUDA.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "aqe_b200.h"
+#include "aqe_kernels.cuh"
+#include "aqe_plan.hpp"
+
+using namespace aqe;
+
+// ------------------------------------------------------------------------------------------------
+// errors / bookkeeping
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return e == cudaErrorMemoryAllocation ? AQE_ERR_NOMEM : AQE_ERR_CUDA;
+}
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);        \
+    } while (0)
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoi(v) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the handle
+// ------------------------------------------------------------------------------------------------
+struct Slot {  // mapped pinned result area: kernels write it, the host reads it after a stream sync
+    aqe_partial partial;
+    aqe_stats stats;
+    aqe_approx_result approx;
+    unsigned int flags[4];
+};
+
+struct aqe_db {
+    int device = 0;
+    bool cuda_ready = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+
+    uint64_t n = 0;  // rows resident on the device
+    MutColumns col{nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool owned = true;
+
+    // host-side rows appended through insert_record / insert_batch and not yet on the device
+    std::vector<aqe_record> host_rows;
+    bool host_authoritative = false;  // host_rows is the whole table and the device copy is stale
+
+    // scratch
+    ScanAcc* scan_partials = nullptr;
+    StatAcc* stat_partials = nullptr;
+    ApproxAcc* approx_slots = nullptr;
+    unsigned int* tickets = nullptr;  // [4]
+    Slot* slot_host = nullptr;
+    Slot* slot_dev = nullptr;
+    aqe_record* gather_buf = nullptr; uint64_t gather_cap = 0;
+    void* plan_buf = nullptr; size_t plan_cap = 0;
+    int64_t* amount_perm = nullptr;  // rows ordered by amount (stratified_block_sample)
+    int max_grid = 0;
+};
+
+static const int kMaxGrid = 148 * 16;
+
+static int db_init_cuda(aqe_db* db) {
+    if (db->cuda_ready) { CU(cudaSetDevice(db->device)); return AQE_OK; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    if (db->device < 0 || db->device >= ndev) return fail(AQE_ERR_CUDA, "no such CUDA device " + std::to_string(db->device));
+    CU(cudaSetDevice(db->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, db->device));
+    if (prop.major < 10) return fail(AQE_ERR_CUDA, std::string("libaqe_b200 is built for sm_100a (B200); found ") + prop.name);
+    db->sm_count = prop.multiProcessorCount;
+    db->max_grid = kMaxGrid;
+    CU(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&db->ev0));
+    CU(cudaEventCreate(&db->ev1));
+    CU(cudaMalloc(&db->scan_partials, sizeof(ScanAcc) * kMaxGrid));
+    CU(cudaMalloc(&db->stat_partials, sizeof(StatAcc) * kMaxGrid));
+    CU(cudaMalloc(&db->approx_slots, sizeof(ApproxAcc) * 2 * kMaxGrid));
+    CU(cudaMalloc(&db->tickets, sizeof(unsigned int) * 4));
+    CU(cudaMemset(db->tickets, 0, sizeof(unsigned int) * 4));
+    CU(cudaHostAlloc(&db->slot_host, sizeof(Slot), cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer(&db->slot_dev, db->slot_host, 0));
+    db->cuda_ready = true;
+    return AQE_OK;
+}
+
+static void free_columns(aqe_db* db) {
+    if (db->owned) {
+        cudaFree(db->col.id); cudaFree(db->col.amount); cudaFree(db->col.region); cudaFree(db->col.product_id); cudaFree(db->col.timestamp);
+    }
+    db->col = MutColumns{nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (db->amount_perm) { cudaFree(db->amount_perm); db->amount_perm = nullptr; }
+    db->n = 0; db->owned = true;
+}
+
+static int alloc_columns(aqe_db* db, uint64_t n, uint32_t mask) {
+    free_columns(db);
+    const size_t m = n ? n : 1;
+    if (mask & (1u << AQE_COL_ID)) CU(cudaMalloc(&db->col.id, m * 8));
+    if (mask & (1u << AQE_COL_AMOUNT)) CU(cudaMalloc(&db->col.amount, m * 8));
+    if (mask & (1u << AQE_COL_REGION)) CU(cudaMalloc(&db->col.region, m * 4));
+    if (mask & (1u << AQE_COL_PRODUCT_ID)) CU(cudaMalloc(&db->col.product_id, m * 4));
+    if (mask & (1u << AQE_COL_TIMESTAMP)) CU(cudaMalloc(&db->col.timestamp, m * 8));
+    db->n = n; db->owned = true;
+    return AQE_OK;
+}
+
+static Columns const_cols(const aqe_db* db) { return Columns{db->col.id, db->col.amount, db->col.region, db->col.product_id, db->col.timestamp}; }
+
+static int grid_for(const aqe_db* db, uint64_t work_items, int per_thread, int threads, int blocks_per_sm) {
+    uint64_t want = (work_items + (uint64_t)threads * per_thread - 1) / ((uint64_t)threads * per_thread);
+    uint64_t cap = (uint64_t)db->sm_count * blocks_per_sm;
+    if (cap > (uint64_t)db->max_grid) cap = db->max_grid;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ingest: host AoS rows -> device columns (K7), chunked through pinned staging
+// ------------------------------------------------------------------------------------------------
+struct Stager {
+    static const size_t kChunkRows = 1u << 20;  // 32 MiB of rows
+    aqe_record* pinned[2] = {nullptr, nullptr};
+    aqe_record* dev[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    unsigned int* unsorted = nullptr;
+    int init() {
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaHostAlloc(&pinned[i], kChunkRows * sizeof(aqe_record), cudaHostAllocDefault));
+            CU(cudaMalloc(&dev[i], kChunkRows * sizeof(aqe_record)));
+            CU(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        }
+        CU(cudaMalloc(&unsorted, 4));
+        CU(cudaMemset(unsorted, 0, 4));
+        return AQE_OK;
+    }
+    ~Stager() {
+        for (int i = 0; i < 2; ++i) { if (pinned[i]) cudaFreeHost(pinned[i]); if (dev[i]) cudaFree(dev[i]); if (done[i]) cudaEventDestroy(done[i]); }
+        if (unsorted) cudaFree(unsorted);
+    }
+};
+
+// Feeds `n` rows obtained chunk-wise from `fill(dst, first, count)` into the columns.  *unsorted_out is
+// set if ids were found out of order.
+template <typename Fill>
+static int ingest_rows(aqe_db* db, uint64_t n, Fill fill, bool* unsorted_out) {
+    int rc = alloc_columns(db, n, 0x1f);
+    if (rc) return rc;
+    Stager st;
+    rc = st.init();
+    if (rc) return rc;
+    int64_t prev_last = 0;
+    int has_prev = 0;
+    uint64_t done_rows = 0;
+    int buf = 0;
+    while (done_rows < n) {
+        const uint64_t cnt = std::min<uint64_t>(Stager::kChunkRows, n - done_rows);
+        CU(cudaEventSynchronize(st.done[buf]));  // the pinned buffer is free again
+        if (!fill(st.pinned[buf], done_rows, cnt)) return fail(AQE_ERR_IO, "short read while loading rows");
+        CU(cudaMemcpyAsync(st.dev[buf], st.pinned[buf], cnt * sizeof(aqe_record), cudaMemcpyHostToDevice, db->stream));
+        const int grid = grid_for(db, cnt, 4, 256, 8);
+        k_aos_to_soa<<<grid, 256, 0, db->stream>>>(st.dev[buf], cnt, db->col, done_rows, prev_last, has_prev, st.unsorted);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(st.done[buf], db->stream));
+        prev_last = st.pinned[buf][cnt - 1].id;
+        has_prev = 1;
+        done_rows += cnt;
+        buf ^= 1;
+    }
+    unsigned int flag = 0;
+    CU(cudaMemcpyAsync(&flag, st.unsorted, 4, cudaMemcpyDeviceToHost, db->stream));
+    CU(cudaStreamSynchronize(db->stream));
+    *unsorted_out = flag != 0;
+    return AQE_OK;
+}
+
+static int upload_host_rows(aqe_db* db, const aqe_record* rows, uint64_t n) {
+    bool unsorted = false;
+    int rc = ingest_rows(db, n, [&](aqe_record* dst, uint64_t first, uint64_t cnt) { std::memcpy(dst, rows + first, cnt * sizeof(aqe_record)); return true; }, &unsorted);
+    if (rc) return rc;
+    if (unsorted) {
+        // load_from_file -> insert_batch orders rows by id (custom_bplus_db.cpp:198-200); stable here
+        std::vector<aqe_record> sorted(rows, rows + n);
+        std::stable_sort(sorted.begin(), sorted.end(), [](const aqe_record& a, const aqe_record& b) { return a.id < b.id; });
+        rc = ingest_rows(db, n, [&](aqe_record* dst, uint64_t first, uint64_t cnt) { std::memcpy(dst, sorted.data() + first, cnt * sizeof(aqe_record)); return true; }, &unsorted);
+    }
+    return rc;
+}
+
+// Brings rows appended on the host (insert_record / insert_batch) onto the device.
+static int ensure_device(aqe_db* db) {
+    int rc = db_init_cuda(db);
+    if (rc) return rc;
+    if (!db->host_authoritative) return AQE_OK;
+    rc = upload_host_rows(db, db->host_rows.data(), db->host_rows.size());
+    if (rc) return rc;
+    db->host_authoritative = false;
+    return AQE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// library-level entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int aqe_abi_version(void) { return AQE_ABI_VERSION; }
+const char* aqe_last_error(void) { return g_err.c_str(); }
+uint64_t aqe_launch_count(void) { return g_launches.load(); }
+
+int aqe_device_count(int* out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { if (out) *out = 0; return cuda_fail(e, "cudaGetDeviceCount"); }
+    if (out) *out = n;
+    return AQE_OK;
+}
+
+int aqe_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(AQE_ERR_INVALID, "NULL out");
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return AQE_OK;
+}
+int aqe_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return AQE_OK;
+}
+
+int aqe_create(int device, aqe_db** out) {
+    if (!out) return fail(AQE_ERR_INVALID, "out is NULL");
+    aqe_db* db = new (std::nothrow) aqe_db();
+    if (!db) return fail(AQE_ERR_NOMEM, "out of host memory");
+    db->device = device;
+    *out = db;
+    return AQE_OK;
+}
+
+int aqe_close(aqe_db* db) {
+    if (!db) return AQE_OK;
+    if (db->cuda_ready) {
+        cudaSetDevice(db->device);
+        cudaStreamSynchronize(db->stream);
+        free_columns(db);
+        cudaFree(db->scan_partials); cudaFree(db->stat_partials); cudaFree(db->approx_slots); cudaFree(db->tickets);
+        cudaFree(db->gather_buf); cudaFree(db->plan_buf);
+        cudaFreeHost(db->slot_host);
+        cudaEventDestroy(db->ev0); cudaEventDestroy(db->ev1);
+        cudaStreamDestroy(db->stream);
+    }
+    delete db;
+    return AQE_OK;
+}
+
+int aqe_load_file(aqe_db* db, const char* path, uint64_t first_row, uint64_t n_rows) {
+    if (!db || !path) return fail(AQE_ERR_INVALID, "NULL argument");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(AQE_ERR_IO, std::string("cannot open ") + path);
+    uint64_t hdr[3];
+    if (std::fread(hdr, 8, 3, f) != 3) { std::fclose(f); return fail(AQE_ERR_IO, std::string("short header in ") + path); }
+    const uint64_t total = hdr[2];  // record_count; the first two words are ignored (custom_bplus_db.cpp:692-698)
+    if (first_row > total) first_row = total;
+    const uint64_t n = std::min<uint64_t>(n_rows, total - first_row);
+    int rc = db_init_cuda(db);
+    if (rc) { std::fclose(f); return rc; }
+    db->host_rows.clear(); db->host_authoritative = false;
+    if (fseeko(f, (off_t)(24 + first_row * 32), SEEK_SET) != 0) { std::fclose(f); return fail(AQE_ERR_IO, "seek failed"); }
+    bool unsorted = false;
+    rc = ingest_rows(db, n, [&](aqe_record* dst, uint64_t, uint64_t cnt) { return std::fread(dst, sizeof(aqe_record), cnt, f) == cnt; }, &unsorted);
+    if (rc == AQE_OK && unsorted) {
+        std::vector<aqe_record> rows(n);
+        if (fseeko(f, (off_t)(24 + first_row * 32), SEEK_SET) != 0 || std::fread(rows.data(), sizeof(aqe_record), n, f) != n) {
+            std::fclose(f);
+            return fail(AQE_ERR_IO, "re-read failed");
+        }
+        rc = upload_host_rows(db, rows.data(), n);
+    }
+    std::fclose(f);
+    return rc;
+}
+
+int aqe_open(const char* path, int device, aqe_db** out) {
+    int rc = aqe_create(device, out);
+    if (rc) return rc;
+    rc = aqe_load_file(*out, path, 0, UINT64_MAX);
+    if (rc) { std::string keep = g_err; aqe_close(*out); *out = nullptr; g_err = keep; }
+    return rc;
+}
+
+int aqe_append_records(aqe_db* db, const aqe_record* rows, size_t n) {
+    if (!db || (!rows && n)) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (!db->host_authoritative) {
+        // first append after a load: pull the table back so that host_rows is the whole table
+        db->host_rows.clear();
+        if (db->n) {
+            db->host_rows.resize(db->n);
+            int rc = aqe_read_records(db, 0, db->n, db->host_rows.data());
+            if (rc) return rc;
+        }
+        db->host_authoritative = true;
+    }
+    db->host_rows.insert(db->host_rows.end(), rows, rows + n);
+    return AQE_OK;
+}
+
+int aqe_from_host_records(aqe_db* db, const aqe_record* rows, size_t n) {
+    if (!db || (!rows && n)) return fail(AQE_ERR_INVALID, "NULL argument");
+    int rc = db_init_cuda(db);
+    if (rc) return rc;
+    db->host_rows.clear(); db->host_authoritative = false;
+    return upload_host_rows(db, rows, n);
+}
+
+int aqe_attach_device_columns(aqe_db* db, const int64_t* id, const double* amount, const int32_t* region,
+                              const int32_t* product_id, const int64_t* timestamp, uint64_t n) {
+    if (!db) return fail(AQE_ERR_INVALID, "NULL handle");
+    int rc = db_init_cuda(db);
+    if (rc) return rc;
+    free_columns(db);
+    db->host_rows.clear(); db->host_authoritative = false;
+    db->col = MutColumns{const_cast<int64_t*>(id), const_cast<double*>(amount), const_cast<int32_t*>(region),
+                         const_cast<int32_t*>(product_id), const_cast<int64_t*>(timestamp)};
+    db->owned = false;
+    db->n = n;
+    return AQE_OK;
+}
+
+int aqe_generate_synthetic(aqe_db* db, uint64_t seed, uint64_t first_row, uint64_t n_rows, int dist, uint32_t columns_mask) {
+    if (!db) return fail(AQE_ERR_INVALID, "NULL handle");
+    int rc = db_init_cuda(db);
+    if (rc) return rc;
+    db->host_rows.clear(); db->host_authoritative = false;
+    rc = alloc_columns(db, n_rows, columns_mask ? columns_mask : 0x1f);
+    if (rc) return rc;
+    if (n_rows == 0) return AQE_OK;
+    const int grid = grid_for(db, n_rows, 4, 256, 8);
+    k_synth<<<grid, 256, 0, db->stream>>>(seed, first_row, n_rows, dist, db->col);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(db->stream));
+    return AQE_OK;
+}
+
+int aqe_synth_rows_host(uint64_t seed, uint64_t first_row, uint64_t n_rows, int dist, aqe_record* rows) {
+    if (!rows && n_rows) return fail(AQE_ERR_INVALID, "NULL rows");
+    for (uint64_t i = 0; i < n_rows; ++i) synth_row(seed, first_row + i, dist, rows[i]);
+    return AQE_OK;
+}
+
+uint64_t aqe_count(const aqe_db* db) { return db ? (db->host_authoritative ? db->host_rows.size() : db->n) : 0; }
+uint64_t aqe_node_count(const aqe_db* db) { return aqe_count(db) / 255 + 1; }  // custom_bplus_db.cpp:654-658
+uint64_t aqe_tree_height(const aqe_db* db) { return tree_height(aqe_count(db)); }
+int aqe_device(const aqe_db* db) { return db ? db->device : -1; }
+
+const void* aqe_column_device_ptr(aqe_db* db, int col) {
+    if (!db || ensure_device(db)) return nullptr;
+    switch (col) {
+        case AQE_COL_ID: return db->col.id;
+        case AQE_COL_AMOUNT: return db->col.amount;
+        case AQE_COL_REGION: return db->col.region;
+        case AQE_COL_PRODUCT_ID: return db->col.product_id;
+        case AQE_COL_TIMESTAMP: return db->col.timestamp;
+        default: return nullptr;
+    }
+}
+
+static int ensure_gather_buf(aqe_db* db, uint64_t rows) {
+    if (rows <= db->gather_cap) return AQE_OK;
+    if (db->gather_buf) cudaFree(db->gather_buf);
+    db->gather_buf = nullptr; db->gather_cap = 0;
+    const uint64_t cap = std::max<uint64_t>(rows, 1u << 16);
+    CU(cudaMalloc(&db->gather_buf, cap * sizeof(aqe_record)));
+    db->gather_cap = cap;
+    return AQE_OK;
+}
+
+int aqe_read_records(aqe_db* db, uint64_t first, uint64_t n, aqe_record* out) {
+    if (!db || (!out && n)) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (db->host_authoritative) {
+        if (first + n > db->host_rows.size()) return fail(AQE_ERR_INVALID, "row range out of bounds");
+        // rows are reported in ascending id, as collect_all_records does (custom_bplus_db.cpp:660)
+        int rc = ensure_device(db);
+        if (rc) return rc;
+    }
+    int rc = db_init_cuda(db);
+    if (rc) return rc;
+    if (first + n > db->n) return fail(AQE_ERR_INVALID, "row range out of bounds");
+    const uint64_t chunk = 1u << 22;
+    rc = ensure_gather_buf(db, std::min<uint64_t>(n, chunk));
+    if (rc) return rc;
+    for (uint64_t off = 0; off < n; off += chunk) {
+        const uint64_t cnt = std::min<uint64_t>(chunk, n - off);
+        k_soa_to_aos<<<grid_for(db, cnt, 4, 256, 8), 256, 0, db->stream>>>(const_cols(db), db->gather_buf, first + off, cnt);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out + off, db->gather_buf, cnt * sizeof(aqe_record), cudaMemcpyDeviceToHost, db->stream));
+        CU(cudaStreamSynchronize(db->stream));
+    }
+    return AQE_OK;
+}
+
+int aqe_save_file(aqe_db* db, const char* path) {
+    if (!db || !path) return fail(AQE_ERR_INVALID, "NULL argument");
+    const uint64_t n = aqe_count(db);
+    std::vector<aqe_record> rows(n);
+    if (n) {
+        int rc = ensure_device(db);
+        if (rc) return rc;
+        rc = aqe_read_records(db, 0, n, rows.data());
+        if (rc) return rc;
+    }
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(AQE_ERR_IO, std::string("cannot create ") + path);
+    const uint64_t hdr[3] = {n, tree_height(n), n};  // custom_bplus_db.cpp:669-676
+    bool ok = std::fwrite(hdr, 8, 3, f) == 3;
+    if (ok && n) ok = std::fwrite(rows.data(), sizeof(aqe_record), n, f) == n;
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? AQE_OK : fail(AQE_ERR_IO, std::string("write failed: ") + path);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// exact scans
+// ------------------------------------------------------------------------------------------------
+enum ColKind { K_F64 = 0, K_I64 = 1, K_I32 = 2 };
+static int col_kind(int col) {
+    switch (col) {
+        case AQE_COL_AMOUNT: return K_F64;
+        case AQE_COL_ID: case AQE_COL_TIMESTAMP: return K_I64;
+        case AQE_COL_REGION: case AQE_COL_PRODUCT_ID: return K_I32;
+        default: return -1;
+    }
+}
+static const void* col_ptr(const aqe_db* db, int col) {
+    switch (col) {
+        case AQE_COL_ID: return db->col.id;
+        case AQE_COL_AMOUNT: return db->col.amount;
+        case AQE_COL_REGION: return db->col.region;
+        case AQE_COL_PRODUCT_ID: return db->col.product_id;
+        case AQE_COL_TIMESTAMP: return db->col.timestamp;
+        default: return nullptr;
+    }
+}
+static size_t kind_size(int k) { return k == K_I32 ? 4 : 8; }
+
+struct ScanTuning { int variant, bps, unroll, stages, chunk_kb; };
+static ScanTuning scan_tuning() {
+    static ScanTuning t = {env_int("AQE_SCAN_VARIANT", 0), env_int("AQE_SCAN_BPS", 0), env_int("AQE_SCAN_UNROLL", 4),
+                           env_int("AQE_SCAN_STAGES", 4), env_int("AQE_SCAN_CHUNK_KB", 16)};
+    return t;
+}
+
+template <typename AggT, int PRED, typename PredT, bool MOMENTS>
+static int launch_scan_t(const aqe_db* db, const ScanArgs& a, bool aligned, cudaStream_t s) {
+    const ScanTuning t = scan_tuning();
+    if (!aligned) {
+        const int grid = grid_for(db, a.n, 8, kScanThreads, 8);
+        k_scan_unaligned<AggT, PRED, PredT, MOMENTS><<<grid, kScanThreads, 0, s>>>(a);
+        LAUNCHED();
+        return AQE_OK;
+    }
+    if constexpr (std::is_same_v<AggT, double> && PRED != 2) {
+        if (t.variant == 2) {  // TMA-staged ring
+            auto go = [&](auto kernel, int stages, int chunk) {
+                const size_t smem = (size_t)stages * chunk;
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                int occ = 1;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBulkThreads, smem);
+                if (occ < 1) occ = 1;
+                const int bps = t.bps > 0 ? std::min(t.bps, occ) : occ;
+                const uint64_t nchunks = (a.n * 8 + chunk - 1) / chunk;
+                int grid = (int)std::min<uint64_t>((uint64_t)db->sm_count * bps, std::max<uint64_t>(nchunks, 1));
+                if (grid > db->max_grid) grid = db->max_grid;
+                kernel<<<grid, kBulkThreads, smem, s>>>(a);
+                LAUNCHED();
+            };
+            if (t.chunk_kb == 32 && t.stages == 4) go(k_scan_bulk<PRED, 4, 32768, MOMENTS>, 4, 32768);
+            else if (t.chunk_kb == 32 && t.stages == 6) go(k_scan_bulk<PRED, 6, 32768, MOMENTS>, 6, 32768);
+            else if (t.chunk_kb == 8) go(k_scan_bulk<PRED, 8, 8192, MOMENTS>, 8, 8192);
+            else if (t.stages == 8) go(k_scan_bulk<PRED, 8, 16384, MOMENTS>, 8, 16384);
+            else go(k_scan_bulk<PRED, 4, 16384, MOMENTS>, 4, 16384);
+            return AQE_OK;
+        }
+        if (t.variant == 1 || t.unroll != 4) {  // tuning sweeps of the headline kernels
+            auto go = [&](auto kernel, int W, int U) {
+                int occ = 1;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kScanThreads, 0);
+                const int bps = t.bps > 0 ? std::min(t.bps, std::max(occ, 1)) : std::max(occ, 1);
+                kernel<<<grid_for(db, a.n / W, U, kScanThreads, bps), kScanThreads, 0, s>>>(a);
+                LAUNCHED();
+            };
+            if (t.variant == 1) {
+                if (t.unroll == 8) go(k_scan<AggT, PRED, PredT, 2, 8, MOMENTS, 1>, 2, 8);
+                else if (t.unroll == 2) go(k_scan<AggT, PRED, PredT, 2, 2, MOMENTS, 1>, 2, 2);
+                else go(k_scan<AggT, PRED, PredT, 2, 4, MOMENTS, 1>, 2, 4);
+            } else {
+                if (t.unroll == 8) go(k_scan<AggT, PRED, PredT, 4, 8, MOMENTS, 1>, 4, 8);
+                else if (t.unroll == 2) go(k_scan<AggT, PRED, PredT, 4, 2, MOMENTS, 1>, 4, 2);
+                else go(k_scan<AggT, PRED, PredT, 4, 1, MOMENTS, 1>, 4, 1);
+            }
+            return AQE_OK;
+        }
+    }
+    auto kernel = k_scan<AggT, PRED, PredT, 4, 4, MOMENTS, 1>;
+    static int occ_cache = 0;  // per instantiation
+    if (occ_cache == 0) {
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kScanThreads, 0);
+        occ_cache = std::max(occ, 1);
+    }
+    const int bps = t.bps > 0 ? std::min(t.bps, occ_cache) : occ_cache;
+    kernel<<<grid_for(db, a.n / 4, 4, kScanThreads, bps), kScanThreads, 0, s>>>(a);
+    LAUNCHED();
+    return AQE_OK;
+}
+
+template <typename AggT, bool MOMENTS>
+static int launch_scan_pred(const aqe_db* db, const ScanArgs& a, int pred_mode, int pred_kind, bool aligned, cudaStream_t s) {
+    if (pred_mode == 0) return launch_scan_t<AggT, 0, AggT, MOMENTS>(db, a, aligned, s);
+    if (pred_mode == 1) return launch_scan_t<AggT, 1, AggT, MOMENTS>(db, a, aligned, s);
+    switch (pred_kind) {
+        case K_F64: return launch_scan_t<AggT, 2, double, MOMENTS>(db, a, aligned, s);
+        case K_I64: return launch_scan_t<AggT, 2, int64_t, MOMENTS>(db, a, aligned, s);
+        default: return launch_scan_t<AggT, 2, int32_t, MOMENTS>(db, a, aligned, s);
+    }
+}
+
+// Launches the scan of rows [first, first+n) of the handle's columns; result lands at out_dev.
+static int scan_launch(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, uint64_t n, bool moments, aqe_partial* out_dev,
+                       cudaStream_t s) {
+    const int ak = col_kind(spec->agg_col);
+    if (ak < 0) return fail(AQE_ERR_INVALID, "bad aggregate column");
+    const char* agg = static_cast<const char*>(col_ptr(db, spec->agg_col));
+    if (!agg && n) return fail(AQE_ERR_STATE, "aggregate column is not resident on the device");
+    int pred_mode = 0, pk = ak;
+    const char* pred = nullptr;
+    if (spec->pred_col != AQE_COL_NONE) {
+        pk = col_kind(spec->pred_col);
+        if (pk < 0) return fail(AQE_ERR_INVALID, "bad predicate column");
+        if (spec->pred_col == spec->agg_col) pred_mode = 1;
+        else {
+            pred_mode = 2;
+            pred = static_cast<const char*>(col_ptr(db, spec->pred_col));
+            if (!pred && n) return fail(AQE_ERR_STATE, "predicate column is not resident on the device");
+        }
+    }
+    ScanArgs a;
+    a.agg = agg ? agg + first * kind_size(ak) : nullptr;
+    a.pred = pred ? pred + first * kind_size(pk) : nullptr;
+    a.n = n; a.lo = spec->lo; a.hi = spec->hi;
+    a.partials = db->scan_partials; a.ticket = db->tickets + 0; a.out = out_dev;
+    // W = 4 elements per vector: 32-byte alignment for 8-byte columns, 16 for 4-byte columns
+    auto aligned_for = [](const void* p, int kind) { return ((uintptr_t)p % (kind == K_I32 ? 16 : 32)) == 0; };
+    const bool aligned = aligned_for(a.agg, ak) && (pred_mode != 2 || aligned_for(a.pred, pk));
+    int rc;
+    if (ak == K_F64) rc = moments ? launch_scan_pred<double, true>(db, a, pred_mode, pk, aligned, s) : launch_scan_pred<double, false>(db, a, pred_mode, pk, aligned, s);
+    else if (ak == K_I64) rc = launch_scan_pred<int64_t, false>(db, a, pred_mode, pk, aligned, s);
+    else rc = launch_scan_pred<int32_t, false>(db, a, pred_mode, pk, aligned, s);
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    return AQE_OK;
+}
+
+static int scan_sync(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, uint64_t n, bool moments, aqe_partial* out) {
+    int rc = scan_launch(db, spec, first, n, moments, &db->slot_dev->partial, db->stream);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(db->stream));
+    *out = db->slot_host->partial;
+    return AQE_OK;
+}
+
+extern "C" {
+
+int aqe_scan(aqe_db* db, const aqe_scan_spec* spec, aqe_partial* out) {
+    if (!db || !spec || !out) return fail(AQE_ERR_INVALID, "NULL argument");
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    return scan_sync(db, spec, 0, db->n, true, out);
+}
+
+int aqe_scan_async(aqe_db* db, const aqe_scan_spec* spec, void* partial_dev, void* stream) {
+    if (!db || !spec || !partial_dev) return fail(AQE_ERR_INVALID, "NULL argument");
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    return scan_launch(db, spec, 0, db->n, false, static_cast<aqe_partial*>(partial_dev), stream ? (cudaStream_t)stream : db->stream);
+}
+
+int aqe_merge_partials(const aqe_partial* parts, int n, int is_integer, aqe_partial* out) {
+    if (!parts || !out || n < 0) return fail(AQE_ERR_INVALID, "bad argument");
+    aqe_partial r;
+    std::memset(&r, 0, sizeof(r));
+    r.minv = INFINITY; r.maxv = -INFINITY;
+    __int128 isum = 0;
+    // double-double fold in rank order (TwoSum), so the merged sum does not depend on the shard count
+    // beyond the last bit
+    double s = 0.0, c = 0.0, q = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const aqe_partial& p = parts[i];
+        r.count += p.count;
+        isum += ((__int128)p.isum_hi << 64) + (__int128)p.isum_lo;
+        volatile double t = s + p.sum;
+        volatile double z = t - s;
+        volatile double e = (s - (t - z)) + (p.sum - z);
+        c += p.comp + e;
+        s = t;
+        q += p.sumsq;
+        if (p.count) { r.minv = std::min(r.minv, p.minv); r.maxv = std::max(r.maxv, p.maxv); }
+    }
+    volatile double t = s + c;
+    r.comp = c - (t - s);
+    r.sum = t;
+    r.sumsq = q;
+    r.isum_lo = (uint64_t)isum; r.isum_hi = (int64_t)(isum >> 64);
+    if (is_integer) { r.sum = (double)isum; r.comp = 0.0; }
+    *out = r;
+    return AQE_OK;
+}
+
+int aqe_sum_f64(aqe_db* db, int col, double* out) {
+    if (!out) return fail(AQE_ERR_INVALID, "NULL out");
+    if (col_kind(col) != K_F64) return fail(AQE_ERR_INVALID, "aqe_sum_f64 needs an f64 column");
+    if (aqe_count(db) == 0) { *out = 0.0; return db ? AQE_OK : fail(AQE_ERR_INVALID, "NULL handle"); }
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    aqe_scan_spec sp{col, AQE_COL_NONE, 0.0, 0.0};
+    aqe_partial p;
+    rc = scan_sync(db, &sp, 0, db->n, false, &p);
+    if (rc) return rc;
+    *out = p.sum;
+    return AQE_OK;
+}
+
+int aqe_sum_where_f64(aqe_db* db, int col, double lo, double hi, double* sum, uint64_t* count) {
+    if (col_kind(col) != K_F64) return fail(AQE_ERR_INVALID, "aqe_sum_where_f64 needs an f64 column");
+    if (aqe_count(db) == 0) { if (sum) *sum = 0.0; if (count) *count = 0; return db ? AQE_OK : fail(AQE_ERR_INVALID, "NULL handle"); }
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    aqe_scan_spec sp{col, col, lo, hi};
+    aqe_partial p;
+    rc = scan_sync(db, &sp, 0, db->n, false, &p);
+    if (rc) return rc;
+    if (sum) *sum = p.sum;
+    if (count) *count = p.count;
+    return AQE_OK;
+}
+
+int aqe_sum_i128(aqe_db* db, int col, uint64_t* lo64, int64_t* hi64) {
+    const int k = col_kind(col);
+    if (k != K_I64 && k != K_I32) return fail(AQE_ERR_INVALID, "aqe_sum_i128 needs an integer column");
+    if (aqe_count(db) == 0) { if (lo64) *lo64 = 0; if (hi64) *hi64 = 0; return db ? AQE_OK : fail(AQE_ERR_INVALID, "NULL handle"); }
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    aqe_scan_spec sp{col, AQE_COL_NONE, 0.0, 0.0};
+    aqe_partial p;
+    rc = scan_sync(db, &sp, 0, db->n, false, &p);
+    if (rc) return rc;
+    if (lo64) *lo64 = p.isum_lo;
+    if (hi64) *hi64 = p.isum_hi;
+    return AQE_OK;
+}
+
+// ---- host-resident column through the device (end-to-end form) -------------------------------------------
+struct HostScanCtx {
+    int device = -1;
+    aqe_db* db = nullptr;           // scratch (partials, tickets) + stream
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    void* dev[2] = {nullptr, nullptr};
+    void* pinned[2] = {nullptr, nullptr};
+    cudaEvent_t freed[2] = {nullptr, nullptr};
+    aqe_partial* parts_dev = nullptr;
+    ScanAcc* partials2 = nullptr;   // second scratch so the two streams never share a partial array
+    unsigned int* tickets2 = nullptr;
+    size_t chunk_bytes = 0;
+    size_t max_chunks = 0;
+};
+static std::mutex g_hs_mu;
+static HostScanCtx g_hs[16];
+
+static int host_scan_ctx(int device, HostScanCtx** out) {
+    if (device < 0 || device >= 16) return fail(AQE_ERR_INVALID, "device out of range");
+    HostScanCtx& c = g_hs[device];
+    if (c.device == device) { CU(cudaSetDevice(device)); *out = &c; return AQE_OK; }
+    int rc = aqe_create(device, &c.db);
+    if (rc) return rc;
+    rc = db_init_cuda(c.db);
+    if (rc) return rc;
+    c.chunk_bytes = (size_t)env_int("AQE_E2E_CHUNK_MB", 64) << 20;
+    c.max_chunks = 4096;
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaStreamCreateWithFlags(&c.streams[i], cudaStreamNonBlocking));
+        CU(cudaMalloc(&c.dev[i], c.chunk_bytes));
+        CU(cudaEventCreateWithFlags(&c.freed[i], cudaEventDisableTiming));
+    }
+    CU(cudaMalloc(&c.parts_dev, sizeof(aqe_partial) * c.max_chunks));
+    CU(cudaMalloc(&c.partials2, sizeof(ScanAcc) * kMaxGrid));
+    CU(cudaMalloc(&c.tickets2, 16));
+    CU(cudaMemset(c.tickets2, 0, 16));
+    c.device = device;
+    *out = &c;
+    return AQE_OK;
+}
+
+int aqe_scan_host_column(int device, const void* host_col, int col_kind_id, uint64_t n, double lo, double hi, int use_pred,
+                         aqe_partial* out) {
+    if (!out || (!host_col && n)) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (col_kind_id < 0 || col_kind_id > 2) return fail(AQE_ERR_INVALID, "col_kind: 0 f64, 1 i64, 2 i32");
+    std::lock_guard<std::mutex> lock(g_hs_mu);
+    HostScanCtx* c = nullptr;
+    int rc = host_scan_ctx(device, &c);
+    if (rc) return rc;
+    const size_t esz = kind_size(col_kind_id);
+    const uint64_t per_chunk = c->chunk_bytes / esz;
+    const uint64_t nchunks = n ? (n + per_chunk - 1) / per_chunk : 0;
+    if (nchunks > c->max_chunks) return fail(AQE_ERR_UNSUPPORTED, "column too large for aqe_scan_host_column; raise AQE_E2E_CHUNK_MB");
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, host_col) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned) {
+        for (int i = 0; i < 2; ++i)
+            if (!c->pinned[i]) CU(cudaHostAlloc(&c->pinned[i], c->chunk_bytes, cudaHostAllocDefault));
+    }
+    aqe_db* db = c->db;
+    // a fake one-column handle view per chunk
+    for (uint64_t k = 0; k < nchunks; ++k) {
+        const int b = (int)(k & 1);
+        const uint64_t first = k * per_chunk, cnt = std::min<uint64_t>(per_chunk, n - first);
+        const char* src = static_cast<const char*>(host_col) + first * esz;
+        if (!pinned) {
+            CU(cudaEventSynchronize(c->freed[b]));
+            std::memcpy(c->pinned[b], src, cnt * esz);
+            src = static_cast<const char*>(c->pinned[b]);
+        }
+        CU(cudaMemcpyAsync(c->dev[b], src, cnt * esz, cudaMemcpyHostToDevice, c->streams[b]));
+        ScanArgs a;
+        a.agg = c->dev[b]; a.pred = nullptr; a.n = cnt; a.lo = lo; a.hi = hi;
+        a.partials = b ? c->partials2 : db->scan_partials;
+        a.ticket = b ? c->tickets2 : db->tickets + 1;
+        a.out = c->parts_dev + k;
+        const int pm = use_pred ? 1 : 0;
+        if (col_kind_id == K_F64) rc = launch_scan_pred<double, false>(db, a, pm, K_F64, true, c->streams[b]);
+        else if (col_kind_id == K_I64) rc = launch_scan_pred<int64_t, false>(db, a, pm, K_I64, true, c->streams[b]);
+        else rc = launch_scan_pred<int32_t, false>(db, a, pm, K_I32, true, c->streams[b]);
+        if (rc) return rc;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(c->freed[b], c->streams[b]));
+    }
+    std::vector<aqe_partial> parts(nchunks);
+    for (int i = 0; i < 2; ++i) CU(cudaStreamSynchronize(c->streams[i]));
+    if (nchunks) CU(cudaMemcpy(parts.data(), c->parts_dev, sizeof(aqe_partial) * nchunks, cudaMemcpyDeviceToHost));
+    return aqe_merge_partials(parts.data(), (int)nchunks, col_kind_id != K_F64, out);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// plans on the device, sampled aggregates
+// ------------------------------------------------------------------------------------------------
+static int plan_to_device(aqe_db* db, const aqe_plan* pl, PlanDev* out) {
+    PlanDev P{};
+    P.count = pl->count; P.nseg = (uint32_t)pl->segs.size(); P.perm = nullptr;
+    const size_t seg_bytes = pl->segs.size() * sizeof(aqe_segment);
+    const size_t start_bytes = pl->seg_start.size() * sizeof(uint64_t);
+    const size_t idx_bytes = pl->segs.empty() ? pl->idx.size() * sizeof(int64_t) : 0;
+    const size_t need = ((seg_bytes + 255) & ~(size_t)255) + ((start_bytes + 255) & ~(size_t)255) + idx_bytes + 256;
+    if (need > db->plan_cap) {
+        if (db->plan_buf) cudaFree(db->plan_buf);
+        db->plan_buf = nullptr; db->plan_cap = 0;
+        const size_t cap = std::max<size_t>(need, 1u << 20);
+        CU(cudaMalloc(&db->plan_buf, cap));
+        db->plan_cap = cap;
+    }
+    char* base = static_cast<char*>(db->plan_buf);
+    if (!pl->segs.empty()) {
+        CU(cudaMemcpyAsync(base, pl->segs.data(), seg_bytes, cudaMemcpyHostToDevice, db->stream));
+        char* st = base + ((seg_bytes + 255) & ~(size_t)255);
+        CU(cudaMemcpyAsync(st, pl->seg_start.data(), start_bytes, cudaMemcpyHostToDevice, db->stream));
+        P.segs = reinterpret_cast<const aqe_segment*>(base);
+        P.seg_start = reinterpret_cast<const uint64_t*>(st);
+    } else if (idx_bytes) {
+        CU(cudaMemcpyAsync(base, pl->idx.data(), idx_bytes, cudaMemcpyHostToDevice, db->stream));
+        P.idx = reinterpret_cast<const int64_t*>(base);
+    }
+    *out = P;
+    return AQE_OK;
+}
+
+static int check_plan_bounds(const aqe_db* db, const aqe_plan* pl) {
+    // explicit lists supplied by callers are validated; generated plans are in range by construction
+    for (int64_t v : pl->idx)
+        if (v < 0 || (uint64_t)v >= db->n) return fail(AQE_ERR_INVALID, "sample index out of range");
+    return AQE_OK;
+}
+
+static int ensure_amount_perm(aqe_db* db);  // below (stratified)
+
+static int stats_launch(aqe_db* db, const aqe_plan* pl, int col, aqe_stats* out, int pred_col = AQE_COL_NONE, double lo = 0.0, double hi = 0.0) {
+    if (col_kind(col) < 0) return fail(AQE_ERR_INVALID, "bad column");
+    if (pred_col != AQE_COL_NONE && (col_kind(pred_col) < 0 || !col_ptr(db, pred_col))) return fail(AQE_ERR_INVALID, "bad predicate column");
+    if (!col_ptr(db, col) && pl->count) return fail(AQE_ERR_STATE, "column is not resident on the device");
+    if (pl->count == 0) { out->n = 0; out->mean = 0; out->m2 = 0; out->sum = 0; return AQE_OK; }
+    StatArgs a;
+    int rc = plan_to_device(db, pl, &a.plan);
+    if (rc) return rc;
+    if (pl->by_amount_order) { rc = ensure_amount_perm(db); if (rc) return rc; a.plan.perm = db->amount_perm; }
+    a.cols = const_cols(db); a.col = col; a.pred_col = pred_col; a.lo = lo; a.hi = hi; a.partials = db->stat_partials; a.ticket = db->tickets + 2; a.out = &db->slot_dev->stats;
+    const int grid = grid_for(db, pl->count, 4, 256, 4);
+    k_plan_stats<<<grid, 256, 0, db->stream>>>(a);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(db->stream));
+    *out = db->slot_host->stats;
+    return AQE_OK;
+}
+
+static int gather_launch(aqe_db* db, const aqe_plan* pl, aqe_record* out, uint64_t cap) {
+    const uint64_t n = std::min<uint64_t>(pl->count, cap);
+    if (n == 0) return AQE_OK;
+    PlanDev P;
+    int rc = plan_to_device(db, pl, &P);
+    if (rc) return rc;
+    if (pl->by_amount_order) { rc = ensure_amount_perm(db); if (rc) return rc; P.perm = db->amount_perm; }
+    const uint64_t chunk = 1u << 22;
+    rc = ensure_gather_buf(db, std::min<uint64_t>(n, chunk));
+    if (rc) return rc;
+    for (uint64_t off = 0; off < n; off += chunk) {
+        const uint64_t cnt = std::min<uint64_t>(chunk, n - off);
+        k_plan_gather<<<grid_for(db, cnt, 2, 256, 8), 256, 0, db->stream>>>(P, const_cols(db), db->gather_buf, off, cnt);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out + off, db->gather_buf, cnt * sizeof(aqe_record), cudaMemcpyDeviceToHost, db->stream));
+        CU(cudaStreamSynchronize(db->stream));
+    }
+    return AQE_OK;
+}
+
+// ---- amount-sorted permutation (stratified_block_sample sorts the table by amount, cbd:1343-1345) ----
+__global__ void k_iota(int64_t* p, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (int64_t)i;
+}
+static int ensure_amount_perm(aqe_db* db) {
+    if (db->amount_perm || db->n == 0) return AQE_OK;
+    if (!db->col.amount) return fail(AQE_ERR_STATE, "amount column is not resident on the device");
+    const uint64_t n = db->n;
+    int64_t *iota = nullptr, *perm = nullptr;
+    double* keys_out = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    CU(cudaMalloc(&iota, n * 8));
+    CU(cudaMalloc(&perm, n * 8));
+    CU(cudaMalloc(&keys_out, n * 8));
+    k_iota<<<grid_for(db, n, 4, 256, 8), 256, 0, db->stream>>>(iota, n);
+    LAUNCHED();
+    // stable LSD radix sort on the f64 keys: ties keep ascending row order
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, db->col.amount, keys_out, iota, perm, (int64_t)n, 0, 64, db->stream));
+    CU(cudaMalloc(&tmp, tmp_bytes));
+    CU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, db->col.amount, keys_out, iota, perm, (int64_t)n, 0, 64, db->stream));
+    LAUNCHED();
+    CU(cudaStreamSynchronize(db->stream));
+    cudaFree(tmp); cudaFree(iota); cudaFree(keys_out);
+    db->amount_perm = perm;
+    return AQE_OK;
+}
+
+// ---- lock-step stop step of clt_validated_dual_pointer_sample on the device ---------------------------------
+// One CTA per sampler thread q walks that thread's stride sequence in chunks of blockDim.x samples, keeps
+// running sums of d = x - K and d^2 (K = first sample) with a block scan, evaluates the reference's check
+// (custom_bplus_db.cpp:936-961 fast, :993-1016 slow) at every checkpoint inside the chunk and records per
+// thread the first step at which ITS OWN rule would fire given the published fast mean; the host then
+// resolves the global first stop in (step, thread) order.
+struct CltArgs {
+    const double* amount;
+    CltThread th[64];
+    int nthreads;
+    int64_t check_interval, T;
+    double z, max_err;
+    // per (thread, checkpoint) outputs for the host resolution
+    double* mean_out;   // [nthreads][max_checks]
+    double* err_out;    // fast: error percent ; slow: unused
+    uint64_t max_checks;
+    uint64_t max_steps; // only steps <= max_steps are evaluated in this launch
+};
+
+__global__ void __launch_bounds__(1024) k_clt_prefix(const CltArgs a) {
+    __shared__ double s_d[32], s_dd[32];
+    __shared__ double carry_d, carry_dd;
+    const int q = blockIdx.x;
+    const CltThread t = a.th[q];
+    const uint64_t every = t.fast ? (uint64_t)a.check_interval : (uint64_t)(a.check_interval / 2);
+    const uint64_t minn = t.fast ? 30 : 20;
+    const uint64_t steps = t.len < a.max_steps ? t.len : a.max_steps;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double K = t.len ? a.amount[t.first] : 0.0;
+    if (threadIdx.x == 0) { carry_d = 0.0; carry_dd = 0.0; }
+    __syncthreads();
+    for (uint64_t base = 0; base < steps; base += blockDim.x) {
+        const uint64_t k = base + threadIdx.x;  // 0-based sample number
+        double d = 0.0, dd = 0.0;
+        if (k < steps) { d = a.amount[t.first + k * t.step] - K; dd = d * d; }
+        // inclusive block scan of (d, dd)
+        double pd = d, pdd = dd;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double x = __shfl_up_sync(0xffffffffu, pd, o), y = __shfl_up_sync(0xffffffffu, pdd, o);
+            if (lane >= o) { pd += x; pdd += y; }
+        }
+        if (lane == 31) { s_d[warp] = pd; s_dd[warp] = pdd; }
+        __syncthreads();
+        if (warp == 0) {
+            double x = lane < nw ? s_d[lane] : 0.0, y = lane < nw ? s_dd[lane] : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double u = __shfl_up_sync(0xffffffffu, x, o), v = __shfl_up_sync(0xffffffffu, y, o);
+                if (lane >= o) { x += u; y += v; }
+            }
+            if (lane < nw) { s_d[lane] = x; s_dd[lane] = y; }
+        }
+        __syncthreads();
+        const double off_d = carry_d + (warp ? s_d[warp - 1] : 0.0), off_dd = carry_dd + (warp ? s_dd[warp - 1] : 0.0);
+        const double Sd = off_d + pd, Sdd = off_dd + pdd;
+        const uint64_t cnt = k + 1;
+        if (k < steps && cnt % every == 0 && cnt >= minn) {
+            const double n = (double)cnt;
+            const double mean = K + Sd / n;
+            double var = (Sdd - Sd * Sd / n) / (n - 1.0);
+            if (var < 0.0) var = 0.0;
+            const uint64_t ci = cnt / every - 1;
+            if (ci < a.max_checks) {
+                a.mean_out[(size_t)q * a.max_checks + ci] = mean;
+                a.err_out[(size_t)q * a.max_checks + ci] = (a.z * sqrt(var / n) / mean) * 100.0;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) { carry_d = Sd; carry_dd = Sdd; }
+        __syncthreads();
+    }
+}
+
+static int clt_resolve(aqe_db* db, const aqe_sample_params& P, PlanData& data) {
+    std::vector<CltThread> th;
+    int64_t T = 0;
+    std::string err;
+    int rc = clt_threads(db->n, P, th, T, err);
+    if (rc) return fail(rc, err);
+    data.clt_kstop = 0; data.clt_stopper = -1;
+    if (th.empty()) return AQE_OK;
+    if (th.size() > 64) return fail(AQE_ERR_UNSUPPORTED, "clt_validated_dual_pointer_sample: at most 64 threads");
+    if (!db->col.amount) return fail(AQE_ERR_STATE, "amount column is not resident on the device");
+    const int64_t ci = P.check_interval;
+    const double z = P.confidence_level >= 0.99 ? 2.576 : (P.confidence_level >= 0.95 ? 1.96 : 1.645);  // cbd:911-912
+    const int F = (int)(P.num_threads / 2);
+    uint64_t maxlen = 0;
+    for (auto& t : th) maxlen = std::max<uint64_t>(maxlen, t.len);
+    // windows of steps; stop as soon as one window contains the stop step
+    const uint64_t every_min = std::max<int64_t>(1, ci / 2);
+    double current_mean = 0.0;
+    uint64_t sample_count = 0;
+    uint64_t window = 1u << 15, begin = 0;
+    std::vector<double> mean_h, err_h;
+    double *mean_d = nullptr, *err_d = nullptr;
+    uint64_t cap_checks = 0;
+    while (begin < maxlen) {
+        const uint64_t end = std::min<uint64_t>(maxlen, begin ? begin * 4 : window);
+        const uint64_t checks = end / every_min + 1;
+        if (checks > cap_checks) {
+            if (mean_d) { cudaFree(mean_d); cudaFree(err_d); }
+            CU(cudaMalloc(&mean_d, th.size() * checks * 8));
+            CU(cudaMalloc(&err_d, th.size() * checks * 8));
+            cap_checks = checks;
+        }
+        CltArgs a;
+        a.amount = db->col.amount; a.nthreads = (int)th.size();
+        for (size_t q = 0; q < th.size(); ++q) a.th[q] = th[q];
+        a.check_interval = ci; a.T = T; a.z = z; a.max_err = P.max_error_percent;
+        a.mean_out = mean_d; a.err_out = err_d; a.max_checks = cap_checks; a.max_steps = end;
+        k_clt_prefix<<<(int)th.size(), 1024, 0, db->stream>>>(a);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        mean_h.resize(th.size() * cap_checks); err_h.resize(th.size() * cap_checks);
+        CU(cudaMemcpyAsync(mean_h.data(), mean_d, mean_h.size() * 8, cudaMemcpyDeviceToHost, db->stream));
+        CU(cudaMemcpyAsync(err_h.data(), err_d, err_h.size() * 8, cudaMemcpyDeviceToHost, db->stream));
+        CU(cudaStreamSynchronize(db->stream));
+        // replay the lock-step schedule over steps (begin, end]: fast threads first, thread order
+        for (uint64_t k = begin + 1; k <= end; ++k) {
+            for (size_t q = 0; q < th.size(); ++q) {
+                if (k > th[q].len) continue;
+                const bool fast = (int)q < F;
+                const uint64_t every = fast ? (uint64_t)ci : (uint64_t)(ci / 2), minn = fast ? 30 : 20;
+                if (k % every != 0 || k < minn) continue;
+                const uint64_t c = k / every - 1;
+                const double mean = mean_h[q * cap_checks + c];
+                if (fast) {
+                    current_mean = mean; sample_count = k;                              // cbd:949-951
+                    if (err_h[q * cap_checks + c] <= P.max_error_percent && k >= 50) {   // cbd:958
+                        data.clt_kstop = (int64_t)k; data.clt_stopper = (int64_t)q; goto done;
+                    }
+                } else if (current_mean > 0) {
+                    const double md = std::fabs(mean - current_mean) / current_mean;   // cbd:1008
+                    if (md <= P.max_error_percent / 100.0 && sample_count >= (uint64_t)(T / 2)) {
+                        data.clt_kstop = (int64_t)k; data.clt_stopper = (int64_t)q; goto done;
+                    }
+                }
+            }
+        }
+        begin = end;
+    }
+done:
+    if (mean_d) { cudaFree(mean_d); cudaFree(err_d); }
+    return AQE_OK;
+}
+
+extern "C" {
+
+void aqe_sample_params_default(aqe_sample_params* p, int method) {  // bindings.cpp:56-101
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->sample_percent = 1.0;
+    p->step_size = method == AQE_M_RANDOM_START_NTH ? 10 : 2;
+    p->num_threads = 4;
+    p->block_size = 1000;
+    if (method == AQE_M_PAGE) p->block_size = 4096;
+    if (method == AQE_M_ADAPTIVE_BLOCK) p->block_size = 500;
+    if (method == AQE_M_MEMORY_STRIDE || method == AQE_M_RANDOM_START_MEMORY_STRIDE) p->block_size = 0;
+    p->block_size_max = method == AQE_M_STRATIFIED_BLOCK ? 4 : 2000;
+    p->check_interval = method == AQE_M_OPTIMIZED_CLT ? 20 : 10;
+    p->confidence_level = 0.95;
+    p->max_error_percent = 2.0;
+    p->seed = 42;
+}
+
+int aqe_plan_build(aqe_db* db, uint64_t n_rows, int method, const aqe_sample_params* p, aqe_plan** out) {
+    if (!p || !out) return fail(AQE_ERR_INVALID, "NULL argument");
+    PlanData data;
+    double zone_var[10];
+    const bool needs_data = method == AQE_M_ADAPTIVE_BLOCK || method == AQE_M_CLT_VALIDATED_DUAL_POINTER;
+    if (needs_data) {
+        if (!db) return fail(AQE_ERR_STATE, "this sampler reads the table: pass a handle");
+        int rc = ensure_device(db);
+        if (rc) return rc;
+        n_rows = db->n;
+        const int64_t T = (int64_t)((double)n_rows * p->sample_percent / 100.0);
+        if (method == AQE_M_ADAPTIVE_BLOCK && n_rows >= 10 && T > 0) {
+            // zone variance = sum_sq/count - mean^2 (custom_bplus_db.cpp:1294-1304) from ten exact scans
+            const uint64_t zs = n_rows / 10;
+            for (int z = 0; z < 10; ++z) {
+                const uint64_t s = z * zs, e = std::min<uint64_t>(s + zs, n_rows);
+                aqe_scan_spec sp{AQE_COL_AMOUNT, AQE_COL_NONE, 0.0, 0.0};
+                aqe_partial part;
+                rc = scan_sync(db, &sp, s, e - s, true, &part);
+                if (rc) return rc;
+                const double cnt = (double)(e - s), mean = part.sum / cnt;
+                zone_var[z] = part.sumsq / cnt - mean * mean;
+            }
+            data.zone_var = zone_var;
+        } else if (method == AQE_M_ADAPTIVE_BLOCK) {
+            for (double& v : zone_var) v = 1.0;
+            data.zone_var = zone_var;
+        }
+        if (method == AQE_M_CLT_VALIDATED_DUAL_POINTER && n_rows > 0 && T > 0) {
+            rc = clt_resolve(db, *p, data);
+            if (rc) return rc;
+        } else if (method == AQE_M_CLT_VALIDATED_DUAL_POINTER) {
+            data.clt_kstop = 0;
+        }
+    } else if (db && n_rows == 0) {
+        n_rows = aqe_count(db);
+    }
+    aqe_plan* pl = new (std::nothrow) aqe_plan();
+    if (!pl) return fail(AQE_ERR_NOMEM, "out of host memory");
+    std::string err;
+    const int rc = plan_build(n_rows, method, *p, data, *pl, err);
+    if (rc) { delete pl; return fail(rc, err); }
+    *out = pl;
+    return AQE_OK;
+}
+
+int aqe_plan_from_indices(const int64_t* idx, uint64_t n, aqe_plan** out) {
+    if (!out || (!idx && n)) return fail(AQE_ERR_INVALID, "NULL argument");
+    aqe_plan* pl = new (std::nothrow) aqe_plan();
+    if (!pl) return fail(AQE_ERR_NOMEM, "out of host memory");
+    pl->idx.assign(idx, idx + n);
+    plan_finalize(*pl);
+    *out = pl;
+    return AQE_OK;
+}
+
+uint64_t aqe_plan_count(const aqe_plan* plan) { return plan ? plan->count : 0; }
+uint32_t aqe_plan_num_segments(const aqe_plan* plan) { return plan ? (uint32_t)plan->segs.size() : 0; }
+int aqe_plan_segments(const aqe_plan* plan, aqe_segment* out, uint32_t cap) {
+    if (!plan || (!out && cap)) return fail(AQE_ERR_INVALID, "NULL argument");
+    const uint32_t n = std::min<uint32_t>(cap, (uint32_t)plan->segs.size());
+    if (n) std::memcpy(out, plan->segs.data(), n * sizeof(aqe_segment));
+    return AQE_OK;
+}
+int aqe_plan_indices(const aqe_plan* plan, int64_t* out, uint64_t cap) {
+    if (!plan || (!out && cap)) return fail(AQE_ERR_INVALID, "NULL argument");
+    const uint64_t n = std::min<uint64_t>(cap, plan->count);
+    for (uint64_t k = 0; k < n; ++k) out[k] = plan_position_host(*plan, k);
+    return AQE_OK;
+}
+int aqe_plan_sorted_by_amount(const aqe_plan* plan) { return plan && plan->by_amount_order ? 1 : 0; }
+void aqe_plan_free(aqe_plan* plan) { delete plan; }
+
+int aqe_stats_from_plan(aqe_db* db, const aqe_plan* plan, int col, aqe_stats* out) {
+    if (!db || !plan || !out) return fail(AQE_ERR_INVALID, "NULL argument");
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    rc = check_plan_bounds(db, plan);
+    if (rc) return rc;
+    return stats_launch(db, plan, col, out);
+}
+
+int aqe_stats_from_plan_where(aqe_db* db, const aqe_plan* plan, int col, int pred_col, double lo, double hi, aqe_stats* out) {
+    if (!db || !plan || !out) return fail(AQE_ERR_INVALID, "NULL argument");
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    rc = check_plan_bounds(db, plan);
+    if (rc) return rc;
+    return stats_launch(db, plan, col, out, pred_col, lo, hi);
+}
+
+int aqe_stats_from_indices(aqe_db* db, const int64_t* idx, uint64_t n, int col, aqe_stats* out) {
+    if (!db || !out || (!idx && n)) return fail(AQE_ERR_INVALID, "NULL argument");
+    aqe_plan pl;
+    pl.idx.assign(idx, idx + n);
+    plan_finalize(pl);
+    return aqe_stats_from_plan(db, &pl, col, out);
+}
+
+int aqe_gather_plan(aqe_db* db, const aqe_plan* plan, aqe_record* out, uint64_t cap) {
+    if (!db || !plan || (!out && cap)) return fail(AQE_ERR_INVALID, "NULL argument");
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    rc = check_plan_bounds(db, plan);
+    if (rc) return rc;
+    return gather_launch(db, plan, out, cap);
+}
+
+int aqe_gather_records(aqe_db* db, const int64_t* idx, uint64_t n, aqe_record* out) {
+    if (!db || (!idx && n) || (!out && n)) return fail(AQE_ERR_INVALID, "NULL argument");
+    aqe_plan pl;
+    pl.idx.assign(idx, idx + n);
+    plan_finalize(pl);
+    return aqe_gather_plan(db, &pl, out, n);
+}
+
+int aqe_fast_aggregated_sum(aqe_db* db, const aqe_sample_params* p, double* sum, uint64_t* n) {
+    if (!db || !p) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (aqe_count(db) == 0) { if (sum) *sum = 0.0; if (n) *n = 0; return AQE_OK; }
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    aqe_plan pl;
+    std::string err;
+    rc = plan_build(db->n, AQE_M_MULTITHREADED_MEMORY_STRIDE, *p, PlanData{}, pl, err);
+    if (rc) return fail(rc, err);
+    aqe_stats st;
+    rc = stats_launch(db, &pl, AQE_COL_AMOUNT, &st);
+    if (rc) return rc;
+    if (sum) *sum = st.n ? st.sum : 0.0;  // raw, unscaled sample sum (custom_bplus_db.cpp:2045-2047)
+    if (n) *n = st.n;
+    return AQE_OK;
+}
+
+int aqe_estimate(const aqe_stats* s, uint64_t population, int agg, double z, int legacy_ci, double* estimate,
+                 double* ci_lower, double* ci_upper) {
+    if (!s) return fail(AQE_ERR_INVALID, "NULL stats");
+    if (s->n == 0) return fail(AQE_ERR_INVALID, "no samples");  // the CLI raises "No samples collected"
+    const double n = (double)s->n, N = (double)population;
+    double e;
+    if (agg == AQE_AGG_SUM) e = s->sum * (N / n);        // enhanced_aqe_cli.py:190-193
+    else if (agg == AQE_AGG_COUNT) e = N;                // :196-197
+    else e = s->sum / n;                                 // :194-195
+    const double var = s->n > 1 ? s->m2 / (n - 1.0) : 0.0;  // :279
+    const double moe = z * std::sqrt(var) / std::sqrt(n);   // :281
+    double m;
+    if (agg == AQE_AGG_SUM) m = legacy_ci ? moe * (N / n) : moe * N;  // :285 vs the correct scaling
+    else if (agg == AQE_AGG_COUNT) m = 0.0;
+    else m = moe;
+    if (estimate) *estimate = e;
+    if (ci_lower) *ci_lower = e - m;
+    if (ci_upper) *ci_upper = e + m;
+    return AQE_OK;
+}
+
+double aqe_z_score(double conf, int exact) {
+    if (!exact) return conf >= 0.99 ? 2.576 : (conf >= 0.95 ? 1.96 : 1.645);  // custom_bplus_db.cpp:911-912
+    // inverse normal CDF (P. Acklam's rational approximation, |rel err| < 1.15e-9), p = 1 - (1-conf)/2
+    const double p = 1.0 - (1.0 - conf) / 2.0;
+    static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02, 1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+    static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02, 6.680131188771972e+01, -1.328068155288572e+01};
+    static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00, -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+    static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00, 3.754408661907416e+00};
+    if (p < 0.02425) {
+        const double q = std::sqrt(-2 * std::log(p));
+        return (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) / ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+    }
+    if (p <= 1 - 0.02425) {
+        const double q = p - 0.5, r = q * q;
+        return (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q / (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1);
+    }
+    const double q = std::sqrt(-2 * std::log(1 - p));
+    return -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) / ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4
+// ------------------------------------------------------------------------------------------------
+int aqe_approx(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* out) {
+    if (!db || !S || !out) return fail(AQE_ERR_INVALID, "NULL argument");
+    std::memset(out, 0, sizeof(*out));
+    if (!(S->error_percent > 0.0)) return fail(AQE_ERR_INVALID, "error_percent must be > 0");
+    if (!(S->confidence_level > 0.0 && S->confidence_level < 1.0)) return fail(AQE_ERR_INVALID, "confidence_level must be in (0,1)");
+    if (S->agg < 0 || S->agg > 2 || S->design < 0 || S->design > 1) return fail(AQE_ERR_INVALID, "bad agg / design");
+    const uint64_t N = aqe_count(db);
+    out->population = N; out->confidence_level = S->confidence_level;
+    if (N == 0) { out->status = AQE_INSUFFICIENT_DATA; return AQE_OK; }
+    if (S->agg == AQE_AGG_COUNT && S->pred_col == AQE_COL_NONE) {  // enhanced_aqe_cli.py:196-197: COUNT is exact
+        out->estimate = out->ci_lower = out->ci_upper = (double)N; out->status = AQE_STABLE;
+        return AQE_OK;
+    }
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    if (S->agg != AQE_AGG_COUNT && col_kind(S->agg_col) < 0) return fail(AQE_ERR_INVALID, "bad aggregate column");
+    if (S->agg != AQE_AGG_COUNT && !col_ptr(db, S->agg_col)) return fail(AQE_ERR_STATE, "aggregate column is not resident on the device");
+    if (S->pred_col != AQE_COL_NONE && !col_ptr(db, S->pred_col)) return fail(AQE_ERR_STATE, "predicate column is not resident on the device");
+
+    ApproxArgs a;
+    a.cols = const_cols(db);
+    a.n_rows = N;
+    a.block_rows = S->design == AQE_DESIGN_BLOCK ? (S->block_size ? S->block_size : 1000) : 1;
+    a.units = (N + a.block_rows - 1) / a.block_rows;
+    a.design = S->design; a.agg = S->agg; a.agg_col = S->agg_col; a.pred_col = S->pred_col;
+    a.lo = S->lo; a.hi = S->hi; a.eps = S->error_percent; a.z = aqe_z_score(S->confidence_level, 1);
+    a.seed = S->seed;
+    a.n0 = S->min_samples ? S->min_samples : (S->design == AQE_DESIGN_BLOCK ? 1024 : 16384);
+    a.nmax = S->max_samples ? S->max_samples : a.units;
+    if (a.n0 > a.nmax) a.n0 = a.nmax;
+    a.slots = db->approx_slots;
+    a.out = &db->slot_dev->approx;
+    if (a.units <= a.n0) {
+        // the first look would already draw as many units as the table has: scan it exactly instead
+        aqe_scan_spec sp{S->agg == AQE_AGG_COUNT ? (int32_t)(S->pred_col) : S->agg_col, S->pred_col, S->lo, S->hi};
+        aqe_partial part;
+        rc = scan_sync(db, &sp, 0, db->n, false, &part);
+        if (rc) return rc;
+        double v;
+        if (S->agg == AQE_AGG_COUNT) v = (double)part.count;
+        else if (S->agg == AQE_AGG_SUM) v = part.sum;
+        else v = part.count ? part.sum / (double)part.count : 0.0;
+        out->estimate = out->ci_lower = out->ci_upper = v;
+        out->n_samples = N; out->n_units = a.units; out->status = AQE_STABLE;
+        return AQE_OK;
+    }
+
+    static int coop_blocks_per_sm = 0;
+    if (!coop_blocks_per_sm) {
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_approx, 256, 0);
+        coop_blocks_per_sm = std::max(1, occ);
+    }
+    int grid = db->sm_count * std::min(coop_blocks_per_sm, env_int("AQE_APPROX_BPS", 1));
+    if (grid > db->max_grid) grid = db->max_grid;
+    void* params[] = {&a};
+    CU(cudaEventRecord(db->ev0, db->stream));
+    CU(cudaLaunchCooperativeKernel((void*)k_approx, dim3(grid), dim3(256), params, 0, db->stream));
+    LAUNCHED();
+    CU(cudaEventRecord(db->ev1, db->stream));
+    CU(cudaStreamSynchronize(db->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, db->ev0, db->ev1));
+    *out = db->slot_host->approx;
+    out->confidence_level = S->confidence_level;
+    out->elapsed_us = (double)ms * 1000.0;
+    return AQE_OK;
+}
+
+int aqe_approx_merge(const aqe_approx_result* parts, int n, int agg, double confidence_level, aqe_approx_result* out) {
+    if (!parts || !out || n <= 0) return fail(AQE_ERR_INVALID, "bad argument");
+    // shards are strata: totals add, variances of the totals add (independent draws per shard)
+    const double z = aqe_z_score(confidence_level, 1);
+    aqe_approx_result r;
+    std::memset(&r, 0, sizeof(r));
+    double total = 0.0, var_total = 0.0;
+    uint64_t pop = 0;
+    int worst = AQE_STABLE;
+    for (int i = 0; i < n; ++i) {
+        const aqe_approx_result& p = parts[i];
+        const double half = (p.ci_upper - p.ci_lower) * 0.5;
+        const double w = agg == AQE_AGG_AVG ? (double)p.population : 1.0;  // AVG: weight shard means by N_g
+        total += p.estimate * w;
+        var_total += (half / z) * (half / z) * w * w;
+        pop += p.population; r.n_samples += p.n_samples; r.n_units += p.n_units;
+        r.rounds = std::max(r.rounds, p.rounds); r.elapsed_us = std::max(r.elapsed_us, p.elapsed_us);
+        if (p.status > worst) worst = p.status;
+    }
+    if (agg == AQE_AGG_AVG && pop) { total /= (double)pop; var_total /= (double)pop * (double)pop; }
+    const double half = z * std::sqrt(var_total);
+    r.estimate = total; r.ci_lower = total - half; r.ci_upper = total + half;
+    r.error_margin = total != 0.0 ? half / std::fabs(total) : 0.0;
+    r.confidence_level = confidence_level; r.population = pop; r.status = worst;
+    *out = r;
+    return AQE_OK;
+}
+
+}  // extern "C"

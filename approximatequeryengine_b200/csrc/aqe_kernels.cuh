@@ -1,0 +1,656 @@
+// aqe_kernels.cuh -- the sm_100a kernels of libaqe_b200.
+//
+//   K1/K2  k_scan / k_scan_bulk   exact SUM/COUNT[/WHERE] full scan, f64 (compensated) and int128
+//   K3/K5  k_plan_stats           moments of a column over a sample plan (affine segments / index list)
+//   K4     k_approx               persistent Philox + Welford-by-shifted-sums + in-kernel CLT stop rule
+//   K6     k_plan_gather          rows at plan positions -> 32-byte AoS (legacy list[Record] path)
+//   K7     k_aos_to_soa           ingest: 32-byte file rows -> 5 column arrays
+//          k_synth                device-side generator of the synthetic sales table
+//
+// Reference loops replaced (src/aqe_backend/core/custom_bplus_db.cpp): sum_amount :242-251,
+// sum_amount_where :263-274, every `samples.push_back(all_records[i])` loop (:737-1960), the thread pool
+// of clt_validated_dual_pointer_sample :885-1043, load_from_file :685-711.
+#pragma once
+
+#include <cooperative_groups.h>
+#include <type_traits>
+
+#include "aqe_device.cuh"
+
+namespace aqe {
+namespace cg = cooperative_groups;
+
+// Read a POD written by another SM: L2 (ld.global.cg), never a stale L1 line.
+template <typename T> __device__ __forceinline__ T load_cg(const T* p) {
+    static_assert(sizeof(T) % 8 == 0, "8-byte multiple");
+    T r;
+    const unsigned long long* s = reinterpret_cast<const unsigned long long*>(p);
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 8); ++i) d[i] = __ldcg(s + i);
+    return r;
+}
+
+// ================================================================================================
+// Shared accumulator of the scan kernels and its fixed-order block reduction
+// ================================================================================================
+struct ScanAcc {
+    uint64_t count;
+    DD sum;
+    uint64_t ilo;  // sum of the low 32 bits of each integer value (as u64)
+    int64_t ihi;   // sum of the (arithmetic) high 32 bits
+    DD sq;
+    double mn, mx;
+};
+
+__device__ __forceinline__ ScanAcc scan_identity() {
+    ScanAcc a;
+    a.count = 0; a.sum = DD{0.0, 0.0}; a.ilo = 0; a.ihi = 0; a.sq = DD{0.0, 0.0};
+    a.mn = __longlong_as_double(0x7ff0000000000000LL); a.mx = __longlong_as_double(0xfff0000000000000LL);
+    return a;
+}
+__device__ __forceinline__ void scan_merge(ScanAcc& a, const ScanAcc& b) {
+    a.count += b.count; dd_merge(a.sum, b.sum); a.ilo += b.ilo; a.ihi += b.ihi; dd_merge(a.sq, b.sq);
+    a.mn = fmin(a.mn, b.mn); a.mx = fmax(a.mx, b.mx);
+}
+template <bool IS_INT, bool MOMENTS> __device__ __forceinline__ ScanAcc scan_warp_reduce(ScanAcc a) {
+    a.count = warp_reduce_u64(a.count);
+    if constexpr (IS_INT) {
+        a.ilo = warp_reduce_u64(a.ilo);
+        a.ihi = (int64_t)warp_reduce_u64((uint64_t)a.ihi);
+    } else {
+        a.sum = warp_reduce_dd(a.sum);
+        if constexpr (MOMENTS) {
+            a.sq = warp_reduce_dd(a.sq);
+            a.mn = warp_reduce_min(a.mn);
+            a.mx = warp_reduce_max(a.mx);
+        }
+    }
+    return a;
+}
+// Result valid in thread 0.  Order: lanes by shuffle-down tree, then warps 0..nw-1 by the same tree.
+template <bool IS_INT, bool MOMENTS> __device__ __forceinline__ ScanAcc scan_block_reduce(ScanAcc a, ScanAcc* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    a = scan_warp_reduce<IS_INT, MOMENTS>(a);
+    __syncthreads();  // sm may still be read by a previous call
+    if (lane == 0) sm[warp] = a;
+    __syncthreads();
+    if (warp == 0) {
+        a = lane < nw ? sm[lane] : scan_identity();
+        a = scan_warp_reduce<IS_INT, MOMENTS>(a);
+    }
+    return a;
+}
+
+struct ScanArgs {
+    const void* agg;
+    const void* pred;
+    uint64_t n;
+    double lo, hi;
+    ScanAcc* partials;      // [gridDim.x]
+    unsigned int* ticket;   // zero before launch; reset by the last block
+    aqe_partial* out;       // device-visible (device memory or mapped pinned host memory)
+};
+
+template <bool IS_INT> __device__ __forceinline__ void scan_write_out(const ScanAcc& t, aqe_partial* out) {
+    aqe_partial r;
+    r.count = t.count;
+    if constexpr (IS_INT) {
+        // value = ihi * 2^32 + ilo  in 128-bit two's complement
+        const uint64_t lo = t.ilo + ((uint64_t)t.ihi << 32);
+        const int64_t hi = (t.ihi >> 32) + (lo < t.ilo ? 1 : 0);
+        r.isum_lo = lo; r.isum_hi = hi;
+        r.sum = (double)hi * 18446744073709551616.0 + (double)lo;
+        r.comp = 0.0; r.sumsq = 0.0; r.minv = 0.0; r.maxv = 0.0;
+    } else {
+        DD s = t.sum; dd_norm(s);
+        DD q = t.sq; dd_norm(q);
+        r.sum = s.s; r.comp = s.c; r.sumsq = q.s; r.minv = t.mn; r.maxv = t.mx;
+        r.isum_lo = 0; r.isum_hi = 0;
+    }
+    *out = r;
+}
+
+// Second stage: the last block to finish folds the per-block partials in block order.
+template <bool IS_INT, bool MOMENTS> __device__ __forceinline__ void scan_finish(ScanAcc block_total, const ScanArgs& a, ScanAcc* sm) {
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        a.partials[blockIdx.x] = block_total;
+        __threadfence();
+        const unsigned int t = atomicAdd(a.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    ScanAcc acc = scan_identity();
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        scan_merge(acc, load_cg(a.partials + b));
+    }
+    acc = scan_block_reduce<IS_INT, MOMENTS>(acc, sm);
+    if (threadIdx.x == 0) {
+        scan_write_out<IS_INT>(acc, a.out);
+        *a.ticket = 0u;
+    }
+}
+
+template <typename T> __device__ __forceinline__ double as_f64(T v) { return (double)v; }
+
+// PRED: 0 none, 1 predicate on the aggregate column itself, 2 predicate on another column (PredT)
+template <typename AggT, int PRED, typename PredT, bool MOMENTS>
+__device__ __forceinline__ void scan_consume(ScanAcc& acc, DD& alt, AggT v, PredT pv, double lo, double hi, int parity) {
+    bool pass = true;
+    if constexpr (PRED == 1) { const double d = as_f64(v); pass = (d >= lo) && (d <= hi); }
+    if constexpr (PRED == 2) { const double d = as_f64(pv); pass = (d >= lo) && (d <= hi); }
+    acc.count += pass ? 1u : 0u;
+    if constexpr (std::is_integral_v<AggT>) {  // int64 / int32: split so a thread never overflows
+        const int64_t x = pass ? (int64_t)v : 0;
+        acc.ilo += (uint64_t)x & 0xffffffffull; acc.ihi += x >> 32;
+    } else {  // f64
+        const double x = pass ? (double)v : 0.0;
+        if (parity) dd_add(alt, x); else dd_add(acc.sum, x);
+        if constexpr (MOMENTS) {
+            acc.sq.s = fma(x, x, acc.sq.s);
+            acc.mn = fmin(acc.mn, pass ? (double)v : acc.mn);
+            acc.mx = fmax(acc.mx, pass ? (double)v : acc.mx);
+        }
+    }
+}
+
+constexpr int kScanThreads = 256;
+
+// K1/K2, register-staged variant: W-element vector loads (W=4: LDG.256 for 8-byte columns), U
+// independent loads in flight per thread, grid-stride so every warp instruction reads one contiguous
+// 32*W*sizeof(T)-byte run.
+template <typename AggT, int PRED, typename PredT, int W, int U, bool MOMENTS, int MINB>
+__global__ void __launch_bounds__(kScanThreads, MINB) k_scan(const ScanArgs a) {
+    constexpr bool IS_INT = std::is_integral_v<AggT>;
+    __shared__ ScanAcc sm[32];
+    const AggT* __restrict__ agg = static_cast<const AggT*>(a.agg);
+    const PredT* __restrict__ pred = static_cast<const PredT*>(a.pred);
+    const uint64_t units = a.n / W;
+    const uint64_t G = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    ScanAcc acc = scan_identity();
+    DD alt{0.0, 0.0};
+
+    for (; u + (uint64_t)(U - 1) * G < units; u += (uint64_t)U * G) {
+        Vec<AggT, W> av[U];
+        Vec<PredT, W> pv[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            av[j] = ldg_stream<W>(agg + (u + (uint64_t)j * G) * W);
+            if constexpr (PRED == 2) pv[j] = ldg_stream<W>(pred + (u + (uint64_t)j * G) * W);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+#pragma unroll
+            for (int e = 0; e < W; ++e)
+                scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, av[j].v[e], PRED == 2 ? pv[j].v[e] : PredT(0), a.lo, a.hi, e & 1);
+    }
+    for (; u < units; u += G) {
+        const Vec<AggT, W> av = ldg_stream<W>(agg + u * W);
+        Vec<PredT, W> pv;
+        if constexpr (PRED == 2) pv = ldg_stream<W>(pred + u * W);
+#pragma unroll
+        for (int e = 0; e < W; ++e)
+            scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, av.v[e], PRED == 2 ? pv.v[e] : PredT(0), a.lo, a.hi, e & 1);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the n % W tail
+        for (uint64_t i = units * W; i < a.n; ++i)
+            scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, agg[i], PRED == 2 ? pred[i] : PredT(0), a.lo, a.hi, 0);
+    }
+    dd_merge(acc.sum, alt);
+    acc = scan_block_reduce<IS_INT, MOMENTS>(acc, sm);
+    scan_finish<IS_INT, MOMENTS>(acc, a, sm);
+}
+
+// Scalar-load fallback for columns whose base pointer is not vector aligned (attached torch slices).
+template <typename AggT, int PRED, typename PredT, bool MOMENTS>
+__global__ void __launch_bounds__(kScanThreads) k_scan_unaligned(const ScanArgs a) {
+    constexpr bool IS_INT = std::is_integral_v<AggT>;
+    __shared__ ScanAcc sm[32];
+    const AggT* __restrict__ agg = static_cast<const AggT*>(a.agg);
+    const PredT* __restrict__ pred = static_cast<const PredT*>(a.pred);
+    const uint64_t G = (uint64_t)gridDim.x * blockDim.x;
+    ScanAcc acc = scan_identity();
+    DD alt{0.0, 0.0};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += G)
+        scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, __ldg(agg + i), PRED == 2 ? __ldg(pred + i) : PredT(0), a.lo, a.hi, 0);
+    acc = scan_block_reduce<IS_INT, MOMENTS>(acc, sm);
+    scan_finish<IS_INT, MOMENTS>(acc, a, sm);
+}
+
+// K1, TMA-staged variant for the headline case (f64 aggregate, predicate none / on itself): one producer
+// warp streams CHUNK-byte tiles of the column into a STAGES-deep shared-memory ring with 1-D bulk
+// copies (cp.async.bulk -> UBLKCP) completing on mbarriers; 8 consumer warps reduce tiles out of
+// shared memory with conflict-free LDS.128.  Tile c goes to CTA (c mod gridDim.x): static, deterministic.
+constexpr int kBulkConsumerWarps = 8;
+constexpr int kBulkThreads = (kBulkConsumerWarps + 1) * 32;
+
+template <int PRED, int STAGES, int CHUNK, bool MOMENTS>
+__global__ void __launch_bounds__(kBulkThreads) k_scan_bulk(const ScanArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ ScanAcc sm[32];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    double* buf = reinterpret_cast<double*>(smem_raw);
+    const double* __restrict__ col = static_cast<const double*>(a.agg);
+    const uint64_t total_bytes = (a.n * 8ull) & ~15ull;  // bulk copies move multiples of 16 bytes
+    const uint64_t nchunks = (total_bytes + CHUNK - 1) / CHUNK;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kBulkConsumerWarps); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    ScanAcc acc = scan_identity();
+    DD alt{0.0, 0.0};
+    if (warp == kBulkConsumerWarps) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+                const int s = it % STAGES;
+                const uint32_t round = it / STAGES;
+                if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+                const uint64_t off = c * (uint64_t)CHUNK;
+                const uint32_t bytes = (uint32_t)((total_bytes - off) < (uint64_t)CHUNK ? (total_bytes - off) : (uint64_t)CHUNK);
+                mbar_expect_tx(&full_bar[s], bytes);
+                bulk_g2s(reinterpret_cast<unsigned char*>(buf) + (size_t)s * CHUNK,
+                         reinterpret_cast<const unsigned char*>(col) + off, bytes, &full_bar[s]);
+            }
+        }
+    } else {
+        const int ct = threadIdx.x;  // 0 .. 255
+        uint32_t it = 0;
+        for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+            const int s = it % STAGES;
+            const uint32_t round = it / STAGES;
+            mbar_wait(&full_bar[s], round & 1);
+            const uint64_t off = c * (uint64_t)CHUNK;
+            const uint32_t bytes = (uint32_t)((total_bytes - off) < (uint64_t)CHUNK ? (total_bytes - off) : (uint64_t)CHUNK);
+            const double2* tile = reinterpret_cast<const double2*>(reinterpret_cast<unsigned char*>(buf) + (size_t)s * CHUNK);
+            const uint32_t nvec = bytes >> 4;
+#pragma unroll 4
+            for (uint32_t i = ct; i < nvec; i += kBulkConsumerWarps * 32) {
+                const double2 v = tile[i];
+                scan_consume<double, PRED, double, MOMENTS>(acc, alt, v.x, 0.0, a.lo, a.hi, 0);
+                scan_consume<double, PRED, double, MOMENTS>(acc, alt, v.y, 0.0, a.lo, a.hi, 1);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            for (uint64_t i = total_bytes >> 3; i < a.n; ++i)
+                scan_consume<double, PRED, double, MOMENTS>(acc, alt, col[i], 0.0, a.lo, a.hi, 0);
+        }
+    }
+    dd_merge(acc.sum, alt);
+    acc = scan_block_reduce<false, MOMENTS>(acc, sm);
+    scan_finish<false, MOMENTS>(acc, a, sm);
+}
+
+// ================================================================================================
+// Sample plans on the device
+// ================================================================================================
+struct PlanDev {
+    const aqe_segment* segs;    // nseg affine runs, or
+    const uint64_t* seg_start;  // exclusive prefix of counts, nseg + 1 entries
+    const int64_t* idx;         // explicit positions (nseg == 0)
+    const int64_t* perm;        // optional: positions index this permutation (amount-sorted order)
+    uint32_t nseg;
+    uint64_t count;
+};
+
+__device__ __forceinline__ int64_t plan_position(const PlanDev& P, uint64_t k) {
+    int64_t pos;
+    if (P.nseg == 0) {
+        pos = __ldg(P.idx + k);
+    } else {
+        uint32_t lo = 0, hi = P.nseg;  // find seg with seg_start[seg] <= k < seg_start[seg+1]
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(P.seg_start + mid) <= k) lo = mid; else hi = mid;
+        }
+        const aqe_segment s = P.segs[lo];
+        const uint64_t r = k - __ldg(P.seg_start + lo);
+        if (s.kind == 1) pos = (int64_t)(uint64_t)__dmul_rn((double)r, s.scale);
+        else if (s.inner_len == 1) pos = s.base + (int64_t)r * s.outer_step;
+        else pos = s.base + (int64_t)(r / (uint64_t)s.inner_len) * s.outer_step + (int64_t)(r % (uint64_t)s.inner_len);
+    }
+    if (P.perm) pos = __ldg(P.perm + pos);
+    return pos;
+}
+
+struct Columns {
+    const int64_t* id;
+    const double* amount;
+    const int32_t* region;
+    const int32_t* product_id;
+    const int64_t* timestamp;
+};
+__device__ __forceinline__ double column_value(const Columns& C, int col, int64_t i) {
+    switch (col) {
+        case AQE_COL_ID: return (double)__ldg(C.id + i);
+        case AQE_COL_AMOUNT: return __ldg(C.amount + i);
+        case AQE_COL_REGION: return (double)__ldg(C.region + i);
+        case AQE_COL_PRODUCT_ID: return (double)__ldg(C.product_id + i);
+        default: return (double)__ldg(C.timestamp + i);
+    }
+}
+
+// ================================================================================================
+// K3/K5: moments of a column over a plan.  Sums are taken of d = x - K with K = the first sampled value,
+// so M2 = sum d^2 - (sum d)^2 / n has no catastrophic cancellation; sum x is carried separately
+// (compensated) because the CLI estimator is sum * N/n (enhanced_aqe_cli.py:190-193).
+// ================================================================================================
+struct StatAcc { uint64_t n; DD sx, sd, sdd; };
+__device__ __forceinline__ StatAcc stat_identity() { return StatAcc{0, DD{0, 0}, DD{0, 0}, DD{0, 0}}; }
+__device__ __forceinline__ void stat_merge(StatAcc& a, const StatAcc& b) {
+    a.n += b.n; dd_merge(a.sx, b.sx); dd_merge(a.sd, b.sd); dd_merge(a.sdd, b.sdd);
+}
+__device__ __forceinline__ StatAcc stat_warp_reduce(StatAcc a) {
+    a.n = warp_reduce_u64(a.n); a.sx = warp_reduce_dd(a.sx); a.sd = warp_reduce_dd(a.sd); a.sdd = warp_reduce_dd(a.sdd);
+    return a;
+}
+__device__ __forceinline__ StatAcc stat_block_reduce(StatAcc a, StatAcc* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    a = stat_warp_reduce(a);
+    __syncthreads();
+    if (lane == 0) sm[warp] = a;
+    __syncthreads();
+    if (warp == 0) { a = lane < nw ? sm[lane] : stat_identity(); a = stat_warp_reduce(a); }
+    return a;
+}
+
+struct StatArgs {
+    PlanDev plan;
+    Columns cols;
+    int col;
+    int pred_col;   // AQE_COL_NONE, or rows failing lo <= pred_col <= hi contribute 0 (still counted in n)
+    double lo, hi;
+    StatAcc* partials;
+    unsigned int* ticket;
+    aqe_stats* out;
+};
+
+__global__ void __launch_bounds__(256) k_plan_stats(const StatArgs a) {
+    __shared__ StatAcc sm[32];
+    __shared__ bool is_last;
+    const uint64_t G = (uint64_t)gridDim.x * blockDim.x;
+    StatAcc acc = stat_identity();
+    auto value_at = [&](uint64_t k) {
+        const int64_t pos = plan_position(a.plan, k);
+        double x = column_value(a.cols, a.col, pos);
+        if (a.pred_col != AQE_COL_NONE) {
+            const double pv = column_value(a.cols, a.pred_col, pos);
+            x = (pv >= a.lo && pv <= a.hi) ? x : 0.0;
+        }
+        return x;
+    };
+    double K = 0.0;
+    if (a.plan.count) K = value_at(0);
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.plan.count; k += G) {
+        const double x = value_at(k);
+        const double d = __dadd_rn(x, -K);
+        acc.n += 1; dd_add(acc.sx, x); dd_add(acc.sd, d); dd_add(acc.sdd, __dmul_rn(d, d));
+    }
+    acc = stat_block_reduce(acc, sm);
+    if (threadIdx.x == 0) {
+        a.partials[blockIdx.x] = acc;
+        __threadfence();
+        is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    acc = stat_identity();
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) stat_merge(acc, load_cg(a.partials + b));
+    acc = stat_block_reduce(acc, sm);
+    if (threadIdx.x == 0) {
+        dd_norm(acc.sx); dd_norm(acc.sd); dd_norm(acc.sdd);
+        aqe_stats r;
+        r.n = acc.n; r.sum = acc.sx.s;
+        const double n = (double)acc.n;
+        r.mean = acc.n ? acc.sx.s / n : 0.0;
+        double m2 = acc.n ? acc.sdd.s - (acc.sd.s * acc.sd.s) / n : 0.0;
+        r.m2 = m2 > 0.0 ? m2 : 0.0;
+        *a.out = r;
+        *a.ticket = 0u;
+    }
+}
+
+// K6: rows at plan positions, AoS, in plan order.
+__global__ void __launch_bounds__(256) k_plan_gather(const PlanDev plan, const Columns C, aqe_record* __restrict__ out, uint64_t first, uint64_t n) {
+    const uint64_t G = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += G) {
+        const int64_t i = plan_position(plan, first + k);
+        aqe_record r;
+        r.id = C.id ? __ldg(C.id + i) : 0;
+        r.amount = C.amount ? __ldg(C.amount + i) : 0.0;
+        r.region = C.region ? __ldg(C.region + i) : 0;
+        r.product_id = C.product_id ? __ldg(C.product_id + i) : 0;
+        r.timestamp = C.timestamp ? __ldg(C.timestamp + i) : 0;
+        uint4* o = reinterpret_cast<uint4*>(out + k);
+        const uint4* s = reinterpret_cast<const uint4*>(&r);
+        o[0] = s[0]; o[1] = s[1];
+    }
+}
+
+// contiguous rows [first, first+n) -> AoS (collect_all_records :660, save_to_file :665)
+__global__ void __launch_bounds__(256) k_soa_to_aos(const Columns C, aqe_record* __restrict__ out, uint64_t first, uint64_t n) {
+    const uint64_t G = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += G) {
+        const uint64_t i = first + k;
+        aqe_record r;
+        r.id = C.id ? C.id[i] : 0;
+        r.amount = C.amount ? C.amount[i] : 0.0;
+        r.region = C.region ? C.region[i] : 0;
+        r.product_id = C.product_id ? C.product_id[i] : 0;
+        r.timestamp = C.timestamp ? C.timestamp[i] : 0;
+        uint4* o = reinterpret_cast<uint4*>(out + k);
+        const uint4* s = reinterpret_cast<const uint4*>(&r);
+        o[0] = s[0]; o[1] = s[1];
+    }
+}
+
+// K7: ingest.  A warp reads 32 rows = 1 KiB contiguous; column stores are 256/128-byte coalesced.
+// `unsorted` is raised if ids are not ascending (then the host re-orders, custom_bplus_db.cpp:198-200).
+struct MutColumns { int64_t* id; double* amount; int32_t* region; int32_t* product_id; int64_t* timestamp; };
+__global__ void __launch_bounds__(256) k_aos_to_soa(const aqe_record* __restrict__ rows, uint64_t n, MutColumns C, uint64_t dst,
+                                                    int64_t prev_last_id, int has_prev, unsigned int* unsorted) {
+    const uint64_t G = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += G) {
+        const uint4* s = reinterpret_cast<const uint4*>(rows + k);
+        const uint4 a = s[0], b = s[1];
+        aqe_record r;
+        reinterpret_cast<uint4*>(&r)[0] = a; reinterpret_cast<uint4*>(&r)[1] = b;
+        C.id[dst + k] = r.id; C.amount[dst + k] = r.amount; C.region[dst + k] = r.region;
+        C.product_id[dst + k] = r.product_id; C.timestamp[dst + k] = r.timestamp;
+        const int64_t prev = k ? rows[k - 1].id : (has_prev ? prev_last_id : r.id);
+        if (r.id < prev) atomicOr(unsorted, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_synth(uint64_t seed, uint64_t first_row, uint64_t n, int dist, MutColumns C) {
+    const uint64_t G = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += G) {
+        aqe_record r;
+        synth_row(seed, first_row + k, dist, r);
+        if (C.id) C.id[k] = r.id;
+        if (C.amount) C.amount[k] = r.amount;
+        if (C.region) C.region[k] = r.region;
+        if (C.product_id) C.product_id[k] = r.product_id;
+        if (C.timestamp) C.timestamp[k] = r.timestamp;
+    }
+}
+
+// ================================================================================================
+// K4: persistent CLT estimator.  One cooperative launch; rounds ("looks") at cumulative sample sizes
+// n_0 < n_1 < ...; sample j is the j-th element of a Philox stream, so the sample set after a look is a
+// prefix of one deterministic sequence (seed, design).  Per look: every block reduces its share to
+// (units, rows, pass count, sum d, sum d^2) with d = y - K, writes it to a double-buffered slot, one grid
+// barrier, then EVERY block folds all slots in block order (identical arithmetic -> identical decision in
+// every block, no broadcast needed) and evaluates the stop rule  z * sqrt(var / n) * scale / |estimate| <= eps.
+// Replaces the std::async fast/slow thread pool + should_stop atomics of custom_bplus_db.cpp:885-1043.
+// ================================================================================================
+struct ApproxAcc { uint64_t units, rows; DD sc, sd, sdd; };
+__device__ __forceinline__ ApproxAcc approx_identity() { return ApproxAcc{0, 0, DD{0, 0}, DD{0, 0}, DD{0, 0}}; }
+__device__ __forceinline__ void approx_merge(ApproxAcc& a, const ApproxAcc& b) {
+    a.units += b.units; a.rows += b.rows; dd_merge(a.sc, b.sc); dd_merge(a.sd, b.sd); dd_merge(a.sdd, b.sdd);
+}
+__device__ __forceinline__ ApproxAcc approx_warp_reduce(ApproxAcc a) {
+    a.units = warp_reduce_u64(a.units); a.rows = warp_reduce_u64(a.rows);
+    a.sc = warp_reduce_dd(a.sc); a.sd = warp_reduce_dd(a.sd); a.sdd = warp_reduce_dd(a.sdd);
+    return a;
+}
+__device__ __forceinline__ ApproxAcc approx_block_reduce(ApproxAcc a, ApproxAcc* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    a = approx_warp_reduce(a);
+    __syncthreads();
+    if (lane == 0) sm[warp] = a;
+    __syncthreads();
+    if (warp == 0) { a = lane < nw ? sm[lane] : approx_identity(); a = approx_warp_reduce(a); }
+    return a;
+}
+
+struct ApproxArgs {
+    Columns cols;
+    uint64_t n_rows, units;
+    uint32_t block_rows;  // 1 for SRS
+    int design, agg, agg_col, pred_col;
+    double lo, hi, eps, z;
+    uint64_t seed, n0, nmax;
+    ApproxAcc* slots;  // [2][gridDim.x]
+    aqe_approx_result* out;
+};
+
+__device__ __forceinline__ void approx_row(const ApproxArgs& a, uint64_t row, double& y, double& c) {
+    bool pass = true;
+    if (a.pred_col != AQE_COL_NONE) { const double pv = column_value(a.cols, a.pred_col, (int64_t)row); pass = (pv >= a.lo) && (pv <= a.hi); }
+    c = pass ? 1.0 : 0.0;
+    y = pass ? (a.agg == AQE_AGG_COUNT ? 1.0 : column_value(a.cols, a.agg_col, (int64_t)row)) : 0.0;
+}
+
+__global__ void __launch_bounds__(256) k_approx(const ApproxArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ ApproxAcc sm[32];
+    __shared__ ApproxAcc sh_total;
+    const uint64_t gthreads = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool ratio = (a.agg == AQE_AGG_AVG && a.pred_col != AQE_COL_NONE);
+
+    // shift K: value of the first row of the first drawn unit, times rows per unit
+    double K;
+    {
+        const uint64_t u0 = draw_position(a.seed, (uint32_t)a.design, 0, a.units);
+        double y0, c0; approx_row(a, u0 * a.block_rows, y0, c0);
+        K = y0 * (double)a.block_rows;
+    }
+
+    ApproxAcc cum = approx_identity();
+    uint64_t n_prev = 0, target = a.n0;
+    uint32_t rounds = 0;
+    int status = AQE_DRIFTING;
+    double est = 0.0, half = 0.0, rel = 0.0, mean = 0.0, m2 = 0.0;
+
+    for (;;) {
+        ApproxAcc acc = approx_identity();
+        if (a.design == AQE_DESIGN_SRS) {
+            // a thread owns Philox counter q: samples 2q and 2q+1
+            for (uint64_t q = (n_prev >> 1) + gtid; q < ((target + 1) >> 1); q += gthreads) {
+                const u32x4 r = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), kDrawStream | (uint32_t)a.design, 0u,
+                                              (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                const uint64_t j0 = 2 * q, j1 = 2 * q + 1;
+                const uint64_t p0 = mulhi64(((uint64_t)r.y << 32) | r.x, a.units);
+                const uint64_t p1 = mulhi64(((uint64_t)r.w << 32) | r.z, a.units);
+                double y0 = 0, c0 = 0, y1 = 0, c1 = 0;
+                const bool v0 = j0 >= n_prev && j0 < target, v1 = j1 >= n_prev && j1 < target;
+                if (v0) approx_row(a, p0, y0, c0);
+                if (v1) approx_row(a, p1, y1, c1);
+                if (v0) { const double d = __dadd_rn(y0, -K); acc.units++; acc.rows++; dd_add(acc.sc, c0); dd_add(acc.sd, d); dd_add(acc.sdd, __dmul_rn(d, d)); }
+                if (v1) { const double d = __dadd_rn(y1, -K); acc.units++; acc.rows++; dd_add(acc.sc, c1); dd_add(acc.sd, d); dd_add(acc.sdd, __dmul_rn(d, d)); }
+            }
+        } else {
+            // a warp owns a tile: lanes stride the tile's rows (coalesced), fixed-order warp fold
+            const uint64_t gwarps = gthreads >> 5, gwarp = gtid >> 5;
+            for (uint64_t j = n_prev + gwarp; j < target; j += gwarps) {
+                const uint64_t u = draw_position(a.seed, (uint32_t)a.design, j, a.units);
+                const uint64_t r0 = u * a.block_rows;
+                const uint64_t r1 = (r0 + a.block_rows < a.n_rows) ? r0 + a.block_rows : a.n_rows;
+                DD ty{0, 0}, tc{0, 0};
+                for (uint64_t r = r0 + lane; r < r1; r += 32) { double y, c; approx_row(a, r, y, c); dd_add(ty, y); dd_add(tc, c); }
+                ty = warp_reduce_dd(ty); tc = warp_reduce_dd(tc);
+                if (lane == 0) {
+                    dd_norm(ty); dd_norm(tc);
+                    const double d = __dadd_rn(ty.s, -K);
+                    acc.units++; acc.rows += (r1 - r0); dd_add(acc.sc, tc.s); dd_add(acc.sd, d); dd_add(acc.sdd, __dmul_rn(d, d));
+                }
+            }
+        }
+        acc = approx_block_reduce(acc, sm);
+        ApproxAcc* slot = a.slots + (size_t)(rounds & 1) * gridDim.x;
+        if (threadIdx.x == 0) slot[blockIdx.x] = acc;
+        grid.sync();
+        // every block folds all slots in block order
+        ApproxAcc t = approx_identity();
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) approx_merge(t, load_cg(slot + b));
+        t = approx_block_reduce(t, sm);
+        if (threadIdx.x == 0) sh_total = t;
+        __syncthreads();
+        approx_merge(cum, sh_total);
+        ++rounds;
+
+        // ---- stop rule (same formulas as oracle/aqe_oracle.c orc_approx) ----
+        ApproxAcc s = cum; dd_norm(s.sd); dd_norm(s.sdd); dd_norm(s.sc);
+        const double n = (double)s.units;
+        const double sy = s.sd.s + n * K;            // sum y
+        const double mu = sy / n;
+        double ss = s.sdd.s - (s.sd.s * s.sd.s) / n;  // sum (y - mean)^2
+        if (ss < 0.0) ss = 0.0;
+        mean = mu; m2 = ss;
+        double var, scale;
+        if (ratio) {
+            if (s.sc.s <= 0.0) { est = 0.0; var = __longlong_as_double(0x7ff0000000000000LL); scale = 1.0; }
+            else {
+                const double R = sy / s.sc.s;
+                // residual e = y - R c ; sum e^2 = sum y^2 - R sum y   (c^2 = c, y c = y)
+                const double syy = ss + sy * mu;
+                double rss = syy - R * sy; if (rss < 0.0) rss = 0.0;
+                const double cbar = s.sc.s / n;
+                var = rss / (n - 1.0) / (cbar * cbar);
+                est = R; scale = 1.0;
+            }
+        } else {
+            var = s.units > 1 ? ss / (n - 1.0) : __longlong_as_double(0x7ff0000000000000LL);
+            if (a.agg == AQE_AGG_AVG) { scale = (double)a.units / (double)a.n_rows; est = mu * scale; }
+            else { scale = (double)a.units; est = mu * scale; }
+        }
+        const double se = sqrt(var / n);
+        half = a.z * se * scale;
+        rel = est != 0.0 ? half / fabs(est) * 100.0 : __longlong_as_double(0x7ff0000000000000LL);
+        n_prev = target;
+        if (rel <= a.eps) { status = AQE_STABLE; break; }
+        if (n_prev >= a.nmax) { status = AQE_DRIFTING; break; }
+        const double rn = rel / a.eps;
+        const double want = ceil(1.1 * (n * rn * rn));
+        const uint64_t lo_n = n_prev + n_prev / 4 + 1, hi_n = n_prev * 8;
+        uint64_t t2 = want >= (double)hi_n ? hi_n : (want <= (double)lo_n ? lo_n : (uint64_t)want);
+        if (t2 > a.nmax) t2 = a.nmax;
+        target = t2;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        aqe_approx_result r;
+        r.estimate = est; r.ci_lower = est - half; r.ci_upper = est + half;
+        r.error_margin = rel / 100.0; r.confidence_level = 0.0;
+        r.n_samples = cum.rows; r.n_units = cum.units; r.population = a.n_rows;
+        r.mean = mean; r.m2 = m2; r.rounds = rounds; r.status = status; r.elapsed_us = 0.0;
+        *a.out = r;
+    }
+}
+
+}  // namespace aqe

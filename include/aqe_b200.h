@@ -29,6 +29,12 @@ extern "C" {
 
 #define AQE_ABI_VERSION 1
 
+#if defined(AQE_BUILDING)
+#define AQE_API __attribute__((visibility("default")))
+#else
+#define AQE_API
+#endif
+
 /* ------------------------------------------------------------------------------------------------
  * Types
  * ---------------------------------------------------------------------------------------------- */
@@ -204,113 +210,119 @@ typedef enum aqe_synth { AQE_SYNTH_UNIFORM = 0, AQE_SYNTH_LOGNORMAL = 1 } aqe_sy
 /* ------------------------------------------------------------------------------------------------
  * Library
  * ---------------------------------------------------------------------------------------------- */
-int         aqe_abi_version(void);
-const char* aqe_last_error(void);          /* thread-local, never NULL */
-int         aqe_device_count(int* out);    /* AQE_ERR_CUDA when no driver / device */
+AQE_API int         aqe_abi_version(void);
+AQE_API const char* aqe_last_error(void);          /* thread-local, never NULL */
+AQE_API int         aqe_device_count(int* out);    /* AQE_ERR_CUDA when no driver / device */
 /* Number of this library's kernels launched since load (bench.py gpu_launches). */
-uint64_t    aqe_launch_count(void);
+AQE_API uint64_t    aqe_launch_count(void);
+/* Page-locked host buffers for the host-column entry points (pageable memory also works, staged). */
+AQE_API int         aqe_host_alloc(size_t bytes, void** out);
+AQE_API int         aqe_host_free(void* p);
 
 /* ------------------------------------------------------------------------------------------------
  * Lifecycle / ingest  (create_database :135, open_database :153, load_from_file :685,
  * save_to_file :665, insert_record :164, insert_batch :196, close_database :157)
  * ---------------------------------------------------------------------------------------------- */
 /* Empty table bound to CUDA device `device` (no CUDA call is made until rows are needed on device). */
-int aqe_create(int device, aqe_db** out);
+AQE_API int aqe_create(int device, aqe_db** out);
 /* create + load_file of the whole file. */
-int aqe_open(const char* path, int device, aqe_db** out);
+AQE_API int aqe_open(const char* path, int device, aqe_db** out);
 /* Replace contents with rows [first_row, first_row + n_rows) of the record file (n_rows = UINT64_MAX:
  * to the end).  Rows are (stably) ordered by id, as load_from_file's insert_batch does (:198-200). */
-int aqe_load_file(aqe_db* db, const char* path, uint64_t first_row, uint64_t n_rows);
+AQE_API int aqe_load_file(aqe_db* db, const char* path, uint64_t first_row, uint64_t n_rows);
 /* Write header (total, height, count) + rows in ascending id (:665-683). */
-int aqe_save_file(aqe_db* db, const char* path);
+AQE_API int aqe_save_file(aqe_db* db, const char* path);
 /* Append host rows (insert_record / insert_batch); the device copy is rebuilt lazily. */
-int aqe_append_records(aqe_db* db, const aqe_record* rows, size_t n);
+AQE_API int aqe_append_records(aqe_db* db, const aqe_record* rows, size_t n);
 /* Replace contents with n host rows (AoS, pageable or pinned), chunked H2D + AoS->SoA on device. */
-int aqe_from_host_records(aqe_db* db, const aqe_record* rows, size_t n);
+AQE_API int aqe_from_host_records(aqe_db* db, const aqe_record* rows, size_t n);
 /* Borrow device-resident columns (Torch hand-off through data_ptr()); any pointer may be NULL if the
  * column is never queried.  The caller keeps ownership and must keep them alive. */
-int aqe_attach_device_columns(aqe_db* db, const int64_t* id, const double* amount, const int32_t* region,
+AQE_API int aqe_attach_device_columns(aqe_db* db, const int64_t* id, const double* amount, const int32_t* region,
                               const int32_t* product_id, const int64_t* timestamp, uint64_t n);
 /* Fill the shard on the device with rows [first_row, first_row+n_rows) of the synthetic table
  * (Philox4x32-10, key = seed, counter = global row).  columns_mask bit c = materialise column c. */
-int aqe_generate_synthetic(aqe_db* db, uint64_t seed, uint64_t first_row, uint64_t n_rows, int dist,
+AQE_API int aqe_generate_synthetic(aqe_db* db, uint64_t seed, uint64_t first_row, uint64_t n_rows, int dist,
                            uint32_t columns_mask);
 /* Host twin of the generator (same bits), for files / oracles.  rows[i] = global row first_row+i. */
-int aqe_synth_rows_host(uint64_t seed, uint64_t first_row, uint64_t n_rows, int dist, aqe_record* rows);
-int aqe_close(aqe_db* db); /* frees device + host memory; db invalid afterwards */
+AQE_API int aqe_synth_rows_host(uint64_t seed, uint64_t first_row, uint64_t n_rows, int dist, aqe_record* rows);
+AQE_API int aqe_close(aqe_db* db); /* frees device + host memory; db invalid afterwards */
 
-uint64_t aqe_count(const aqe_db* db);                 /* get_total_records :646 */
-uint64_t aqe_node_count(const aqe_db* db);            /* get_node_count :654 (N/255+1) */
-uint64_t aqe_tree_height(const aqe_db* db);           /* get_tree_height :650 (bulk-load shape) */
-int      aqe_device(const aqe_db* db);
+AQE_API uint64_t aqe_count(const aqe_db* db);                 /* get_total_records :646 */
+AQE_API uint64_t aqe_node_count(const aqe_db* db);            /* get_node_count :654 (N/255+1) */
+AQE_API uint64_t aqe_tree_height(const aqe_db* db);           /* get_tree_height :650 (bulk-load shape) */
+AQE_API int      aqe_device(const aqe_db* db);
 /* Device pointer of a column (NULL if absent) -- zero-copy export to torch / cupy. */
-const void* aqe_column_device_ptr(aqe_db* db, int col);
+AQE_API const void* aqe_column_device_ptr(aqe_db* db, int col);
 /* Copy rows [first,first+n) back to host AoS (collect_all_records :660). */
-int aqe_read_records(aqe_db* db, uint64_t first, uint64_t n, aqe_record* out);
+AQE_API int aqe_read_records(aqe_db* db, uint64_t first, uint64_t n, aqe_record* out);
 
 /* ------------------------------------------------------------------------------------------------
  * Exact full scans (K1/K2)  -- sum_amount :242, avg_amount :253, count_records :259,
  * sum_amount_where :263
  * ---------------------------------------------------------------------------------------------- */
-int aqe_scan(aqe_db* db, const aqe_scan_spec* spec, aqe_partial* out);
+AQE_API int aqe_scan(aqe_db* db, const aqe_scan_spec* spec, aqe_partial* out);
 /* Asynchronous form: launches on `stream` (a cudaStream_t, 0 = the handle's own stream) and leaves
  * the 64-byte partial in device memory at `partial_dev` (e.g. a torch tensor's data_ptr()). */
-int aqe_scan_async(aqe_db* db, const aqe_scan_spec* spec, void* partial_dev, void* stream);
+AQE_API int aqe_scan_async(aqe_db* db, const aqe_scan_spec* spec, void* partial_dev, void* stream);
 /* Scan host-resident column data through the device: chunked, double-buffered H2D from `host_col`
  * (n elements of agg column type; pinned recommended) overlapped with the reduction.  This is the
  * end-to-end (host buffers in, scalar out) form of sum_amount / sum_amount_where. */
-int aqe_scan_host_column(int device, const void* host_col, int col_kind, uint64_t n, double lo, double hi,
+AQE_API int aqe_scan_host_column(int device, const void* host_col, int col_kind, uint64_t n, double lo, double hi,
                          int use_pred, aqe_partial* out);
 /* Fixed-order merge of per-shard partials (rank order) -- pure host code. */
-int aqe_merge_partials(const aqe_partial* parts, int n, int is_integer, aqe_partial* out);
+AQE_API int aqe_merge_partials(const aqe_partial* parts, int n, int is_integer, aqe_partial* out);
 /* Conveniences over aqe_scan: */
-int aqe_sum_f64(aqe_db* db, int col, double* out);                                   /* :242 */
-int aqe_sum_where_f64(aqe_db* db, int col, double lo, double hi, double* sum, uint64_t* count); /* :263 */
-int aqe_sum_i128(aqe_db* db, int col, uint64_t* lo64, int64_t* hi64);                /* new */
+AQE_API int aqe_sum_f64(aqe_db* db, int col, double* out);                                   /* :242 */
+AQE_API int aqe_sum_where_f64(aqe_db* db, int col, double lo, double hi, double* sum, uint64_t* count); /* :263 */
+AQE_API int aqe_sum_i128(aqe_db* db, int col, uint64_t* lo64, int64_t* hi64);                /* new */
 
 /* ------------------------------------------------------------------------------------------------
  * Sample plans (Appendix A index generators) -- host arithmetic only, no device needed
  * ---------------------------------------------------------------------------------------------- */
-void aqe_sample_params_default(aqe_sample_params* p, int method); /* pybind defaults */
+AQE_API void aqe_sample_params_default(aqe_sample_params* p, int method); /* pybind defaults */
 /* Build the position list of `method` for a table of n_rows rows.  Methods that depend on data
  * (ADAPTIVE_BLOCK, STRATIFIED_BLOCK, CLT_VALIDATED_DUAL_POINTER) need `db` (may be NULL otherwise). */
-int  aqe_plan_build(aqe_db* db, uint64_t n_rows, int method, const aqe_sample_params* p, aqe_plan** out);
-int  aqe_plan_from_indices(const int64_t* idx, uint64_t n, aqe_plan** out);
-uint64_t aqe_plan_count(const aqe_plan* plan);
-uint32_t aqe_plan_num_segments(const aqe_plan* plan);  /* 0 => explicit index list */
-int  aqe_plan_segments(const aqe_plan* plan, aqe_segment* out, uint32_t cap);
-int  aqe_plan_indices(const aqe_plan* plan, int64_t* out, uint64_t cap); /* expand on host */
-int  aqe_plan_sorted_by_amount(const aqe_plan* plan);  /* 1: positions index the amount-sorted order */
-void aqe_plan_free(aqe_plan* plan);
+AQE_API int  aqe_plan_build(aqe_db* db, uint64_t n_rows, int method, const aqe_sample_params* p, aqe_plan** out);
+AQE_API int  aqe_plan_from_indices(const int64_t* idx, uint64_t n, aqe_plan** out);
+AQE_API uint64_t aqe_plan_count(const aqe_plan* plan);
+AQE_API uint32_t aqe_plan_num_segments(const aqe_plan* plan);  /* 0 => explicit index list */
+AQE_API int  aqe_plan_segments(const aqe_plan* plan, aqe_segment* out, uint32_t cap);
+AQE_API int  aqe_plan_indices(const aqe_plan* plan, int64_t* out, uint64_t cap); /* expand on host */
+AQE_API int  aqe_plan_sorted_by_amount(const aqe_plan* plan);  /* 1: positions index the amount-sorted order */
+AQE_API void aqe_plan_free(aqe_plan* plan);
 
 /* ------------------------------------------------------------------------------------------------
  * Sampled aggregates (K3/K5/K6)
  * ---------------------------------------------------------------------------------------------- */
 /* Moments of column `col` (as double) over the plan's positions. */
-int aqe_stats_from_plan(aqe_db* db, const aqe_plan* plan, int col, aqe_stats* out);
+AQE_API int aqe_stats_from_plan(aqe_db* db, const aqe_plan* plan, int col, aqe_stats* out);
+/* Same, but sampled rows failing lo <= pred_col <= hi contribute 0 (parallel_sum_where_sample :317-343). */
+AQE_API int aqe_stats_from_plan_where(aqe_db* db, const aqe_plan* plan, int col, int pred_col, double lo, double hi,
+                              aqe_stats* out);
 /* Same for a caller-supplied host index list ("same sample index list" parity, E1/E2). */
-int aqe_stats_from_indices(aqe_db* db, const int64_t* idx, uint64_t n, int col, aqe_stats* out);
+AQE_API int aqe_stats_from_indices(aqe_db* db, const int64_t* idx, uint64_t n, int col, aqe_stats* out);
 /* Rows at the plan's positions, AoS, in plan order (the legacy list[Record] return path). */
-int aqe_gather_plan(aqe_db* db, const aqe_plan* plan, aqe_record* out, uint64_t cap);
-int aqe_gather_records(aqe_db* db, const int64_t* idx, uint64_t n, aqe_record* out);
+AQE_API int aqe_gather_plan(aqe_db* db, const aqe_plan* plan, aqe_record* out, uint64_t cap);
+AQE_API int aqe_gather_records(aqe_db* db, const int64_t* idx, uint64_t n, aqe_record* out);
 /* fast_aggregated_memory_stride_sum :1962 -- raw (unscaled) sample sum, plus the sample count. */
-int aqe_fast_aggregated_sum(aqe_db* db, const aqe_sample_params* p, double* sum, uint64_t* n);
+AQE_API int aqe_fast_aggregated_sum(aqe_db* db, const aqe_sample_params* p, double* sum, uint64_t* n);
 
 /* CLI estimators (enhanced_aqe_cli.py:188-200 random, 257-291 clt) from sample moments.
  * legacy_ci != 0 reproduces the reference's SUM interval (margin * N/n). */
-int aqe_estimate(const aqe_stats* s, uint64_t population, int agg, double z, int legacy_ci,
+AQE_API int aqe_estimate(const aqe_stats* s, uint64_t population, int agg, double z, int legacy_ci,
                  double* estimate, double* ci_lower, double* ci_upper);
 
 /* ------------------------------------------------------------------------------------------------
  * Persistent CLT kernel (K4): Philox draws, Welford partials, in-kernel stop rule
  * ---------------------------------------------------------------------------------------------- */
-int aqe_approx(aqe_db* db, const aqe_approx_spec* spec, aqe_approx_result* out);
+AQE_API int aqe_approx(aqe_db* db, const aqe_approx_spec* spec, aqe_approx_result* out);
 /* Merge per-shard results (stratified by shard, rank order) into the table-level estimate. */
-int aqe_approx_merge(const aqe_approx_result* parts, int n, int agg, double confidence_level,
+AQE_API int aqe_approx_merge(const aqe_approx_result* parts, int n, int agg, double confidence_level,
                      aqe_approx_result* out);
 /* z for a two-sided confidence level: the reference's table 2.576/1.96/1.645 (:911-912) when
  * exact == 0, else the inverse normal CDF. */
-double aqe_z_score(double confidence_level, int exact);
+AQE_API double aqe_z_score(double confidence_level, int exact);
 
 #ifdef __cplusplus
 }

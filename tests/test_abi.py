@@ -1,0 +1,119 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/aqe_b200.h declares; the
+drop-in module imports and carries the reference's surface (bindings.cpp:10-137).  No compute calls."""
+import os
+import re
+
+import pytest
+
+import approximatequeryengine_b200 as aqe
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "aqe_b200.h")).read()
+    return sorted(set(re.findall(r"^AQE_API\s+[\w \*]+?\b(aqe_\w+)\s*\(", src, flags=re.M)))
+
+
+def test_header_declares_symbols():
+    syms = declared_symbols()
+    assert len(syms) >= 45
+    for must in ("aqe_open", "aqe_scan", "aqe_sum_f64", "aqe_sum_where_f64", "aqe_sum_i128", "aqe_plan_build",
+                 "aqe_stats_from_indices", "aqe_gather_records", "aqe_approx", "aqe_last_error"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    L = aqe.lib()
+    for s in declared_symbols():
+        assert hasattr(L, s), f"{s} declared in include/aqe_b200.h but not exported"
+    assert set(L._signatures) == set(declared_symbols()), "ctypes table out of sync with the header"
+    assert L.aqe_abi_version() == 1
+
+
+def test_struct_sizes_match_header():
+    import ctypes as C
+    assert C.sizeof(aqe.Partial) == 64
+    assert C.sizeof(aqe.Stats) == 32
+    assert C.sizeof(aqe.Segment) == 48
+    assert C.sizeof(aqe.SampleParams) == 72
+    assert C.sizeof(aqe.ApproxSpec) == 80
+    assert C.sizeof(aqe.ApproxResult) == 96
+    assert aqe.RECORD_DTYPE.itemsize == 32
+
+
+REFERENCE_DB_METHODS = {  # bindings.cpp:42-101, name -> keyword defaults
+    "create_database": {}, "open_database": {}, "close_database": {}, "insert_record": {}, "sum_amount": {},
+    "sum_amount_where": {}, "sample_records": {}, "optimized_sequential_sample": {}, "get_total_records": {},
+    "get_node_count": {}, "save_to_file": {}, "load_from_file": {},
+    "fast_pointer_sample": {"step_size": 2}, "slow_pointer_sample": {}, "dual_pointer_sample": {},
+    "parallel_pointer_sample": {"num_threads": 4}, "random_pointer_sample": {"seed": 42},
+    "clt_validated_dual_pointer_sample": {"confidence_level": 0.95, "check_interval": 10, "num_threads": 4, "max_error_percent": 2.0},
+    "optimized_clt_sample": {"confidence_level": 0.95, "check_interval": 20, "num_threads": 4, "max_error_percent": 2.0},
+    "block_sample": {"block_size": 1000}, "page_sample": {"page_size": 4096},
+    "parallel_block_sample": {"block_size": 1000, "num_threads": 4},
+    "adaptive_block_sample": {"min_block_size": 500, "max_block_size": 2000},
+    "stratified_block_sample": {"block_size": 1000, "strata_count": 4}, "index_based_sample": {},
+    "node_skip_sample": {"skip_factor": 2}, "balanced_tree_sample": {}, "direct_access_sample": {},
+    "byte_offset_sample": {}, "random_start_nth_sample": {"nth": 10}, "memory_stride_sample": {"stride_bytes": 0},
+    "address_arithmetic_sample": {}, "optimized_address_arithmetic_sample": {},
+    "random_start_memory_stride_sample": {"stride_bytes": 0}, "multithreaded_memory_stride_sample": {"num_threads": 4},
+    "fast_aggregated_memory_stride_sum": {"num_threads": 4}, "signal_based_clt_sample": {"check_interval": 10},
+}
+
+
+def test_dropin_module_surface():
+    b = aqe.backend()
+    assert len(REFERENCE_DB_METHODS) == 37
+    for name, defaults in REFERENCE_DB_METHODS.items():
+        f = getattr(b.CustomBPlusDB, name)
+        doc = f.__doc__
+        for k, v in defaults.items():
+            assert re.search(rf"\b{k}: [^,)]+ = {re.escape(str(v))}(?![\w.])", doc), (name, k, doc)
+    for name in ("create_database", "open_database", "close_database", "insert_record", "insert_batch", "execute_sum_query",
+                 "execute_avg_query", "execute_count_query", "execute_exact_sum", "execute_exact_avg", "execute_exact_count",
+                 "benchmark_query", "get_total_records", "get_tree_height", "get_database_size_mb"):
+        assert hasattr(b.CustomApproximateScheduler, name)
+    doc = b.CustomApproximateScheduler.execute_sum_query.__doc__
+    assert re.search(r"sample_percent: [^,)]+ = 10.0, num_threads: [^,)]+ = 4\)", doc), doc
+    for name in ("run_query", "run_query_groupby", "run_query_with_ci", "run_query_groupby_with_ci"):
+        assert callable(getattr(b, name))
+    assert [s for s in ("STABLE", "DRIFTING", "INSUFFICIENT_DATA", "ERROR") if hasattr(b.CustomApproximationStatus, s)] == ["STABLE", "DRIFTING", "INSUFFICIENT_DATA", "ERROR"]
+    r = b.Record()
+    assert (r.id, r.amount, r.region, r.product_id, r.timestamp) == (0, 0.0, 0, 0, 0)
+    for f in ("value", "status", "confidence_level", "error_margin", "samples_used", "computation_time"):
+        assert hasattr(b.CustomValidationResult, f)
+    for f in ("value", "ci_lower", "ci_upper"):
+        assert hasattr(b.QueryResult, f)
+    assert not hasattr(b, "ApproximationStatus")  # the CLI probes this name and falls back (enhanced_aqe_cli.py:142-155)
+
+
+def test_sqlite_path_is_loudly_out_of_scope():
+    b = aqe.backend()
+    with pytest.raises(RuntimeError, match="SQLite"):
+        b.run_query("SELECT SUM(amount) FROM sales", "x.db", 0)
+
+
+def test_where_clause_forms():
+    w = aqe.backend().CustomApproximateScheduler._where_conditions  # custom_scheduler.cpp:277-294
+    assert w("SELECT SUM(amount) FROM s WHERE amount BETWEEN 100 AND 500") == (100.0, 500.0)
+    assert w("... WHERE amount  BETWEEN 1.5   AND 2.25") == (1.5, 2.25)
+    assert w("WHERE amount >= 3 AND amount <= 7") == (3.0, 7.0)
+    assert w("WHERE amount>9") == (9.0, 99999.99)
+    assert w("WHERE amount between 1 and 2") == (-1.0, -1.0)  # keywords are case-sensitive in the reference
+    assert w("SELECT SUM(amount) FROM s") == (-1.0, -1.0)
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU the product must fail loudly, not compute on the CPU."""
+    b = aqe.backend()
+    if b.device_count() > 0:
+        pytest.skip("a GPU is present")
+    db = b.CustomBPlusDB()
+    r = b.Record(); r.id = 1; r.amount = 2.0
+    assert db.insert_record(r) and db.get_total_records() == 1
+    with pytest.raises(RuntimeError, match="cuda|CUDA"):
+        db.sum_amount()
+    e = aqe.Engine(0)
+    with pytest.raises(aqe.AqeError):
+        e.generate(100)
