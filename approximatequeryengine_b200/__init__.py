@@ -135,6 +135,7 @@ def lib() -> C.CDLL:
         "aqe_device": (i32, [vp]),
         "aqe_column_device_ptr": (vp, [vp, i32]),
         "aqe_read_records": (i32, [vp, u64, u64, vp]),
+        "aqe_read_column": (i32, [vp, i32, u64, u64, vp]),
         "aqe_scan": (i32, [vp, C.POINTER(ScanSpec), C.POINTER(Partial)]),
         "aqe_scan_async": (i32, [vp, C.POINTER(ScanSpec), vp, vp]),
         "aqe_scan_host_column": (i32, [i32, vp, i32, u64, dbl, dbl, i32, C.POINTER(Partial)]),
@@ -310,6 +311,16 @@ class Engine:
         n = self.count - first if n is None else n
         out = np.empty(n, dtype=RECORD_DTYPE)
         check(self.L.aqe_read_records(self.h, first, n, _ptr(out)))
+        return out
+
+    def read_column(self, col: str, first: int = 0, n: int | None = None, out_ptr: int | None = None):
+        """Column slice -> host.  With out_ptr the copy lands in caller memory (e.g. a pinned buffer)."""
+        n = self.count - first if n is None else n
+        if out_ptr is not None:
+            check(self.L.aqe_read_column(self.h, COLS[col], first, n, C.c_void_p(out_ptr)))
+            return None
+        out = np.empty(n, dtype={0: np.float64, 1: np.int64, 2: np.int32}[COL_KIND[col]])
+        check(self.L.aqe_read_column(self.h, COLS[col], first, n, _ptr(out)))
         return out
 
     @property

@@ -228,6 +228,15 @@ static int ensure_device(aqe_db* db) {
     return AQE_OK;
 }
 
+static int col_kind_of(int col) {  // 0 f64, 1 i64, 2 i32
+    switch (col) {
+        case AQE_COL_AMOUNT: return 0;
+        case AQE_COL_ID: case AQE_COL_TIMESTAMP: return 1;
+        case AQE_COL_REGION: case AQE_COL_PRODUCT_ID: return 2;
+        default: return -1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // library-level entry points
 // ------------------------------------------------------------------------------------------------
@@ -427,6 +436,20 @@ int aqe_read_records(aqe_db* db, uint64_t first, uint64_t n, aqe_record* out) {
     return AQE_OK;
 }
 
+int aqe_read_column(aqe_db* db, int col, uint64_t first, uint64_t n, void* out) {
+    if (!db || (!out && n)) return fail(AQE_ERR_INVALID, "NULL argument");
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    const int k = col_kind_of(col);
+    const char* base = static_cast<const char*>(aqe_column_device_ptr(db, col));
+    if (k < 0 || !base) return fail(AQE_ERR_STATE, "column is not resident on the device");
+    if (first + n > db->n) return fail(AQE_ERR_INVALID, "row range out of bounds");
+    const size_t esz = k == 2 ? 4 : 8;
+    CU(cudaMemcpyAsync(out, base + first * esz, n * esz, cudaMemcpyDeviceToHost, db->stream));
+    CU(cudaStreamSynchronize(db->stream));
+    return AQE_OK;
+}
+
 int aqe_save_file(aqe_db* db, const char* path) {
     if (!db || !path) return fail(AQE_ERR_INVALID, "NULL argument");
     const uint64_t n = aqe_count(db);
@@ -474,7 +497,7 @@ static size_t kind_size(int k) { return k == K_I32 ? 4 : 8; }
 
 struct ScanTuning { int variant, bps, unroll, stages, chunk_kb; };
 static ScanTuning scan_tuning() {
-    static ScanTuning t = {env_int("AQE_SCAN_VARIANT", 0), env_int("AQE_SCAN_BPS", 0), env_int("AQE_SCAN_UNROLL", 4),
+    ScanTuning t = {env_int("AQE_SCAN_VARIANT", 0), env_int("AQE_SCAN_BPS", 0), env_int("AQE_SCAN_UNROLL", 4),
                            env_int("AQE_SCAN_STAGES", 4), env_int("AQE_SCAN_CHUNK_KB", 16)};
     return t;
 }

@@ -1,0 +1,110 @@
+"""Range-sharded tables: one process per GPU, contiguous record ranges, tiny partials merged in rank order.
+
+The reference has no multi-process story; its own region split is ``[N*t/T, N*(t+1)/T)`` per thread
+(custom_bplus_db.cpp:925-926, 1904-1918) and that is the split used here per rank.  The only exchange is
+one all-gather of a 64-byte ``aqe_partial`` (exact scans) or a 96-byte ``aqe_approx_result`` (sampled
+estimates) per query -- ``torch.distributed`` carries it (NCCL over NVLink on GPUs, gloo in the CPU
+tests); the merge itself is the fixed-rank-order host code of the C-ABI (``aqe_merge_partials`` /
+``aqe_approx_merge``), so every rank computes bit-identical results.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import AGG, ApproxResult, Engine, Partial, check, lib
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Rows [a, b) owned by `rank` (custom_bplus_db.cpp:925-926 with t=rank, T=world)."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def _struct_to_i64(obj, words: int) -> np.ndarray:
+    return np.frombuffer(bytes(obj), dtype=np.int64, count=words).copy()
+
+
+def _i64_to_struct(arr: np.ndarray, cls):
+    return cls.from_buffer_copy(np.ascontiguousarray(arr, dtype=np.int64).tobytes())
+
+
+def allgather_struct(obj, cls, group=None, device=None):
+    """All-gather one POD struct (as raw 8-byte words so no bit is altered) -> list in rank order."""
+    import torch
+    import torch.distributed as dist
+
+    words = C.sizeof(cls) // 8
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return [obj]
+    world = dist.get_world_size(group)
+    dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    mine = torch.from_numpy(_struct_to_i64(obj, words)).to(dev)
+    out = torch.empty(world * words, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    flat = out.cpu().numpy().reshape(world, words)
+    return [_i64_to_struct(flat[r], cls) for r in range(world)]
+
+
+def merge_partials(parts, is_integer: bool = False) -> Partial:
+    arr = (Partial * len(parts))(*parts)
+    out = Partial()
+    check(lib().aqe_merge_partials(arr, len(parts), int(is_integer), C.byref(out)))
+    return out
+
+
+def merge_approx(parts, agg: str, confidence_level: float) -> ApproxResult:
+    arr = (ApproxResult * len(parts))(*parts)
+    out = ApproxResult()
+    check(lib().aqe_approx_merge(arr, len(parts), AGG[agg], confidence_level, C.byref(out)))
+    return out
+
+
+class ShardedTable:
+    """This rank's shard + the collective merge.  Every query is called by all ranks (SPMD)."""
+
+    def __init__(self, engine: Engine, total_rows: int, first_row: int, group=None):
+        self.engine = engine
+        self.total_rows = total_rows
+        self.first_row = first_row
+        self.group = group
+
+    @classmethod
+    def synthetic(cls, total_rows: int, rank: int, world: int, seed: int = 7, device: int | None = None,
+                  columns=("id", "amount", "region", "product_id", "timestamp"), dist: int = 0, group=None):
+        a, b = shard_range(total_rows, rank, world)
+        e = Engine(device).generate(b - a, seed=seed, first_row=a, dist=dist, columns=columns)
+        return cls(e, total_rows, a, group)
+
+    @classmethod
+    def from_file(cls, path: str, rank: int, world: int, device: int | None = None, group=None):
+        import struct
+        with open(path, "rb") as f:
+            total = struct.unpack("<QQQ", f.read(24))[2]
+        a, b = shard_range(total, rank, world)
+        e = Engine(device).load_file(path, first_row=a, n_rows=b - a)
+        return cls(e, total, a, group)
+
+    def scan(self, agg_col="amount", pred_col=None, lo=0.0, hi=0.0) -> Partial:
+        local = self.engine.scan(agg_col, pred_col, lo, hi) if self.engine.count else Partial(minv=float("inf"), maxv=float("-inf"))
+        parts = allgather_struct(local, Partial, self.group)
+        return merge_partials(parts, is_integer=agg_col != "amount")
+
+    def sum_amount(self) -> float:
+        return self.scan("amount").sum
+
+    def sum_amount_where(self, lo: float, hi: float):
+        p = self.scan("amount", "amount", lo, hi)
+        return p.sum, p.count
+
+    def count(self) -> int:
+        return self.total_rows
+
+    def approx(self, agg="sum", error_percent=1.0, confidence_level=0.95, seed=0, **kw) -> ApproxResult:
+        """Shards are strata: each rank runs its persistent CLT kernel to the same relative target with
+        an independent Philox key (seed, rank); totals and variances add (aqe_approx_merge)."""
+        import torch.distributed as dist
+        rank = dist.get_rank(self.group) if dist.is_available() and dist.is_initialized() else 0
+        local = self.engine.approx(agg, error_percent, confidence_level, seed=(seed << 8) + rank, **kw)
+        parts = allgather_struct(local, ApproxResult, self.group)
+        return merge_approx(parts, agg, confidence_level)

@@ -1,0 +1,360 @@
+#!/usr/bin/env python3
+"""bench.py -- the reference's headline benchmark on B200: exact SUM/COUNT(amount) with a range predicate
+over the synthetic sales table (BASELINE.json configs[2]), plus the CLT-terminated APPROX latency
+(configs[1]) as a secondary figure.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--scaling weak|strong] [--impl reference]
+
+N > 1 is launched by the driver under torchrun (one rank per GPU, NCCL).  A "step" is one pass of the hot
+path over the rank's shard: the fused predicate scan kernel (k_scan, aqe_kernels.cuh) over the HBM-resident
+amount column, one all-gather of the 64-byte partials, and an async copy of the gathered partials to
+pinned host memory.  Rank 0 prints ONE JSON line.
+
+  value     whole-job records/s with the table resident in HBM (CUDA events on the launching stream,
+            barrier + synchronize on both sides, max over ranks)
+  e2e       the same metric through the C-ABI with HOST buffers: aqe_scan_host_column() streams each rank's
+            pinned host column through the device every step (H2D inside the timed region)
+  roofline  the scan kernel alone: 8 algorithmic bytes per record / its CUDA-event duration vs the
+            measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's own CPU path (oracle/_ref = the unmodified reference compiled in place) on a
+            bounded 1 M-record sample, same query, timed on this box's host cores (rank 0, N=1 only)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LO, HI = 100.0, 500.0           # `amount BETWEEN 100 AND 500` (custom_scheduler.cpp:279), selectivity ~40 %
+SEED = 7
+METRIC = "exact_sum_count_where_records_per_sec"
+UNIT = "records/s"
+CPU_SAMPLE_ROWS = 1_000_000
+
+
+def ncu_traffic_per_record():
+    """DRAM bytes per record of the scan kernel from the committed ncu --set full capture (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            t = json.load(f)["k_scan"]
+        return (t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]) / t["records_per_launch"]
+    except Exception:
+        return None
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # "under load": samples in the upper half of the observed power range
+        if sm:
+            cut = (max(power) + min(power)) / 2 if power else 0
+            load = [c for c, p in zip(sm, power) if p >= cut] or sm
+            return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                    "power_w_max": max(power) if power else None}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(reasons), "samples": 0}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own implementation of the query
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference(steps: int, warmup: int, port_too: bool = True) -> dict:
+    """sum_amount_where(100, 500) of the UNMODIFIED reference (oracle/_ref) over a 1 M-record sample.  The
+    reference's exact scan is single-threaded by construction (custom_bplus_db.cpp:263-274), so cores = 1 is
+    every thread it can use.  Loading goes through insert_batch (untimed; open_database deadlocks)."""
+    import numpy as np
+    from oracle import Oracle, Ref
+    O = Oracle()
+    rows = O.synth(CPU_SAMPLE_ROWS, seed=SEED)
+    out = {"unit": UNIT}
+    if Ref.available():
+        t0 = time.time()
+        R = Ref(rows)
+        load_s = time.time() - t0
+        R.time(1, max(1, warmup), LO, HI)
+        per = []
+        for _ in range(max(steps, 3)):
+            t, v = R.time(1, 1, LO, HI)
+            per.append(t)
+        t_step = statistics.median(per)
+        want, _ = O.sum_amount_where(rows, LO, HI)
+        assert v == want, "reference and oracle disagree"
+        out.update({"value": CPU_SAMPLE_ROWS / t_step, "cores": 1, "kind": "reference", "ms_per_step": t_step * 1e3,
+                    "sample": f"{CPU_SAMPLE_ROWS} records (32-byte rows in the reference B+ tree, loaded by insert_batch in {load_s:.1f} s, untimed); "
+                              f"CustomBPlusDB::sum_amount_where(100,500), median of {len(per)} calls, single-threaded as shipped"})
+        del R
+    else:
+        per = []
+        for _ in range(max(steps, 3)):
+            t0 = time.perf_counter(); O.sum_amount_where(rows, LO, HI); per.append(time.perf_counter() - t0)
+        t_step = statistics.median(per)
+        out.update({"value": CPU_SAMPLE_ROWS / t_step, "cores": 1, "kind": "port", "ms_per_step": t_step * 1e3,
+                    "sample": f"{CPU_SAMPLE_ROWS} records, oracle/aqe_oracle.c orc_sum_amount_where (oracle/_ref not built)"})
+    if port_too:
+        # the restated multithreaded scan, all host cores, for an honest upper bound of the CPU side
+        cores = os.cpu_count() or 1
+        n = 100_000_000
+        col = np.empty(n, dtype=np.float64)
+        blk = O.synth(1_000_000, seed=SEED)["amount"]
+        for i in range(0, n, len(blk)):
+            col[i:i + len(blk)] = blk
+        best = min(_timeit(lambda: O.scan_mt(col, aos=False, threads=cores, pred=(LO, HI))) for _ in range(3))
+        out["port_mt"] = {"value": n / best, "unit": UNIT, "cores": cores, "kind": "port",
+                          "sample": f"{n} records, 8-byte amount column (SoA), orc_scan_mt: contiguous regions x {cores} threads"}
+    return out
+
+
+def _timeit(f):
+    t0 = time.perf_counter(); f(); return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(args.steps, args.warmup, port_too=False)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, per_gpu_rows(args), cpu=True),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def per_gpu_rows(args) -> int:
+    return args.records if args.scaling == "weak" else args.records // args.gpus
+
+
+def workload_config(args, rows_per_gpu, cpu=False):
+    return {"workload": "BASELINE.json configs[2]: 1B-record synthetic sales table, exact SUM+COUNT(amount) WHERE amount BETWEEN 100 AND 500, "
+                        "range-sharded across the GPUs",
+            "records_per_gpu": rows_per_gpu, "total_records": rows_per_gpu * args.gpus, "predicate": f"amount BETWEEN {LO:g} AND {HI:g}",
+            "data_seed": SEED, "distribution": "amount ~ U(1,1000) fp64 (Philox4x32-10)",
+            "l2": "inputs larger than L2: 8 bytes x records_per_gpu per pass vs 126 MB L2, no flush needed",
+            "parallelism": f"range-shard x{args.gpus}, all-gather of 64-byte partials"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--records", type=int, default=int(os.environ.get("AQE_BENCH_RECORDS", 1_000_000_000)),
+                    help="records per GPU (weak) or in total (strong)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-approx", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import approximatequeryengine_b200 as aqe
+    from approximatequeryengine_b200 import sharded
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("bench.py --gpus N>1 must be launched under torchrun (one rank per GPU)")
+        args.gpus = world
+    if not torch.cuda.is_available():
+        sys.exit("bench.py needs a CUDA device: this engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    L = aqe.lib()
+    rows = per_gpu_rows(args)
+    first = rank * rows
+    eng = aqe.Engine(local).generate(rows, seed=SEED, first_row=first, columns=("amount",))
+    # a dedicated stream: aqe_scan_async(stream=0) means "the handle's own stream", so never hand it the
+    # default stream's 0 handle -- kernels, collectives, copies and the timing events all go on `stream`
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    partial = torch.zeros(8, dtype=torch.int64, device="cuda")               # one 64-byte aqe_partial
+    gathered = torch.zeros(8 * world, dtype=torch.int64, device="cuda")
+    host_out = torch.zeros(8 * world, dtype=torch.int64).pin_memory()
+
+    def step():
+        eng.scan_async(partial.data_ptr(), "amount", "amount", LO, HI, stream=stream.cuda_stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, partial)
+            host_out.copy_(gathered, non_blocking=True)
+        else:
+            host_out.copy_(partial, non_blocking=True)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, k):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = L.aqe_launch_count()
+    total_ms = timed(step, args.steps)
+    launches = L.aqe_launch_count() - launches0
+    # the scan kernel alone, same stream, for the roofline
+    kern_ms = timed(lambda: eng.scan_async(partial.data_ptr(), "amount", "amount", LO, HI, stream=stream.cuda_stream), args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    # result check: merged partials == known count / plausible sum (every rank holds the same gathered bytes)
+    sync_all()
+    parts = [aqe.Partial.from_buffer_copy(host_out[8 * r:8 * r + 8].numpy().tobytes()) for r in range(world)]
+    merged = sharded.merge_partials(parts)
+    sel = merged.count / (rows * world)
+    assert 0.39 < sel < 0.41 and 290.0 < merged.sum / merged.count < 310.0, (merged.count, merged.sum)
+
+    lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(lt)
+    ms_per_step = total_ms / args.steps
+    value = rows * world / (ms_per_step * 1e-3)
+    peak, peak_src = measured_peak()
+    kms = kern_ms / args.steps
+    achieved = 8.0 * rows / (kms * 1e-3) / 1e9
+
+    # ---- e2e: host buffers in, scalar out, through the C-ABI ------------------------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        e2e_steps = args.e2e_steps or min(args.steps, 10)
+        hptr = C.c_void_p()
+        aqe.check(L.aqe_host_alloc(rows * 8, C.byref(hptr)))
+        eng.read_column("amount", out_ptr=hptr.value)          # device -> pinned host (setup, untimed)
+        def e2e_step():
+            return aqe.host_scan_column(None, LO, HI, use_pred=True, device=local, ptr=hptr.value, n=rows, kind=0)
+        for _ in range(3):
+            p = e2e_step()
+        assert p.count == parts[rank].count and p.sum == parts[rank].sum or abs(p.sum - parts[rank].sum) <= 1e-12 * abs(p.sum)
+        l0 = L.aqe_launch_count()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        chunk_mb = int(os.environ.get("AQE_E2E_CHUNK_MB", 64))
+        nchunks = -(-rows * 8 // (chunk_mb << 20))
+        e2e = {"value": rows * world / (float(dt.item()) / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": rows * 8 * world,
+               "d2h_bytes_per_step": 64 * nchunks * world, "steps": e2e_steps, "ms_per_step": float(dt.item()) / e2e_steps * 1e3,
+               "api": "aqe_scan_host_column (C-ABI): pinned host amount column -> chunked H2D overlapped with k_scan -> merged partial",
+               "launches_per_step": (L.aqe_launch_count() - l0) // e2e_steps}
+        L.aqe_host_free(hptr)
+
+    # ---- secondary: CLT-terminated APPROX AVG at 1 % on 10 M records (configs[1]) through the drop-in module ----
+    approx = None
+    if rank == 0 and not args.skip_approx:
+        b = aqe.backend()
+        db = b.CustomBPlusDB(local)
+        db.generate_synthetic(10_000_000, SEED)
+        exact = db.sum_amount() / 10_000_000
+        lat, kus, ns, errs = [], [], [], []
+        for s in range(220):
+            t0 = time.perf_counter(); r = db.approx_avg(error_percent=1.0, confidence_level=0.95, seed=s); t1 = time.perf_counter()
+            if s >= 20:
+                lat.append((t1 - t0) * 1e6); kus.append(r.kernel_us); ns.append(r.samples_used); errs.append(abs(r.value - exact) / exact * 100)
+        approx = {"workload": "BASELINE.json configs[1]: 10M records, APPROX AVG(amount), CLT early termination at 1% error, 95% confidence",
+                  "latency_us_p50": statistics.median(lat), "latency_us_p99": sorted(lat)[int(len(lat) * 0.99) - 1], "kernel_us_p50": statistics.median(kus),
+                  "samples_p50": statistics.median(ns), "abs_error_percent_p50": statistics.median(errs), "abs_error_percent_max": max(errs),
+                  "api": "aqe_backend.CustomBPlusDB.approx_avg (pybind11 -> aqe_approx -> k_approx, one cooperative launch)"}
+        del db
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu = cpu_reference(steps=10, warmup=2)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, rows),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": (ncu_traffic_per_record() * rows) if ncu_traffic_per_record() else None,
+                             "kernel": "aqe::k_scan<double, PRED=1 (amount on itself), W=4 (LDG.256), U=4>", "kernel_ms": kms,
+                             "algorithmic_bytes_per_launch": 8 * rows, "peak_source": peak_src},
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clk, "approx": approx,
+                "result": {"count": merged.count, "sum": merged.sum}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

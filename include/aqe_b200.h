@@ -254,6 +254,8 @@ AQE_API uint64_t aqe_tree_height(const aqe_db* db);           /* get_tree_height
 AQE_API int      aqe_device(const aqe_db* db);
 /* Device pointer of a column (NULL if absent) -- zero-copy export to torch / cupy. */
 AQE_API const void* aqe_column_device_ptr(aqe_db* db, int col);
+/* Copy elements [first,first+n) of one column to host memory (pinned or pageable). */
+AQE_API int aqe_read_column(aqe_db* db, int col, uint64_t first, uint64_t n, void* out);
 /* Copy rows [first,first+n) back to host AoS (collect_all_records :660). */
 AQE_API int aqe_read_records(aqe_db* db, uint64_t first, uint64_t n, aqe_record* out);
 
@@ -262,7 +264,8 @@ AQE_API int aqe_read_records(aqe_db* db, uint64_t first, uint64_t n, aqe_record*
  * sum_amount_where :263
  * ---------------------------------------------------------------------------------------------- */
 AQE_API int aqe_scan(aqe_db* db, const aqe_scan_spec* spec, aqe_partial* out);
-/* Asynchronous form: launches on `stream` (a cudaStream_t, 0 = the handle's own stream) and leaves
+/* Asynchronous form: launches on `stream` (a cudaStream_t; 0 = the handle's own non-blocking stream -- to
+ * target CUDA's default stream pass cudaStreamLegacy / cudaStreamPerThread explicitly) and leaves
  * the 64-byte partial in device memory at `partial_dev` (e.g. a torch tensor's data_ptr()). */
 AQE_API int aqe_scan_async(aqe_db* db, const aqe_scan_spec* spec, void* partial_dev, void* stream);
 /* Scan host-resident column data through the device: chunked, double-buffered H2D from `host_col`
