@@ -140,6 +140,11 @@ def lib() -> C.CDLL:
         "aqe_scan_async": (i32, [vp, C.POINTER(ScanSpec), vp, vp]),
         "aqe_scan_host_column": (i32, [i32, vp, i32, u64, dbl, dbl, i32, C.POINTER(Partial)]),
         "aqe_merge_partials": (i32, [C.POINTER(Partial), i32, i32, C.POINTER(Partial)]),
+        "aqe_exchange_init": (i32, [vp, i32, i32, vp]),
+        "aqe_exchange_connect": (i32, [vp, vp]),
+        "aqe_exchange_check": (i32, [vp]),
+        "aqe_scan_exchange": (i32, [vp, C.POINTER(ScanSpec), C.POINTER(Partial)]),
+        "aqe_scan_exchange_async": (i32, [vp, C.POINTER(ScanSpec), vp, vp]),
         "aqe_sum_f64": (i32, [vp, i32, C.POINTER(dbl)]),
         "aqe_sum_where_f64": (i32, [vp, i32, dbl, dbl, C.POINTER(dbl), C.POINTER(u64)]),
         "aqe_sum_i128": (i32, [vp, i32, C.POINTER(u64), C.POINTER(C.c_int64)]),
@@ -340,6 +345,29 @@ class Engine:
     def scan_async(self, partial_dev_ptr: int, agg_col="amount", pred_col=None, lo=0.0, hi=0.0, stream: int = 0):
         sp = ScanSpec(COLS[agg_col], COLS[pred_col], lo, hi)
         check(self.L.aqe_scan_async(self.h, C.byref(sp), C.c_void_p(partial_dev_ptr), C.c_void_p(stream)))
+
+    # ---- fused cross-GPU exchange (see include/aqe_b200.h) ----
+    def exchange_init(self, rank: int, world: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(self.L.aqe_exchange_init(self.h, rank, world, buf))
+        return buf.raw
+
+    def exchange_connect(self, handles) -> None:
+        blob = b"".join(handles)
+        check(self.L.aqe_exchange_connect(self.h, blob))
+
+    def scan_exchange(self, agg_col="amount", pred_col=None, lo=0.0, hi=0.0) -> Partial:
+        sp = ScanSpec(COLS[agg_col], COLS[pred_col], lo, hi)
+        out = Partial()
+        check(self.L.aqe_scan_exchange(self.h, C.byref(sp), C.byref(out)))
+        return out
+
+    def scan_exchange_async(self, merged_dev_ptr: int, agg_col="amount", pred_col=None, lo=0.0, hi=0.0, stream: int = 0):
+        sp = ScanSpec(COLS[agg_col], COLS[pred_col], lo, hi)
+        check(self.L.aqe_scan_exchange_async(self.h, C.byref(sp), C.c_void_p(merged_dev_ptr), C.c_void_p(stream)))
+
+    def exchange_check(self) -> None:
+        check(self.L.aqe_exchange_check(self.h))
 
     def sum_amount(self) -> float:
         v = C.c_double()

@@ -83,6 +83,13 @@ struct aqe_db {
     void* plan_buf = nullptr; size_t plan_cap = 0;
     int64_t* amount_perm = nullptr;  // rows ordered by amount (stratified_block_sample)
     int max_grid = 0;
+
+    // fused cross-GPU exchange (see Exchange in aqe_kernels.cuh)
+    int ex_rank = 0, ex_world = 0;
+    ExSlot* ex_mailbox = nullptr;
+    ExSlot* ex_peers[kMaxRanks] = {nullptr};
+    unsigned long long ex_seq = 0;
+    bool ex_connected = false;
 };
 
 static const int kMaxGrid = 148 * 16;
@@ -281,6 +288,9 @@ int aqe_close(aqe_db* db) {
         free_columns(db);
         cudaFree(db->scan_partials); cudaFree(db->stat_partials); cudaFree(db->approx_slots); cudaFree(db->tickets);
         cudaFree(db->gather_buf); cudaFree(db->plan_buf);
+        for (int r = 0; r < db->ex_world; ++r)
+            if (db->ex_connected && r != db->ex_rank && db->ex_peers[r]) cudaIpcCloseMemHandle(db->ex_peers[r]);
+        cudaFree(db->ex_mailbox);
         cudaFreeHost(db->slot_host);
         cudaEventDestroy(db->ev0); cudaEventDestroy(db->ev1);
         cudaStreamDestroy(db->stream);
@@ -495,11 +505,46 @@ static const void* col_ptr(const aqe_db* db, int col) {
 }
 static size_t kind_size(int k) { return k == K_I32 ? 4 : 8; }
 
-struct ScanTuning { int variant, bps, unroll, stages, chunk_kb; };
+struct ScanTuning { int variant, bps, unroll, stages, chunk_kb, minb; };
 static ScanTuning scan_tuning() {
+    // Defaults = the configuration that won the round-1 sweep (profiles/r1_scan_sweep*.jsonl).  The knobs exist
+    // for tools/scan_sweep.py; they are read per call so one process can sweep them.
     ScanTuning t = {env_int("AQE_SCAN_VARIANT", 0), env_int("AQE_SCAN_BPS", 0), env_int("AQE_SCAN_UNROLL", 4),
-                           env_int("AQE_SCAN_STAGES", 4), env_int("AQE_SCAN_CHUNK_KB", 16)};
+                    env_int("AQE_SCAN_STAGES", 4), env_int("AQE_SCAN_CHUNK_KB", 16), env_int("AQE_SCAN_MINB", 1)};
     return t;
+}
+
+// occupancy (and the one-time dynamic-smem opt-in) per kernel, looked up once
+static int kernel_occupancy(const void* kernel, int threads, size_t smem) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, int>> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto& e : cache) if (e.first == kernel) return e.second;
+    if (smem) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+    occ = std::max(occ, 1);
+    cache.emplace_back(kernel, occ);
+    return occ;
+}
+
+template <typename K> static int launch_regs_kernel(const aqe_db* db, K kernel, const ScanArgs& a, int W, int U, int bps_req, cudaStream_t s) {
+    const int occ = kernel_occupancy((const void*)kernel, kScanThreads, 0);
+    const int bps = bps_req > 0 ? std::min(bps_req, occ) : occ;
+    kernel<<<grid_for(db, a.n / W, U, kScanThreads, bps), kScanThreads, 0, s>>>(a);
+    LAUNCHED();
+    return AQE_OK;
+}
+template <typename K> static int launch_bulk_kernel(const aqe_db* db, K kernel, const ScanArgs& a, int stages, int chunk, int bps_req, cudaStream_t s) {
+    const size_t smem = (size_t)stages * chunk;
+    const int occ = kernel_occupancy((const void*)kernel, kBulkThreads, smem);
+    const int bps = bps_req > 0 ? std::min(bps_req, occ) : occ;
+    const uint64_t nchunks = (a.n * 8 + chunk - 1) / chunk;
+    int grid = (int)std::min<uint64_t>((uint64_t)db->sm_count * bps, std::max<uint64_t>(nchunks, 1));
+    if (grid > db->max_grid) grid = db->max_grid;
+    kernel<<<grid, kBulkThreads, smem, s>>>(a);
+    LAUNCHED();
+    return AQE_OK;
 }
 
 template <typename AggT, int PRED, typename PredT, bool MOMENTS>
@@ -511,46 +556,28 @@ static int launch_scan_t(const aqe_db* db, const ScanArgs& a, bool aligned, cuda
         LAUNCHED();
         return AQE_OK;
     }
-    if constexpr (std::is_same_v<AggT, double> && PRED != 2) {
-        if (t.variant == 2) {  // TMA-staged ring
-            auto go = [&](auto kernel, int stages, int chunk) {
-                const size_t smem = (size_t)stages * chunk;
-                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                int occ = 1;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBulkThreads, smem);
-                if (occ < 1) occ = 1;
-                const int bps = t.bps > 0 ? std::min(t.bps, occ) : occ;
-                const uint64_t nchunks = (a.n * 8 + chunk - 1) / chunk;
-                int grid = (int)std::min<uint64_t>((uint64_t)db->sm_count * bps, std::max<uint64_t>(nchunks, 1));
-                if (grid > db->max_grid) grid = db->max_grid;
-                kernel<<<grid, kBulkThreads, smem, s>>>(a);
-                LAUNCHED();
-            };
-            if (t.chunk_kb == 32 && t.stages == 4) go(k_scan_bulk<PRED, 4, 32768, MOMENTS>, 4, 32768);
-            else if (t.chunk_kb == 32 && t.stages == 6) go(k_scan_bulk<PRED, 6, 32768, MOMENTS>, 6, 32768);
-            else if (t.chunk_kb == 8) go(k_scan_bulk<PRED, 8, 8192, MOMENTS>, 8, 8192);
-            else if (t.stages == 8) go(k_scan_bulk<PRED, 8, 16384, MOMENTS>, 8, 16384);
-            else go(k_scan_bulk<PRED, 4, 16384, MOMENTS>, 4, 16384);
-            return AQE_OK;
+    if constexpr (std::is_same_v<AggT, double> && PRED != 2 && !MOMENTS) {
+        // Headline kernels (exact SUM / SUM WHERE over amount).  Default = the TMA-staged ring, 4 x 16 KiB,
+        // 2 CTAs/SM (128 KiB in flight per SM): 7.23-7.40 TB/s in both round-1 sweeps vs 7.0-7.3 for the
+        // register-staged kernel (profiles/r1_scan_sweep*.jsonl).  AQE_SCAN_VARIANT=4 forces the latter.
+        if (t.variant == 0) return launch_bulk_kernel(db, k_scan_bulk<PRED, 4, 16384, false>, a, 4, 16384, t.bps > 0 ? t.bps : 2, s);
+        if (t.variant == 2) {
+#define AQE_BULK(ST, KB) if (t.stages == ST && t.chunk_kb == KB) return launch_bulk_kernel(db, k_scan_bulk<PRED, ST, KB * 1024, false>, a, ST, KB * 1024, t.bps, s);
+            AQE_BULK(3, 16) AQE_BULK(4, 16) AQE_BULK(5, 16) AQE_BULK(6, 16) AQE_BULK(8, 16)
+            AQE_BULK(3, 32) AQE_BULK(4, 32) AQE_BULK(6, 32) AQE_BULK(8, 8) AQE_BULK(12, 8) AQE_BULK(2, 64) AQE_BULK(3, 64)
+#undef AQE_BULK
+            return launch_bulk_kernel(db, k_scan_bulk<PRED, 4, 16384, false>, a, 4, 16384, t.bps, s);
         }
-        if (t.variant == 1 || t.unroll != 4) {  // tuning sweeps of the headline kernels
-            auto go = [&](auto kernel, int W, int U) {
-                int occ = 1;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kScanThreads, 0);
-                const int bps = t.bps > 0 ? std::min(t.bps, std::max(occ, 1)) : std::max(occ, 1);
-                kernel<<<grid_for(db, a.n / W, U, kScanThreads, bps), kScanThreads, 0, s>>>(a);
-                LAUNCHED();
-            };
-            if (t.variant == 1) {
-                if (t.unroll == 8) go(k_scan<AggT, PRED, PredT, 2, 8, MOMENTS, 1>, 2, 8);
-                else if (t.unroll == 2) go(k_scan<AggT, PRED, PredT, 2, 2, MOMENTS, 1>, 2, 2);
-                else go(k_scan<AggT, PRED, PredT, 2, 4, MOMENTS, 1>, 2, 4);
-            } else {
-                if (t.unroll == 8) go(k_scan<AggT, PRED, PredT, 4, 8, MOMENTS, 1>, 4, 8);
-                else if (t.unroll == 2) go(k_scan<AggT, PRED, PredT, 4, 2, MOMENTS, 1>, 4, 2);
-                else go(k_scan<AggT, PRED, PredT, 4, 1, MOMENTS, 1>, 4, 1);
-            }
-            return AQE_OK;
+        if (t.variant == 1) {
+#define AQE_REGS(WW, UU, MB) if (t.unroll == UU && t.minb == MB) return launch_regs_kernel(db, k_scan<AggT, PRED, PredT, WW, UU, false, MB>, a, WW, UU, t.bps, s);
+            AQE_REGS(2, 2, 1) AQE_REGS(2, 4, 1) AQE_REGS(2, 8, 1) AQE_REGS(2, 8, 2) AQE_REGS(2, 8, 4)
+            return launch_regs_kernel(db, k_scan<AggT, PRED, PredT, 2, 4, false, 1>, a, 2, 4, t.bps, s);
+        }
+        if (t.variant == 3) {
+            AQE_REGS(4, 1, 1) AQE_REGS(4, 2, 1) AQE_REGS(4, 8, 1)
+            AQE_REGS(4, 2, 2) AQE_REGS(4, 2, 3) AQE_REGS(4, 2, 4) AQE_REGS(4, 4, 2) AQE_REGS(4, 4, 3) AQE_REGS(4, 4, 4)
+            AQE_REGS(4, 8, 2) AQE_REGS(4, 8, 3) AQE_REGS(4, 6, 2) AQE_REGS(4, 6, 3) AQE_REGS(4, 3, 4) AQE_REGS(4, 3, 3)
+#undef AQE_REGS
         }
     }
     auto kernel = k_scan<AggT, PRED, PredT, 4, 4, MOMENTS, 1>;
@@ -579,7 +606,7 @@ static int launch_scan_pred(const aqe_db* db, const ScanArgs& a, int pred_mode, 
 
 // Launches the scan of rows [first, first+n) of the handle's columns; result lands at out_dev.
 static int scan_launch(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, uint64_t n, bool moments, aqe_partial* out_dev,
-                       cudaStream_t s) {
+                       cudaStream_t s, bool exchange = false) {
     const int ak = col_kind(spec->agg_col);
     if (ak < 0) return fail(AQE_ERR_INVALID, "bad aggregate column");
     const char* agg = static_cast<const char*>(col_ptr(db, spec->agg_col));
@@ -597,6 +624,15 @@ static int scan_launch(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, ui
         }
     }
     ScanArgs a;
+    std::memset(&a.ex, 0, sizeof(a.ex));
+    if (exchange) {
+        if (!db->ex_connected) return fail(AQE_ERR_STATE, "aqe_exchange_connect has not been called");
+        a.ex.world = db->ex_world; a.ex.rank = db->ex_rank; a.ex.is_integer = ak != K_F64;
+        a.ex.seq = ++db->ex_seq;
+        a.ex.timeout_cycles = (unsigned long long)env_int("AQE_EXCHANGE_TIMEOUT_MS", 5000) * 2000000ull;
+        for (int r = 0; r < db->ex_world; ++r) a.ex.peers[r] = db->ex_peers[r];
+        a.ex.status = db->tickets + 3;
+    }
     a.agg = agg ? agg + first * kind_size(ak) : nullptr;
     a.pred = pred ? pred + first * kind_size(pk) : nullptr;
     a.n = n; a.lo = spec->lo; a.hi = spec->hi;
@@ -635,6 +671,68 @@ int aqe_scan_async(aqe_db* db, const aqe_scan_spec* spec, void* partial_dev, voi
     int rc = ensure_device(db);
     if (rc) return rc;
     return scan_launch(db, spec, 0, db->n, false, static_cast<aqe_partial*>(partial_dev), stream ? (cudaStream_t)stream : db->stream);
+}
+
+int aqe_exchange_init(aqe_db* db, int rank, int world, void* ipc_handle_out) {
+    if (!db || !ipc_handle_out) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(AQE_ERR_INVALID, "rank/world out of range (at most 16 ranks)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    int rc = db_init_cuda(db);
+    if (rc) return rc;
+    if (!db->ex_mailbox) {
+        CU(cudaMalloc(&db->ex_mailbox, sizeof(ExSlot) * kMaxRanks * 2));
+        CU(cudaMemset(db->ex_mailbox, 0, sizeof(ExSlot) * kMaxRanks * 2));
+    }
+    db->ex_rank = rank; db->ex_world = world; db->ex_seq = 0; db->ex_connected = false;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, db->ex_mailbox));
+    std::memcpy(ipc_handle_out, &h, sizeof(h));
+    return AQE_OK;
+}
+
+int aqe_exchange_connect(aqe_db* db, const void* all_handles) {
+    if (!db || !all_handles) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (!db->ex_mailbox) return fail(AQE_ERR_STATE, "call aqe_exchange_init first");
+    CU(cudaSetDevice(db->device));
+    for (int r = 0; r < db->ex_world; ++r) {
+        if (r == db->ex_rank) { db->ex_peers[r] = db->ex_mailbox; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char*>(all_handles) + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        db->ex_peers[r] = static_cast<ExSlot*>(p);
+    }
+    db->ex_connected = true;
+    return AQE_OK;
+}
+
+int aqe_scan_exchange_async(aqe_db* db, const aqe_scan_spec* spec, void* merged_dev, void* stream) {
+    if (!db || !spec || !merged_dev) return fail(AQE_ERR_INVALID, "NULL argument");
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    return scan_launch(db, spec, 0, db->n, false, static_cast<aqe_partial*>(merged_dev), stream ? (cudaStream_t)stream : db->stream, db->ex_world > 1);
+}
+
+int aqe_exchange_check(aqe_db* db) {
+    if (!db || !db->cuda_ready) return fail(AQE_ERR_STATE, "no device state");
+    unsigned int st = 0;
+    CU(cudaMemcpy(&st, db->tickets + 3, 4, cudaMemcpyDeviceToHost));
+    if (st) { cudaMemset(db->tickets + 3, 0, 4); return fail(AQE_ERR_CUDA, "fused exchange timed out waiting for a peer rank"); }
+    return AQE_OK;
+}
+
+int aqe_scan_exchange(aqe_db* db, const aqe_scan_spec* spec, aqe_partial* out) {
+    if (!db || !spec || !out) return fail(AQE_ERR_INVALID, "NULL argument");
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    rc = scan_launch(db, spec, 0, db->n, true, &db->slot_dev->partial, db->stream, db->ex_world > 1);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(db->stream));
+    unsigned int st = 0;
+    CU(cudaMemcpy(&st, db->tickets + 3, 4, cudaMemcpyDeviceToHost));
+    if (st) { cudaMemset(db->tickets + 3, 0, 4); return fail(AQE_ERR_CUDA, "fused exchange timed out waiting for a peer rank"); }
+    *out = db->slot_host->partial;
+    return AQE_OK;
 }
 
 int aqe_merge_partials(const aqe_partial* parts, int n, int is_integer, aqe_partial* out) {
@@ -784,6 +882,7 @@ int aqe_scan_host_column(int device, const void* host_col, int col_kind_id, uint
         }
         CU(cudaMemcpyAsync(c->dev[b], src, cnt * esz, cudaMemcpyHostToDevice, c->streams[b]));
         ScanArgs a;
+        std::memset(&a.ex, 0, sizeof(a.ex));
         a.agg = c->dev[b]; a.pred = nullptr; a.n = cnt; a.lo = lo; a.hi = hi;
         a.partials = b ? c->partials2 : db->scan_partials;
         a.ticket = b ? c->tickets2 : db->tickets + 1;

@@ -82,6 +82,26 @@ template <bool IS_INT, bool MOMENTS> __device__ __forceinline__ ScanAcc scan_blo
     return a;
 }
 
+// Cross-GPU exchange fused into the scan kernel (one process per GPU, peers mapped with CUDA IPC over
+// NVLink).  Every rank owns a mailbox of kMaxRanks x 2 slots; the LAST block of rank g stores its 64-byte
+// shard partial + the query's sequence number into slot [g][seq & 1] of EVERY rank's mailbox (peer stores),
+// then waits until its own mailbox holds sequence `seq` from all ranks and folds them in rank order -- the
+// all-gather + merge that followed the scan (NCCL launch + kernel) becomes a few NVLink stores inside it.
+// Two slots per sender suffice: a rank can write query k+2 only after it merged query k+1, which needs every
+// peer's k+1 partial, which a peer publishes only after it consumed query k.
+constexpr int kMaxRanks = 16;
+struct ExSlot { aqe_partial p; unsigned long long seq; unsigned long long pad[7]; };  // 128 bytes
+struct Exchange {
+    int world;                 // 0/1 = disabled
+    int rank;
+    int is_integer;
+    int pad;
+    unsigned long long seq;
+    unsigned long long timeout_cycles;
+    ExSlot* peers[kMaxRanks];  // peers[r] = rank r's mailbox as mapped in this process (peers[rank] = own)
+    unsigned int* status;      // set to 1 if a peer did not show up in time
+};
+
 struct ScanArgs {
     const void* agg;
     const void* pred;
@@ -90,7 +110,49 @@ struct ScanArgs {
     ScanAcc* partials;      // [gridDim.x]
     unsigned int* ticket;   // zero before launch; reset by the last block
     aqe_partial* out;       // device-visible (device memory or mapped pinned host memory)
+    Exchange ex;
 };
+
+// Fixed-rank-order fold of shard partials; the same IEEE operations as the host's aqe_merge_partials
+// (aqe_engine.cu), so device-merged and host-merged results are bit-identical.
+__device__ __forceinline__ void merge_partials_dev(const aqe_partial* parts, int n, bool is_integer, aqe_partial* out) {
+    aqe_partial r;
+    r.count = 0; r.isum_lo = 0; r.isum_hi = 0;
+    r.minv = __longlong_as_double(0x7ff0000000000000LL); r.maxv = __longlong_as_double(0xfff0000000000000LL);
+    double s = 0.0, c = 0.0, q = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const aqe_partial& p = parts[i];
+        r.count += p.count;
+        const unsigned long long lo = r.isum_lo + p.isum_lo;
+        r.isum_hi += p.isum_hi + (lo < r.isum_lo ? 1 : 0);
+        r.isum_lo = lo;
+        const double t = __dadd_rn(s, p.sum);
+        const double z = __dadd_rn(t, -s);
+        const double e = __dadd_rn(__dadd_rn(s, -__dadd_rn(t, -z)), __dadd_rn(p.sum, -z));
+        c = __dadd_rn(c, __dadd_rn(p.comp, e));
+        s = t;
+        q = __dadd_rn(q, p.sumsq);
+        if (p.count) { r.minv = fmin(r.minv, p.minv); r.maxv = fmax(r.maxv, p.maxv); }
+    }
+    const double t = __dadd_rn(s, c);
+    r.comp = __dadd_rn(c, -__dadd_rn(t, -s));
+    r.sum = t;
+    r.sumsq = q;
+    if (is_integer) {
+        r.sum = (double)r.isum_hi * 18446744073709551616.0 + (double)r.isum_lo;
+        r.comp = 0.0;
+    }
+    *out = r;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 template <bool IS_INT> __device__ __forceinline__ void scan_write_out(const ScanAcc& t, aqe_partial* out) {
     aqe_partial r;
@@ -128,10 +190,48 @@ template <bool IS_INT, bool MOMENTS> __device__ __forceinline__ void scan_finish
         scan_merge(acc, load_cg(a.partials + b));
     }
     acc = scan_block_reduce<IS_INT, MOMENTS>(acc, sm);
+    if (a.ex.world <= 1) {
+        if (threadIdx.x == 0) {
+            scan_write_out<IS_INT>(acc, a.out);
+            *a.ticket = 0u;
+        }
+        return;
+    }
+    // ---- fused all-gather + merge over peer memory ----
+    __shared__ aqe_partial sh_parts[kMaxRanks];
+    __shared__ aqe_partial sh_local;
+    const int world = a.ex.world, par = (int)(a.ex.seq & 1ull);
     if (threadIdx.x == 0) {
-        scan_write_out<IS_INT>(acc, a.out);
+        scan_write_out<IS_INT>(acc, &sh_local);
         *a.ticket = 0u;
     }
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        ExSlot* dst = a.ex.peers[threadIdx.x] + (a.ex.rank * 2 + par);
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&sh_local);
+        volatile unsigned long long* d = reinterpret_cast<volatile unsigned long long*>(&dst->p);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(aqe_partial) / 8); ++i) d[i] = src[i];
+        __threadfence_system();
+        st_release_sys(&dst->seq, a.ex.seq);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        const ExSlot* src = a.ex.peers[a.ex.rank] + (threadIdx.x * 2 + par);
+        const long long t0 = clock64();
+        bool ok = true;
+        while (ld_acquire_sys(&src->seq) != a.ex.seq) {
+            if ((unsigned long long)(clock64() - t0) > a.ex.timeout_cycles) { ok = false; break; }
+            __nanosleep(64);
+        }
+        if (!ok) atomicExch(a.ex.status, 1u);
+        const volatile unsigned long long* sp = reinterpret_cast<const volatile unsigned long long*>(&src->p);
+        unsigned long long* dp = reinterpret_cast<unsigned long long*>(&sh_parts[threadIdx.x]);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(aqe_partial) / 8); ++i) dp[i] = sp[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) merge_partials_dev(sh_parts, world, a.ex.is_integer != 0, a.out);
 }
 
 template <typename T> __device__ __forceinline__ double as_f64(T v) { return (double)v; }

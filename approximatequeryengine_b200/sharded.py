@@ -85,7 +85,25 @@ class ShardedTable:
         e = Engine(device).load_file(path, first_row=a, n_rows=b - a)
         return cls(e, total, a, group)
 
+    def enable_fused_exchange(self) -> bool:
+        """Map every rank's mailbox over CUDA IPC so scans merge inside the kernel (NVLink peer stores) instead of
+        through an NCCL all-gather.  Needs one process per GPU on one box; returns False (and keeps the
+        all-gather path) for a single rank."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return False
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        mine = self.engine.exchange_init(rank, world)
+        handles = [None] * world
+        dist.all_gather_object(handles, mine, group=self.group)
+        self.engine.exchange_connect(handles)
+        dist.barrier(self.group)
+        self.fused = True
+        return True
+
     def scan(self, agg_col="amount", pred_col=None, lo=0.0, hi=0.0) -> Partial:
+        if getattr(self, "fused", False):
+            return self.engine.scan_exchange(agg_col, pred_col, lo, hi)
         local = self.engine.scan(agg_col, pred_col, lo, hi) if self.engine.count else Partial(minv=float("inf"), maxv=float("-inf"))
         parts = allgather_struct(local, Partial, self.group)
         return merge_partials(parts, is_integer=agg_col != "amount")

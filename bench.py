@@ -182,7 +182,8 @@ def workload_config(args, rows_per_gpu, cpu=False):
             "records_per_gpu": rows_per_gpu, "total_records": rows_per_gpu * args.gpus, "predicate": f"amount BETWEEN {LO:g} AND {HI:g}",
             "data_seed": SEED, "distribution": "amount ~ U(1,1000) fp64 (Philox4x32-10)",
             "l2": "inputs larger than L2: 8 bytes x records_per_gpu per pass vs 126 MB L2, no flush needed",
-            "parallelism": f"range-shard x{args.gpus}, all-gather of 64-byte partials"}
+            "parallelism": f"range-shard x{args.gpus}; 64-byte shard partials exchanged " +
+                           ("by an NCCL all-gather" if getattr(args, "no_fused", False) or args.gpus == 1 else "inside the scan kernel (NVLink peer stores, CUDA IPC mailboxes)")}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -196,6 +197,7 @@ def main():
     ap.add_argument("--records", type=int, default=int(os.environ.get("AQE_BENCH_RECORDS", 1_000_000_000)),
                     help="records per GPU (weak) or in total (strong)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--no-fused", action="store_true", help="merge shards with an NCCL all-gather instead of the in-kernel NVLink exchange")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-approx", action="store_true")
@@ -232,15 +234,28 @@ def main():
     torch.cuda.set_stream(stream)
     partial = torch.zeros(8, dtype=torch.int64, device="cuda")               # one 64-byte aqe_partial
     gathered = torch.zeros(8 * world, dtype=torch.int64, device="cuda")
-    host_out = torch.zeros(8 * world, dtype=torch.int64).pin_memory()
+    host_out = torch.zeros(8 * world, dtype=torch.int64).pin_memory()        # pinned + UVA: kernels can store into it
+    fused = world > 1 and not args.no_fused
+    if fused:
+        # one process per GPU on one NVSwitch box: map every rank's mailbox (CUDA IPC) so that the scan kernel's last
+        # block publishes the shard partial to all peers over NVLink and folds all of them itself
+        mine = eng.exchange_init(rank, world)
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        eng.exchange_connect(handles)
+        dist.barrier()
 
-    def step():
-        eng.scan_async(partial.data_ptr(), "amount", "amount", LO, HI, stream=stream.cuda_stream)
-        if world > 1:
+    if fused:
+        def step():       # scan + exchange + rank-order merge in ONE kernel; the table-level result lands in pinned memory
+            eng.scan_exchange_async(host_out.data_ptr(), "amount", "amount", LO, HI, stream=stream.cuda_stream)
+    elif world > 1:
+        def step():
+            eng.scan_async(partial.data_ptr(), "amount", "amount", LO, HI, stream=stream.cuda_stream)
             dist.all_gather_into_tensor(gathered, partial)
             host_out.copy_(gathered, non_blocking=True)
-        else:
-            host_out.copy_(partial, non_blocking=True)
+    else:
+        def step():       # single shard: the kernel stores its 64-byte result straight into pinned host memory
+            eng.scan_async(host_out.data_ptr(), "amount", "amount", LO, HI, stream=stream.cuda_stream)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -275,8 +290,14 @@ def main():
 
     # result check: merged partials == known count / plausible sum (every rank holds the same gathered bytes)
     sync_all()
-    parts = [aqe.Partial.from_buffer_copy(host_out[8 * r:8 * r + 8].numpy().tobytes()) for r in range(world)]
-    merged = sharded.merge_partials(parts)
+    if fused:
+        eng.exchange_check()
+        merged = aqe.Partial.from_buffer_copy(host_out[:8].numpy().tobytes())     # already the table-level partial
+        local_part = eng.scan("amount", "amount", LO, HI)
+    else:
+        parts = [aqe.Partial.from_buffer_copy(host_out[8 * r:8 * r + 8].numpy().tobytes()) for r in range(world)]
+        merged = sharded.merge_partials(parts)
+        local_part = parts[rank]
     sel = merged.count / (rows * world)
     assert 0.39 < sel < 0.41 and 290.0 < merged.sum / merged.count < 310.0, (merged.count, merged.sum)
 
@@ -300,7 +321,7 @@ def main():
             return aqe.host_scan_column(None, LO, HI, use_pred=True, device=local, ptr=hptr.value, n=rows, kind=0)
         for _ in range(3):
             p = e2e_step()
-        assert p.count == parts[rank].count and p.sum == parts[rank].sum or abs(p.sum - parts[rank].sum) <= 1e-12 * abs(p.sum)
+        assert p.count == local_part.count and abs(p.sum - local_part.sum) <= 1e-12 * abs(p.sum)
         l0 = L.aqe_launch_count()
         sync_all()
         t0 = time.perf_counter()

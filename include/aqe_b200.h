@@ -273,6 +273,19 @@ AQE_API int aqe_scan_async(aqe_db* db, const aqe_scan_spec* spec, void* partial_
  * end-to-end (host buffers in, scalar out) form of sum_amount / sum_amount_where. */
 AQE_API int aqe_scan_host_column(int device, const void* host_col, int col_kind, uint64_t n, double lo, double hi,
                          int use_pred, aqe_partial* out);
+/* Fused cross-GPU exchange (one process per GPU on one NVLink/NVSwitch box).  aqe_exchange_init allocates this
+ * rank's mailbox and returns its 64-byte CUDA IPC handle; after the ranks have all-gathered the handles
+ * (any transport), aqe_exchange_connect maps every peer's mailbox.  aqe_scan_exchange[_async] then runs the
+ * scan and, inside the same kernel, stores the shard's 64-byte partial into every rank's mailbox over NVLink,
+ * waits for all ranks and folds them in rank order: the result is the TABLE-level partial on every rank,
+ * bit-identical to aqe_merge_partials over the per-shard results.  All ranks must issue the same sequence
+ * of exchange scans.  world <= 16. */
+AQE_API int aqe_exchange_init(aqe_db* db, int rank, int world, void* ipc_handle_out /* 64 bytes */);
+AQE_API int aqe_exchange_connect(aqe_db* db, const void* all_handles /* world x 64 bytes, rank order */);
+AQE_API int aqe_scan_exchange(aqe_db* db, const aqe_scan_spec* spec, aqe_partial* out);
+AQE_API int aqe_scan_exchange_async(aqe_db* db, const aqe_scan_spec* spec, void* merged_dev, void* stream);
+/* After synchronising the stream of asynchronous exchange scans: AQE_ERR_CUDA if a peer never showed up. */
+AQE_API int aqe_exchange_check(aqe_db* db);
 /* Fixed-order merge of per-shard partials (rank order) -- pure host code. */
 AQE_API int aqe_merge_partials(const aqe_partial* parts, int n, int is_integer, aqe_partial* out);
 /* Conveniences over aqe_scan: */

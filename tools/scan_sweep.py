@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Sweep the scan-kernel variants / launch geometry on one B200 and print GB/s (8 algorithmic bytes per record).
-Usage (GPU box): python tools/scan_sweep.py [records]"""
+Usage (GPU box): python tools/scan_sweep.py [records] [round]"""
 import json
 import os
 import sys
@@ -12,14 +12,16 @@ import torch
 import approximatequeryengine_b200 as aqe
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000_000
+which = sys.argv[2] if len(sys.argv) > 2 else "2"
 eng = aqe.Engine(0).generate(n, seed=7, columns=("amount",))
 partial = torch.zeros(8, dtype=torch.int64, device="cuda")
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
+KEYS = ("AQE_SCAN_VARIANT", "AQE_SCAN_BPS", "AQE_SCAN_UNROLL", "AQE_SCAN_STAGES", "AQE_SCAN_CHUNK_KB", "AQE_SCAN_MINB")
 
 
 def run(env, pred=True, reps=20):
-    for k in ("AQE_SCAN_VARIANT", "AQE_SCAN_BPS", "AQE_SCAN_UNROLL", "AQE_SCAN_STAGES", "AQE_SCAN_CHUNK_KB"):
+    for k in KEYS:
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
     args = ("amount", "amount", 100.0, 500.0) if pred else ("amount", None, 0.0, 0.0)
@@ -37,21 +39,16 @@ def run(env, pred=True, reps=20):
     return {"env": env, "pred": pred, "ms": round(ms, 4), "GBps": round(8 * n / ms / 1e6, 1), "count": p.count, "sum": p.sum}
 
 
-configs = []
-for bps in (0, 1, 2, 3, 4, 6, 8):
-    configs.append({"AQE_SCAN_VARIANT": 0, "AQE_SCAN_BPS": bps})
-for u in (1, 2, 8):
-    for bps in (0, 4, 8):
-        configs.append({"AQE_SCAN_VARIANT": 0, "AQE_SCAN_UNROLL": u, "AQE_SCAN_BPS": bps})
-for u in (2, 4, 8):
-    for bps in (0, 4):
-        configs.append({"AQE_SCAN_VARIANT": 1, "AQE_SCAN_UNROLL": u, "AQE_SCAN_BPS": bps})
-for st, ck in ((4, 16), (8, 16), (4, 32), (6, 32), (8, 8)):
-    for bps in (0, 1, 2):
-        configs.append({"AQE_SCAN_VARIANT": 2, "AQE_SCAN_STAGES": st, "AQE_SCAN_CHUNK_KB": ck, "AQE_SCAN_BPS": bps})
-ref = None
+configs = [{"AQE_SCAN_VARIANT": 0}]
+if which == "2":
+    for u, mb in ((2, 2), (2, 3), (2, 4), (3, 3), (3, 4), (4, 2), (4, 3), (4, 4), (6, 2), (6, 3), (8, 1), (8, 2), (8, 3)):
+        configs.append({"AQE_SCAN_VARIANT": 3, "AQE_SCAN_UNROLL": u, "AQE_SCAN_MINB": mb})
+    for u, mb in ((8, 2), (8, 4)):
+        configs.append({"AQE_SCAN_VARIANT": 1, "AQE_SCAN_UNROLL": u, "AQE_SCAN_MINB": mb})
+    for st, ck in ((3, 16), (4, 16), (5, 16), (6, 16), (8, 16), (3, 32), (4, 32), (6, 32), (12, 8), (2, 64), (3, 64)):
+        for bps in (0, 1, 2, 3):
+            configs.append({"AQE_SCAN_VARIANT": 2, "AQE_SCAN_STAGES": st, "AQE_SCAN_CHUNK_KB": ck, "AQE_SCAN_BPS": bps})
+configs.append({"AQE_SCAN_VARIANT": 0})
 for c in configs:
     for pred in (True, False):
-        r = run(c, pred)
-        key = (r["count"], r["sum"])
-        print(json.dumps(r), flush=True)
+        print(json.dumps(run(c, pred)), flush=True)
