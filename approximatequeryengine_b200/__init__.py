@@ -214,8 +214,11 @@ class Plan:
         self.h = handle
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().aqe_plan_free(self.h)
+        if getattr(self, "h", None) and _lib is not None:
+            try:
+                _lib.aqe_plan_free(self.h)
+            except Exception:  # interpreter shutdown
+                pass
             self.h = None
 
     @property

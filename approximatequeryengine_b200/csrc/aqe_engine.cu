@@ -535,18 +535,23 @@ template <typename K> static int launch_regs_kernel(const aqe_db* db, K kernel, 
     LAUNCHED();
     return AQE_OK;
 }
-template <typename K> static int launch_bulk_kernel(const aqe_db* db, K kernel, const ScanArgs& a, int stages, int chunk, int bps_req, cudaStream_t s) {
-    const size_t smem = (size_t)stages * chunk;
+template <typename K> static int launch_ring_kernel(const aqe_db* db, K kernel, const ScanArgs& a, int stages, int rows_per_tile, int bps_req, cudaStream_t s) {
+    const size_t smem = (size_t)stages * kStageBytes;
     const int occ = kernel_occupancy((const void*)kernel, kBulkThreads, smem);
     const int bps = bps_req > 0 ? std::min(bps_req, occ) : occ;
-    const uint64_t nchunks = (a.n * 8 + chunk - 1) / chunk;
-    int grid = (int)std::min<uint64_t>((uint64_t)db->sm_count * bps, std::max<uint64_t>(nchunks, 1));
+    const uint64_t ntiles = (a.n + rows_per_tile - 1) / rows_per_tile;
+    int grid = (int)std::min<uint64_t>((uint64_t)db->sm_count * bps, std::max<uint64_t>(ntiles, 1));
     if (grid > db->max_grid) grid = db->max_grid;
     kernel<<<grid, kBulkThreads, smem, s>>>(a);
     LAUNCHED();
     return AQE_OK;
 }
 
+// Kernel selection.  Default for every aligned scan: the TMA-staged ring, 4 stages x 16 KiB, 2 CTAs/SM
+// (128 KiB in flight per SM) -- 7.2-7.4 TB/s on the headline query in the round-1 sweeps vs 7.0-7.3 for the
+// register-staged kernel, and immune to ptxas sinking loads (which cost the integer-predicate register kernel half
+// its bandwidth).  AQE_SCAN_VARIANT: 0 ring (default) | 2 ring with AQE_SCAN_STAGES in {2,3,4,6} | 4 register-staged
+// LDG.256 kernel | 1 register-staged LDG.128 kernel.  Read per call so tools/scan_sweep.py can sweep in one process.
 template <typename AggT, int PRED, typename PredT, bool MOMENTS>
 static int launch_scan_t(const aqe_db* db, const ScanArgs& a, bool aligned, cudaStream_t s) {
     const ScanTuning t = scan_tuning();
@@ -556,41 +561,43 @@ static int launch_scan_t(const aqe_db* db, const ScanArgs& a, bool aligned, cuda
         LAUNCHED();
         return AQE_OK;
     }
+    using G = RingGeom<AggT, PRED, PredT>;
+    if (t.variant == 0) return launch_ring_kernel(db, k_scan_ring<AggT, PRED, PredT, 4, MOMENTS>, a, 4, G::kRows, t.bps > 0 ? t.bps : 2, s);
     if constexpr (std::is_same_v<AggT, double> && PRED != 2 && !MOMENTS) {
-        // Headline kernels (exact SUM / SUM WHERE over amount).  Default = the TMA-staged ring, 4 x 16 KiB,
-        // 2 CTAs/SM (128 KiB in flight per SM): 7.23-7.40 TB/s in both round-1 sweeps vs 7.0-7.3 for the
-        // register-staged kernel (profiles/r1_scan_sweep*.jsonl).  AQE_SCAN_VARIANT=4 forces the latter.
-        if (t.variant == 0) return launch_bulk_kernel(db, k_scan_bulk<PRED, 4, 16384, false>, a, 4, 16384, t.bps > 0 ? t.bps : 2, s);
         if (t.variant == 2) {
-#define AQE_BULK(ST, KB) if (t.stages == ST && t.chunk_kb == KB) return launch_bulk_kernel(db, k_scan_bulk<PRED, ST, KB * 1024, false>, a, ST, KB * 1024, t.bps, s);
-            AQE_BULK(3, 16) AQE_BULK(4, 16) AQE_BULK(5, 16) AQE_BULK(6, 16) AQE_BULK(8, 16)
-            AQE_BULK(3, 32) AQE_BULK(4, 32) AQE_BULK(6, 32) AQE_BULK(8, 8) AQE_BULK(12, 8) AQE_BULK(2, 64) AQE_BULK(3, 64)
-#undef AQE_BULK
-            return launch_bulk_kernel(db, k_scan_bulk<PRED, 4, 16384, false>, a, 4, 16384, t.bps, s);
+            if (t.stages == 2) return launch_ring_kernel(db, k_scan_ring<AggT, PRED, PredT, 2, false>, a, 2, G::kRows, t.bps, s);
+            if (t.stages == 3) return launch_ring_kernel(db, k_scan_ring<AggT, PRED, PredT, 3, false>, a, 3, G::kRows, t.bps, s);
+            if (t.stages == 6) return launch_ring_kernel(db, k_scan_ring<AggT, PRED, PredT, 6, false>, a, 6, G::kRows, t.bps, s);
+            return launch_ring_kernel(db, k_scan_ring<AggT, PRED, PredT, 4, false>, a, 4, G::kRows, t.bps, s);
         }
-        if (t.variant == 1) {
-#define AQE_REGS(WW, UU, MB) if (t.unroll == UU && t.minb == MB) return launch_regs_kernel(db, k_scan<AggT, PRED, PredT, WW, UU, false, MB>, a, WW, UU, t.bps, s);
-            AQE_REGS(2, 2, 1) AQE_REGS(2, 4, 1) AQE_REGS(2, 8, 1) AQE_REGS(2, 8, 2) AQE_REGS(2, 8, 4)
-            return launch_regs_kernel(db, k_scan<AggT, PRED, PredT, 2, 4, false, 1>, a, 2, 4, t.bps, s);
-        }
-        if (t.variant == 3) {
-            AQE_REGS(4, 1, 1) AQE_REGS(4, 2, 1) AQE_REGS(4, 8, 1)
-            AQE_REGS(4, 2, 2) AQE_REGS(4, 2, 3) AQE_REGS(4, 2, 4) AQE_REGS(4, 4, 2) AQE_REGS(4, 4, 3) AQE_REGS(4, 4, 4)
-            AQE_REGS(4, 8, 2) AQE_REGS(4, 8, 3) AQE_REGS(4, 6, 2) AQE_REGS(4, 6, 3) AQE_REGS(4, 3, 4) AQE_REGS(4, 3, 3)
-#undef AQE_REGS
-        }
+        if (t.variant == 1) return launch_regs_kernel(db, k_scan<AggT, PRED, PredT, 2, 8, false, 2>, a, 2, 8, t.bps, s);
+        if (t.variant == 4 && t.unroll == 6) return launch_regs_kernel(db, k_scan<AggT, PRED, PredT, 4, 6, false, 2>, a, 4, 6, t.bps, s);
+        if (t.variant == 4 && t.minb == 3) return launch_regs_kernel(db, k_scan<AggT, PRED, PredT, 4, 4, false, 3>, a, 4, 4, t.bps, s);
     }
-    auto kernel = k_scan<AggT, PRED, PredT, 4, 4, MOMENTS, 1>;
-    static int occ_cache = 0;  // per instantiation
-    if (occ_cache == 0) {
-        int occ = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kScanThreads, 0);
-        occ_cache = std::max(occ, 1);
-    }
-    const int bps = t.bps > 0 ? std::min(t.bps, occ_cache) : occ_cache;
-    kernel<<<grid_for(db, a.n / 4, 4, kScanThreads, bps), kScanThreads, 0, s>>>(a);
-    LAUNCHED();
-    return AQE_OK;
+    // register-staged kernel: all-4-byte scans read 8 elements per 256-bit load, everything else 4 per unit
+    constexpr int W = (sizeof(AggT) == 4 && (PRED != 2 || sizeof(PredT) == 4)) ? 8 : 4;
+    return launch_regs_kernel(db, k_scan<AggT, PRED, PredT, W, 4, MOMENTS, 1>, a, W, 4, t.bps, s);
+}
+
+// {v in int64 : lo <= (double)v <= hi} is an interval because int64 -> double conversion is monotone; its end points
+// are found by bisection on that monotone predicate, so the integer compare in the kernel selects exactly the rows
+// the reference-shaped double compare would (also beyond 2^53 where the conversion rounds).
+static void integer_bounds(double lo, double hi, long long* ilo, long long* ihi) {
+    *ilo = 1; *ihi = 0;  // empty
+    if (!(lo == lo) || !(hi == hi) || lo > hi) return;
+    auto first_true = [](auto pred) -> unsigned long long {  // smallest offset u in [0, 2^64) with pred(u); 2^64-1 assumed true
+        unsigned long long a = 0, b = ~0ull;
+        while (a < b) { const unsigned long long m = a + (b - a) / 2; if (pred(m)) b = m; else a = m + 1; }
+        return a;
+    };
+    auto from_off = [](unsigned long long u) { return (long long)(u ^ 0x8000000000000000ull); };  // order-preserving u64 -> i64
+    if ((double)INT64_MAX < lo || (double)INT64_MIN > hi) return;
+    const unsigned long long ul = first_true([&](unsigned long long u) { return (double)from_off(u) >= lo; });
+    // largest v with (double)v <= hi  =  (smallest v with (double)v > hi) - 1, or INT64_MAX if none
+    long long up;
+    if ((double)INT64_MAX <= hi) up = INT64_MAX;
+    else up = from_off(first_true([&](unsigned long long u) { return (double)from_off(u) > hi; })) - 1;
+    *ilo = from_off(ul); *ihi = up;
 }
 
 template <typename AggT, bool MOMENTS>
@@ -636,9 +643,10 @@ static int scan_launch(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, ui
     a.agg = agg ? agg + first * kind_size(ak) : nullptr;
     a.pred = pred ? pred + first * kind_size(pk) : nullptr;
     a.n = n; a.lo = spec->lo; a.hi = spec->hi;
+    integer_bounds(spec->lo, spec->hi, &a.ilo, &a.ihi);
     a.partials = db->scan_partials; a.ticket = db->tickets + 0; a.out = out_dev;
-    // W = 4 elements per vector: 32-byte alignment for 8-byte columns, 16 for 4-byte columns
-    auto aligned_for = [](const void* p, int kind) { return ((uintptr_t)p % (kind == K_I32 ? 16 : 32)) == 0; };
+    // 256-bit vector loads on every column
+    auto aligned_for = [](const void* p, int) { return ((uintptr_t)p % 32) == 0; };
     const bool aligned = aligned_for(a.agg, ak) && (pred_mode != 2 || aligned_for(a.pred, pk));
     int rc;
     if (ak == K_F64) rc = moments ? launch_scan_pred<double, true>(db, a, pred_mode, pk, aligned, s) : launch_scan_pred<double, false>(db, a, pred_mode, pk, aligned, s);
@@ -884,6 +892,7 @@ int aqe_scan_host_column(int device, const void* host_col, int col_kind_id, uint
         ScanArgs a;
         std::memset(&a.ex, 0, sizeof(a.ex));
         a.agg = c->dev[b]; a.pred = nullptr; a.n = cnt; a.lo = lo; a.hi = hi;
+        integer_bounds(lo, hi, &a.ilo, &a.ihi);
         a.partials = b ? c->partials2 : db->scan_partials;
         a.ticket = b ? c->tickets2 : db->tickets + 1;
         a.out = c->parts_dev + k;
@@ -1380,7 +1389,7 @@ int aqe_approx(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* out) {
     a.block_rows = S->design == AQE_DESIGN_BLOCK ? (S->block_size ? S->block_size : 1000) : 1;
     a.units = (N + a.block_rows - 1) / a.block_rows;
     a.design = S->design; a.agg = S->agg; a.agg_col = S->agg_col; a.pred_col = S->pred_col;
-    a.lo = S->lo; a.hi = S->hi; a.eps = S->error_percent; a.z = aqe_z_score(S->confidence_level, 1);
+    a.lo = S->lo; a.hi = S->hi; a.eps = S->error_percent; a.z = aqe_z_score(S->confidence_level, 1) * AQE_CI_CONSERVATIVE;
     a.seed = S->seed;
     a.n0 = S->min_samples ? S->min_samples : (S->design == AQE_DESIGN_BLOCK ? 1024 : 16384);
     a.nmax = S->max_samples ? S->max_samples : a.units;
@@ -1427,7 +1436,7 @@ int aqe_approx(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* out) {
 int aqe_approx_merge(const aqe_approx_result* parts, int n, int agg, double confidence_level, aqe_approx_result* out) {
     if (!parts || !out || n <= 0) return fail(AQE_ERR_INVALID, "bad argument");
     // shards are strata: totals add, variances of the totals add (independent draws per shard)
-    const double z = aqe_z_score(confidence_level, 1);
+    const double z = aqe_z_score(confidence_level, 1) * AQE_CI_CONSERVATIVE;
     aqe_approx_result r;
     std::memset(&r, 0, sizeof(r));
     double total = 0.0, var_total = 0.0;

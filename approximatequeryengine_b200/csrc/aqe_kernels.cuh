@@ -1,6 +1,6 @@
 // aqe_kernels.cuh -- the sm_100a kernels of libaqe_b200.
 //
-//   K1/K2  k_scan / k_scan_bulk   exact SUM/COUNT[/WHERE] full scan, f64 (compensated) and int128
+//   K1/K2  k_scan_ring / k_scan   exact SUM/COUNT[/WHERE] full scan, f64 (compensated) and int128
 //   K3/K5  k_plan_stats           moments of a column over a sample plan (affine segments / index list)
 //   K4     k_approx               persistent Philox + Welford-by-shifted-sums + in-kernel CLT stop rule
 //   K6     k_plan_gather          rows at plan positions -> 32-byte AoS (legacy list[Record] path)
@@ -107,6 +107,7 @@ struct ScanArgs {
     const void* pred;
     uint64_t n;
     double lo, hi;
+    long long ilo, ihi;     // the same closed interval on an INTEGER predicate column: {v : lo <= (double)v <= hi} = [ilo, ihi]
     ScanAcc* partials;      // [gridDim.x]
     unsigned int* ticket;   // zero before launch; reset by the last block
     aqe_partial* out;       // device-visible (device memory or mapped pinned host memory)
@@ -237,11 +238,20 @@ template <bool IS_INT, bool MOMENTS> __device__ __forceinline__ void scan_finish
 template <typename T> __device__ __forceinline__ double as_f64(T v) { return (double)v; }
 
 // PRED: 0 none, 1 predicate on the aggregate column itself, 2 predicate on another column (PredT)
+// Integer predicate columns are compared as integers against [ilo, ihi] (computed once on the host so that it
+// selects exactly the rows `lo <= (double)v <= hi` would): no per-row I2F.F64 conversions on the FP64 pipe.
 template <typename AggT, int PRED, typename PredT, bool MOMENTS>
-__device__ __forceinline__ void scan_consume(ScanAcc& acc, DD& alt, AggT v, PredT pv, double lo, double hi, int parity) {
+__device__ __forceinline__ void scan_consume(ScanAcc& acc, DD& alt, AggT v, PredT pv, const ScanArgs& a, int parity) {
+    const double lo = a.lo, hi = a.hi;
     bool pass = true;
-    if constexpr (PRED == 1) { const double d = as_f64(v); pass = (d >= lo) && (d <= hi); }
-    if constexpr (PRED == 2) { const double d = as_f64(pv); pass = (d >= lo) && (d <= hi); }
+    if constexpr (PRED == 1) {
+        if constexpr (std::is_integral_v<AggT>) pass = ((long long)v >= a.ilo) && ((long long)v <= a.ihi);
+        else { const double d = as_f64(v); pass = (d >= lo) && (d <= hi); }
+    }
+    if constexpr (PRED == 2) {
+        if constexpr (std::is_integral_v<PredT>) pass = ((long long)pv >= a.ilo) && ((long long)pv <= a.ihi);
+        else { const double d = as_f64(pv); pass = (d >= lo) && (d <= hi); }
+    }
     acc.count += pass ? 1u : 0u;
     if constexpr (std::is_integral_v<AggT>) {  // int64 / int32: split so a thread never overflows
         const int64_t x = pass ? (int64_t)v : 0;
@@ -283,10 +293,15 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k_scan(const ScanArgs a) {
             if constexpr (PRED == 2) pv[j] = ldg_stream<W>(pred + (u + (uint64_t)j * G) * W);
         }
 #pragma unroll
+        for (int j = 0; j < U; ++j) {  // all 2U loads are in flight before the first use
+            pin(av[j]);
+            if constexpr (PRED == 2) pin(pv[j]);
+        }
+#pragma unroll
         for (int j = 0; j < U; ++j)
 #pragma unroll
             for (int e = 0; e < W; ++e)
-                scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, av[j].v[e], PRED == 2 ? pv[j].v[e] : PredT(0), a.lo, a.hi, e & 1);
+                scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, av[j].v[e], PRED == 2 ? pv[j].v[e] : PredT(0), a, e & 1);
     }
     for (; u < units; u += G) {
         const Vec<AggT, W> av = ldg_stream<W>(agg + u * W);
@@ -294,11 +309,11 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k_scan(const ScanArgs a) {
         if constexpr (PRED == 2) pv = ldg_stream<W>(pred + u * W);
 #pragma unroll
         for (int e = 0; e < W; ++e)
-            scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, av.v[e], PRED == 2 ? pv.v[e] : PredT(0), a.lo, a.hi, e & 1);
+            scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, av.v[e], PRED == 2 ? pv.v[e] : PredT(0), a, e & 1);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // the n % W tail
         for (uint64_t i = units * W; i < a.n; ++i)
-            scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, agg[i], PRED == 2 ? pred[i] : PredT(0), a.lo, a.hi, 0);
+            scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, agg[i], PRED == 2 ? pred[i] : PredT(0), a, 0);
     }
     dd_merge(acc.sum, alt);
     acc = scan_block_reduce<IS_INT, MOMENTS>(acc, sm);
@@ -316,28 +331,57 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_unaligned(const ScanArgs 
     ScanAcc acc = scan_identity();
     DD alt{0.0, 0.0};
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += G)
-        scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, __ldg(agg + i), PRED == 2 ? __ldg(pred + i) : PredT(0), a.lo, a.hi, 0);
+        scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, __ldg(agg + i), PRED == 2 ? __ldg(pred + i) : PredT(0), a, 0);
     acc = scan_block_reduce<IS_INT, MOMENTS>(acc, sm);
     scan_finish<IS_INT, MOMENTS>(acc, a, sm);
 }
 
-// K1, TMA-staged variant for the headline case (f64 aggregate, predicate none / on itself): one producer
-// warp streams CHUNK-byte tiles of the column into a STAGES-deep shared-memory ring with 1-D bulk
-// copies (cp.async.bulk -> UBLKCP) completing on mbarriers; 8 consumer warps reduce tiles out of
-// shared memory with conflict-free LDS.128.  Tile c goes to CTA (c mod gridDim.x): static, deterministic.
+// K1/K2, TMA-staged ring (the default scan kernel for every column-type combination): one producer warp streams
+// tiles of the aggregate column (and, for a predicate on another column, the matching tile of that column) into a
+// STAGES-deep shared-memory ring with 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) that complete on mbarriers;
+// 8 consumer warps reduce tiles out of shared memory with conflict-free 64/128-bit LDS.  Bytes in flight are set
+// by the ring (STAGES x 16 KiB x CTAs/SM), not by how ptxas schedules loads.  Tile c goes to CTA (c mod gridDim.x):
+// static, deterministic.  Tiles hold a power-of-two number of rows so that <= 16 KiB per stage is used.
 constexpr int kBulkConsumerWarps = 8;
 constexpr int kBulkThreads = (kBulkConsumerWarps + 1) * 32;
+constexpr int kStageBytes = 16384;
 
-template <int PRED, int STAGES, int CHUNK, bool MOMENTS>
-__global__ void __launch_bounds__(kBulkThreads) k_scan_bulk(const ScanArgs a) {
+template <typename AggT, int PRED, typename PredT> struct RingGeom {
+    static constexpr int kRowBytes = (int)sizeof(AggT) + (PRED == 2 ? (int)sizeof(PredT) : 0);
+    static constexpr int kRows = kRowBytes <= 4 ? 4096 : (kRowBytes <= 8 ? 2048 : 1024);   // rows per tile
+    static constexpr int kAggBytes = kRows * (int)sizeof(AggT);
+    static constexpr int kPredBytes = PRED == 2 ? kRows * (int)sizeof(PredT) : 0;
+    static_assert(kAggBytes + kPredBytes <= kStageBytes, "tile exceeds the stage");
+    // rows handled per consumer-thread step: 2 if any column is 8 bytes wide (LDS.128 / LDS.64), else 4 (LDS.128)
+    static constexpr int kUnit = (sizeof(AggT) == 8 || (PRED == 2 && sizeof(PredT) == 8)) ? 2 : 4;
+};
+
+template <typename T, int N> __device__ __forceinline__ Vec<T, N> lds_vec(const unsigned char* base, uint32_t unit_index) {
+    Vec<T, N> r;
+    if constexpr (sizeof(T) * N == 16) {
+        const uint4 q = *reinterpret_cast<const uint4*>(base + (size_t)unit_index * 16);
+        *reinterpret_cast<uint4*>(&r) = q;
+    } else {
+        static_assert(sizeof(T) * N == 8, "8- or 16-byte units");
+        const uint2 q = *reinterpret_cast<const uint2*>(base + (size_t)unit_index * 8);
+        *reinterpret_cast<uint2*>(&r) = q;
+    }
+    return r;
+}
+
+template <typename AggT, int PRED, typename PredT, int STAGES, bool MOMENTS>
+__global__ void __launch_bounds__(kBulkThreads) k_scan_ring(const ScanArgs a) {
+    using G = RingGeom<AggT, PRED, PredT>;
+    constexpr bool IS_INT = std::is_integral_v<AggT>;
+    constexpr int U = G::kUnit;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ ScanAcc sm[32];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
-    double* buf = reinterpret_cast<double*>(smem_raw);
-    const double* __restrict__ col = static_cast<const double*>(a.agg);
-    const uint64_t total_bytes = (a.n * 8ull) & ~15ull;  // bulk copies move multiples of 16 bytes
-    const uint64_t nchunks = (total_bytes + CHUNK - 1) / CHUNK;
+    const unsigned char* __restrict__ agg = static_cast<const unsigned char*>(a.agg);
+    const unsigned char* __restrict__ pred = static_cast<const unsigned char*>(a.pred);
+    const uint64_t n_main = a.n & ~3ull;  // bulk copies move multiples of 16 bytes: 4 rows of the narrowest type
+    const uint64_t ntiles = (n_main + G::kRows - 1) / G::kRows;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -352,45 +396,51 @@ __global__ void __launch_bounds__(kBulkThreads) k_scan_bulk(const ScanArgs a) {
     if (warp == kBulkConsumerWarps) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+            for (uint64_t c = blockIdx.x; c < ntiles; c += gridDim.x, ++it) {
                 const int s = it % STAGES;
                 const uint32_t round = it / STAGES;
                 if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
-                const uint64_t off = c * (uint64_t)CHUNK;
-                const uint32_t bytes = (uint32_t)((total_bytes - off) < (uint64_t)CHUNK ? (total_bytes - off) : (uint64_t)CHUNK);
-                mbar_expect_tx(&full_bar[s], bytes);
-                bulk_g2s(reinterpret_cast<unsigned char*>(buf) + (size_t)s * CHUNK,
-                         reinterpret_cast<const unsigned char*>(col) + off, bytes, &full_bar[s]);
+                const uint64_t row0 = c * (uint64_t)G::kRows;
+                const uint32_t rows = (uint32_t)((n_main - row0) < (uint64_t)G::kRows ? (n_main - row0) : (uint64_t)G::kRows);
+                unsigned char* stage = smem_raw + (size_t)s * kStageBytes;
+                mbar_expect_tx(&full_bar[s], rows * (uint32_t)G::kRowBytes);
+                bulk_g2s(stage, agg + row0 * sizeof(AggT), rows * (uint32_t)sizeof(AggT), &full_bar[s]);
+                if constexpr (PRED == 2) bulk_g2s(stage + G::kAggBytes, pred + row0 * sizeof(PredT), rows * (uint32_t)sizeof(PredT), &full_bar[s]);
             }
         }
     } else {
-        const int ct = threadIdx.x;  // 0 .. 255
+        const uint32_t ct = threadIdx.x;  // 0 .. 255
         uint32_t it = 0;
-        for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+        for (uint64_t c = blockIdx.x; c < ntiles; c += gridDim.x, ++it) {
             const int s = it % STAGES;
             const uint32_t round = it / STAGES;
             mbar_wait(&full_bar[s], round & 1);
-            const uint64_t off = c * (uint64_t)CHUNK;
-            const uint32_t bytes = (uint32_t)((total_bytes - off) < (uint64_t)CHUNK ? (total_bytes - off) : (uint64_t)CHUNK);
-            const double2* tile = reinterpret_cast<const double2*>(reinterpret_cast<unsigned char*>(buf) + (size_t)s * CHUNK);
-            const uint32_t nvec = bytes >> 4;
+            const uint64_t row0 = c * (uint64_t)G::kRows;
+            const uint32_t rows = (uint32_t)((n_main - row0) < (uint64_t)G::kRows ? (n_main - row0) : (uint64_t)G::kRows);
+            const unsigned char* stage = smem_raw + (size_t)s * kStageBytes;
+            const uint32_t nunits = rows / U;
 #pragma unroll 4
-            for (uint32_t i = ct; i < nvec; i += kBulkConsumerWarps * 32) {
-                const double2 v = tile[i];
-                scan_consume<double, PRED, double, MOMENTS>(acc, alt, v.x, 0.0, a.lo, a.hi, 0);
-                scan_consume<double, PRED, double, MOMENTS>(acc, alt, v.y, 0.0, a.lo, a.hi, 1);
+            for (uint32_t i = ct; i < nunits; i += kBulkConsumerWarps * 32) {
+                const Vec<AggT, U> av = lds_vec<AggT, U>(stage, i);
+                Vec<PredT, U> pv;
+                if constexpr (PRED == 2) pv = lds_vec<PredT, U>(stage + G::kAggBytes, i);
+#pragma unroll
+                for (int e = 0; e < U; ++e)
+                    scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, av.v[e], PRED == 2 ? pv.v[e] : PredT(0), a, e & 1);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            for (uint64_t i = total_bytes >> 3; i < a.n; ++i)
-                scan_consume<double, PRED, double, MOMENTS>(acc, alt, col[i], 0.0, a.lo, a.hi, 0);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {  // the n % 4 tail
+            const AggT* ag = static_cast<const AggT*>(a.agg);
+            const PredT* pr = static_cast<const PredT*>(a.pred);
+            for (uint64_t i = n_main; i < a.n; ++i)
+                scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, ag[i], PRED == 2 ? pr[i] : PredT(0), a, 0);
         }
     }
     dd_merge(acc.sum, alt);
-    acc = scan_block_reduce<false, MOMENTS>(acc, sm);
-    scan_finish<false, MOMENTS>(acc, a, sm);
+    acc = scan_block_reduce<IS_INT, MOMENTS>(acc, sm);
+    scan_finish<IS_INT, MOMENTS>(acc, a, sm);
 }
 
 // ================================================================================================

@@ -200,7 +200,9 @@ public:
         aqe_plan* pl = nullptr;
         check(aqe_plan_build(h_, aqe_count(h_), method, &p, &pl));
         const size_t n = aqe_plan_count(pl);
-        py::array out(record_dtype(), {n});
+        const py::dtype dt = record_dtype();
+        py::array out(dt, std::vector<py::ssize_t>{(py::ssize_t)n}, std::vector<py::ssize_t>{32});
+        if (out.itemsize() != 32 || out.nbytes() != (py::ssize_t)(n * 32)) throw std::runtime_error("record array allocation failed");
         const int rc = n ? aqe_gather_plan(h_, pl, static_cast<aqe_record*>(out.mutable_data()), n) : AQE_OK;
         aqe_plan_free(pl);
         check(rc);

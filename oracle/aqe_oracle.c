@@ -1004,13 +1004,20 @@ ORC_API int orc_approx(const aqe_record* R, uint64_t N, const aqe_approx_spec* S
     if (N == 0) { out->status = AQE_INSUFFICIENT_DATA; return 0; }
     uint64_t B = S->design == AQE_DESIGN_BLOCK ? (S->block_size ? S->block_size : 1000) : 1;
     uint64_t units = (N + B - 1) / B;
-    double z = orc_z_score(S->confidence_level, 1);
+    double z = orc_z_score(S->confidence_level, 1) * AQE_CI_CONSERVATIVE;
     if (S->agg == AQE_AGG_COUNT && S->pred_col == AQE_COL_NONE) { /* cli:197: COUNT is always exact */
         out->estimate = out->ci_lower = out->ci_upper = (double)N; out->status = AQE_STABLE; return 0;
     }
     uint64_t n0 = S->min_samples ? S->min_samples : (S->design == AQE_DESIGN_BLOCK ? 1024 : 16384);
     uint64_t nmax = S->max_samples ? S->max_samples : units;
     if (n0 > nmax) n0 = nmax;
+    if (units <= n0) { /* the first look would draw as many units as the table has: exact scan instead */
+        aqe_partial part;
+        orc_scan(R, N, S->agg == AQE_AGG_COUNT ? S->pred_col : S->agg_col, S->pred_col, S->lo, S->hi, &part);
+        double v = S->agg == AQE_AGG_COUNT ? (double)part.count : (S->agg == AQE_AGG_SUM ? part.sum : (part.count ? part.sum / (double)part.count : 0.0));
+        out->estimate = out->ci_lower = out->ci_upper = v; out->n_samples = N; out->n_units = units; out->status = AQE_STABLE;
+        return 0;
+    }
     int ratio = (S->agg == AQE_AGG_AVG && S->pred_col != AQE_COL_NONE);
     /* running sums in long double: the checker is allowed to be more exact than the device */
     long double sy = 0, syy = 0, sc = 0, rows = 0;

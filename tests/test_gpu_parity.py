@@ -150,6 +150,34 @@ def test_int128_overflow_range(oracle):
     assert e.sum_int("timestamp") == int(rows["timestamp"].astype(object).sum()) < -(2 ** 64)
 
 
+def test_integer_predicate_bounds(oracle):
+    """Integer predicate columns are compared as integers against [ilo, ihi]; that must select exactly the rows the
+    reference-shaped `lo <= (double)v <= hi` selects, including fractional, huge (> 2^53), negative and empty bounds."""
+    n = 40000
+    rows = oracle.synth(n, seed=4)
+    big = 2 ** 53
+    rows["timestamp"][:] = np.concatenate([np.arange(-5, 5), big + np.arange(-20, 20), -big + np.arange(-20, 20),
+                                           [2 ** 63 - 1, -(2 ** 63), 2 ** 62, -(2 ** 62)],
+                                           np.random.default_rng(1).integers(-(2 ** 63), 2 ** 63 - 1, size=n - 94)])
+    rows["region"][:] = np.random.default_rng(2).integers(-(2 ** 31), 2 ** 31 - 1, size=n)
+    rows["region"][:6] = [-(2 ** 31), 2 ** 31 - 1, 0, -1, 1, 7]
+    e = aqe.Engine(0).from_rows(rows)
+    inf = float("inf")
+    bounds = [(-0.5, 0.5), (0.0, 0.0), (-3.999, 3.001), (float(big) - 2, float(big) + 2), (float(big), float(big) + 6), (-float(big) - 4, -float(big) + 4),
+              (9.2e18, inf), (-inf, -9.2e18), (2.0 ** 63, inf), (-inf, inf), (5.0, 4.0), (float("nan"), 1.0), (0.0, float("nan")),
+              (-2.0 ** 31, 2.0 ** 31), (2.0 ** 31 - 1, 2.0 ** 31 - 1), (-2147483648.5, -2147483647.5), (1e-300, 6.9999999), (9.223372036854775e18, 9.223372036854776e18)]
+    for lo, hi in bounds:
+        for agg, pred in (("amount", "timestamp"), ("id", "timestamp"), ("timestamp", "timestamp"), ("amount", "region"), ("region", "region"),
+                          ("product_id", "region"), ("region", "timestamp")):
+            p = e.scan(agg, pred, lo, hi)
+            q = oracle.scan(rows, agg, pred, lo, hi)
+            assert p.count == q.count, (agg, pred, lo, hi, p.count, q.count)
+            if agg == "amount":
+                assert rel(p.sum, q.sum) <= REL if q.count else p.sum == 0.0
+            else:
+                assert p.isum == q.isum, (agg, pred, lo, hi)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # file format, generator
 # ---------------------------------------------------------------------------------------------------------
@@ -293,6 +321,19 @@ def test_approx_matches_restated_kernel(tables, oracle):
                 assert a.estimate == 0
 
 
+def test_approx_small_tables_are_scanned_exactly(oracle):
+    for n in (1, 100, 16384, 16385):
+        rows = oracle.synth(n, seed=3)
+        e = aqe.Engine(0).from_rows(rows)
+        for agg, where in (("sum", None), ("avg", None), ("sum", (100.0, 500.0)), ("avg", (100.0, 500.0)), ("count", (100.0, 500.0)), ("count", None)):
+            a = e.approx(agg, error_percent=1.0, seed=1, where=where)
+            o = oracle.approx(rows, ospec(agg=agg, where=where, seed=1))
+            assert (a.n_units, a.n_samples, a.status, a.rounds) == (o.n_units, o.n_samples, o.status, o.rounds), (n, agg, where)
+            assert rel(a.estimate, o.estimate) <= 1e-10 if o.estimate else a.estimate == 0.0
+            if n <= 16384:
+                assert a.ci_lower == a.estimate == a.ci_upper
+
+
 def test_approx_ci_coverage(tables, oracle):
     """CI coverage on repeated seeds >= nominal (minus 2.5 binomial sigma of the finite seed count)."""
     g, rows, e = [t for t in tables if t[0]["n"] == 1000000][0] if any(t[0]["n"] == 1000000 for t in tables) else tables[-1]
@@ -356,6 +397,16 @@ def test_dropin_cli_flows(oracle, tmp_path):
     assert r.ci_lower < r.value < r.ci_upper and r.confidence_level == 0.95
     assert hasattr(r.computation_time, "total_seconds")
     assert db.sum_column("id") == N * (N + 1) // 2
+    # numpy / device-stats forms of the same samplers (no per-row Python objects)
+    arr = db.sample_array("memory_stride", 1.0)
+    assert arr.dtype == b.CustomBPlusDB.record_dtype and sha(arr["id"] - 1) == by[("memory_stride", 1.0)]["idx_sha256"]
+    assert np.array_equal(arr["amount"], rows["amount"][arr["id"] - 1])
+    st = db.sample_array("memory_stride", 1.0, stats=True)
+    assert st["n"] == len(arr) and rel(st["sum"], fhex(by[("memory_stride", 1.0)]["est"]["sample_sum"])) <= REL
+    assert len(db.sample_array("block", 5.0, block_size=1000)) == by[("block", 5.0)]["count"]
+    assert len(db.sample_array("slow_pointer", 0.0)) == 0
+    with pytest.raises(ValueError):
+        db.sample_array("no_such_sampler", 1.0)
     db.close_database()
 
 

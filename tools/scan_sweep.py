@@ -40,14 +40,10 @@ def run(env, pred=True, reps=20):
 
 
 configs = [{"AQE_SCAN_VARIANT": 0}]
-if which == "2":
-    for u, mb in ((2, 2), (2, 3), (2, 4), (3, 3), (3, 4), (4, 2), (4, 3), (4, 4), (6, 2), (6, 3), (8, 1), (8, 2), (8, 3)):
-        configs.append({"AQE_SCAN_VARIANT": 3, "AQE_SCAN_UNROLL": u, "AQE_SCAN_MINB": mb})
-    for u, mb in ((8, 2), (8, 4)):
-        configs.append({"AQE_SCAN_VARIANT": 1, "AQE_SCAN_UNROLL": u, "AQE_SCAN_MINB": mb})
-    for st, ck in ((3, 16), (4, 16), (5, 16), (6, 16), (8, 16), (3, 32), (4, 32), (6, 32), (12, 8), (2, 64), (3, 64)):
-        for bps in (0, 1, 2, 3):
-            configs.append({"AQE_SCAN_VARIANT": 2, "AQE_SCAN_STAGES": st, "AQE_SCAN_CHUNK_KB": ck, "AQE_SCAN_BPS": bps})
+for st in (2, 3, 4, 6):
+    for bps in (1, 2, 3):
+        configs.append({"AQE_SCAN_VARIANT": 2, "AQE_SCAN_STAGES": st, "AQE_SCAN_BPS": bps})
+configs += [{"AQE_SCAN_VARIANT": 4}, {"AQE_SCAN_VARIANT": 4, "AQE_SCAN_UNROLL": 6}, {"AQE_SCAN_VARIANT": 4, "AQE_SCAN_MINB": 3}, {"AQE_SCAN_VARIANT": 1}]
 configs.append({"AQE_SCAN_VARIANT": 0})
 for c in configs:
     for pred in (True, False):
