@@ -165,6 +165,8 @@ def lib() -> C.CDLL:
         "aqe_fast_aggregated_sum": (i32, [vp, C.POINTER(SampleParams), C.POINTER(dbl), C.POINTER(u64)]),
         "aqe_estimate": (i32, [C.POINTER(Stats), u64, i32, dbl, i32, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)]),
         "aqe_approx": (i32, [vp, C.POINTER(ApproxSpec), C.POINTER(ApproxResult)]),
+        "aqe_exchange_set_total_rows": (i32, [vp, u64]),
+        "aqe_approx_exchange": (i32, [vp, C.POINTER(ApproxSpec), C.POINTER(ApproxResult)]),
         "aqe_approx_merge": (i32, [C.POINTER(ApproxResult), i32, i32, dbl, C.POINTER(ApproxResult)]),
         "aqe_z_score": (dbl, [dbl, i32]),
     }
@@ -428,13 +430,16 @@ class Engine:
         return s.value, n.value
 
     def approx(self, agg="sum", error_percent=1.0, confidence_level=0.95, design="srs", seed=0, where=None,
-               where_col="amount", agg_col="amount", block_size=0, min_samples=0, max_samples=0) -> ApproxResult:
+               where_col="amount", agg_col="amount", block_size=0, min_samples=0, max_samples=0, exchange=False) -> ApproxResult:
         sp = ApproxSpec(AGG[agg], DESIGN[design], COLS[agg_col], COLS[where_col] if where else -1,
                         where[0] if where else 0.0, where[1] if where else 0.0, error_percent, confidence_level, seed,
                         min_samples, max_samples, block_size, 0)
         out = ApproxResult()
-        check(self.L.aqe_approx(self.h, C.byref(sp), C.byref(out)))
+        check((self.L.aqe_approx_exchange if exchange else self.L.aqe_approx)(self.h, C.byref(sp), C.byref(out)))
         return out
+
+    def exchange_set_total_rows(self, total_rows: int) -> None:
+        check(self.L.aqe_exchange_set_total_rows(self.h, total_rows))
 
 
 def estimate(stats: Stats, population: int, agg: str, z: float = 1.96, legacy_ci: bool = False):

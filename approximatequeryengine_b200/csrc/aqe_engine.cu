@@ -89,6 +89,8 @@ struct aqe_db {
     ExSlot* ex_mailbox = nullptr;
     ExSlot* ex_peers[kMaxRanks] = {nullptr};
     unsigned long long ex_seq = 0;
+    unsigned long long ax_msg = 0;       // next message index of the sampled-estimate exchange (lock-step on all ranks)
+    uint64_t ex_total_rows = 0;          // rows of the whole table (all shards)
     bool ex_connected = false;
 };
 
@@ -688,10 +690,11 @@ int aqe_exchange_init(aqe_db* db, int rank, int world, void* ipc_handle_out) {
     int rc = db_init_cuda(db);
     if (rc) return rc;
     if (!db->ex_mailbox) {
-        CU(cudaMalloc(&db->ex_mailbox, sizeof(ExSlot) * kMaxRanks * 2));
-        CU(cudaMemset(db->ex_mailbox, 0, sizeof(ExSlot) * kMaxRanks * 2));
+        // [0, 2*kMaxRanks): scan partials; [2*kMaxRanks, 4*kMaxRanks): per-look messages of the sampled estimators
+        CU(cudaMalloc(&db->ex_mailbox, sizeof(ExSlot) * kMaxRanks * 4));
     }
-    db->ex_rank = rank; db->ex_world = world; db->ex_seq = 0; db->ex_connected = false;
+    CU(cudaMemset(db->ex_mailbox, 0, sizeof(ExSlot) * kMaxRanks * 4));
+    db->ex_rank = rank; db->ex_world = world; db->ex_seq = 0; db->ax_msg = 0; db->ex_connected = false;
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, db->ex_mailbox));
     std::memcpy(ipc_handle_out, &h, sizeof(h));
@@ -1364,51 +1367,74 @@ double aqe_z_score(double conf, int exact) {
 // ------------------------------------------------------------------------------------------------
 // K4
 // ------------------------------------------------------------------------------------------------
-int aqe_approx(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* out) {
+static int approx_run(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* out, bool multi) {
     if (!db || !S || !out) return fail(AQE_ERR_INVALID, "NULL argument");
     std::memset(out, 0, sizeof(*out));
     if (!(S->error_percent > 0.0)) return fail(AQE_ERR_INVALID, "error_percent must be > 0");
     if (!(S->confidence_level > 0.0 && S->confidence_level < 1.0)) return fail(AQE_ERR_INVALID, "confidence_level must be in (0,1)");
     if (S->agg < 0 || S->agg > 2 || S->design < 0 || S->design > 1) return fail(AQE_ERR_INVALID, "bad agg / design");
     const uint64_t N = aqe_count(db);
-    out->population = N; out->confidence_level = S->confidence_level;
-    if (N == 0) { out->status = AQE_INSUFFICIENT_DATA; return AQE_OK; }
+    const uint32_t B = S->design == AQE_DESIGN_BLOCK ? (S->block_size ? S->block_size : 1000) : 1;
+    uint64_t rows_total = N, units_total = (N + B - 1) / B;
+    if (multi) {
+        if (!db->ex_connected) return fail(AQE_ERR_STATE, "aqe_exchange_connect has not been called");
+        if (!db->ex_total_rows) return fail(AQE_ERR_STATE, "aqe_exchange_set_total_rows has not been called");
+        rows_total = db->ex_total_rows;
+        units_total = 0;
+        for (int g = 0; g < db->ex_world; ++g) {  // contiguous shards [N g/G, N (g+1)/G)
+            const uint64_t ng = (uint64_t)(((unsigned __int128)rows_total * (g + 1)) / db->ex_world) - (uint64_t)(((unsigned __int128)rows_total * g) / db->ex_world);
+            if (g == db->ex_rank && ng != N) return fail(AQE_ERR_STATE, "this shard does not hold rows [N*rank/world, N*(rank+1)/world) of the table");
+            units_total += (ng + B - 1) / B;
+        }
+    }
+    out->population = rows_total; out->confidence_level = S->confidence_level;
+    if (rows_total == 0) { out->status = AQE_INSUFFICIENT_DATA; return AQE_OK; }
     if (S->agg == AQE_AGG_COUNT && S->pred_col == AQE_COL_NONE) {  // enhanced_aqe_cli.py:196-197: COUNT is exact
-        out->estimate = out->ci_lower = out->ci_upper = (double)N; out->status = AQE_STABLE;
+        out->estimate = out->ci_lower = out->ci_upper = (double)rows_total; out->status = AQE_STABLE;
         return AQE_OK;
     }
     int rc = ensure_device(db);
     if (rc) return rc;
     if (S->agg != AQE_AGG_COUNT && col_kind(S->agg_col) < 0) return fail(AQE_ERR_INVALID, "bad aggregate column");
-    if (S->agg != AQE_AGG_COUNT && !col_ptr(db, S->agg_col)) return fail(AQE_ERR_STATE, "aggregate column is not resident on the device");
-    if (S->pred_col != AQE_COL_NONE && !col_ptr(db, S->pred_col)) return fail(AQE_ERR_STATE, "predicate column is not resident on the device");
+    if (N && S->agg != AQE_AGG_COUNT && !col_ptr(db, S->agg_col)) return fail(AQE_ERR_STATE, "aggregate column is not resident on the device");
+    if (N && S->pred_col != AQE_COL_NONE && !col_ptr(db, S->pred_col)) return fail(AQE_ERR_STATE, "predicate column is not resident on the device");
 
     ApproxArgs a;
+    std::memset(&a, 0, sizeof(a));
     a.cols = const_cols(db);
     a.n_rows = N;
-    a.block_rows = S->design == AQE_DESIGN_BLOCK ? (S->block_size ? S->block_size : 1000) : 1;
-    a.units = (N + a.block_rows - 1) / a.block_rows;
+    a.block_rows = B;
+    a.units = (N + B - 1) / B;
     a.design = S->design; a.agg = S->agg; a.agg_col = S->agg_col; a.pred_col = S->pred_col;
     a.lo = S->lo; a.hi = S->hi; a.eps = S->error_percent; a.z = aqe_z_score(S->confidence_level, 1) * AQE_CI_CONSERVATIVE;
-    a.seed = S->seed;
-    a.n0 = S->min_samples ? S->min_samples : (S->design == AQE_DESIGN_BLOCK ? 1024 : 16384);
-    a.nmax = S->max_samples ? S->max_samples : a.units;
-    if (a.n0 > a.nmax) a.n0 = a.nmax;
+    a.seed = S->seed + (multi ? 0x9E3779B97F4A7C15ull * (uint64_t)db->ex_rank : 0ull);  // independent stream per stratum
+    const uint64_t n0 = S->min_samples ? S->min_samples : (S->design == AQE_DESIGN_BLOCK ? 1024 : 16384);
+    const uint64_t nmax = S->max_samples ? S->max_samples : units_total;
+    a.n0 = std::min(n0, nmax); a.nmax = nmax;
+    a.units_total = units_total; a.rows_total = rows_total; a.n0_total = a.n0; a.nmax_total = nmax;
     a.slots = db->approx_slots;
     a.out = &db->slot_dev->approx;
-    if (a.units <= a.n0) {
+    if (units_total <= a.n0) {
         // the first look would already draw as many units as the table has: scan it exactly instead
         aqe_scan_spec sp{S->agg == AQE_AGG_COUNT ? (int32_t)(S->pred_col) : S->agg_col, S->pred_col, S->lo, S->hi};
-        aqe_partial part;
-        rc = scan_sync(db, &sp, 0, db->n, false, &part);
+        rc = scan_launch(db, &sp, 0, db->n, false, &db->slot_dev->partial, db->stream, multi);
         if (rc) return rc;
+        CU(cudaStreamSynchronize(db->stream));
+        if (multi) { rc = aqe_exchange_check(db); if (rc) return rc; }
+        const aqe_partial part = db->slot_host->partial;
         double v;
         if (S->agg == AQE_AGG_COUNT) v = (double)part.count;
         else if (S->agg == AQE_AGG_SUM) v = part.sum;
         else v = part.count ? part.sum / (double)part.count : 0.0;
         out->estimate = out->ci_lower = out->ci_upper = v;
-        out->n_samples = N; out->n_units = a.units; out->status = AQE_STABLE;
+        out->n_samples = rows_total; out->n_units = units_total; out->status = AQE_STABLE;
         return AQE_OK;
+    }
+    if (multi) {
+        a.ex.world = db->ex_world; a.ex.rank = db->ex_rank; a.ex.seq = db->ax_msg;
+        a.ex.timeout_cycles = (unsigned long long)env_int("AQE_EXCHANGE_TIMEOUT_MS", 5000) * 2000000ull;
+        for (int r = 0; r < db->ex_world; ++r) a.ex.peers[r] = db->ex_peers[r];
+        a.ex.status = db->tickets + 3;
     }
 
     static int coop_blocks_per_sm = 0;
@@ -1430,7 +1456,25 @@ int aqe_approx(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* out) {
     *out = db->slot_host->approx;
     out->confidence_level = S->confidence_level;
     out->elapsed_us = (double)ms * 1000.0;
+    if (multi) {
+        db->ax_msg += out->rounds;  // every rank ran the same number of looks (one global decision per look)
+        rc = aqe_exchange_check(db);
+        if (rc) return rc;
+    }
     return AQE_OK;
+}
+
+int aqe_approx(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* out) { return approx_run(db, S, out, false); }
+
+int aqe_exchange_set_total_rows(aqe_db* db, uint64_t total_rows) {
+    if (!db) return fail(AQE_ERR_INVALID, "NULL handle");
+    db->ex_total_rows = total_rows;
+    return AQE_OK;
+}
+
+int aqe_approx_exchange(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* out) {
+    if (!db) return fail(AQE_ERR_INVALID, "NULL handle");
+    return approx_run(db, S, out, db->ex_world > 1);
 }
 
 int aqe_approx_merge(const aqe_approx_result* parts, int n, int agg, double confidence_level, aqe_approx_result* out) {

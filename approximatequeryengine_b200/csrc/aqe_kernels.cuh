@@ -676,7 +676,70 @@ struct ApproxArgs {
     uint64_t seed, n0, nmax;
     ApproxAcc* slots;  // [2][gridDim.x]
     aqe_approx_result* out;
+    // multi-GPU (shards are strata, one GLOBAL stop rule): ex.world > 1.  ex.seq = index of this query's first message.
+    Exchange ex;
+    uint64_t units_total, rows_total, n0_total, nmax_total;
 };
+
+// What a rank publishes after every look: its cumulative sample moments (about its own shift K) and its stratum size.
+struct ApproxMsg { unsigned long long n_units, n_rows; double sc, sd, sdd, K; unsigned long long pop_units, pop_rows; };
+static_assert(sizeof(ApproxMsg) == sizeof(aqe_partial), "messages travel in 64-byte mailbox payloads");
+
+// rank's share of a global cumulative sample size T (proportional allocation)
+__host__ __device__ __forceinline__ uint64_t approx_share(uint64_t T, uint64_t units_g, uint64_t units_total) {
+    if (units_g == 0) return 0;
+    const double x = ceil((double)T * ((double)units_g / (double)units_total));
+    const uint64_t v = x >= (double)units_g ? units_g : (uint64_t)x;
+    return v < 1 ? 1 : v;
+}
+
+// Stratified estimate over all ranks' messages (rank order).  Returns the relative half width in percent.
+// SUM/COUNT: T = sum_g U_g mean_g, Var = sum_g U_g^2 s_g^2 / n_g.  AVG: the same over the total row count.  AVG with a
+// predicate: ratio estimator R = Num/Den with the linearised residual e = y - R c in every stratum.
+__host__ __device__ inline double approx_global(const ApproxMsg* msgs, int world, int agg, bool ratio, double z, double* est_out, double* half_out,
+                                                uint64_t* n_tot_out, uint64_t* rows_tot_out) {
+    const double inf = HUGE_VAL;
+    double T = 0.0, V = 0.0, num = 0.0, den = 0.0, pop_rows = 0.0;
+    uint64_t n_tot = 0, rows_tot = 0;
+    for (int g = 0; g < world; ++g) {
+        const ApproxMsg& m = msgs[g];
+        n_tot += m.n_units; rows_tot += m.n_rows; pop_rows += (double)m.pop_rows;
+        if (m.pop_units == 0 || m.n_units == 0) continue;
+        const double n = (double)m.n_units, U = (double)m.pop_units;
+        const double sy = m.sd + n * m.K;
+        num += U * (sy / n); den += U * (m.sc / n);
+    }
+    const double R = den > 0.0 ? num / den : 0.0;
+    for (int g = 0; g < world; ++g) {
+        const ApproxMsg& m = msgs[g];
+        if (m.pop_units == 0 || m.n_units == 0) continue;
+        const double n = (double)m.n_units, U = (double)m.pop_units;
+        const double sy = m.sd + n * m.K;
+        const double mu = sy / n;
+        double ss = m.sdd - (m.sd * m.sd) / n;
+        if (ss < 0.0) ss = 0.0;
+        double var;
+        if (ratio) {
+            const double syy = ss + sy * mu;
+            double se2 = syy - 2.0 * R * sy + R * R * m.sc;
+            const double ebar = (sy - R * m.sc) / n;
+            se2 -= n * ebar * ebar;
+            if (se2 < 0.0) se2 = 0.0;
+            var = m.n_units > 1 ? se2 / (n - 1.0) : inf;
+        } else {
+            var = m.n_units > 1 ? ss / (n - 1.0) : inf;
+        }
+        T += U * mu;
+        V += U * U * var / n;
+    }
+    double est, half;
+    if (ratio) { est = R; half = den > 0.0 ? z * sqrt(V) / den : inf; }
+    else if (agg == AQE_AGG_AVG) { est = pop_rows > 0.0 ? T / pop_rows : 0.0; half = pop_rows > 0.0 ? z * sqrt(V) / pop_rows : inf; }
+    else { est = T; half = z * sqrt(V); }
+    *est_out = est; *half_out = half; *n_tot_out = n_tot; *rows_tot_out = rows_tot;
+    if (ratio && !(den > 0.0)) return inf;
+    return est != 0.0 ? half / fabs(est) * 100.0 : inf;
+}
 
 __device__ __forceinline__ void approx_row(const ApproxArgs& a, uint64_t row, double& y, double& c) {
     bool pass = true;
@@ -695,15 +758,18 @@ __global__ void __launch_bounds__(256) k_approx(const ApproxArgs a) {
     const bool ratio = (a.agg == AQE_AGG_AVG && a.pred_col != AQE_COL_NONE);
 
     // shift K: value of the first row of the first drawn unit, times rows per unit
-    double K;
-    {
+    double K = 0.0;
+    if (a.units) {
         const uint64_t u0 = draw_position(a.seed, (uint32_t)a.design, 0, a.units);
         double y0, c0; approx_row(a, u0 * a.block_rows, y0, c0);
         K = y0 * (double)a.block_rows;
     }
 
+    const bool multi = a.ex.world > 1;
+    __shared__ ApproxMsg sh_msgs[kMaxRanks];
+    uint64_t Tg = a.n0_total, n_tot = 0, rows_tot = 0;  // global cumulative look size (multi)
     ApproxAcc cum = approx_identity();
-    uint64_t n_prev = 0, target = a.n0;
+    uint64_t n_prev = 0, target = multi ? approx_share(Tg, a.units, a.units_total) : a.n0;
     uint32_t rounds = 0;
     int status = AQE_DRIFTING;
     double est = 0.0, half = 0.0, rel = 0.0, mean = 0.0, m2 = 0.0;
@@ -755,6 +821,51 @@ __global__ void __launch_bounds__(256) k_approx(const ApproxArgs a) {
         approx_merge(cum, sh_total);
         ++rounds;
 
+        if (multi) {
+            // ---- exchange the per-rank cumulative moments through the mailboxes, then ONE global stop rule ----
+            const int world = a.ex.world;
+            const unsigned long long m = a.ex.seq + (rounds - 1), tag = m + 1;
+            const int par = (int)(m & 1ull);
+            if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+                ApproxAcc s = cum; dd_norm(s.sd); dd_norm(s.sdd); dd_norm(s.sc);
+                ApproxMsg msg{s.units, s.rows, s.sc.s, s.sd.s, s.sdd.s, K, a.units, a.n_rows};
+                ExSlot* dst = a.ex.peers[threadIdx.x] + (2 * kMaxRanks + a.ex.rank * 2 + par);  // second half of the mailbox
+                const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&msg);
+                volatile unsigned long long* d = reinterpret_cast<volatile unsigned long long*>(&dst->p);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] = src[i];
+                __threadfence_system();
+                st_release_sys(&dst->seq, tag);
+            }
+            if ((int)threadIdx.x < world) {
+                const ExSlot* src = a.ex.peers[a.ex.rank] + (2 * kMaxRanks + threadIdx.x * 2 + par);
+                const long long t0 = clock64();
+                while (ld_acquire_sys(&src->seq) != tag) {
+                    if ((unsigned long long)(clock64() - t0) > a.ex.timeout_cycles) { atomicExch(a.ex.status, 1u); break; }
+                    __nanosleep(32);
+                }
+                const volatile unsigned long long* sp = reinterpret_cast<const volatile unsigned long long*>(&src->p);
+                unsigned long long* dp = reinterpret_cast<unsigned long long*>(&sh_msgs[threadIdx.x]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dp[i] = sp[i];
+            }
+            __syncthreads();
+            rel = approx_global(sh_msgs, world, a.agg, ratio, a.z, &est, &half, &n_tot, &rows_tot);
+            mean = 0.0; m2 = 0.0;
+            n_prev = target;
+            if (rel <= a.eps) { status = AQE_STABLE; break; }
+            if (Tg >= a.nmax_total) { status = AQE_DRIFTING; break; }
+            const double rn = rel / a.eps;
+            const double want = ceil(1.1 * ((double)n_tot * rn * rn));
+            const uint64_t lo_n = Tg + Tg / 4 + 1, hi_n = Tg * 8;
+            uint64_t t2 = want >= (double)hi_n ? hi_n : (want <= (double)lo_n ? lo_n : (uint64_t)want);
+            if (t2 > a.nmax_total) t2 = a.nmax_total;
+            Tg = t2;
+            const uint64_t nt = approx_share(Tg, a.units, a.units_total);
+            target = nt > n_prev ? nt : n_prev;
+            continue;
+        }
+
         // ---- stop rule (same formulas as oracle/aqe_oracle.c orc_approx) ----
         ApproxAcc s = cum; dd_norm(s.sd); dd_norm(s.sdd); dd_norm(s.sc);
         const double n = (double)s.units;
@@ -797,7 +908,7 @@ __global__ void __launch_bounds__(256) k_approx(const ApproxArgs a) {
         aqe_approx_result r;
         r.estimate = est; r.ci_lower = est - half; r.ci_upper = est + half;
         r.error_margin = rel / 100.0; r.confidence_level = 0.0;
-        r.n_samples = cum.rows; r.n_units = cum.units; r.population = a.n_rows;
+        r.n_samples = multi ? rows_tot : cum.rows; r.n_units = multi ? n_tot : cum.units; r.population = multi ? a.rows_total : a.n_rows;
         r.mean = mean; r.m2 = m2; r.rounds = rounds; r.status = status; r.elapsed_us = 0.0;
         *a.out = r;
     }

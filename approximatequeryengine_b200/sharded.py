@@ -97,6 +97,7 @@ class ShardedTable:
         handles = [None] * world
         dist.all_gather_object(handles, mine, group=self.group)
         self.engine.exchange_connect(handles)
+        self.engine.exchange_set_total_rows(self.total_rows)
         dist.barrier(self.group)
         self.fused = True
         return True
@@ -122,6 +123,9 @@ class ShardedTable:
         """Shards are strata: each rank runs its persistent CLT kernel to the same relative target with
         an independent Philox key (seed, rank); totals and variances add (aqe_approx_merge)."""
         import torch.distributed as dist
+        if getattr(self, "fused", False):
+            # one global stop rule: per-look moments exchanged inside the persistent kernel (NVLink mailboxes)
+            return self.engine.approx(agg, error_percent, confidence_level, seed=seed, exchange=True, **kw)
         rank = dist.get_rank(self.group) if dist.is_available() and dist.is_initialized() else 0
         local = self.engine.approx(agg, error_percent, confidence_level, seed=(seed << 8) + rank, **kw)
         parts = allgather_struct(local, ApproxResult, self.group)

@@ -243,6 +243,7 @@ def main():
         handles = [None] * world
         dist.all_gather_object(handles, mine)
         eng.exchange_connect(handles)
+        eng.exchange_set_total_rows(rows * world)
         dist.barrier()
 
     if fused:
@@ -360,6 +361,23 @@ def main():
                   "api": "aqe_backend.CustomBPlusDB.approx_avg (pybind11 -> aqe_approx -> k_approx, one cooperative launch)"}
         del db
 
+    # ---- secondary, N > 1: BASELINE.json configs[3] -- block sampling, APPROX SUM at 0.5 % over the sharded table, one global
+    # stop rule evaluated inside the persistent kernels (per-look moments exchanged through the NVLink mailboxes) ----
+    approx_multi = None
+    if fused and not args.skip_approx:
+        res = {}
+        for design in ("block", "srs"):
+            lat, kus, nrows, relerr = [], [], [], []
+            for sd in range(60):
+                torch.cuda.synchronize(); dist.barrier()
+                t0 = time.perf_counter(); r = eng.approx("sum", error_percent=0.5, confidence_level=0.95, design=design, seed=sd, exchange=True); t1 = time.perf_counter()
+                if sd >= 10:
+                    lat.append((t1 - t0) * 1e6); kus.append(r.elapsed_us); nrows.append(r.n_samples); relerr.append(abs(r.estimate - 500.5 * rows * world) / (500.5 * rows * world) * 100)
+            res[design] = {"latency_us_p50": statistics.median(lat), "kernel_us_p50": statistics.median(kus), "rows_read_p50": statistics.median(nrows),
+                           "abs_error_percent_p50_vs_expectation": statistics.median(relerr)}
+        approx_multi = {"workload": f"BASELINE.json configs[3]: {rows * world} records sharded over {world} GPUs, APPROX SUM(amount) at 0.5% error, 95% confidence, "
+                                    "block (1000-row tiles) and SRS designs, global CLT stop rule", "api": "aqe_approx_exchange (C-ABI), all ranks", **res}
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_reference(steps=10, warmup=2)
@@ -373,7 +391,7 @@ def main():
                              "kernel": "aqe::k_scan_ring<double, PRED=1 (amount on itself), double, STAGES=4, MOMENTS=false> (TMA bulk-copy ring, 16 KiB tiles, 2 CTAs/SM)", "kernel_ms": kms,
                              "kernel_ms_source": "timed region (a step is exactly one launch of this kernel)" if step_is_one_kernel else "kernel-only loop, same stream",
                              "kernel_ms_isolated_loop": kern_ms / args.steps, "algorithmic_bytes_per_launch": 8 * rows, "peak_source": peak_src},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clk, "approx": approx,
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clk, "approx": approx, "approx_multi_gpu": approx_multi,
                 "result": {"count": merged.count, "sum": merged.sum}}
         print(json.dumps(line), flush=True)
     if world > 1:

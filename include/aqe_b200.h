@@ -338,6 +338,14 @@ AQE_API int aqe_estimate(const aqe_stats* s, uint64_t population, int agg, doubl
  * Persistent CLT kernel (K4): Philox draws, Welford partials, in-kernel stop rule
  * ---------------------------------------------------------------------------------------------- */
 AQE_API int aqe_approx(aqe_db* db, const aqe_approx_spec* spec, aqe_approx_result* out);
+/* Multi-GPU form (after aqe_exchange_connect + aqe_exchange_set_total_rows on every rank; shards must be the
+ * contiguous ranges [N*g/G, N*(g+1)/G)): shards are strata with proportional allocation and ONE global stop
+ * rule -- after every look each rank's kernel publishes its cumulative moments to all ranks' mailboxes over
+ * NVLink and every rank evaluates the same stratified estimate (sum_g U_g mean_g, Var = sum_g U_g^2 s_g^2/n_g),
+ * so all ranks stop at the same look and return the identical table-level result.  Replaces the reference's
+ * should_stop / current_mean atomics between its fast and slow threads (custom_bplus_db.cpp:901-904). */
+AQE_API int aqe_exchange_set_total_rows(aqe_db* db, uint64_t total_rows);
+AQE_API int aqe_approx_exchange(aqe_db* db, const aqe_approx_spec* spec, aqe_approx_result* out);
 /* Merge per-shard results (stratified by shard, rank order) into the table-level estimate. */
 AQE_API int aqe_approx_merge(const aqe_approx_result* parts, int n, int agg, double confidence_level,
                      aqe_approx_result* out);

@@ -146,6 +146,7 @@ class Oracle:
         L.orc_fast_aggregated.restype = C.c_double
         L.orc_z_score.argtypes = [C.c_double, C.c_int]; L.orc_z_score.restype = C.c_double
         L.orc_approx.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ApproxSpec), C.POINTER(ApproxResult)]
+        L.orc_approx_sharded.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(ApproxSpec), C.POINTER(ApproxResult)]
         L.orc_draw_position.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64]
         L.orc_draw_position.restype = C.c_uint64
         L.orc_scan_mt.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
@@ -240,6 +241,12 @@ class Oracle:
     def approx(self, rows, spec: ApproxSpec) -> ApproxResult:
         rows = _rows(rows); out = ApproxResult()
         self.L.orc_approx(_ptr(rows), len(rows), C.byref(spec), C.byref(out))
+        return out
+
+    def approx_sharded(self, rows, world: int, spec: ApproxSpec) -> ApproxResult:
+        rows = _rows(rows); out = ApproxResult()
+        if self.L.orc_approx_sharded(_ptr(rows), len(rows), world, C.byref(spec), C.byref(out)) != 0:
+            raise ValueError("orc_approx_sharded")
         return out
 
     def draw_position(self, seed: int, design: int, j: int, units: int) -> int:

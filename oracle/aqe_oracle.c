@@ -1071,6 +1071,102 @@ ORC_API int orc_approx(const aqe_record* R, uint64_t N, const aqe_approx_spec* S
     return 0;
 }
 
+/* Multi-GPU form of section 7 restated on one CPU: `world` contiguous shards [N g/G, N (g+1)/G) are strata with
+ * proportional allocation; rank g draws from Philox key seed + g*0x9E3779B97F4A7C15; after every look the GLOBAL
+ * stratified estimate  T = sum_g U_g mean_g,  Var = sum_g U_g^2 s_g^2 / n_g  decides (same growth rule on the global
+ * cumulative size).  Checker for aqe_approx_exchange (tests/multi_gpu_check.py). */
+static uint64_t share_of(uint64_t T, uint64_t ug, uint64_t utot) {
+    if (ug == 0) return 0;
+    double x = ceil((double)T * ((double)ug / (double)utot));
+    uint64_t v = x >= (double)ug ? ug : (uint64_t)x;
+    return v < 1 ? 1 : v;
+}
+ORC_API int orc_approx_sharded(const aqe_record* R, uint64_t N, int world, const aqe_approx_spec* S, aqe_approx_result* out) {
+    memset(out, 0, sizeof(*out));
+    out->population = N; out->confidence_level = S->confidence_level;
+    if (N == 0) { out->status = AQE_INSUFFICIENT_DATA; return 0; }
+    if (world < 1 || world > 16) return 1;
+    uint64_t B = S->design == AQE_DESIGN_BLOCK ? (S->block_size ? S->block_size : 1000) : 1;
+    double z = orc_z_score(S->confidence_level, 1) * AQE_CI_CONSERVATIVE;
+    if (S->agg == AQE_AGG_COUNT && S->pred_col == AQE_COL_NONE) {
+        out->estimate = out->ci_lower = out->ci_upper = (double)N; out->status = AQE_STABLE; return 0;
+    }
+    uint64_t first[16], rows[16], units[16], n[16], target[16], utot = 0;
+    long double sy[16], syy[16], sc[16], nrows[16];
+    for (int g = 0; g < world; ++g) {
+        first[g] = (uint64_t)(((unsigned __int128)N * g) / world);
+        rows[g] = (uint64_t)(((unsigned __int128)N * (g + 1)) / world) - first[g];
+        units[g] = (rows[g] + B - 1) / B; utot += units[g];
+        n[g] = 0; sy[g] = syy[g] = sc[g] = nrows[g] = 0;
+    }
+    uint64_t n0 = S->min_samples ? S->min_samples : (S->design == AQE_DESIGN_BLOCK ? 1024 : 16384);
+    uint64_t nmax = S->max_samples ? S->max_samples : utot;
+    if (n0 > nmax) n0 = nmax;
+    if (utot <= n0) {
+        aqe_partial part;
+        orc_scan(R, N, S->agg == AQE_AGG_COUNT ? S->pred_col : S->agg_col, S->pred_col, S->lo, S->hi, &part);
+        double v = S->agg == AQE_AGG_COUNT ? (double)part.count : (S->agg == AQE_AGG_SUM ? part.sum : (part.count ? part.sum / (double)part.count : 0.0));
+        out->estimate = out->ci_lower = out->ci_upper = v; out->n_samples = N; out->n_units = utot; out->status = AQE_STABLE;
+        return 0;
+    }
+    int ratio = (S->agg == AQE_AGG_AVG && S->pred_col != AQE_COL_NONE);
+    uint64_t Tg = n0; uint32_t rounds = 0;
+    double est = 0, half = 0, rel = INFINITY;
+    uint64_t ntot = 0; long double rows_read = 0;
+    for (;;) {
+        for (int g = 0; g < world; ++g) {
+            uint64_t t = share_of(Tg, units[g], utot);
+            target[g] = t > n[g] ? t : n[g];
+            uint64_t seed = S->seed + 0x9E3779B97F4A7C15ull * (uint64_t)g;
+            for (; n[g] < target[g]; ++n[g]) {
+                uint64_t u = draw_position(seed, (uint32_t)S->design, n[g], units[g]);
+                double y, c; unit_value(R + first[g], rows[g], S, u, &y, &c);
+                sy[g] += y; syy[g] += (long double)y * y; sc[g] += c;
+                if (S->design == AQE_DESIGN_BLOCK) { uint64_t a = u * B; nrows[g] += (long double)((a + B < rows[g] ? a + B : rows[g]) - a); }
+                else nrows[g] += 1;
+            }
+        }
+        ++rounds;
+        long double T = 0, V = 0, num = 0, den = 0;
+        ntot = 0; rows_read = 0;
+        for (int g = 0; g < world; ++g) {
+            ntot += n[g]; rows_read += nrows[g];
+            if (!units[g] || !n[g]) continue;
+            num += (long double)units[g] * (sy[g] / (long double)n[g]); den += (long double)units[g] * (sc[g] / (long double)n[g]);
+        }
+        long double Rr = den > 0 ? num / den : 0;
+        for (int g = 0; g < world; ++g) {
+            if (!units[g] || !n[g]) continue;
+            long double nn = (long double)n[g], U = (long double)units[g], mu = sy[g] / nn, var;
+            if (ratio) {
+                long double se2 = syy[g] - 2 * Rr * sy[g] + Rr * Rr * sc[g];
+                long double eb = (sy[g] - Rr * sc[g]) / nn;
+                se2 -= nn * eb * eb; if (se2 < 0) se2 = 0;
+                var = n[g] > 1 ? se2 / (nn - 1) : INFINITY;
+            } else {
+                long double ss = syy[g] - sy[g] * mu; if (ss < 0) ss = 0;
+                var = n[g] > 1 ? ss / (nn - 1) : INFINITY;
+            }
+            T += U * mu; V += U * U * var / nn;
+        }
+        if (ratio) { est = (double)Rr; half = den > 0 ? (double)(z * sqrtl(V) / den) : INFINITY; }
+        else if (S->agg == AQE_AGG_AVG) { est = (double)(T / (long double)N); half = (double)(z * sqrtl(V) / (long double)N); }
+        else { est = (double)T; half = (double)(z * sqrtl(V)); }
+        rel = (ratio && !(den > 0)) ? INFINITY : (est != 0 ? half / fabs(est) * 100.0 : INFINITY);
+        if (rel <= S->error_percent) { out->status = AQE_STABLE; break; }
+        if (Tg >= nmax) { out->status = AQE_DRIFTING; break; }
+        double rn = rel / S->error_percent;
+        double want = ceil(1.1 * ((double)ntot * rn * rn));
+        uint64_t lo_n = Tg + Tg / 4 + 1, hi_n = Tg * 8;
+        uint64_t t2 = want >= (double)hi_n ? hi_n : (want <= (double)lo_n ? lo_n : (uint64_t)want);
+        if (t2 > nmax) t2 = nmax;
+        Tg = t2;
+    }
+    out->estimate = est; out->ci_lower = est - half; out->ci_upper = est + half; out->error_margin = rel / 100.0;
+    out->n_units = ntot; out->n_samples = (uint64_t)rows_read; out->rounds = rounds;
+    return 0;
+}
+
 /* ================================================================================================
  * 8. Restated multithreaded scan for the CPU baseline at sizes the reference cannot load (SURVEY D10,
  *    8d-ii): contiguous regions (the split of cbd:1984-2011 at 100 %), serial sum per region, ordered

@@ -38,6 +38,40 @@ for it in range(2000):
     f = t.scan("amount", "amount", 100.0, 500.0) if it % 500 == 0 else None
     if f is not None:
         assert bytes(f) == bytes(ref[1])
+# ---- sampled estimates with ONE global stop rule (per-look moments exchanged inside k_approx) vs the CPU restatement ----
+import numpy as np
+from oracle import ApproxSpec, Oracle
+O = Oracle()
+n_small = 4_000_003
+ts = sharded.ShardedTable.synthetic(n_small, rank, world, seed=11, device=local, columns=("amount", "timestamp"))
+assert ts.enable_fused_exchange()
+rows_all = O.synth(n_small, seed=11)
+approx_cases = [dict(agg="sum"), dict(agg="avg", eps=0.25), dict(agg="sum", where=(100.0, 500.0)), dict(agg="count", where=(100.0, 500.0)),
+                dict(agg="avg", where=(100.0, 500.0), eps=0.5), dict(agg="sum", design="block", min_samples=64, block=500), dict(agg="sum", eps=0.02, max_samples=300000),
+                dict(agg="count")]
+for kw in approx_cases:
+    for seed in (0, 9):
+        a = ts.approx(kw["agg"], error_percent=kw.get("eps", 1.0), seed=seed, design=kw.get("design", "srs"), where=kw.get("where"),
+                      min_samples=kw.get("min_samples", 0), max_samples=kw.get("max_samples", 0), block_size=kw.get("block", 0))
+        spec = ApproxSpec(agg=aqe.AGG[kw["agg"]], design=aqe.DESIGN[kw.get("design", "srs")], agg_col=1, pred_col=1 if kw.get("where") else -1,
+                          lo=kw["where"][0] if kw.get("where") else 0.0, hi=kw["where"][1] if kw.get("where") else 0.0, error_percent=kw.get("eps", 1.0),
+                          confidence_level=0.95, seed=seed, min_samples=kw.get("min_samples", 0), max_samples=kw.get("max_samples", 0), block_size=kw.get("block", 0))
+        o = O.approx_sharded(rows_all, world, spec)
+        assert (a.n_units, a.n_samples, a.rounds, a.status, a.population) == (o.n_units, o.n_samples, o.rounds, o.status, n_small), (rank, kw, seed, (a.n_units, a.n_samples, a.rounds, a.status), (o.n_units, o.n_samples, o.rounds, o.status))
+        assert abs(a.estimate - o.estimate) <= 1e-10 * abs(o.estimate) and abs((a.ci_upper - a.ci_lower) - (o.ci_upper - o.ci_lower)) <= 1e-8 * abs(o.ci_upper - o.ci_lower + 1e-300), (kw, seed)
+# every rank holds the identical result; latency of the fused multi-GPU estimator on the big table (configs[3])
+approx_lat = {}
+import time
+for design, eps in (("srs", 0.5), ("block", 0.5), ("srs", 0.1)):
+    lat = []
+    for seed in range(40):
+        torch.cuda.synchronize(); dist.barrier()
+        t1 = time.perf_counter(); r = t.approx("sum", error_percent=eps, design=design, seed=seed); lat.append((time.perf_counter() - t1) * 1e6)
+    assert r.status == 0 and abs(r.estimate - ref[0].sum) / ref[0].sum < 3 * eps / 100
+    approx_lat[f"{design}_sum_{eps}pct_us_p50"] = sorted(lat)[len(lat) // 2]
+    approx_lat[f"{design}_sum_{eps}pct_kernel_us"] = r.elapsed_us
+    approx_lat[f"{design}_sum_{eps}pct_rows_read"] = r.n_samples
+
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 merged = torch.zeros(8, dtype=torch.int64, device="cuda")
 partial = torch.zeros(8, dtype=torch.int64, device="cuda"); gathered = torch.zeros(8 * world, dtype=torch.int64, device="cuda")
@@ -74,7 +108,7 @@ def timed(fn, k=200):
     return float(ms)
 
 
-res = {"world": world, "rows_total": N, "ms_kernel_only": timed(kernel_only), "ms_nccl_allgather": timed(nccl), "ms_fused_exchange": timed(fused)}
+res = {"world": world, "rows_total": N, "approx_fused": approx_lat, "ms_kernel_only": timed(kernel_only), "ms_nccl_allgather": timed(nccl), "ms_fused_exchange": timed(fused)}
 torch.cuda.synchronize()
 f = aqe.Partial.from_buffer_copy(host[:8].numpy().tobytes())     # async form: no moments, same count / sum / comp bits
 assert (f.count, f.sum, f.comp) == (ref[1].count, ref[1].sum, ref[1].comp)
