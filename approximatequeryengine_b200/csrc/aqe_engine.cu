@@ -14,7 +14,11 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <fcntl.h>
+#include <unistd.h>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -156,60 +160,91 @@ static int grid_for(const aqe_db* db, uint64_t work_items, int per_thread, int t
 // ------------------------------------------------------------------------------------------------
 // ingest: host AoS rows -> device columns (K7), chunked through pinned staging
 // ------------------------------------------------------------------------------------------------
-struct Stager {
-    static const size_t kChunkRows = 1u << 20;  // 32 MiB of rows
+// Replaces load_from_file's per-record ifstream::read + tree rebuild (custom_bplus_db.cpp:700-710).  W worker threads
+// each run an independent pipeline over the chunks c = w, w+W, ... of the row range: fill a pinned buffer (pread from
+// the file / memcpy from caller memory) -> cudaMemcpyAsync -> k_aos_to_soa on the worker's own stream, two buffers
+// per worker so the next fill overlaps the previous copy.  Page-cache reads run at a few GB/s per thread, the H2D
+// link at ~55 GB/s, so several readers are needed to approach the link.  Out-of-order ids are detected inside a
+// chunk on the device and across chunk boundaries on the host.
+struct IngestWorker {
+    static const size_t kChunkRows = 1u << 19;  // 16 MiB of rows
     aqe_record* pinned[2] = {nullptr, nullptr};
     aqe_record* dev[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
-    unsigned int* unsorted = nullptr;
+    cudaStream_t stream = nullptr;
+    int rc = AQE_OK;
+    std::string err;
     int init() {
+        CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             CU(cudaHostAlloc(&pinned[i], kChunkRows * sizeof(aqe_record), cudaHostAllocDefault));
             CU(cudaMalloc(&dev[i], kChunkRows * sizeof(aqe_record)));
             CU(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
         }
-        CU(cudaMalloc(&unsorted, 4));
-        CU(cudaMemset(unsorted, 0, 4));
         return AQE_OK;
     }
-    ~Stager() {
+    ~IngestWorker() {
         for (int i = 0; i < 2; ++i) { if (pinned[i]) cudaFreeHost(pinned[i]); if (dev[i]) cudaFree(dev[i]); if (done[i]) cudaEventDestroy(done[i]); }
-        if (unsorted) cudaFree(unsorted);
+        if (stream) cudaStreamDestroy(stream);
     }
 };
 
-// Feeds `n` rows obtained chunk-wise from `fill(dst, first, count)` into the columns.  *unsorted_out is
-// set if ids were found out of order.
+// Feeds `n` rows obtained chunk-wise from the thread-safe `fill(dst, first, count)` into the columns.
+// *unsorted_out is set if ids were found out of order.
 template <typename Fill>
 static int ingest_rows(aqe_db* db, uint64_t n, Fill fill, bool* unsorted_out) {
     int rc = alloc_columns(db, n, 0x1f);
     if (rc) return rc;
-    Stager st;
-    rc = st.init();
-    if (rc) return rc;
-    int64_t prev_last = 0;
-    int has_prev = 0;
-    uint64_t done_rows = 0;
-    int buf = 0;
-    while (done_rows < n) {
-        const uint64_t cnt = std::min<uint64_t>(Stager::kChunkRows, n - done_rows);
-        CU(cudaEventSynchronize(st.done[buf]));  // the pinned buffer is free again
-        if (!fill(st.pinned[buf], done_rows, cnt)) return fail(AQE_ERR_IO, "short read while loading rows");
-        CU(cudaMemcpyAsync(st.dev[buf], st.pinned[buf], cnt * sizeof(aqe_record), cudaMemcpyHostToDevice, db->stream));
-        const int grid = grid_for(db, cnt, 4, 256, 8);
-        k_aos_to_soa<<<grid, 256, 0, db->stream>>>(st.dev[buf], cnt, db->col, done_rows, prev_last, has_prev, st.unsorted);
-        LAUNCHED();
-        CU(cudaGetLastError());
-        CU(cudaEventRecord(st.done[buf], db->stream));
-        prev_last = st.pinned[buf][cnt - 1].id;
-        has_prev = 1;
-        done_rows += cnt;
-        buf ^= 1;
-    }
+    *unsorted_out = false;
+    if (n == 0) return AQE_OK;
+    const uint64_t nchunks = (n + IngestWorker::kChunkRows - 1) / IngestWorker::kChunkRows;
+    int W = env_int("AQE_INGEST_THREADS", 0);
+    if (W <= 0) W = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    W = (int)std::min<uint64_t>((uint64_t)W, nchunks);
+    unsigned int* unsorted = nullptr;
+    CU(cudaMalloc(&unsorted, 4));
+    CU(cudaMemset(unsorted, 0, 4));
+    std::vector<IngestWorker> workers(W);
+    for (auto& w : workers) { rc = w.init(); if (rc) { cudaFree(unsorted); return rc; } }
+    std::vector<int64_t> first_id(nchunks), last_id(nchunks);
+    const int device = db->device;
+    const MutColumns cols = db->col;
+    const int sm_count = db->sm_count;
+    auto body = [&](int wi) {
+        IngestWorker& w = workers[wi];
+        if (cudaSetDevice(device) != cudaSuccess) { w.rc = AQE_ERR_CUDA; w.err = "cudaSetDevice failed in ingest worker"; return; }
+        int buf = 0;
+        for (uint64_t c = (uint64_t)wi; c < nchunks; c += (uint64_t)W, buf ^= 1) {
+            const uint64_t first = c * IngestWorker::kChunkRows, cnt = std::min<uint64_t>(IngestWorker::kChunkRows, n - first);
+            cudaError_t e = cudaEventSynchronize(w.done[buf]);  // the pinned buffer is free again
+            if (e == cudaSuccess && !fill(w.pinned[buf], first, cnt)) { w.rc = AQE_ERR_IO; w.err = "short read while loading rows"; return; }
+            first_id[c] = w.pinned[buf][0].id; last_id[c] = w.pinned[buf][cnt - 1].id;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(w.dev[buf], w.pinned[buf], cnt * sizeof(aqe_record), cudaMemcpyHostToDevice, w.stream);
+            if (e == cudaSuccess) {
+                const uint64_t want = (cnt + 1023) / 1024;
+                const int grid = (int)std::min<uint64_t>(want, (uint64_t)sm_count * 8);
+                k_aos_to_soa<<<grid, 256, 0, w.stream>>>(w.dev[buf], cnt, cols, first, 0, 0, unsorted);
+                LAUNCHED();
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(w.done[buf], w.stream);
+            if (e != cudaSuccess) { w.rc = AQE_ERR_CUDA; w.err = std::string("ingest worker: ") + cudaGetErrorString(e); return; }
+        }
+        if (cudaStreamSynchronize(w.stream) != cudaSuccess) { w.rc = AQE_ERR_CUDA; w.err = "ingest worker: stream sync failed"; }
+    };
+    std::vector<std::thread> threads;
+    for (int wi = 1; wi < W; ++wi) threads.emplace_back(body, wi);
+    body(0);
+    for (auto& t : threads) t.join();
+    CU(cudaSetDevice(db->device));
+    for (auto& w : workers)
+        if (w.rc) { cudaFree(unsorted); return fail(w.rc, w.err); }
     unsigned int flag = 0;
-    CU(cudaMemcpyAsync(&flag, st.unsorted, 4, cudaMemcpyDeviceToHost, db->stream));
-    CU(cudaStreamSynchronize(db->stream));
-    *unsorted_out = flag != 0;
+    CU(cudaMemcpy(&flag, unsorted, 4, cudaMemcpyDeviceToHost));
+    cudaFree(unsorted);
+    bool bad = flag != 0;
+    for (uint64_t c = 1; c < nchunks && !bad; ++c) bad = first_id[c] < last_id[c - 1];
+    *unsorted_out = bad;
     return AQE_OK;
 }
 
@@ -303,28 +338,33 @@ int aqe_close(aqe_db* db) {
 
 int aqe_load_file(aqe_db* db, const char* path, uint64_t first_row, uint64_t n_rows) {
     if (!db || !path) return fail(AQE_ERR_INVALID, "NULL argument");
-    FILE* f = std::fopen(path, "rb");
-    if (!f) return fail(AQE_ERR_IO, std::string("cannot open ") + path);
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return fail(AQE_ERR_IO, std::string("cannot open ") + path);
+    auto read_at = [fd](void* dst, size_t bytes, uint64_t off) {
+        char* p = static_cast<char*>(dst);
+        while (bytes) {
+            const ssize_t k = ::pread(fd, p, bytes, (off_t)off);
+            if (k <= 0) return false;
+            p += k; off += (uint64_t)k; bytes -= (size_t)k;
+        }
+        return true;
+    };
     uint64_t hdr[3];
-    if (std::fread(hdr, 8, 3, f) != 3) { std::fclose(f); return fail(AQE_ERR_IO, std::string("short header in ") + path); }
+    if (!read_at(hdr, 24, 0)) { ::close(fd); return fail(AQE_ERR_IO, std::string("short header in ") + path); }
     const uint64_t total = hdr[2];  // record_count; the first two words are ignored (custom_bplus_db.cpp:692-698)
     if (first_row > total) first_row = total;
     const uint64_t n = std::min<uint64_t>(n_rows, total - first_row);
     int rc = db_init_cuda(db);
-    if (rc) { std::fclose(f); return rc; }
+    if (rc) { ::close(fd); return rc; }
     db->host_rows.clear(); db->host_authoritative = false;
-    if (fseeko(f, (off_t)(24 + first_row * 32), SEEK_SET) != 0) { std::fclose(f); return fail(AQE_ERR_IO, "seek failed"); }
     bool unsorted = false;
-    rc = ingest_rows(db, n, [&](aqe_record* dst, uint64_t, uint64_t cnt) { return std::fread(dst, sizeof(aqe_record), cnt, f) == cnt; }, &unsorted);
+    rc = ingest_rows(db, n, [&](aqe_record* dst, uint64_t first, uint64_t cnt) { return read_at(dst, cnt * sizeof(aqe_record), 24 + (first_row + first) * 32); }, &unsorted);
     if (rc == AQE_OK && unsorted) {
         std::vector<aqe_record> rows(n);
-        if (fseeko(f, (off_t)(24 + first_row * 32), SEEK_SET) != 0 || std::fread(rows.data(), sizeof(aqe_record), n, f) != n) {
-            std::fclose(f);
-            return fail(AQE_ERR_IO, "re-read failed");
-        }
+        if (!read_at(rows.data(), n * sizeof(aqe_record), 24 + first_row * 32)) { ::close(fd); return fail(AQE_ERR_IO, "re-read failed"); }
         rc = upload_host_rows(db, rows.data(), n);
     }
-    std::fclose(f);
+    ::close(fd);
     return rc;
 }
 

@@ -139,6 +139,24 @@ def test_special_values(oracle):
         assert e.sum_int(col) == int(srt[col].astype(object).sum())
 
 
+def test_duplicate_ids_and_all_equal_values(oracle):
+    """Collisions: duplicate ids are allowed by the format (lower_bound insert, custom_bplus_db.cpp:32-37); aggregates do not
+    care, rows stay ordered by id (stably), and a constant column has zero variance."""
+    n = 30000
+    rows = oracle.synth(n, seed=6)
+    rows["id"][:] = np.repeat(np.arange(1, n // 3 + 1), 3)            # every id three times
+    rows["amount"][:] = 123.25
+    e = aqe.Engine(0).from_rows(rows[np.random.default_rng(3).permutation(n)])
+    back = e.read_rows()
+    assert np.array_equal(back["id"], rows["id"]) and e.count == n
+    assert e.sum_amount() == 123.25 * n and e.sum_amount_where(123.25, 123.25) == (123.25 * n, n)
+    assert e.sum_int("id") == int(rows["id"].astype(object).sum())
+    st = e.stats(e.plan("memory_stride", aqe.make_params("memory_stride", 10.0)))
+    assert st.mean == 123.25 and st.m2 == 0.0 and st.sum == 123.25 * st.n
+    a = e.approx("avg", error_percent=1.0, seed=2)                     # zero variance: converges at the first look
+    assert a.estimate == 123.25 and a.ci_lower == a.ci_upper == 123.25 and a.status == 0 and a.rounds == 1
+
+
 def test_int128_overflow_range(oracle):
     n = 70000
     rows = oracle.synth(n, seed=2)

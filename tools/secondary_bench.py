@@ -30,6 +30,7 @@ def note(msg):
 ap = argparse.ArgumentParser()
 ap.add_argument("--records", type=int, default=1_000_000_000)
 ap.add_argument("--ingest-records", type=int, default=50_000_000)
+ap.add_argument("--only-ingest", action="store_true")
 args = ap.parse_args()
 N = args.records
 out = {"records": N}
@@ -55,6 +56,25 @@ def dev_ms(f, reps=20):
     e1.record(stream); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
+
+if args.only_ingest:
+    n_in = args.ingest_records
+    g = aqe.Engine(0).generate(n_in, seed=7)
+    res = {}
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+        path = os.path.join(td, "t.aqe")
+        g.save_file(path)
+        for th in (1, 2, 4, 8, 16):
+            os.environ["AQE_INGEST_THREADS"] = str(th)
+            ts = []
+            for _ in range(3):
+                x = aqe.Engine(0); t1 = time.perf_counter(); x.load_file(path); ts.append(time.perf_counter() - t1)
+                assert x.count == n_in and x.sum_int("id") == n_in * (n_in + 1) // 2
+                x.close()
+            res[f"threads_{th}"] = {"load_s_best": min(ts), "GBps": 32 * n_in / min(ts) / 1e9, "records_per_s": n_in / min(ts)}
+            note(f"ingest threads={th}: {res[f'threads_{th}']}")
+    print(json.dumps({"ingest_sweep": res, "records": n_in, "medium": "/dev/shm (page cache)"}, indent=1))
+    sys.exit(0)
 
 # ---- 1. exact scans over every column type / predicate combination (bytes = algorithmic bytes per record) ----
 e = aqe.Engine(0).generate(N, seed=7)
