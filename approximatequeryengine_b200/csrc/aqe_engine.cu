@@ -558,15 +558,18 @@ static ScanTuning scan_tuning() {
 
 // occupancy (and the one-time dynamic-smem opt-in) per kernel, looked up once
 static int kernel_occupancy(const void* kernel, int threads, size_t smem) {
+    struct Key { const void* k; int dev; int occ; };
     static std::mutex mu;
-    static std::vector<std::pair<const void*, int>> cache;
+    static std::vector<Key> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);  // function attributes are per device
     std::lock_guard<std::mutex> lock(mu);
-    for (auto& e : cache) if (e.first == kernel) return e.second;
+    for (auto& e : cache) if (e.k == kernel && e.dev == dev) return e.occ;
     if (smem) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
     occ = std::max(occ, 1);
-    cache.emplace_back(kernel, occ);
+    cache.push_back(Key{kernel, dev, occ});
     return occ;
 }
 
