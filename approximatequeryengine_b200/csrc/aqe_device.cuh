@@ -55,6 +55,37 @@ __host__ __device__ __forceinline__ uint64_t draw_position(uint64_t seed, uint32
     return mulhi64(u, units);
 }
 
+// Pseudo-random permutation of [0, n): a 4-round balanced Feistel network over the smallest even number of bits
+// covering n, splitmix64 as the round function, cycle-walking back into [0, n).  perm(0), perm(1), ... perm(k-1) are
+// k DISTINCT, uniformly scattered positions -- simple random sampling WITHOUT replacement in O(1) memory, computed
+// where it is needed (replaces copy-all + std::shuffle of sample_records, custom_bplus_db.cpp:345-363).
+__host__ __device__ __forceinline__ uint64_t feistel_round(uint64_t r, uint32_t round, uint64_t seed) {
+    uint64_t z = (r + 0x9E3779B97F4A7C15ull * (uint64_t)(round + 1)) ^ seed;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint32_t feistel_half_bits(uint64_t n) {  // half width h: 2^(2h) >= n, h >= 1
+    uint32_t h = 1;
+    while (h < 32 && (1ull << (2 * h)) < n) ++h;
+    return h;
+}
+__host__ __device__ __forceinline__ uint64_t feistel_perm(uint64_t k, uint64_t n, uint64_t seed, uint32_t half) {
+    const uint64_t mask = (1ull << half) - 1;
+    uint64_t x = k;
+    do {
+        uint64_t l = x >> half, r = x & mask;
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) {
+            const uint64_t f = feistel_round(r, i, seed) & mask;
+            const uint64_t t = l ^ f;
+            l = r; r = t;
+        }
+        x = (l << half) | r;
+    } while (x >= n);
+    return x;
+}
+
 // One row of the synthetic sales table.  UNIFORM is bit-identical on host and device.
 __host__ __device__ __forceinline__ void synth_row(uint64_t seed, uint64_t row, int dist, aqe_record& r) {
     const u32x4 o = philox4x32_10((uint32_t)row, (uint32_t)(row >> 32), kSynthStream, 0u, (uint32_t)seed,

@@ -1009,7 +1009,7 @@ static int stats_launch(aqe_db* db, const aqe_plan* pl, int col, aqe_stats* out,
     if (rc) return rc;
     if (pl->by_amount_order) { rc = ensure_amount_perm(db); if (rc) return rc; a.plan.perm = db->amount_perm; }
     a.cols = const_cols(db); a.col = col; a.pred_col = pred_col; a.lo = lo; a.hi = hi; a.partials = db->stat_partials; a.ticket = db->tickets + 2; a.out = &db->slot_dev->stats;
-    const int grid = grid_for(db, pl->count, 4, 256, 4);
+    const int grid = grid_for(db, pl->count, 4, 256, 8);
     k_plan_stats<<<grid, 256, 0, db->stream>>>(a);
     LAUNCHED();
     CU(cudaGetLastError());

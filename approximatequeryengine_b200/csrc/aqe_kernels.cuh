@@ -468,6 +468,13 @@ __device__ __forceinline__ int64_t plan_position(const PlanDev& P, uint64_t k) {
         const aqe_segment s = P.segs[lo];
         const uint64_t r = k - __ldg(P.seg_start + lo);
         if (s.kind == 1) pos = (int64_t)(uint64_t)__dmul_rn((double)r, s.scale);
+        else if (s.kind == 2) pos = (int64_t)feistel_perm(r, (uint64_t)s.base, (uint64_t)s.outer_step, (uint32_t)s.inner_len);
+        else if (s.kind == 3) {  // jittered stride: (r*stride + U{0..stride/2}) mod M   (address_arithmetic_sample)
+            const uint64_t stride = (uint64_t)s.outer_step, M = (uint64_t)s.base;
+            const u32x4 q = philox4x32_10((uint32_t)r, (uint32_t)(r >> 32), kSeedStream, (uint32_t)AQE_M_ADDRESS_ARITHMETIC, (uint32_t)s.inner_len,
+                                          (uint32_t)((uint64_t)s.inner_len >> 32));
+            pos = (int64_t)((r * stride + mulhi64(((uint64_t)q.y << 32) | q.x, stride / 2 + 1)) % M);
+        }
         else if (s.inner_len == 1) pos = s.base + (int64_t)r * s.outer_step;
         else pos = s.base + (int64_t)(r / (uint64_t)s.inner_len) * s.outer_step + (int64_t)(r % (uint64_t)s.inner_len);
     }
@@ -543,7 +550,20 @@ __global__ void __launch_bounds__(256) k_plan_stats(const StatArgs a) {
     };
     double K = 0.0;
     if (a.plan.count) K = value_at(0);
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.plan.count; k += G) {
+    // 4 independent gathers in flight per thread (random 8-byte reads are latency bound: one 32-byte sector each)
+    constexpr int GU = 4;
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; k + (uint64_t)(GU - 1) * G < a.plan.count; k += (uint64_t)GU * G) {
+        double x[GU];
+#pragma unroll
+        for (int j = 0; j < GU; ++j) x[j] = value_at(k + (uint64_t)j * G);
+#pragma unroll
+        for (int j = 0; j < GU; ++j) {
+            const double d = __dadd_rn(x[j], -K);
+            acc.n += 1; dd_add(acc.sx, x[j]); dd_add(acc.sd, d); dd_add(acc.sdd, __dmul_rn(d, d));
+        }
+    }
+    for (; k < a.plan.count; k += G) {
         const double x = value_at(k);
         const double d = __dadd_rn(x, -K);
         acc.n += 1; dd_add(acc.sx, x); dd_add(acc.sd, d); dd_add(acc.sdd, __dmul_rn(d, d));

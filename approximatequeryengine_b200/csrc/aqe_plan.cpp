@@ -11,7 +11,6 @@
 #include <algorithm>
 #include <cmath>
 #include <random>
-#include <unordered_map>
 
 #include "aqe_device.cuh"
 
@@ -82,6 +81,11 @@ int64_t plan_position_host(const aqe_plan& pl, uint64_t k) {
     const aqe_segment& s = pl.segs[lo];
     const uint64_t r = k - pl.seg_start[lo];
     if (s.kind == 1) { volatile double t = (double)r * s.scale; return (int64_t)(uint64_t)t; }
+    if (s.kind == 2) return (int64_t)feistel_perm(r, (uint64_t)s.base, (uint64_t)s.outer_step, (uint32_t)s.inner_len);
+    if (s.kind == 3) {
+        const uint64_t stride = (uint64_t)s.outer_step, M = (uint64_t)s.base;
+        return (int64_t)((r * stride + seeded_below((uint64_t)s.inner_len, (uint32_t)AQE_M_ADDRESS_ARITHMETIC, r, stride / 2 + 1)) % M);
+    }
     if (s.inner_len == 1) return s.base + (int64_t)r * s.outer_step;
     return s.base + (int64_t)(r / (uint64_t)s.inner_len) * s.outer_step + (int64_t)(r % (uint64_t)s.inner_len);
 }
@@ -359,21 +363,15 @@ int plan_build(uint64_t N, int method, const aqe_sample_params& P, const PlanDat
             }
             break;
         }
-        case AQE_M_SAMPLE_RECORDS: { // cbd:345-363: SRSWOR of floor(N p/100) rows; seeded partial Fisher-Yates
+        case AQE_M_SAMPLE_RECORDS: { // cbd:345-363: SRSWOR of floor(N p/100) rows = prefix of a seeded permutation of [0,N)
             if (N == 0) break;
             if (p >= 100.0) { add_all(pl, N); break; }
             if (p <= 0.0) break;
             const uint64_t k = umin((uint64_t)((double)N * p / 100.0), N);
-            std::unordered_map<uint64_t, uint64_t> moved;
-            moved.reserve(2 * k);
-            pl.idx.reserve(k);
-            for (uint64_t i = 0; i < k; ++i) {
-                const uint64_t j = i + seeded_below(P.seed, (uint32_t)method, i, N - i);
-                auto fi = moved.find(i), fj = moved.find(j);
-                const uint64_t vi = fi == moved.end() ? i : fi->second, vj = fj == moved.end() ? j : fj->second;
-                pl.idx.push_back((int64_t)vj);
-                moved[j] = vi;
-            }
+            if (k == 0) break;
+            aqe_segment s{};
+            s.kind = 2; s.base = (int64_t)N; s.outer_step = (int64_t)P.seed; s.inner_len = (int64_t)feistel_half_bits(N); s.count = (int64_t)k;
+            pl.segs.push_back(s);
             break;
         }
         case AQE_M_OPTIMIZED_SEQUENTIAL: { // cbd:366-428: 1-based count c is taken when c >= next; next += step
@@ -408,9 +406,9 @@ int plan_build(uint64_t N, int method, const aqe_sample_params& P, const PlanDat
         case AQE_M_ADDRESS_ARITHMETIC: { // cbd:1605-1665: i*stride + U{0..stride/2}, wrapped
             if (N == 0 || T <= 0) break;
             const uint64_t M = cache_rows(N), stride = umax(1, M / (uint64_t)T);
-            pl.idx.reserve((size_t)T);
-            for (int64_t i = 0; i < T; ++i)
-                pl.idx.push_back((int64_t)(((uint64_t)i * stride + seeded_below(P.seed, (uint32_t)method, (uint64_t)i, stride / 2 + 1)) % M));
+            aqe_segment s{};
+            s.kind = 3; s.base = (int64_t)M; s.outer_step = (int64_t)stride; s.inner_len = (int64_t)P.seed; s.count = T;
+            pl.segs.push_back(s);
             break;
         }
         case AQE_M_MULTITHREADED_MEMORY_STRIDE: { // cbd:1880-1960 (and the index sets of cbd:1962-2048)

@@ -157,6 +157,28 @@ public:
                                         reinterpret_cast<const int32_t*>(region), reinterpret_cast<const int32_t*>(product_id),
                                         reinterpret_cast<const int64_t*>(timestamp), n));
     }
+    // Torch hand-off without a torch dependency: any object with data_ptr() / numel() / dtype / is_cuda (CUDA tensors).
+    void from_torch(py::object id, py::object amount, py::object region, py::object product_id, py::object timestamp) {
+        uint64_t n = 0;
+        bool have_n = false;
+        auto ptr_of = [&](py::object t, const char* name, const char* want) -> uintptr_t {
+            if (t.is_none()) return 0;
+            if (!py::hasattr(t, "data_ptr")) throw py::value_error(std::string(name) + ": expected a CUDA tensor");
+            if (!t.attr("is_cuda").cast<bool>()) throw py::value_error(std::string(name) + ": tensor must live on the GPU");
+            if (!t.attr("is_contiguous")().cast<bool>()) throw py::value_error(std::string(name) + ": tensor must be contiguous");
+            const std::string dt = py::str(t.attr("dtype")).cast<std::string>();
+            if (dt != want) throw py::value_error(std::string(name) + ": dtype must be " + want + ", got " + dt);
+            const uint64_t m = t.attr("numel")().cast<uint64_t>();
+            if (have_n && m != n) throw py::value_error("all columns must have the same length");
+            n = m; have_n = true;
+            return t.attr("data_ptr")().cast<uintptr_t>();
+        };
+        const uintptr_t a = ptr_of(id, "id", "torch.int64"), b = ptr_of(amount, "amount", "torch.float64"), c = ptr_of(region, "region", "torch.int32"),
+                        d = ptr_of(product_id, "product_id", "torch.int32"), e = ptr_of(timestamp, "timestamp", "torch.int64");
+        if (!have_n) throw py::value_error("from_torch: give at least one column");
+        attach_columns(a, b, c, d, e, n);
+        keep_alive_ = py::make_tuple(id, amount, region, product_id, timestamp);  // the engine borrows the memory
+    }
     uintptr_t column_ptr(const std::string& col) { return reinterpret_cast<uintptr_t>(aqe_column_device_ptr(h_, column_id(col))); }
 
     // ---- exact (cbd:242-274, 646-658) ----
@@ -287,6 +309,7 @@ private:
         check(aqe_create(dev, &h_));
     }
     aqe_db* h_ = nullptr;
+    py::object keep_alive_;
     std::string path_;
     uint64_t seed_ = 0x9E3779B97F4A7C15ull ^ (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count();
     bool fixed_seed_ = false;
@@ -562,6 +585,9 @@ PYBIND11_MODULE(aqe_backend, m) {
         .def("generate_synthetic", &DB::generate_synthetic, py::arg("n_rows"), py::arg("seed") = 7, py::arg("first_row") = 0, py::arg("dist") = 0,
              py::arg("columns_mask") = 0x1f)
         .def("attach_columns", &DB::attach_columns, py::arg("id"), py::arg("amount"), py::arg("region"), py::arg("product_id"), py::arg("timestamp"), py::arg("n"))
+        .def("from_torch", &DB::from_torch, py::arg("id") = py::none(), py::arg("amount") = py::none(), py::arg("region") = py::none(),
+             py::arg("product_id") = py::none(), py::arg("timestamp") = py::none(),
+             "borrow CUDA tensors as the table's columns (zero copy); columns that are never queried may be omitted")
         .def("column_ptr", &DB::column_ptr)
         .def("sum_column", &DB::sum_column)
         .def("scan", &DB::scan, py::arg("agg_col") = "amount", py::arg("pred_col") = py::none(), py::arg("lo") = 0.0, py::arg("hi") = 0.0)

@@ -146,7 +146,11 @@ typedef struct aqe_sample_params {
 
 /* One affine run of sample positions:  for k in [0,count):
  *   kind 0:  idx = base + (k / inner_len) * outer_step + (k % inner_len)
- *   kind 1:  idx = (int64) ((double) k * scale)              (index_based_sample, :462-470)        */
+ *   kind 1:  idx = (int64) ((double) k * scale)              (index_based_sample, :462-470)
+ *   kind 2:  idx = feistel_perm(k; n = base, seed = outer_step, half bits = inner_len): k-th element of a seeded
+ *            pseudo-random permutation of [0, n) -- distinct positions, SRSWOR (sample_records, :345-363)
+ *   kind 3:  idx = (k * outer_step + U_k{0 .. outer_step/2}) mod base, U_k = Philox(seed = inner_len, draw k)
+ *            (address_arithmetic_sample, :1640-1646)                                                   */
 typedef struct aqe_segment {
     int64_t base;
     int64_t outer_step;

@@ -678,34 +678,35 @@ static void gen_optimized_sequential(uint64_t N, double p, uint64_t seed, ivec* 
     }
 }
 
-/* sample_records cbd:345-363: SRSWOR of floor(N*p/100) rows.  Engine stand-in: partial Fisher-Yates with
- * seeded draws; the returned order is the shuffle order (first `k` slots). */
+/* sample_records cbd:345-363: SRSWOR of floor(N*p/100) rows.  The reference shuffles a copy of the table with a
+ * random_device-seeded mt19937, so only the design is pinned (k distinct rows, each k-subset equally likely up to
+ * the quality of the permutation).  Engine design restated here: position j = perm(j), perm = 4-round balanced Feistel
+ * network on the smallest even bit width covering N, splitmix64 round function, cycle-walked into [0, N). */
+static uint64_t feistel_mix(uint64_t r, uint32_t round, uint64_t seed) {
+    uint64_t z = (r + 0x9E3779B97F4A7C15ull * (uint64_t)(round + 1)) ^ seed;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static uint64_t feistel_index(uint64_t k, uint64_t n, uint64_t seed) {
+    uint32_t half = 1;
+    while (half < 32 && (1ull << (2 * half)) < n) ++half;
+    const uint64_t mask = (1ull << half) - 1;
+    uint64_t x = k;
+    do {
+        uint64_t l = x >> half, r = x & mask;
+        for (uint32_t i = 0; i < 4; ++i) { uint64_t t = l ^ (feistel_mix(r, i, seed) & mask); l = r; r = t; }
+        x = (l << half) | r;
+    } while (x >= n);
+    return x;
+}
 static int gen_sample_records(uint64_t N, double p, uint64_t seed, ivec* o) {
     if (N == 0) return 0;
     if (p >= 100.0) { gen_all(N, o); return 0; }
     if (p <= 0.0) return 0;
     uint64_t k = (uint64_t)((double)N * p / 100.0);
     if (k > N) k = N;
-    if (k == 0) return 0;
-    /* sparse Fisher-Yates: open-addressing map of displaced slots */
-    uint64_t cap = 1; while (cap < 4 * k) cap <<= 1;
-    uint64_t* keys = (uint64_t*)malloc(cap * 8); uint64_t* vals = (uint64_t*)malloc(cap * 8);
-    if (!keys || !vals) { free(keys); free(vals); return AQE_ERR_NOMEM; }
-    memset(keys, 0xff, cap * 8);
-#define MAP_GET(K, OUT) do { uint64_t h_ = ((K) * 0x9E3779B97F4A7C15ull) & (cap - 1); OUT = (K); \
-        while (keys[h_] != UINT64_MAX) { if (keys[h_] == (K)) { OUT = vals[h_]; break; } h_ = (h_ + 1) & (cap - 1); } } while (0)
-#define MAP_SET(K, V) do { uint64_t h_ = ((K) * 0x9E3779B97F4A7C15ull) & (cap - 1); \
-        while (keys[h_] != UINT64_MAX && keys[h_] != (K)) h_ = (h_ + 1) & (cap - 1); keys[h_] = (K); vals[h_] = (V); } while (0)
-    for (uint64_t i = 0; i < k; ++i) {
-        uint64_t j = i + seeded_below(seed, AQE_M_SAMPLE_RECORDS, i, N - i);
-        uint64_t vi, vj;
-        MAP_GET(i, vi); MAP_GET(j, vj);
-        push(o, (int64_t)vj);
-        MAP_SET(j, vi);
-    }
-#undef MAP_GET
-#undef MAP_SET
-    free(keys); free(vals);
+    for (uint64_t i = 0; i < k; ++i) push(o, (int64_t)feistel_index(i, N, seed));
     return 0;
 }
 

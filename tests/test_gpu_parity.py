@@ -122,6 +122,26 @@ def test_unaligned_attached_columns(oracle):
         e.close()
 
 
+def test_dropin_from_torch(oracle):
+    import torch
+    b = aqe.backend()
+    rows = oracle.synth(77777, seed=12)
+    amt = torch.from_numpy(rows["amount"].copy()).cuda(); ts = torch.from_numpy(rows["timestamp"].copy()).cuda()
+    db = b.CustomBPlusDB()
+    db.from_torch(amount=amt, timestamp=ts)
+    assert db.get_total_records() == len(rows) and rel(db.sum_amount(), oracle.sum_amount(rows)) <= REL
+    assert db.sum_column("timestamp") == int(rows["timestamp"].astype(object).sum())
+    d = db.scan("amount", "timestamp", 1700000000 + 10, 1700000000 + 50000)
+    q = oracle.scan(rows, "amount", "timestamp", 1700000000 + 10, 1700000000 + 50000)
+    assert d["count"] == q.count and rel(d["sum"], q.sum) <= REL
+    with pytest.raises(ValueError):
+        db.from_torch(amount=amt.float())
+    with pytest.raises(ValueError):
+        db.from_torch(amount=amt.cpu())
+    with pytest.raises(RuntimeError):
+        db.sum_column("id")                                  # column was not handed over
+
+
 def test_special_values(oracle):
     rows = oracle.synth(10000, seed=1)
     rows["amount"][::7] = -rows["amount"][::7]

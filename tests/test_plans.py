@@ -63,10 +63,32 @@ def test_segment_plans_stay_small():
     """The affine samplers never materialise an index list: a handful of segments whatever N is."""
     n = 1_000_000_000
     for m, limit in [("memory_stride", 1), ("slow_pointer", 1), ("block", 2), ("parallel_block", 8), ("parallel_pointer", 4),
-                     ("optimized_clt", 4), ("index_based", 1), ("node_skip", 2), ("multithreaded_memory_stride", 4)]:
+                     ("optimized_clt", 4), ("index_based", 1), ("node_skip", 2), ("multithreaded_memory_stride", 4),
+                     ("sample_records", 1), ("address_arithmetic", 1), ("random_start_nth", 2), ("signal_based_clt", 2)]:
         pl = aqe.build_plan(n, m, aqe.make_params(m, 1.0))
         assert 1 <= pl.num_segments <= limit, (m, pl.num_segments)
         assert pl.count > 0
+
+
+def test_sample_records_is_srswor():
+    """sample_records (custom_bplus_db.cpp:345-363) = k distinct rows, uniformly scattered: the prefix of a seeded permutation."""
+    n = 1_000_003
+    a = aqe.build_plan(n, "sample_records", aqe.make_params("sample_records", 10.0, seed=1)).indices()
+    b = aqe.build_plan(n, "sample_records", aqe.make_params("sample_records", 10.0, seed=2)).indices()
+    assert len(a) == n // 10 and len(np.unique(a)) == len(a) and a.min() >= 0 and a.max() < n
+    assert len(np.intersect1d(a, b)) < 0.12 * len(a)                 # independent seeds overlap ~10 %
+    hist = np.bincount(a * 64 // n, minlength=64)                     # uniform over the table: chi-square, 63 dof
+    exp = len(a) / 64
+    assert ((hist - exp) ** 2 / exp).sum() < 120
+    lag = np.corrcoef(a[:-1].astype(float), a[1:].astype(float))[0, 1]
+    assert abs(lag) < 0.01                                             # consecutive draws are not correlated
+    for small in (1, 2, 3, 5, 16, 17, 1000):                           # a full prefix of the permutation is a bijection
+        pl = aqe.build_plan(small, "sample_records", aqe.make_params("sample_records", 99.9999999, seed=9))
+        full = [aqe.lib().aqe_plan_count(pl.h)]
+        idx = pl.indices()
+        assert len(np.unique(idx)) == len(idx) and (len(idx) == 0 or idx.max() < small)
+    big = aqe.build_plan(10**9, "sample_records", aqe.make_params("sample_records", 10.0, seed=3))
+    assert big.num_segments == 1 and big.count == 10**8              # no index list at any size
 
 
 def test_invalid_arguments_raise_instead_of_ub():
