@@ -244,14 +244,26 @@ def main():
     gathered = torch.zeros(8 * world, dtype=torch.int64, device="cuda")
     host_out = torch.zeros(8 * world, dtype=torch.int64).pin_memory()        # pinned + UVA: kernels can store into it
     fused = world > 1 and not args.no_fused
+    fused_note = None
     if fused:
         # one process per GPU on one NVSwitch box: map every rank's mailbox (CUDA IPC) so that the scan kernel's last
-        # block publishes the shard partial to all peers over NVLink and folds all of them itself
-        mine = eng.exchange_init(rank, world)
-        handles = [None] * world
-        dist.all_gather_object(handles, mine)
-        eng.exchange_connect(handles)
-        eng.exchange_set_total_rows(rows * world)
+        # block publishes the shard partial to all peers over NVLink and folds all of them itself.  If peer mapping is
+        # not possible in this environment every rank switches (together) to the NCCL all-gather path -- still the GPU path.
+        ok = 1
+        try:
+            mine = eng.exchange_init(rank, world)
+            handles = [None] * world
+            dist.all_gather_object(handles, mine)
+            eng.exchange_connect(handles)
+            eng.exchange_set_total_rows(rows * world)
+        except Exception as e:  # noqa: BLE001
+            ok, fused_note = 0, f"CUDA IPC peer mapping unavailable ({e}); NCCL all-gather used"
+        okt = torch.tensor([ok], device="cuda")
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if int(okt.item()) == 0:
+            fused = False
+            fused_note = fused_note or "CUDA IPC peer mapping unavailable on another rank; NCCL all-gather used"
+            args.no_fused = True
         dist.barrier()
 
     if fused:
@@ -400,7 +412,7 @@ def main():
                              "kernel": "aqe::k_scan_ring<double, PRED=1 (amount on itself), double, STAGES=4, MOMENTS=false> (TMA bulk-copy ring, 16 KiB tiles, 2 CTAs/SM)", "kernel_ms": kms,
                              "kernel_ms_source": "timed region (a step is exactly one launch of this kernel)" if step_is_one_kernel else "kernel-only loop, same stream",
                              "kernel_ms_isolated_loop": kern_ms / args.steps, "algorithmic_bytes_per_launch": 8 * rows, "peak_source": peak_src},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clk, "approx": approx, "approx_multi_gpu": approx_multi,
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clk, "approx": approx, "approx_multi_gpu": approx_multi, "exchange": ("fused in-kernel NVLink mailbox" if fused else ("nccl all_gather" if world > 1 else None)), "exchange_note": fused_note,
                 "result": {"count": merged.count, "sum": merged.sum}}
         print(json.dumps(line), flush=True)
     if world > 1:
