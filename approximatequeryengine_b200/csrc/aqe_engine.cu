@@ -661,6 +661,8 @@ static int scan_launch(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, ui
                        cudaStream_t s, bool exchange = false) {
     const int ak = col_kind(spec->agg_col);
     if (ak < 0) return fail(AQE_ERR_INVALID, "bad aggregate column");
+    if (ak != K_F64 && n > (1ull << 32))  // the split 32/32-bit integer accumulators are exact up to 2^32 rows per launch
+        return fail(AQE_ERR_UNSUPPORTED, "integer aggregates over more than 2^32 rows per shard: split the shard");
     const char* agg = static_cast<const char*>(col_ptr(db, spec->agg_col));
     if (!agg && n) return fail(AQE_ERR_STATE, "aggregate column is not resident on the device");
     int pred_mode = 0, pk = ak;

@@ -278,17 +278,23 @@ def test_samplers_against_reference_golden(tables, oracle):
                 assert rel(ahi - alo, fhex(v["est"]["avg_ci"][1]) - fhex(v["est"]["avg_ci"][0])) <= 1e-9, tag
 
 
-def test_samplers_1m_cli_methods(tables):
+def test_samplers_1m_all_reference_vectors(tables):
+    """All 144 sampler vectors minted from the reference at 1 M rows: identical rows, estimator parity on the stats path."""
     big = [t for t in tables if t[0]["n"] == 1000000]
     if not big:
         pytest.skip("1M golden not present")
     g, rows, e = big[0]
     for v in g["samplers"]:
-        if v["kw"] or v["method"] not in ("memory_stride", "parallel_pointer", "block", "parallel_block", "optimized_clt",
-                                           "random_pointer", "index_based", "adaptive_block", "stratified_block", "balanced_tree"):
-            continue
-        got = e.gather(e.plan(v["method"], aqe.make_params(v["method"], v["percent"])))
-        assert len(got) == v["count"] and sha(got["id"] - 1) == v["idx_sha256"], (v["method"], v["percent"])
+        pl = e.plan(v["method"], aqe.make_params(v["method"], v["percent"], **v["kw"]))
+        got = e.gather(pl)
+        tag = (v["method"], v["percent"], v["kw"])
+        assert len(got) == v["count"] and sha(got["id"] - 1) == v["idx_sha256"], tag
+        if v["est"] and "m2" in v["est"]:
+            s = e.stats(pl)
+            assert rel(s.sum, fhex(v["est"]["sample_sum"])) <= REL, tag
+            assert rel(aqe.estimate(s, g["n"], "sum", 1.96, True)[0], fhex(v["est"]["sum"])) <= REL, tag
+            if fhex(v["est"]["m2"]) > 0:
+                assert rel(s.m2, fhex(v["est"]["m2"])) <= 1e-9, tag
 
 
 def test_same_index_list_estimates(tables, oracle):
