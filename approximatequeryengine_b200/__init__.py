@@ -100,6 +100,43 @@ class ApproxResult(C.Structure):
     ]
 
 
+class SqlTerm(C.Structure):
+    _fields_ = [("col", C.c_int32), ("has_ne", C.c_int32), ("lo", C.c_double), ("hi", C.c_double),
+                ("ilo", C.c_int64), ("ihi", C.c_int64), ("ne", C.c_double), ("ine", C.c_int64)]
+
+
+class SqlQuery(C.Structure):
+    """Parsed + compiled query: the reference's ``struct Query`` (parser.h:17-24) with names resolved."""
+    _fields_ = [("agg", C.c_int32), ("agg_col", C.c_int32), ("group_col", C.c_int32), ("sample_percent", C.c_int32),
+                ("n_terms", C.c_int32), ("always_false", C.c_int32), ("terms", SqlTerm * 5),
+                ("agg_text", C.c_char * 32), ("column", C.c_char * 64), ("table", C.c_char * 64),
+                ("group_by", C.c_char * 64), ("where", C.c_char * 512)]
+
+
+class SqlRow(C.Structure):
+    _fields_ = [("key", C.c_int64), ("value", C.c_double), ("ci_lower", C.c_double), ("ci_upper", C.c_double),
+                ("count", C.c_uint64), ("sum", C.c_double), ("sumsq", C.c_double), ("isum_lo", C.c_uint64),
+                ("isum_hi", C.c_int64), ("is_null", C.c_int32), ("_pad", C.c_int32)]
+
+    @property
+    def isum(self) -> int:
+        return (int(self.isum_hi) << 64) + int(self.isum_lo)
+
+
+class SqlFacts(C.Structure):
+    _fields_ = [("key_min", C.c_int64), ("key_max", C.c_int64), ("agg_absmax", C.c_double),
+                ("agg_is_integer", C.c_int32), ("_pad", C.c_int32)]
+
+
+class SqlLayout(C.Structure):
+    _fields_ = [("key_min", C.c_int64), ("n_groups", C.c_uint32), ("sum_shift", C.c_int32), ("sq_shift", C.c_int32),
+                ("is_integer", C.c_int32)]
+
+
+SQL_MODE = {"value": 0, "ci_reference": 1, "ci_correct": 2}
+SQL_MOMENTS, SQL_UNSAMPLED = 1, 2
+SQL_MAX_GROUPS = 4096
+
 _lib = None
 
 
@@ -169,6 +206,15 @@ def lib() -> C.CDLL:
         "aqe_approx_exchange": (i32, [vp, C.POINTER(ApproxSpec), C.POINTER(ApproxResult)]),
         "aqe_approx_merge": (i32, [C.POINTER(ApproxResult), i32, i32, dbl, C.POINTER(ApproxResult)]),
         "aqe_z_score": (dbl, [dbl, i32]),
+        "aqe_sql_parse": (i32, [C.c_char_p, i32, C.POINTER(SqlQuery)]),
+        "aqe_sql_execute": (i32, [vp, C.POINTER(SqlQuery), i32, C.POINTER(SqlRow), C.c_uint32, C.POINTER(C.c_uint32)]),
+        "aqe_sql_run": (i32, [vp, C.c_char_p, i32, i32, C.POINTER(SqlRow), C.c_uint32, C.POINTER(C.c_uint32)]),
+        "aqe_sql_facts_of": (i32, [vp, C.POINTER(SqlQuery), C.POINTER(SqlFacts)]),
+        "aqe_sql_layout_of": (i32, [C.POINTER(SqlQuery), C.POINTER(SqlFacts), i32, C.POINTER(SqlLayout)]),
+        "aqe_sql_scan": (i32, [vp, C.POINTER(SqlQuery), C.POINTER(SqlLayout), i32, vp]),
+        "aqe_sql_merge": (i32, [vp, vp, C.c_uint32]),
+        "aqe_sql_finish": (i32, [C.POINTER(SqlQuery), i32, C.POINTER(SqlLayout), vp, vp, C.POINTER(SqlRow), C.c_uint32, C.POINTER(C.c_uint32)]),
+        "aqe_sql_shifts": (i32, [dbl, i32, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -441,11 +487,56 @@ class Engine:
     def exchange_set_total_rows(self, total_rows: int) -> None:
         check(self.L.aqe_exchange_set_total_rows(self.h, total_rows))
 
+    # ---- SQL-string path (run_query*, bindings.cpp:126-136) ----
+    def sql(self, query: str, sample_percent: int = 0, mode: str = "value"):
+        """List of SqlRow (one without GROUP BY), ascending key."""
+        rows = (SqlRow * SQL_MAX_GROUPS)()
+        n = C.c_uint32()
+        check(self.L.aqe_sql_run(self.h, query.encode(), sample_percent, SQL_MODE[mode], rows, SQL_MAX_GROUPS, C.byref(n)))
+        return list(rows[: n.value])
+
+    def sql_facts(self, q: SqlQuery) -> SqlFacts:
+        f = SqlFacts()
+        check(self.L.aqe_sql_facts_of(self.h, C.byref(q), C.byref(f)))
+        return f
+
+    def sql_scan(self, q: SqlQuery, layout: SqlLayout, flags: int = 0) -> np.ndarray:
+        acc = np.zeros(layout.n_groups * 5, dtype=np.uint64)
+        check(self.L.aqe_sql_scan(self.h, C.byref(q), C.byref(layout), flags, _ptr(acc)))
+        return acc
+
 
 def estimate(stats: Stats, population: int, agg: str, z: float = 1.96, legacy_ci: bool = False):
     e, lo, hi = C.c_double(), C.c_double(), C.c_double()
     check(lib().aqe_estimate(C.byref(stats), population, AGG[agg], z, int(legacy_ci), C.byref(e), C.byref(lo), C.byref(hi)))
     return e.value, lo.value, hi.value
+
+
+def sql_parse(query: str, sample_percent: int = 0) -> SqlQuery:
+    """Host-only: the reference's parser (parser.cpp:20-75) + WHERE compilation."""
+    q = SqlQuery()
+    check(lib().aqe_sql_parse(query.encode(), sample_percent, C.byref(q)))
+    return q
+
+
+def sql_layout(q: SqlQuery, facts) -> SqlLayout:
+    arr = (SqlFacts * len(facts))(*facts)
+    out = SqlLayout()
+    check(lib().aqe_sql_layout_of(C.byref(q), arr, len(facts), C.byref(out)))
+    return out
+
+
+def sql_merge(acc: np.ndarray, other: np.ndarray) -> np.ndarray:
+    check(lib().aqe_sql_merge(_ptr(acc), _ptr(np.ascontiguousarray(other, dtype=np.uint64)), len(acc) // 5))
+    return acc
+
+
+def sql_finish(q: SqlQuery, layout: SqlLayout, acc: np.ndarray, mode: str = "value", exists: np.ndarray | None = None):
+    rows = (SqlRow * max(layout.n_groups, 1))()
+    n = C.c_uint32()
+    check(lib().aqe_sql_finish(C.byref(q), SQL_MODE[mode], C.byref(layout), _ptr(acc), _ptr(exists) if exists is not None else None,
+                               rows, layout.n_groups, C.byref(n)))
+    return list(rows[: n.value])
 
 
 def synth_rows_host(n: int, seed: int = 7, first_row: int = 0, dist: int = 0) -> np.ndarray:

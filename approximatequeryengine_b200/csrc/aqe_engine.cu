@@ -25,6 +25,8 @@
 #include "aqe_b200.h"
 #include "aqe_kernels.cuh"
 #include "aqe_plan.hpp"
+#include "aqe_sql.hpp"
+#include "aqe_sql_kernels.cuh"
 
 using namespace aqe;
 
@@ -96,6 +98,15 @@ struct aqe_db {
     unsigned long long ax_msg = 0;       // next message index of the sampled-estimate exchange (lock-step on all ranks)
     uint64_t ex_total_rows = 0;          // rows of the whole table (all shards)
     bool ex_connected = false;
+
+    // SQL-string path (aqe_sql_*): lazily computed column statistics + accumulators of the grouped scan
+    struct ColStat { bool valid = false; unsigned long long min_key = 0, max_key = 0; bool dense = false; long long first_id = 0; };
+    ColStat col_stat[5];
+    unsigned long long* sql_acc = nullptr;       // [AQE_SQL_MAX_GROUPS][5], device, all zero between launches
+    unsigned long long* sql_out_host = nullptr;  // same shape, mapped pinned: the last CTA writes it
+    unsigned long long* sql_out_dev = nullptr;
+    unsigned long long* sql_stat_dev = nullptr;  // [3] min key, max key, not-dense flag
+    unsigned int* sql_ticket = nullptr;
 };
 
 static const int kMaxGrid = 148 * 16;
@@ -132,6 +143,7 @@ static void free_columns(aqe_db* db) {
     }
     db->col = MutColumns{nullptr, nullptr, nullptr, nullptr, nullptr};
     if (db->amount_perm) { cudaFree(db->amount_perm); db->amount_perm = nullptr; }
+    for (auto& st : db->col_stat) st.valid = false;
     db->n = 0; db->owned = true;
 }
 
@@ -325,6 +337,8 @@ int aqe_close(aqe_db* db) {
         free_columns(db);
         cudaFree(db->scan_partials); cudaFree(db->stat_partials); cudaFree(db->approx_slots); cudaFree(db->tickets);
         cudaFree(db->gather_buf); cudaFree(db->plan_buf);
+        cudaFree(db->sql_acc); cudaFree(db->sql_stat_dev); cudaFree(db->sql_ticket);
+        if (db->sql_out_host) cudaFreeHost(db->sql_out_host);
         for (int r = 0; r < db->ex_world; ++r)
             if (db->ex_connected && r != db->ex_rank && db->ex_peers[r]) cudaIpcCloseMemHandle(db->ex_peers[r]);
         cudaFree(db->ex_mailbox);
@@ -1548,6 +1562,263 @@ int aqe_approx_merge(const aqe_approx_result* parts, int n, int agg, double conf
     r.confidence_level = confidence_level; r.population = pop; r.status = worst;
     *out = r;
     return AQE_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// SQL-string path: run_query* of bindings.cpp:126-136 on the columnar table
+// ------------------------------------------------------------------------------------------------
+static int sql_init(aqe_db* db) {
+    if (db->sql_acc) return AQE_OK;
+    const size_t bytes = sizeof(unsigned long long) * 5 * AQE_SQL_MAX_GROUPS;
+    CU(cudaMalloc(&db->sql_acc, bytes));
+    CU(cudaMemset(db->sql_acc, 0, bytes));
+    CU(cudaMalloc(&db->sql_stat_dev, 3 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&db->sql_ticket, sizeof(unsigned int)));
+    CU(cudaMemset(db->sql_ticket, 0, sizeof(unsigned int)));
+    CU(cudaHostAlloc(&db->sql_out_host, bytes, cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer(&db->sql_out_dev, db->sql_out_host, 0));
+    return AQE_OK;
+}
+
+// min / max of a column (and, for id, whether ids are first_id + row), computed once per table version
+static int sql_col_stat(aqe_db* db, int col, const aqe_db::ColStat** out) {
+    aqe_db::ColStat& st = db->col_stat[col];
+    if (!st.valid) {
+        const void* ptr = col_ptr(db, col);
+        if (!ptr && db->n) return fail(AQE_ERR_STATE, "a column the query needs is not resident on the device");
+        st.min_key = ~0ull; st.max_key = 0ull; st.dense = false; st.first_id = 0;
+        if (db->n) {
+            const unsigned long long init[3] = {~0ull, 0ull, 0ull};
+            CU(cudaMemcpyAsync(db->sql_stat_dev, init, sizeof(init), cudaMemcpyHostToDevice, db->stream));
+            ColStatsArgs a;
+            a.col = ptr; a.kind = col_kind(col); a.n = db->n; a.check_dense = col == AQE_COL_ID ? 1 : 0; a.first_id = 0; a.out = db->sql_stat_dev;
+            if (a.check_dense) {
+                CU(cudaMemcpyAsync(&a.first_id, ptr, 8, cudaMemcpyDeviceToHost, db->stream));
+                CU(cudaStreamSynchronize(db->stream));
+            }
+            k_col_stats<<<grid_for(db, db->n, 8, 256, 8), 256, 0, db->stream>>>(a);
+            LAUNCHED();
+            CU(cudaGetLastError());
+            unsigned long long res[3];
+            CU(cudaMemcpyAsync(res, db->sql_stat_dev, sizeof(res), cudaMemcpyDeviceToHost, db->stream));
+            CU(cudaStreamSynchronize(db->stream));
+            st.min_key = res[0]; st.max_key = res[1];
+            st.dense = a.check_dense && res[2] == 0;
+            st.first_id = a.first_id;
+        }
+        st.valid = true;
+    }
+    *out = &st;
+    return AQE_OK;
+}
+
+static double okey_f64(unsigned long long k) {
+    const unsigned long long b = okey_to_bits_f64(k);
+    double d;
+    std::memcpy(&d, &b, 8);
+    return d;
+}
+
+template <int MODE, bool MOMENTS> static int sql_launch_v(const aqe_db* db, const SqlArgs& a, bool vec, size_t smem, cudaStream_t s) {
+    const void* k = vec ? (const void*)k_sql_agg<MODE, MOMENTS, true> : (const void*)k_sql_agg<MODE, MOMENTS, false>;
+    const int occ = kernel_occupancy(k, kSqlThreads, smem);
+    const uint64_t items = vec ? (a.count + 3) / 4 : a.count;
+    const int grid = grid_for(db, items, 1, kSqlThreads, occ);
+    if (vec) k_sql_agg<MODE, MOMENTS, true><<<grid, kSqlThreads, smem, s>>>(a);
+    else k_sql_agg<MODE, MOMENTS, false><<<grid, kSqlThreads, smem, s>>>(a);
+    LAUNCHED();
+    return AQE_OK;
+}
+
+static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* L, int flags, uint64_t* acc) {
+    const uint32_t G = L->n_groups;
+    if (G < 1 || G > AQE_SQL_MAX_GROUPS) return fail(AQE_ERR_INVALID, "layout: n_groups out of range");
+    std::memset(acc, 0, sizeof(uint64_t) * 5 * G);
+    if (q->always_false || db->n == 0) return AQE_OK;
+    if (db->n > (1ull << 32)) return fail(AQE_ERR_UNSUPPORTED, "SQL path: more than 2^32 rows per shard: split the shard");
+    int rc = sql_init(db);
+    if (rc) return rc;
+    const bool unsampled = (flags & AQE_SQL_UNSAMPLED) != 0;
+    const bool moments = (flags & AQE_SQL_MOMENTS) != 0 && !unsampled;
+    const bool sums = q->agg_col != AQE_COL_NONE && !unsampled && (q->agg != AQE_AGG_COUNT || moments);
+    const int step = unsampled ? 0 : sql_sample_step(q->sample_percent);
+
+    SqlArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.agg_slot = -1; a.group_slot = -1;
+    auto slot_of = [&](int col) -> int {
+        const void* ptr = col_ptr(db, col);
+        for (int i = 0; i < a.ncols; ++i) if (a.cols[i].ptr == ptr) return i;
+        a.cols[a.ncols].ptr = ptr; a.cols[a.ncols].kind = col_kind(col);
+        return a.ncols++;
+    };
+    auto need = [&](int col) -> int {
+        if (col_kind(col) < 0) return fail(AQE_ERR_INVALID, "bad column in query");
+        if (!col_ptr(db, col)) return fail(AQE_ERR_STATE, "a column the query needs is not resident on the device");
+        return AQE_OK;
+    };
+    if (sums) {
+        if ((rc = need(q->agg_col))) return rc;
+        a.agg_slot = slot_of(q->agg_col); a.agg_kind = col_kind(q->agg_col);
+    }
+    if (q->group_col != AQE_COL_NONE) {
+        if ((rc = need(q->group_col))) return rc;
+        a.group_slot = slot_of(q->group_col);
+    }
+    for (int t = 0; t < q->n_terms; ++t) {
+        const aqe_sql_term& term = q->terms[t];
+        if ((rc = need(term.col))) return rc;
+        SqlCol& c = a.cols[slot_of(term.col)];
+        c.has_pred = 1; c.has_ne = term.has_ne;
+        if (c.kind == K_F64) { std::memcpy(&c.lo, &term.lo, 8); std::memcpy(&c.hi, &term.hi, 8); std::memcpy(&c.ne, &term.ne, 8); }
+        else { c.lo = term.ilo; c.hi = term.ihi; c.ne = term.ine; }
+    }
+    a.first = 0; a.stride = 1; a.count = db->n;
+    if (step > 1) {  // rowid % step = 0 (executor.cpp:38-42); rowid = id
+        if ((rc = need(AQE_COL_ID))) return rc;
+        const aqe_db::ColStat* ids;
+        if ((rc = sql_col_stat(db, AQE_COL_ID, &ids))) return rc;
+        if (ids->dense) {
+            // ids are first_id + row: the sampled rows are an arithmetic progression of row numbers, visited directly
+            const long long r = ((ids->first_id % step) + step) % step;
+            a.first = (uint64_t)((step - r) % step); a.stride = (uint64_t)step;
+            a.count = a.first < db->n ? (db->n - a.first + step - 1) / step : 0;
+        } else {
+            a.cols[slot_of(AQE_COL_ID)].mod_step = step;
+        }
+    }
+    if (a.count == 0) return AQE_OK;
+    if (a.ncols == 0) {  // COUNT without WHERE / GROUP BY: metadata (0 bytes per record)
+        acc[0] = a.count;
+        return AQE_OK;
+    }
+    a.key_min = L->key_min; a.n_groups = G;
+    a.sum_scale = std::ldexp(1.0, L->sum_shift); a.sq_scale = std::ldexp(1.0, L->sq_shift);
+    a.global_acc = db->sql_acc; a.out = db->sql_out_dev; a.ticket = db->sql_ticket;
+    bool vec = a.stride == 1;
+    for (int i = 0; i < a.ncols; ++i) vec = vec && ((uintptr_t)a.cols[i].ptr % 32) == 0;
+    const int mode = a.group_slot < 0 ? 0 : (G <= (uint32_t)kSqlPrivateMaxGroups ? 1 : 2);
+    size_t smem = 0;
+    if (mode == 1) smem = (size_t)G * kSqlThreads * (4 + 16 + (moments ? 16 : 0));
+    if (mode == 2) smem = (size_t)G * (4 + 16 + (moments ? 16 : 0));
+    cudaStream_t s = db->stream;
+    if (mode == 0) rc = moments ? sql_launch_v<0, true>(db, a, vec, smem, s) : sql_launch_v<0, false>(db, a, vec, smem, s);
+    else if (mode == 1) rc = moments ? sql_launch_v<1, true>(db, a, vec, smem, s) : sql_launch_v<1, false>(db, a, vec, smem, s);
+    else rc = moments ? sql_launch_v<2, true>(db, a, vec, smem, s) : sql_launch_v<2, false>(db, a, vec, smem, s);
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(db->stream));
+    std::memcpy(acc, db->sql_out_host, sizeof(uint64_t) * 5 * G);
+    return AQE_OK;
+}
+
+extern "C" {
+
+int aqe_sql_parse(const char* sql, int sample_percent, aqe_sql_query* out) {
+    if (!sql || !out) return fail(AQE_ERR_INVALID, "NULL argument");
+    std::string err;
+    const int rc = sql_parse(sql, sample_percent, *out, err);
+    return rc ? fail(rc, err) : AQE_OK;
+}
+
+int aqe_sql_facts_of(aqe_db* db, const aqe_sql_query* q, aqe_sql_facts* out) {
+    if (!db || !q || !out) return fail(AQE_ERR_INVALID, "NULL argument");
+    std::memset(out, 0, sizeof(*out));
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    rc = sql_init(db);
+    if (rc) return rc;
+    out->key_min = 0; out->key_max = db->n ? 0 : -1;
+    if (q->group_col != AQE_COL_NONE) {
+        if (col_kind(q->group_col) < 0 || col_kind(q->group_col) == K_F64) return fail(AQE_ERR_INVALID, "GROUP BY needs an integer column");
+        const aqe_db::ColStat* st;
+        if ((rc = sql_col_stat(db, q->group_col, &st))) return rc;
+        if (db->n) { out->key_min = okey_to_i64(st->min_key); out->key_max = okey_to_i64(st->max_key); }
+    }
+    if (q->agg_col != AQE_COL_NONE) {
+        const int k = col_kind(q->agg_col);
+        if (k < 0) return fail(AQE_ERR_INVALID, "bad aggregate column");
+        out->agg_is_integer = k != K_F64;
+        const aqe_db::ColStat* st;
+        if ((rc = sql_col_stat(db, q->agg_col, &st))) return rc;
+        if (db->n) {
+            const double lo = k == K_F64 ? okey_f64(st->min_key) : (double)okey_to_i64(st->min_key);
+            const double hi = k == K_F64 ? okey_f64(st->max_key) : (double)okey_to_i64(st->max_key);
+            out->agg_absmax = (lo != lo || hi != hi) ? NAN : std::max(std::fabs(lo), std::fabs(hi));
+        }
+    }
+    return AQE_OK;
+}
+
+int aqe_sql_layout_of(const aqe_sql_query* q, const aqe_sql_facts* facts, int n_shards, aqe_sql_layout* out) {
+    if (!q || !facts || !out || n_shards < 1) return fail(AQE_ERR_INVALID, "bad argument");
+    std::string err;
+    const int rc = sql_layout(*q, facts, n_shards, *out, err);
+    return rc ? fail(rc, err) : AQE_OK;
+}
+
+int aqe_sql_shifts(double agg_absmax, int agg_is_integer, int* sum_shift, int* sq_shift) {
+    int a = 0, b = 0;
+    std::string err;
+    const int rc = sql_shifts(agg_absmax, agg_is_integer != 0, a, b, err);
+    if (rc) return fail(rc, err);
+    if (sum_shift) *sum_shift = a;
+    if (sq_shift) *sq_shift = b;
+    return AQE_OK;
+}
+
+int aqe_sql_scan(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* layout, int flags, uint64_t* acc) {
+    if (!db || !q || !layout || !acc) return fail(AQE_ERR_INVALID, "NULL argument");
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    return sql_scan_impl(db, q, layout, flags, acc);
+}
+
+int aqe_sql_merge(uint64_t* acc, const uint64_t* other, uint32_t n_groups) {
+    if (!acc || !other) return fail(AQE_ERR_INVALID, "NULL argument");
+    sql_merge(acc, other, n_groups);
+    return AQE_OK;
+}
+
+int aqe_sql_finish(const aqe_sql_query* q, int mode, const aqe_sql_layout* layout, const uint64_t* acc, const uint64_t* exists,
+                   aqe_sql_row* rows, uint32_t cap, uint32_t* n_rows) {
+    if (!q || !layout || !acc) return fail(AQE_ERR_INVALID, "NULL argument");
+    std::string err;
+    const int rc = sql_finish(*q, mode, *layout, acc, exists, rows, cap, n_rows, err);
+    return rc ? fail(rc, err) : AQE_OK;
+}
+
+int aqe_sql_execute(aqe_db* db, const aqe_sql_query* q, int mode, aqe_sql_row* rows, uint32_t cap, uint32_t* n_rows) {
+    if (!db || !q) return fail(AQE_ERR_INVALID, "NULL argument");
+    aqe_sql_facts facts;
+    int rc = aqe_sql_facts_of(db, q, &facts);
+    if (rc) return rc;
+    aqe_sql_layout L;
+    if ((rc = aqe_sql_layout_of(q, &facts, 1, &L))) return rc;
+    std::vector<uint64_t> acc((size_t)L.n_groups * 5), exists;
+    const int flags = sql_needs_moments(*q, mode) ? AQE_SQL_MOMENTS : 0;
+    if ((rc = sql_scan_impl(db, q, &L, flags, acc.data()))) return rc;
+    const uint64_t* ex = nullptr;
+    if (q->group_col != AQE_COL_NONE && sql_sample_step(q->sample_percent) > 1) {
+        // a group none of whose rows were sampled still exists for the reference (SELECT DISTINCT runs unsampled)
+        bool hole = false;
+        for (uint32_t g = 0; g < L.n_groups && !hole; ++g) hole = acc[(size_t)g * 5] == 0;
+        if (hole) {
+            exists.resize(acc.size());
+            if ((rc = sql_scan_impl(db, q, &L, AQE_SQL_UNSAMPLED, exists.data()))) return rc;
+            ex = exists.data();
+        }
+    }
+    return aqe_sql_finish(q, mode, &L, acc.data(), ex, rows, cap, n_rows);
+}
+
+int aqe_sql_run(aqe_db* db, const char* sql, int sample_percent, int mode, aqe_sql_row* rows, uint32_t cap, uint32_t* n_rows) {
+    aqe_sql_query q;
+    const int rc = aqe_sql_parse(sql, sample_percent, &q);
+    if (rc) return rc;
+    return aqe_sql_execute(db, &q, mode, rows, cap, n_rows);
 }
 
 }  // extern "C"

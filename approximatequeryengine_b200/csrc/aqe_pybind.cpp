@@ -15,14 +15,19 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
+
+#include <sys/stat.h>
 
 #include "aqe_b200.h"
 
@@ -301,6 +306,43 @@ public:
 
     aqe_db* handle() { return h_; }
 
+    // ---- SQL-string path on this table (the four run_query* functions of bindings.cpp:126-136 without the file) ----
+    // grouped = the *_groupby forms; ci: 0 value, 1 the reference's interval (executor.cpp:177-338), 2 corrected interval
+    std::vector<aqe_sql_row> sql(const std::string& query, int sample_percent, bool grouped, int ci) {
+        // every failure of the reference's SQL path is a std::runtime_error (parser.cpp:32, :64, :72; core/db.cpp:40)
+        auto check = [](int rc) { if (rc != AQE_OK) throw std::runtime_error(aqe_last_error()); };
+        aqe_sql_query q;
+        check(aqe_sql_parse(query.c_str(), sample_percent, &q));
+        if (grouped) {
+            if (q.group_col == AQE_COL_NONE) throw std::runtime_error("No GROUP BY column found");  // executor.cpp:63
+        } else {
+            q.group_col = AQE_COL_NONE;  // execute_query never looks at q.group_by (executor.cpp:28-58)
+        }
+        std::vector<aqe_sql_row> rows(grouped ? AQE_SQL_MAX_GROUPS : 1);
+        uint32_t n = 0;
+        check(aqe_sql_execute(h_, &q, ci, rows.data(), (uint32_t)rows.size(), &n));
+        rows.resize(std::min<size_t>(n, rows.size()));
+        for (const aqe_sql_row& r : rows)
+            if (r.is_null) throw std::invalid_argument("stod");  // std::stod("NULL"), executor.cpp:46 -> ValueError
+        return rows;
+    }
+    double query(const std::string& q, int p) { return sql(q, p, false, AQE_SQL_VALUE)[0].value; }
+    QueryResult query_with_ci(const std::string& q, int p, bool correct) {
+        const aqe_sql_row r = sql(q, p, false, correct ? AQE_SQL_CI_CORRECT : AQE_SQL_CI_REFERENCE)[0];
+        return QueryResult{r.value, r.ci_lower, r.ci_upper};
+    }
+    std::map<std::string, double> query_groupby(const std::string& q, int p) {
+        std::map<std::string, double> out;  // std::map<std::string, ...> as in executor.h:5: keys sort as text
+        for (const aqe_sql_row& r : sql(q, p, true, AQE_SQL_VALUE)) out[std::to_string(r.key)] = r.value;
+        return out;
+    }
+    std::map<std::string, QueryResult> query_groupby_with_ci(const std::string& q, int p, bool correct) {
+        std::map<std::string, QueryResult> out;
+        for (const aqe_sql_row& r : sql(q, p, true, correct ? AQE_SQL_CI_CORRECT : AQE_SQL_CI_REFERENCE))
+            out[std::to_string(r.key)] = QueryResult{r.value, r.ci_lower, r.ci_upper};
+        return out;
+    }
+
 private:
     void reset() {
         const int dev = aqe_device(h_);
@@ -430,11 +472,42 @@ private:
     double error_threshold_;
 };
 
-[[noreturn]] void sqlite_path() {
-    throw std::runtime_error(
-        "aqe_backend.run_query*: the SQL-string path of the reference runs on SQLite files (executor.cpp, core/db.cpp); "
-        "it is outside the record-file hot path this engine replaces (DESIGN.md, out of scope)");
-}
+// ---- run_query*(sql, db_path, ...): tables opened by path ------------------------------------------------------
+// The reference opens the SQLite file anew for every call (core/db.cpp:18-24).  Here db_path names a record file
+// (custom_bplus_db.cpp:665-683); loading it into HBM per call would dominate, so the last few tables stay resident,
+// keyed by path and invalidated when the file's size or mtime changes.
+struct TableCache {
+    struct Entry { std::string path; off_t size; int64_t mtime_ns; std::unique_ptr<CustomBPlusDB> db; uint64_t used; };
+    std::vector<Entry> entries;
+    uint64_t tick = 0;
+    static constexpr size_t kMax = 4;
+    CustomBPlusDB& get(const std::string& path) {
+        struct stat st;
+        if (::stat(path.c_str(), &st) != 0) throw std::runtime_error("Cannot open database: unable to open database file");  // core/db.cpp:19-23
+        const int64_t mt = (int64_t)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec;
+        for (auto& e : entries)
+            if (e.path == path) {
+                if (e.size == st.st_size && e.mtime_ns == mt) { e.used = ++tick; return *e.db; }
+                e.db.reset();
+            }
+        entries.erase(std::remove_if(entries.begin(), entries.end(), [](const Entry& e) { return !e.db; }), entries.end());
+        char magic[16] = {0};
+        if (FILE* f = std::fopen(path.c_str(), "rb")) { const size_t got = std::fread(magic, 1, 16, f); (void)got; std::fclose(f); }
+        if (std::memcmp(magic, "SQLite format 3", 15) == 0)
+            throw std::runtime_error("run_query: '" + path + "' is a SQLite file; this engine runs the SQL path on the record file that "
+                                     "CustomBPlusDB.save_to_file writes (INTEGRATION.md, section 7)");
+        auto db = std::make_unique<CustomBPlusDB>();
+        if (!db->load_from_file(path)) throw std::runtime_error("Cannot open database: not a record file: " + path);
+        if (entries.size() >= kMax) {
+            auto lru = std::min_element(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return a.used < b.used; });
+            entries.erase(lru);
+        }
+        entries.push_back(Entry{path, st.st_size, mt, std::move(db), ++tick});
+        return *entries.back().db;
+    }
+    void clear() { entries.clear(); }
+};
+TableCache& table_cache() { static TableCache* c = new TableCache(); return *c; }  // leaked on purpose: no CUDA calls at exit
 
 }  // namespace
 
@@ -591,6 +664,11 @@ PYBIND11_MODULE(aqe_backend, m) {
         .def("column_ptr", &DB::column_ptr)
         .def("sum_column", &DB::sum_column)
         .def("scan", &DB::scan, py::arg("agg_col") = "amount", py::arg("pred_col") = py::none(), py::arg("lo") = 0.0, py::arg("hi") = 0.0)
+        .def("query", &DB::query, py::arg("sql_query"), py::arg("sample_percent") = 0, "run_query on this table")
+        .def("query_groupby", &DB::query_groupby, py::arg("sql_query"), py::arg("sample_percent") = 0, "run_query_groupby on this table")
+        .def("query_with_ci", &DB::query_with_ci, py::arg("sql_query"), py::arg("sample_percent") = 0, py::arg("correct_ci") = false,
+             "run_query_with_ci on this table; correct_ci=True scales the SUM interval as a total")
+        .def("query_groupby_with_ci", &DB::query_groupby_with_ci, py::arg("sql_query"), py::arg("sample_percent") = 0, py::arg("correct_ci") = false)
         .def("set_seed", &DB::set_seed, py::arg("seed") = py::none(), "fix the seed that replaces std::random_device (None = fresh per call)")
         .def("sample_array",
              [](DB& d, const std::string& method, double pct, py::kwargs kw) {
@@ -657,14 +735,17 @@ PYBIND11_MODULE(aqe_backend, m) {
         .def_property_readonly("db", &S::db, py::return_value_policy::reference_internal)
         .def_static("_where_conditions", &where_conditions);
 
-    m.def("run_query", [](const std::string&, const std::string&, int) -> double { sqlite_path(); }, "SQLite SQL-string path (not part of this engine)",
-          py::arg("sql_query"), py::arg("db_path"), py::arg("sample_percent") = 0);
-    m.def("run_query_groupby", [](const std::string&, const std::string&, int, int) -> std::map<std::string, double> { sqlite_path(); },
-          py::arg("sql_query"), py::arg("db_path"), py::arg("sample_percent") = 0, py::arg("num_threads") = 4);
-    m.def("run_query_with_ci", [](const std::string&, const std::string&, int) -> QueryResult { sqlite_path(); },
-          py::arg("sql_query"), py::arg("db_path"), py::arg("sample_percent") = 0);
-    m.def("run_query_groupby_with_ci", [](const std::string&, const std::string&, int, int) -> std::map<std::string, QueryResult> { sqlite_path(); },
-          py::arg("sql_query"), py::arg("db_path"), py::arg("sample_percent") = 0, py::arg("num_threads") = 4);
+    // bindings.cpp:126-136.  db_path names a record file (save_to_file format), not a SQLite file; num_threads is accepted
+    // and ignored (one grouped-scan kernel serves every group).
+    m.def("run_query", [](const std::string& q, const std::string& path, int p) { return table_cache().get(path).query(q, p); },
+          "Execute SQL query with sampling and automatic scaling", py::arg("sql_query"), py::arg("db_path"), py::arg("sample_percent") = 0);
+    m.def("run_query_groupby", [](const std::string& q, const std::string& path, int p, int) { return table_cache().get(path).query_groupby(q, p); },
+          "Execute GROUP BY query with sampling", py::arg("sql_query"), py::arg("db_path"), py::arg("sample_percent") = 0, py::arg("num_threads") = 4);
+    m.def("run_query_with_ci", [](const std::string& q, const std::string& path, int p) { return table_cache().get(path).query_with_ci(q, p, false); },
+          "Execute query with confidence intervals", py::arg("sql_query"), py::arg("db_path"), py::arg("sample_percent") = 0);
+    m.def("run_query_groupby_with_ci", [](const std::string& q, const std::string& path, int p, int) { return table_cache().get(path).query_groupby_with_ci(q, p, false); },
+          "Execute GROUP BY query with confidence intervals", py::arg("sql_query"), py::arg("db_path"), py::arg("sample_percent") = 0, py::arg("num_threads") = 4);
+    m.def("close_cached_tables", [] { table_cache().clear(); }, "drop the tables run_query* keeps resident");
     m.def("device_count", [] { int n = 0; aqe_device_count(&n); return n; });
     m.def("launch_count", [] { return aqe_launch_count(); });
     m.def("z_score", &aqe_z_score, py::arg("confidence_level"), py::arg("exact") = 1);

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AQE_ABI_VERSION 1
+#define AQE_ABI_VERSION 2
 
 #if defined(AQE_BUILDING)
 #define AQE_API __attribute__((visibility("default")))
@@ -356,6 +356,105 @@ AQE_API int aqe_approx_merge(const aqe_approx_result* parts, int n, int agg, dou
 /* z for a two-sided confidence level: the reference's table 2.576/1.96/1.645 (:911-912) when
  * exact == 0, else the inverse normal CDF. */
 AQE_API double aqe_z_score(double confidence_level, int exact);
+
+/* ------------------------------------------------------------------------------------------------
+ * SQL-string path on the columnar table: run_query / run_query_groupby /
+ * run_query_with_ci / run_query_groupby_with_ci  (bindings.cpp:126-136 -> executor.cpp:28-338,
+ * parser.cpp:20-75).  The reference turns `SELECT agg(col) FROM t [WHERE ...] [GROUP BY g]` into SQLite
+ * statements over a SQLite file, sampling with `rowid % (100/p) = 0` and scaling SUM/COUNT by 100/p.
+ * Here the same query runs as ONE grouped-scan kernel (k_sql_agg) over the HBM-resident columns:
+ * rowid = id; WHERE = a conjunction of comparisons / BETWEENs of columns with numeric literals, compiled
+ * to one closed interval (+ optional "!=" value) per column; GROUP BY on an integer column with a dense
+ * key range of at most AQE_SQL_MAX_GROUPS values.  Sums are accumulated in 128-bit fixed point
+ * (order-independent, so results are bit-reproducible and shard merges are exact).
+ * ---------------------------------------------------------------------------------------------- */
+#define AQE_SQL_MAX_GROUPS 4096
+
+/* One conjunct per column after merging:  lo <= col <= hi  [and col != ne]. */
+typedef struct aqe_sql_term {
+    int32_t col;          /* aqe_column */
+    int32_t has_ne;       /* 1: also requires col != ne / ine */
+    double  lo, hi;       /* bounds when col is f64 */
+    int64_t ilo, ihi;     /* bounds when col is an integer column (ilo > ihi: empty) */
+    double  ne;
+    int64_t ine;
+} aqe_sql_term;
+
+/* Parsed + compiled query: the reference's `struct Query` (parser.h:17-24) with names resolved. */
+typedef struct aqe_sql_query {
+    int32_t agg;              /* aqe_agg */
+    int32_t agg_col;          /* aqe_column; AQE_COL_NONE for COUNT(*) */
+    int32_t group_col;        /* aqe_column or AQE_COL_NONE */
+    int32_t sample_percent;   /* as passed; step = 100 / p for 0 < p < 100 (executor.cpp:20-26) */
+    int32_t n_terms;          /* 0..5 */
+    int32_t always_false;     /* WHERE is unsatisfiable */
+    aqe_sql_term terms[5];
+    char agg_text[32], column[64], table[64], group_by[64];
+    char where[512];          /* raw WHERE text as parser.cpp:36-51 extracts it */
+} aqe_sql_query;
+
+/* How the *_with_ci results are formed. */
+typedef enum aqe_sql_mode {
+    AQE_SQL_VALUE = 0,        /* run_query / run_query_groupby: value only (ci_lower = ci_upper = value) */
+    AQE_SQL_CI_REFERENCE = 1, /* run_query_with_ci / run_query_groupby_with_ci exactly as executor.cpp:177-338
+                                 (SUM reports mean*100/p, margin 1.96*SE*100/p) */
+    AQE_SQL_CI_CORRECT = 2    /* additive: SUM = sample sum * 100/p with margin 1.96 * sqrt(n) * s * 100/p */
+} aqe_sql_mode;
+
+typedef struct aqe_sql_row {
+    int64_t  key;             /* group key (0 when the query has no GROUP BY) */
+    double   value, ci_lower, ci_upper;
+    uint64_t count;           /* sampled rows that passed WHERE (unscaled) */
+    double   sum, sumsq;      /* their sum / sum of squares (unscaled) */
+    uint64_t isum_lo;         /* exact sum of an integer aggregate column, two's complement 128 bit */
+    int64_t  isum_hi;
+    int32_t  is_null;         /* 1: SUM/AVG over no rows -- SQLite yields NULL and the reference's std::stod throws */
+    int32_t  _pad;
+} aqe_sql_row;
+
+/* Host-only: parse + compile (no device needed).  AQE_ERR_INVALID for what parser.cpp rejects
+ * (std::runtime_error there), AQE_ERR_UNSUPPORTED for SQL that SQLite would accept but this engine
+ * does not (OR, expressions, GROUP BY on amount, ...). */
+AQE_API int aqe_sql_parse(const char* sql, int sample_percent, aqe_sql_query* out);
+/* Execute on one shard.  rows[0..*n_rows) in ascending key order; *n_rows may exceed cap (then only cap
+ * rows were written).  Without GROUP BY exactly one row comes back. */
+AQE_API int aqe_sql_execute(aqe_db* db, const aqe_sql_query* q, int mode, aqe_sql_row* rows, uint32_t cap, uint32_t* n_rows);
+/* parse + execute. */
+AQE_API int aqe_sql_run(aqe_db* db, const char* sql, int sample_percent, int mode, aqe_sql_row* rows, uint32_t cap, uint32_t* n_rows);
+/* ---- pieces of aqe_sql_execute, exposed so that shards of several GPUs can be merged exactly ----
+ * The kernel leaves, per group, five 64-bit words {count, sum_lo, sum_hi, sq_lo, sq_hi}: (sum_hi:sum_lo) is the
+ * two's-complement 128-bit sum of round(x * 2^sum_shift) (x itself for integer columns, shift 0), likewise the
+ * squares.  Integer adds commute, so summing these words over shards (with carry) gives the table-level
+ * accumulators bit-for-bit whatever the shard count; all shards must use the same key range and shifts. */
+typedef struct aqe_sql_facts {    /* what a shard knows about the columns a query touches */
+    int64_t key_min, key_max;     /* GROUP BY column range on this shard (0,0 without GROUP BY; min > max: no rows) */
+    double  agg_absmax;           /* max |x| of the aggregate column on this shard */
+    int32_t agg_is_integer;
+    int32_t _pad;
+} aqe_sql_facts;
+typedef struct aqe_sql_layout {   /* agreed by all shards before the scan */
+    int64_t  key_min;
+    uint32_t n_groups;            /* key_max - key_min + 1  (1 without GROUP BY), <= AQE_SQL_MAX_GROUPS */
+    int32_t  sum_shift, sq_shift;
+    int32_t  is_integer;
+} aqe_sql_layout;
+#define AQE_SQL_MOMENTS   1       /* also accumulate squares (the *_with_ci forms) */
+#define AQE_SQL_UNSAMPLED 2       /* ignore sample_percent and count only: which groups pass WHERE at all
+                                     (executor.cpp:68-79 lists groups with SELECT DISTINCT, unsampled) */
+AQE_API int aqe_sql_facts_of(aqe_db* db, const aqe_sql_query* q, aqe_sql_facts* out);
+/* Host only: fixed-point shifts for values of magnitude <= agg_absmax (|x| * 2^sum_shift < 2^62). */
+AQE_API int aqe_sql_shifts(double agg_absmax, int agg_is_integer, int* sum_shift, int* sq_shift);
+/* Host only: merge the facts of all shards into the common layout. */
+AQE_API int aqe_sql_layout_of(const aqe_sql_query* q, const aqe_sql_facts* facts, int n_shards, aqe_sql_layout* out);
+AQE_API int aqe_sql_scan(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* layout, int flags,
+                         uint64_t* acc /* n_groups x 5 words, host */);
+/* Host only: acc[i] += other[i] over the 5-word groups with 128-bit carries. */
+AQE_API int aqe_sql_merge(uint64_t* acc, const uint64_t* other, uint32_t n_groups);
+/* Host only: the arithmetic of executor.cpp on merged accumulators.  `exists` (n_groups x 5 words from an
+ * AQE_SQL_UNSAMPLED scan, or NULL = "every group with sampled rows, plus nothing else") decides which groups
+ * are reported. */
+AQE_API int aqe_sql_finish(const aqe_sql_query* q, int mode, const aqe_sql_layout* layout, const uint64_t* acc,
+                           const uint64_t* exists, aqe_sql_row* rows, uint32_t cap, uint32_t* n_rows);
 
 #ifdef __cplusplus
 }

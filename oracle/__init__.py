@@ -21,6 +21,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libaqe_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libaqe_ref.so")
+REFSQL_SO = os.path.join(HERE, "_ref", "libaqe_refsql.so")
 
 RECORD_DTYPE = np.dtype(
     [("id", "<i8"), ("amount", "<f8"), ("region", "<i4"), ("product_id", "<i4"), ("timestamp", "<i8")]
@@ -106,6 +107,8 @@ def build(ref: bool = True, quiet: bool = True) -> None:
     targets = ["oracle"]
     if ref and os.path.isdir(os.environ.get("AQE_REFERENCE", "/root/reference")):
         targets.append("ref")
+        if any(os.path.exists(p) for p in ("/usr/lib/x86_64-linux-gnu/libsqlite3.so.0", "/usr/lib64/libsqlite3.so.0", "/usr/lib/libsqlite3.so.0")):
+            targets.append("refsql")
     cmd = ["make", "-C", HERE, "-s"] + targets
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL if quiet else None)
 
@@ -117,6 +120,29 @@ def _rows(a) -> np.ndarray:
 
 def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class SqlParsed(C.Structure):
+    _fields_ = [("agg", C.c_char * 32), ("column", C.c_char * 64), ("table", C.c_char * 64), ("where", C.c_char * 512),
+                ("group_by", C.c_char * 64)]
+
+
+class SqlRow(C.Structure):
+    _fields_ = [("key", C.c_int64), ("value", C.c_double), ("ci_lower", C.c_double), ("ci_upper", C.c_double)]
+
+
+class SqlError(Exception):
+    """kind: 'runtime_error' (std::runtime_error in the reference), 'stod' (std::stod on "NULL": ValueError through
+    pybind11), 'unsupported' (valid SQL outside the restated grammar)."""
+
+    def __init__(self, kind: str, msg: str):
+        super().__init__(f"{kind}: {msg}")
+        self.kind = kind
+        self.msg = msg
+
+
+SQL_MODES = {"run_query": 0, "run_query_with_ci": 1, "run_query_groupby": 2, "run_query_groupby_with_ci": 3}
+_SQL_ERR = {1: "runtime_error", 2: "stod", 3: "unsupported"}
 
 
 class Oracle:
@@ -155,6 +181,9 @@ class Oracle:
         for f in ("orc_tree_height", "orc_leaf_count", "orc_node_count"):
             getattr(L, f).argtypes = [C.c_uint64]; getattr(L, f).restype = C.c_uint64
         L.orc_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32 * 4)]
+        L.orc_sql_parse.argtypes = [C.c_char_p, C.POINTER(SqlParsed), C.c_char_p, C.c_size_t]
+        L.orc_sql_run.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_int, C.c_int, C.POINTER(SqlRow), C.c_uint32,
+                                  C.POINTER(C.c_uint32), C.c_char_p, C.c_size_t]
 
     # -- data -------------------------------------------------------------------------------------
     def synth(self, n: int, seed: int = 7, first_row: int = 0, dist: int = 0) -> np.ndarray:
@@ -256,6 +285,24 @@ class Oracle:
         out = (C.c_uint32 * 4)()
         self.L.orc_philox(key, ctr_lo, ctr_hi, C.byref(out))
         return list(out)
+
+    # -- SQL-string path (executor.cpp / parser.cpp) ----------------------------------------------
+    def sql_parse(self, sql: str) -> dict:
+        q = SqlParsed(); err = C.create_string_buffer(256)
+        rc = self.L.orc_sql_parse(sql.encode(), C.byref(q), err, 256)
+        if rc:
+            raise SqlError(_SQL_ERR[rc], err.value.decode())
+        return {k: getattr(q, k).decode() for k in ("agg", "column", "table", "where", "group_by")}
+
+    def sql(self, rows, sql: str, sample_percent: int = 0, mode: str = "run_query"):
+        """[(key, value, ci_lower, ci_upper)] in ascending numeric key order (one entry, key 0, without GROUP BY)."""
+        rows = _rows(rows)
+        cap = 8192
+        out = (SqlRow * cap)(); n = C.c_uint32(); err = C.create_string_buffer(256)
+        rc = self.L.orc_sql_run(_ptr(rows), len(rows), sql.encode(), sample_percent, SQL_MODES[mode], out, cap, C.byref(n), err, 256)
+        if rc:
+            raise SqlError(_SQL_ERR[rc], err.value.decode())
+        return [(out[i].key, out[i].value, out[i].ci_lower, out[i].ci_upper) for i in range(min(n.value, cap))]
 
     def tree_height(self, n): return self.L.orc_tree_height(n)
     def leaf_count(self, n): return self.L.orc_leaf_count(n)
@@ -366,3 +413,77 @@ class RefScheduler:
         return r
 
     def size_mb(self): return self.L.ref_sched_size_mb(self.h)
+
+
+class RefSqlRow(C.Structure):
+    _fields_ = [("key", C.c_char * 64), ("value", C.c_double), ("ci_lower", C.c_double), ("ci_upper", C.c_double)]
+
+
+class RefSql:
+    """The unmodified reference SQL-string path (executor.cpp, parser.cpp, core/db.cpp) over a SQLite file holding the
+    record table as ``sales(id INTEGER PRIMARY KEY, amount REAL, region INTEGER, product_id INTEGER, timestamp INTEGER)``."""
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REFSQL_SO)
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(REFSQL_SO)
+            L.ref_sql_error.restype = C.c_char_p
+            L.ref_sql_parse.argtypes = [C.c_char_p, C.c_int] + [C.c_char_p] * 5 + [C.c_size_t]
+            L.ref_run_query.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_double)]
+            L.ref_run_query_with_ci.argtypes = [C.c_char_p, C.c_char_p, C.c_int] + [C.POINTER(C.c_double)] * 3
+            for f in ("ref_run_query_groupby", "ref_run_query_groupby_with_ci"):
+                getattr(L, f).argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(RefSqlRow), C.c_size_t, C.POINTER(C.c_size_t)]
+            cls._lib = L
+        return cls._lib
+
+    @staticmethod
+    def make_sqlite(path: str, rows, table: str = "sales") -> None:
+        import sqlite3
+        if os.path.exists(path):
+            os.remove(path)
+        con = sqlite3.connect(path)
+        con.execute(f"CREATE TABLE {table} (id INTEGER PRIMARY KEY, amount REAL, region INTEGER, product_id INTEGER, timestamp INTEGER)")
+        rows = _rows(rows)
+        con.executemany(f"INSERT INTO {table} VALUES (?,?,?,?,?)",
+                        zip(rows["id"].tolist(), rows["amount"].tolist(), rows["region"].tolist(), rows["product_id"].tolist(), rows["timestamp"].tolist()))
+        con.commit()
+        con.close()
+
+    def __init__(self, sqlite_path: str):
+        self.L = self.lib()
+        self.path = sqlite_path.encode()
+
+    def _err(self):
+        msg = self.L.ref_sql_error().decode()
+        return SqlError("stod" if msg == "stod" else "runtime_error", msg)
+
+    def parse(self, sql: str, p: int = 0) -> dict:
+        bufs = [C.create_string_buffer(512) for _ in range(5)]
+        if self.L.ref_sql_parse(sql.encode(), p, *bufs, 512):
+            raise self._err()
+        return dict(zip(("agg", "column", "table", "where", "group_by"), (b.value.decode() for b in bufs)))
+
+    def run(self, sql: str, p: int = 0, mode: str = "run_query", threads: int = 4):
+        """Same shape as Oracle.sql (keys as int, ascending numeric order)."""
+        if mode == "run_query":
+            v = C.c_double()
+            if self.L.ref_run_query(sql.encode(), self.path, p, C.byref(v)):
+                raise self._err()
+            return [(0, v.value, v.value, v.value)]
+        if mode == "run_query_with_ci":
+            v, lo, hi = C.c_double(), C.c_double(), C.c_double()
+            if self.L.ref_run_query_with_ci(sql.encode(), self.path, p, C.byref(v), C.byref(lo), C.byref(hi)):
+                raise self._err()
+            return [(0, v.value, lo.value, hi.value)]
+        cap = 8192
+        out = (RefSqlRow * cap)(); n = C.c_size_t()
+        f = self.L.ref_run_query_groupby if mode == "run_query_groupby" else self.L.ref_run_query_groupby_with_ci
+        if f(sql.encode(), self.path, p, threads, out, cap, C.byref(n)):
+            raise self._err()
+        return sorted((int(out[i].key.decode()), out[i].value, out[i].ci_lower, out[i].ci_upper) for i in range(min(n.value, cap)))

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(L, s), f"{s} declared in include/aqe_b200.h but not exported"
     assert set(L._signatures) == set(declared_symbols()), "ctypes table out of sync with the header"
-    assert L.aqe_abi_version() == 1
+    assert L.aqe_abi_version() == 2
 
 
 def test_struct_sizes_match_header():

@@ -1,0 +1,264 @@
+"""SQL-string path on the GPU (run with `-m gpu` on a B200): aqe_sql_* through the C-ABI and run_query* through the
+drop-in module, against golden vectors minted from the unmodified reference executor (tests/golden/make_sql_golden.py)
+and against the oracle's restatement (oracle/aqe_oracle_sql.c).
+
+Stated tolerances: group keys, row counts and integer-column sums bit-exact; fp64 values relative <= 1e-12 of the
+reference's result (which itself is rounded to 15 significant digits by SQLite's TEXT interface); interval ends to
+1e-12 of the value's magnitude or 1e-6 of the half width (the reference's own sum_sq - sum^2/n cancels 15-digit
+inputs).  The engine's fp64 sums are additionally checked to be the EXACTLY rounded sums (math.fsum) for U(1,1000)
+data, and bit-identical across runs, shard counts and row visiting order.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import approximatequeryengine_b200 as aqe
+from oracle import SqlError
+from sql_helpers import MODE_OF, REL, engine_rows, golden_rows, load, rows_close, sql_golden_files
+
+pytestmark = pytest.mark.gpu
+
+FILES = sql_golden_files()
+
+
+@pytest.fixture(scope="module")
+def tables(oracle):
+    out = []
+    for path in FILES:
+        g = load(path)
+        rows = oracle.synth(g["n"], seed=g["seed"])
+        out.append((g, rows, aqe.Engine(0).from_rows(rows)))
+    return out
+
+
+def run_engine(e, sql, p, mode):
+    """What the binding does (aqe_pybind.cpp CustomBPlusDB::sql): the non-grouped calls ignore GROUP BY, the grouped
+    ones require it."""
+    q = aqe.sql_parse(sql, p)
+    grouped = "groupby" in mode
+    if grouped and q.group_col < 0:
+        raise RuntimeError("No GROUP BY column found")
+    if not grouped:
+        q.group_col = -1
+    rows = (aqe.SqlRow * aqe.SQL_MAX_GROUPS)()
+    n = aqe.C.c_uint32()
+    aqe.check(e.L.aqe_sql_execute(e.h, aqe.C.byref(q), aqe.SQL_MODE[MODE_OF[mode]], rows, aqe.SQL_MAX_GROUPS, aqe.C.byref(n)))
+    return engine_rows(rows[: n.value])
+
+
+def check_case(e, c):
+    tag = (c["sql"], c["p"], c["mode"])
+    want_err = c.get("error")
+    try:
+        got = run_engine(e, c["sql"], c["p"], c["mode"])
+    except ValueError:
+        return None if want_err in ("stod", "terminate") else (tag, "engine raised stod", want_err)
+    except RuntimeError as ex:  # AqeError is a RuntimeError
+        return None if want_err == "runtime_error" else (tag, f"engine raised {ex}", want_err)
+    if want_err == "terminate" or (want_err == "runtime_error" and "integer overflow" in c.get("msg", "")):
+        return None  # the reference aborts / SQLite's int64 SUM(col*col) overflows; the 128-bit accumulators do not
+    if want_err:
+        return (tag, "engine returned rows", want_err)
+    why = rows_close(got, golden_rows(c), REL)
+    return (tag, why) if why else None
+
+
+def test_sql_against_reference_golden(tables):
+    for g, rows, e in tables:
+        bad = [b for b in (check_case(e, c) for c in g["cases"]) if b]
+        assert not bad, (g["n"], bad[:5])
+
+
+def test_sql_against_oracle_extra_queries(tables, oracle):
+    g, rows, e = [t for t in tables if t[0]["n"] == 20000][0]
+    t0 = 1700000000
+    queries = [
+        f"SELECT SUM(amount) FROM sales WHERE timestamp BETWEEN {t0 + 100} AND {t0 + 15000} AND region >= 2 AND product_id < 500 AND amount > 3.5 AND id != 777",
+        "SELECT AVG(region) FROM sales WHERE amount <= 10",
+        "SELECT COUNT(region) FROM sales WHERE product_id = 999 GROUP BY region",
+        "SELECT SUM(id) FROM sales WHERE amount BETWEEN 400 AND 600 GROUP BY product_id",
+        "SELECT AVG(amount) FROM sales WHERE id > 19990 GROUP BY region",
+        "SELECT SUM(timestamp) FROM sales WHERE region = 7 GROUP BY region",
+        "SELECT COUNT(*) FROM sales GROUP BY product_id",
+        "SELECT SUM(amount) FROM sales WHERE amount < 0",
+        "SELECT COUNT(amount) FROM sales WHERE amount < 0 GROUP BY region",
+    ]
+    for sql in queries:
+        for p in (0, 3, 10, 25, 50, 99):
+            for mode in ("run_query", "run_query_with_ci", "run_query_groupby", "run_query_groupby_with_ci"):
+                if ("GROUP BY" in sql) != ("groupby" in mode):
+                    continue
+                tag = (sql, p, mode)
+                try:
+                    want = oracle.sql(rows, sql, p, mode)
+                except SqlError as ex:
+                    if ex.kind == "stod" or "integer overflow" in ex.msg:
+                        if ex.kind == "stod":
+                            with pytest.raises(ValueError):
+                                run_engine(e, sql, p, mode)
+                        continue
+                    with pytest.raises(RuntimeError):
+                        run_engine(e, sql, p, mode)
+                    continue
+                got = run_engine(e, sql, p, mode)
+                assert rows_close(got, want, REL) is None, (tag, rows_close(got, want, REL))
+
+
+def test_sql_sums_are_exactly_rounded_and_integer_sums_exact(tables):
+    for g, rows, e in tables:
+        r = e.sql("SELECT SUM(amount) FROM sales")[0]
+        assert r.value == math.fsum(rows["amount"]) and r.count == len(rows)
+        for k, row in zip(range(8), e.sql("SELECT SUM(amount) FROM sales GROUP BY region")):
+            m = rows["region"] == row.key
+            assert row.count == int(m.sum()) and row.value == math.fsum(rows["amount"][m])
+        for col in ("id", "timestamp", "region", "product_id"):
+            assert e.sql(f"SELECT SUM({col}) FROM sales WHERE amount >= 500")[0].isum == int(rows[col][rows["amount"] >= 500].astype(object).sum())
+        by_pid = e.sql("SELECT SUM(timestamp) FROM sales GROUP BY product_id")
+        assert sum(r.isum for r in by_pid) == int(rows["timestamp"].astype(object).sum())
+        a, b = (e.sql("SELECT SUM(amount) FROM sales GROUP BY product_id", 10) for _ in range(2))    # shared-atomic bins: still bit stable
+        assert [(r.key, r.count, r.sum) for r in a] == [(r.key, r.count, r.sum) for r in b]
+
+
+def test_sql_non_dense_ids_take_the_modulus_predicate(oracle):
+    rng = np.random.default_rng(3)
+    rows = oracle.synth(30011, seed=21)
+    rows["id"] = np.sort(rng.choice(10**7, size=len(rows), replace=False)) - 5000   # gaps, some negative ids
+    e = aqe.Engine(0).from_rows(rows)
+    for sql, mode in (("SELECT SUM(amount) FROM sales WHERE region < 6", "run_query"), ("SELECT AVG(amount) FROM sales", "run_query_with_ci"),
+                      ("SELECT COUNT(amount) FROM sales GROUP BY region", "run_query_groupby"),
+                      ("SELECT SUM(amount) FROM sales WHERE amount > 20 GROUP BY region", "run_query_groupby_with_ci")):
+        for p in (0, 7, 20, 50):
+            want = oracle.sql(rows, sql, p, mode)
+            got = run_engine(e, sql, p, mode)
+            assert rows_close(got, want, REL) is None, (sql, p, mode, rows_close(got, want, REL))
+    e.close()
+
+
+def test_sql_dense_ids_with_offset_and_ragged_sizes(oracle):
+    for n, first_id in ((0, 1), (1, 1), (3, 5), (4, 2), (257, -100), (4099, 1000003), (65537, 1)):
+        rows = oracle.synth(n, seed=33)
+        rows["id"] = np.arange(first_id, first_id + n)
+        e = aqe.Engine(0).from_rows(rows)
+        for p in (0, 10, 33, 50):
+            for sql, mode in (("SELECT COUNT(*) FROM sales", "run_query"), ("SELECT COUNT(amount) FROM sales WHERE amount > 500", "run_query"),
+                              ("SELECT COUNT(amount) FROM sales GROUP BY region", "run_query_groupby")):
+                want = oracle.sql(rows, sql, p, mode)
+                assert rows_close(run_engine(e, sql, p, mode), want, REL) is None, (n, first_id, p, sql)
+            if n:
+                try:
+                    want = oracle.sql(rows, "SELECT SUM(amount) FROM sales", p, "run_query_with_ci")
+                except SqlError:
+                    with pytest.raises(ValueError):
+                        run_engine(e, "SELECT SUM(amount) FROM sales", p, "run_query_with_ci")
+                    continue
+                assert rows_close(run_engine(e, "SELECT SUM(amount) FROM sales", p, "run_query_with_ci"), want, REL) is None, (n, first_id, p)
+        e.close()
+
+
+def test_sql_unaligned_attached_columns(oracle):
+    import torch
+    rows = oracle.synth(50001, seed=9)
+    cols = {c: torch.from_numpy(rows[c].copy()).cuda() for c in ("id", "amount", "region", "product_id", "timestamp")}
+    for off in (0, 1, 3):
+        sub = rows[off:]
+        e = aqe.Engine(0).attach(len(sub), **{c: t[off:].data_ptr() for c, t in cols.items()})
+        for sql, p, mode in (("SELECT SUM(amount) FROM sales WHERE timestamp > 1700000100 GROUP BY region", 0, "run_query_groupby"),
+                             ("SELECT AVG(amount) FROM sales WHERE product_id < 300", 10, "run_query_with_ci"),
+                             ("SELECT SUM(amount) FROM sales GROUP BY product_id", 0, "run_query_groupby")):
+            assert rows_close(run_engine(e, sql, p, mode), oracle.sql(sub, sql, p, mode), REL) is None, (off, sql)
+        e.close()
+
+
+def test_sql_shards_merge_bit_exactly(tables, oracle):
+    """Three shards' accumulators merged on the host == the single-table accumulators, word for word."""
+    g, rows, e = [t for t in tables if t[0]["n"] == 100000][0]
+    cuts = [0, 33333, 71003, len(rows)]
+    shards = [aqe.Engine(0).from_rows(rows[a:b]) for a, b in zip(cuts, cuts[1:])]
+    for sql, p, flags in (("SELECT SUM(amount) FROM sales WHERE amount < 900 GROUP BY region", 10, aqe.SQL_MOMENTS),
+                          ("SELECT AVG(amount) FROM sales GROUP BY product_id", 0, aqe.SQL_MOMENTS), ("SELECT SUM(timestamp) FROM sales", 7, aqe.SQL_MOMENTS)):
+        q = aqe.sql_parse(sql, p)
+        layout = aqe.sql_layout(q, [s.sql_facts(q) for s in shards])
+        whole_layout = aqe.sql_layout(q, [e.sql_facts(q)])
+        assert bytes(layout) == bytes(whole_layout)
+        acc = np.zeros(layout.n_groups * 5, dtype=np.uint64)
+        for s in shards:
+            aqe.sql_merge(acc, s.sql_scan(q, layout, flags))
+        whole = e.sql_scan(q, layout, flags)
+        assert (acc == whole).all(), sql
+        a = aqe.sql_finish(q, layout, acc, "ci_reference")
+        b = e.sql(sql, p, "ci_reference")
+        assert [(r.key, r.count, r.value, r.ci_lower, r.ci_upper) for r in a] == [(r.key, r.count, r.value, r.ci_lower, r.ci_upper) for r in b], sql
+    for s in shards:
+        s.close()
+
+
+def test_sql_large_table_properties():
+    """100 M rows generated on the device: linearity of the integer accumulators and agreement with the exact scan."""
+    n = 100_000_000
+    e = aqe.Engine(0).generate(n, seed=7)
+    q_all = aqe.sql_parse("SELECT SUM(amount) FROM sales GROUP BY region", 0)
+    layout = aqe.sql_layout(q_all, [e.sql_facts(q_all)])
+    assert layout.n_groups == 8 and layout.sum_shift == 52
+    whole = e.sql_scan(q_all, layout)
+    lo = e.sql_scan(aqe.sql_parse("SELECT SUM(amount) FROM sales WHERE amount < 300 GROUP BY region", 0), layout)
+    hi = e.sql_scan(aqe.sql_parse("SELECT SUM(amount) FROM sales WHERE amount >= 300 GROUP BY region", 0), layout)
+    assert (aqe.sql_merge(lo.copy(), hi) == whole).all()
+    assert (e.sql_scan(q_all, layout) == whole).all()                      # run-to-run identical
+    rows = aqe.sql_finish(q_all, layout, whole)
+    assert sum(r.count for r in rows) == n
+    total = e.sql("SELECT SUM(amount) FROM sales")[0]
+    p = e.scan("amount")
+    assert abs(total.value - p.sum) <= 4 * math.ulp(p.sum)                 # compensated scan vs exactly rounded fixed point
+    assert abs(math.fsum(r.value for r in rows) - total.value) <= 8 * math.ulp(total.value)
+    by_pid = e.sql("SELECT COUNT(amount) FROM sales WHERE amount BETWEEN 100 AND 500 GROUP BY product_id")
+    w = e.scan("amount", "amount", 100.0, 500.0)
+    assert len(by_pid) == 1000 and sum(r.count for r in by_pid) == w.count
+    # 1-in-10 systematic sample through the strided visit: count is exact, estimate is close
+    s = e.sql("SELECT SUM(amount) FROM sales", 10, "ci_correct")[0]
+    half = (s.ci_upper - s.ci_lower) / 2
+    assert s.count == n // 10 and 0 < half < 2e-3 * total.value and abs(s.value - total.value) < 4 * half / 1.96, (s.value, total.value, half)
+    e.close()
+
+
+def test_dropin_run_query_functions(oracle, tmp_path):
+    b = aqe.backend()
+    rows = oracle.synth(20000, seed=7)
+    path = str(tmp_path / "sales.aqe")
+    oracle.save_file(path, rows)
+    v = b.run_query("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 100 AND 500", path, 10)
+    assert abs(v - oracle.sql(rows, "SELECT SUM(amount) FROM sales WHERE amount BETWEEN 100 AND 500", 10)[0][1]) <= REL * abs(v)
+    # the non-grouped entry points ignore GROUP BY, as execute_query does
+    assert b.run_query("SELECT COUNT(amount) FROM sales GROUP BY region", path) == 20000.0
+    d = b.run_query_groupby("SELECT AVG(amount) FROM sales GROUP BY region", path, 20, 2)
+    want = oracle.sql(rows, "SELECT AVG(amount) FROM sales GROUP BY region", 20, "run_query_groupby")
+    assert list(d) == sorted(str(k) for k, *_ in want) and all(abs(d[str(k)] - val) <= REL * abs(val) for k, val, *_ in want)
+    r = b.run_query_with_ci("SELECT AVG(amount) FROM sales", path, 5)
+    k, val, lo, hi = oracle.sql(rows, "SELECT AVG(amount) FROM sales", 5, "run_query_with_ci")[0]
+    assert abs(r.value - val) <= REL * val and abs(r.ci_lower - lo) <= REL * val and abs(r.ci_upper - hi) <= REL * val
+    dc = b.run_query_groupby_with_ci("SELECT SUM(amount) FROM sales GROUP BY region", path, 10)
+    want = {str(k): (val, lo, hi) for k, val, lo, hi in oracle.sql(rows, "SELECT SUM(amount) FROM sales GROUP BY region", 10, "run_query_groupby_with_ci")}
+    assert set(dc) == set(want) and all(abs(dc[k].value - want[k][0]) <= REL * abs(want[k][0]) for k in want)
+    keys = list(b.run_query_groupby("SELECT COUNT(amount) FROM sales GROUP BY product_id", path))
+    assert keys == sorted(keys) and keys[:3] == ["0", "1", "10"]        # std::map<std::string,...>: keys sort as text
+    # error behaviour (bindings.cpp: std::runtime_error -> RuntimeError, std::invalid_argument -> ValueError)
+    with pytest.raises(RuntimeError, match="Unsupported aggregation function"):
+        b.run_query("SELECT MAX(amount) FROM sales", path)
+    with pytest.raises(RuntimeError, match="No GROUP BY"):
+        b.run_query_groupby("SELECT SUM(amount) FROM sales", path)
+    with pytest.raises(ValueError, match="stod"):
+        b.run_query("SELECT SUM(amount) FROM sales WHERE amount > 5000", path)
+    with pytest.raises(RuntimeError, match="Cannot open database"):
+        b.run_query("SELECT SUM(amount) FROM sales", str(tmp_path / "missing.aqe"))
+    # the resident copy follows the file
+    rows2 = oracle.synth(5000, seed=8)
+    oracle.save_file(path, rows2)
+    os.utime(path, ns=(1, 1))
+    assert b.run_query("SELECT COUNT(*) FROM sales", path) == 5000.0
+    # the same calls on an open table
+    db = b.CustomBPlusDB(); db.open_database(path)
+    assert db.query("SELECT COUNT(*) FROM sales WHERE region = 1") == float((rows2["region"] == 1).sum())
+    c = db.query_with_ci("SELECT SUM(amount) FROM sales", 10, correct_ci=True)
+    assert c.ci_lower < math.fsum(rows2["amount"]) < c.ci_upper
+    b.close_cached_tables()
