@@ -39,6 +39,11 @@ def test_struct_sizes_match_header():
     assert C.sizeof(aqe.SampleParams) == 72
     assert C.sizeof(aqe.ApproxSpec) == 80
     assert C.sizeof(aqe.ApproxResult) == 96
+    assert C.sizeof(aqe.SqlTerm) == 56
+    assert C.sizeof(aqe.SqlQuery) == 24 + 5 * 56 + 32 + 64 + 64 + 64 + 512
+    assert C.sizeof(aqe.SqlRow) == 80
+    assert C.sizeof(aqe.SqlFacts) == 32
+    assert C.sizeof(aqe.SqlLayout) == 24
     assert aqe.RECORD_DTYPE.itemsize == 32
 
 
@@ -88,10 +93,20 @@ def test_dropin_module_surface():
     assert not hasattr(b, "ApproximationStatus")  # the CLI probes this name and falls back (enhanced_aqe_cli.py:142-155)
 
 
-def test_sqlite_path_is_loudly_out_of_scope():
+def test_run_query_rejects_what_it_cannot_open(tmp_path):
+    """run_query* take a record file; a missing file or a SQLite file (the reference's storage for this path) fail loudly."""
     b = aqe.backend()
-    with pytest.raises(RuntimeError, match="SQLite"):
-        b.run_query("SELECT SUM(amount) FROM sales", "x.db", 0)
+    with pytest.raises(RuntimeError, match="Cannot open database"):
+        b.run_query("SELECT SUM(amount) FROM sales", str(tmp_path / "missing.aqe"), 0)
+    import sqlite3
+    p = str(tmp_path / "x.db")
+    con = sqlite3.connect(p); con.execute("CREATE TABLE sales (id INTEGER PRIMARY KEY, amount REAL)"); con.commit(); con.close()
+    with pytest.raises(RuntimeError, match="SQLite file"):
+        b.run_query("SELECT SUM(amount) FROM sales", p, 0)
+    for name, defaults in (("run_query", "sample_percent: [^,)]+ = 0\\)"), ("run_query_groupby", "sample_percent: [^,)]+ = 0, num_threads: [^,)]+ = 4\\)"),
+                           ("run_query_with_ci", "sample_percent: [^,)]+ = 0\\)"), ("run_query_groupby_with_ci", "sample_percent: [^,)]+ = 0, num_threads: [^,)]+ = 4\\)")):
+        doc = getattr(b, name).__doc__
+        assert re.search(r"sql_query: [^,)]+, db_path: [^,)]+, " + defaults, doc), doc   # bindings.cpp:126-136
 
 
 def test_where_clause_forms():
