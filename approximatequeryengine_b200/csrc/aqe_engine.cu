@@ -1621,15 +1621,76 @@ static double okey_f64(unsigned long long k) {
     return d;
 }
 
-template <int MODE, bool MOMENTS> static int sql_launch_v(const aqe_db* db, const SqlArgs& a, bool vec, size_t smem, cudaStream_t s) {
+// Dynamic shared memory of the SQL kernels varies per query (bins grow with the group count): opt every kernel in to
+// the full 227 KiB once per device and ask the occupancy calculator per launch (host arithmetic, no driver round trip).
+static int sql_occupancy(const void* kernel, int threads, size_t smem) {
+    struct Key { const void* k; int dev; };
+    static std::mutex mu;
+    static std::vector<Key> opted;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        bool seen = false;
+        for (auto& e : opted) seen = seen || (e.k == kernel && e.dev == dev);
+        if (!seen) {
+            cudaFuncAttributes fa;
+            if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess)  // the opt-in limit covers static + dynamic
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);
+            cudaGetLastError();
+            opted.push_back(Key{kernel, dev});
+        }
+    }
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+    return occ;
+}
+
+template <int MODE, bool MOMENTS> static int sql_launch_regs(const aqe_db* db, const SqlArgs& a, bool vec, cudaStream_t s) {
+    const size_t smem = SqlBins<MODE, MOMENTS, kSqlThreads>::smem_bytes(a.n_groups);
     const void* k = vec ? (const void*)k_sql_agg<MODE, MOMENTS, true> : (const void*)k_sql_agg<MODE, MOMENTS, false>;
-    const int occ = kernel_occupancy(k, kSqlThreads, smem);
+    const int occ = sql_occupancy(k, kSqlThreads, smem);
+    if (occ < 1) return fail(AQE_ERR_UNSUPPORTED, "SQL path: group bins do not fit shared memory");
     const uint64_t items = vec ? (a.count + 3) / 4 : a.count;
     const int grid = grid_for(db, items, 1, kSqlThreads, occ);
     if (vec) k_sql_agg<MODE, MOMENTS, true><<<grid, kSqlThreads, smem, s>>>(a);
     else k_sql_agg<MODE, MOMENTS, false><<<grid, kSqlThreads, smem, s>>>(a);
     LAUNCHED();
     return AQE_OK;
+}
+
+template <int MODE, bool MOMENTS> static int sql_launch_ring(const aqe_db* db, SqlRingArgs& ra, cudaStream_t s) {
+    constexpr int T = kBulkConsumerWarps * 32;
+    uint32_t row_bytes = 0;
+    for (int i = 0; i < ra.q.ncols; ++i) row_bytes += ra.q.cols[i].kind == K_I32 ? 4 : 8;
+    uint32_t tile = (uint32_t)(kStageBytes / row_bytes) / T * T;  // rows per stage: a multiple of 256, stage <= 16 KiB
+    if (tile < (uint32_t)T) tile = T;
+    if (tile > (uint32_t)(T * kSqlRowsPerThread)) tile = T * kSqlRowsPerThread;
+    ra.tile_rows = tile;
+    uint32_t off = 0;
+    for (int i = 0; i < ra.q.ncols; ++i) { ra.col_off[i] = off; off += tile * (ra.q.cols[i].kind == K_I32 ? 4u : 8u); }
+    ra.stage_bytes = off;
+    // the consumers touch row slot T * kSqlRowsPerThread - 1 of every column whatever the tile holds: map that far
+    uint32_t reach = 0;
+    for (int i = 0; i < ra.q.ncols; ++i) reach = std::max(reach, ra.col_off[i] + (uint32_t)(T * kSqlRowsPerThread) * (ra.q.cols[i].kind == K_I32 ? 4u : 8u));
+    const uint32_t slack = reach > ra.stage_bytes ? (reach - ra.stage_bytes + 127u) & ~127u : 0u;
+    const size_t bins = SqlBins<MODE, MOMENTS, T>::smem_bytes(ra.q.n_groups);
+    const uint64_t ntiles = (ra.q.count + tile - 1) / tile;
+    auto go = [&](auto kernel, int stages) -> int {
+        ra.ring_bytes = (uint32_t)stages * ra.stage_bytes + (bins >= slack ? 0u : slack);  // the bins themselves serve as slack when large enough
+        const size_t smem = (size_t)ra.ring_bytes + bins;
+        const int occ = sql_occupancy((const void*)kernel, kBulkThreads, smem);
+        if (occ < 1) return -1;
+        int grid = (int)std::min<uint64_t>((uint64_t)db->sm_count * std::min(occ, 2), std::max<uint64_t>(ntiles, 1));
+        if (grid > db->max_grid) grid = db->max_grid;
+        kernel<<<grid, kBulkThreads, smem, s>>>(ra);
+        LAUNCHED();
+        return AQE_OK;
+    };
+    int rc = go(k_sql_ring<MODE, MOMENTS, 4>, 4);
+    if (rc == -1) rc = go(k_sql_ring<MODE, MOMENTS, 2>, 2);
+    if (rc == -1) return fail(AQE_ERR_UNSUPPORTED, "SQL path: group bins do not fit shared memory");
+    return rc;
 }
 
 static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* L, int flags, uint64_t* acc) {
@@ -1645,8 +1706,9 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
     const bool sums = q->agg_col != AQE_COL_NONE && !unsampled && (q->agg != AQE_AGG_COUNT || moments);
     const int step = unsampled ? 0 : sql_sample_step(q->sample_percent);
 
-    SqlArgs a;
-    std::memset(&a, 0, sizeof(a));
+    SqlRingArgs ra;
+    std::memset(&ra, 0, sizeof(ra));
+    SqlArgs& a = ra.q;
     a.agg_slot = -1; a.group_slot = -1;
     auto slot_of = [&](int col) -> int {
         const void* ptr = col_ptr(db, col);
@@ -1675,38 +1737,61 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
         if (c.kind == K_F64) { std::memcpy(&c.lo, &term.lo, 8); std::memcpy(&c.hi, &term.hi, 8); std::memcpy(&c.ne, &term.ne, 8); }
         else { c.lo = term.ilo; c.hi = term.ihi; c.ne = term.ine; }
     }
+    // ---- rowid % step = 0 (executor.cpp:38-42); rowid = id ----
     a.first = 0; a.stride = 1; a.count = db->n;
-    if (step > 1) {  // rowid % step = 0 (executor.cpp:38-42); rowid = id
+    bool dense = false;
+    long long phase = 0;  // row i is sampled iff (i + phase) % step == 0
+    if (step > 1) {
         if ((rc = need(AQE_COL_ID))) return rc;
         const aqe_db::ColStat* ids;
         if ((rc = sql_col_stat(db, AQE_COL_ID, &ids))) return rc;
-        if (ids->dense) {
-            // ids are first_id + row: the sampled rows are an arithmetic progression of row numbers, visited directly
-            const long long r = ((ids->first_id % step) + step) % step;
-            a.first = (uint64_t)((step - r) % step); a.stride = (uint64_t)step;
-            a.count = a.first < db->n ? (db->n - a.first + step - 1) / step : 0;
-        } else {
-            a.cols[slot_of(AQE_COL_ID)].mod_step = step;
-        }
+        dense = ids->dense;
+        if (dense) phase = ((ids->first_id % step) + step) % step;
+        else a.cols[slot_of(AQE_COL_ID)].mod_step = step;  // ids with gaps: read the id column and test it
     }
-    if (a.count == 0) return AQE_OK;
     if (a.ncols == 0) {  // COUNT without WHERE / GROUP BY: metadata (0 bytes per record)
-        acc[0] = a.count;
+        const uint64_t first = dense ? (uint64_t)((step - phase) % step) : 0;
+        acc[0] = dense ? (first < db->n ? (db->n - first + step - 1) / step : 0) : db->n;
         return AQE_OK;
     }
     a.key_min = L->key_min; a.n_groups = G;
     a.sum_scale = std::ldexp(1.0, L->sum_shift); a.sq_scale = std::ldexp(1.0, L->sq_shift);
     a.global_acc = db->sql_acc; a.out = db->sql_out_dev; a.ticket = db->sql_ticket;
-    bool vec = a.stride == 1;
-    for (int i = 0; i < a.ncols; ++i) vec = vec && ((uintptr_t)a.cols[i].ptr % 32) == 0;
+    bool aligned16 = true, aligned32 = true;
+    for (int i = 0; i < a.ncols; ++i) {
+        aligned16 = aligned16 && ((uintptr_t)a.cols[i].ptr % 16) == 0;
+        aligned32 = aligned32 && ((uintptr_t)a.cols[i].ptr % 32) == 0;
+    }
+    // Visit plan.  Dense ids turn the sample into an arithmetic progression of row numbers: for small steps every 32-byte
+    // sector is touched anyway, so the ring streams everything and filters on the row number; from step 8 on the strided
+    // gather reads less.  AQE_SQL_VARIANT: 0 auto | 1 register-staged kernel only (tools/sql_bench.py compares them).
+    const int variant = env_int("AQE_SQL_VARIANT", 0);
+    const bool strided = dense && (step >= 8 || !aligned16 || variant == 1);
+    if (strided) {
+        a.first = (uint64_t)((step - phase) % step); a.stride = (uint64_t)step;
+        a.count = a.first < db->n ? (db->n - a.first + step - 1) / step : 0;
+        if (a.count == 0) return AQE_OK;
+    } else if (dense) {
+        ra.samp_step = (uint32_t)step; ra.samp_phase = (uint32_t)phase;
+    }
+    const bool ring = !strided && aligned16 && variant != 1;
     const int mode = a.group_slot < 0 ? 0 : (G <= (uint32_t)kSqlPrivateMaxGroups ? 1 : 2);
-    size_t smem = 0;
-    if (mode == 1) smem = (size_t)G * kSqlThreads * (4 + 16 + (moments ? 16 : 0));
-    if (mode == 2) smem = (size_t)G * (4 + 16 + (moments ? 16 : 0));
     cudaStream_t s = db->stream;
-    if (mode == 0) rc = moments ? sql_launch_v<0, true>(db, a, vec, smem, s) : sql_launch_v<0, false>(db, a, vec, smem, s);
-    else if (mode == 1) rc = moments ? sql_launch_v<1, true>(db, a, vec, smem, s) : sql_launch_v<1, false>(db, a, vec, smem, s);
-    else rc = moments ? sql_launch_v<2, true>(db, a, vec, smem, s) : sql_launch_v<2, false>(db, a, vec, smem, s);
+    if (ring) {
+        if (mode == 0) rc = moments ? sql_launch_ring<0, true>(db, ra, s) : sql_launch_ring<0, false>(db, ra, s);
+        else if (mode == 1) rc = moments ? sql_launch_ring<1, true>(db, ra, s) : sql_launch_ring<1, false>(db, ra, s);
+        else rc = moments ? sql_launch_ring<2, true>(db, ra, s) : sql_launch_ring<2, false>(db, ra, s);
+    } else {
+        if (!strided && dense) {  // register kernel has no row-number filter: visit the progression
+            a.first = (uint64_t)((step - phase) % step); a.stride = (uint64_t)step;
+            a.count = a.first < db->n ? (db->n - a.first + step - 1) / step : 0;
+            if (a.count == 0) return AQE_OK;
+        }
+        const bool vec = a.stride == 1 && aligned32;
+        if (mode == 0) rc = moments ? sql_launch_regs<0, true>(db, a, vec, s) : sql_launch_regs<0, false>(db, a, vec, s);
+        else if (mode == 1) rc = moments ? sql_launch_regs<1, true>(db, a, vec, s) : sql_launch_regs<1, false>(db, a, vec, s);
+        else rc = moments ? sql_launch_regs<2, true>(db, a, vec, s) : sql_launch_regs<2, false>(db, a, vec, s);
+    }
     if (rc) return rc;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(db->stream));

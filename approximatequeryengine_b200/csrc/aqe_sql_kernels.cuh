@@ -164,65 +164,48 @@ __device__ __forceinline__ void shared_add128(unsigned int* limbs, long long v) 
     limb_add(limbs + 3, sign, c);
 }
 
-// MODE 0: no GROUP BY (registers) | 1: thread-private shared bins | 2: CTA-shared bins with atomics
-// VEC: rows are visited with stride 1 from a multiple of four and every column is 32-byte aligned -> 4 rows per load
-template <int MODE, bool MOMENTS, bool VEC>
-__global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
-    extern __shared__ __align__(16) unsigned char sql_smem[];
-    const unsigned int G = a.n_groups;
-    const int tid = threadIdx.x;
-    constexpr int T = kSqlThreads;
-
-    // ---- bins ----
+// ---- bins: where a row's (count, value, value^2) lands ------------------------------------------------------
+// MODE 0: no GROUP BY (registers) | 1: thread-private shared bins | 2: CTA-shared bins with atomics.
+// T = threads that add rows (the private bins are laid out [bin][T]); every thread of the CTA must call flush().
+template <int MODE, bool MOMENTS, int T> struct SqlBins {
+    unsigned int G;
     // MODE 1: cnt[G][T] u32 | slo[G][T] u64 | shi[G][T] u64 | (qlo, qhi)
     // MODE 2: cnt[G] u32 | sum limbs [G][4] u32 | (sq limbs [G][4])
-    unsigned int* b_cnt = reinterpret_cast<unsigned int*>(sql_smem);
-    unsigned long long* p_slo = nullptr; unsigned long long* p_shi = nullptr; unsigned long long* p_qlo = nullptr; unsigned long long* p_qhi = nullptr;
-    unsigned int* s_sum = nullptr; unsigned int* s_sq = nullptr;
-    if constexpr (MODE == 1) {
-        p_slo = reinterpret_cast<unsigned long long*>(sql_smem + (size_t)G * T * 4);
-        p_shi = p_slo + (size_t)G * T;
-        p_qlo = p_shi + (size_t)G * T;
-        p_qhi = p_qlo + (size_t)G * T;
-        for (unsigned int g = 0; g < G; ++g) {
-            b_cnt[g * T + tid] = 0; p_slo[g * T + tid] = 0; p_shi[g * T + tid] = 0;
-            if constexpr (MOMENTS) { p_qlo[g * T + tid] = 0; p_qhi[g * T + tid] = 0; }
+    unsigned int* b_cnt;
+    unsigned long long *p_slo, *p_shi, *p_qlo, *p_qhi;
+    unsigned int *s_sum, *s_sq;
+    unsigned long long r_cnt, r_slo, r_qlo;
+    long long r_shi, r_qhi;
+
+    static size_t smem_bytes(unsigned int G) {
+        if (MODE == 1) return (size_t)G * T * (4 + 16 + (MOMENTS ? 16 : 0));
+        if (MODE == 2) return (size_t)G * (4 + 16 + (MOMENTS ? 16 : 0));
+        return 0;
+    }
+    // all threads of the CTA call init (it contains a barrier); tid < T owns a private column of bins
+    __device__ __forceinline__ void init(unsigned char* smem, unsigned int groups, int tid, int nthreads) {
+        G = groups;
+        b_cnt = reinterpret_cast<unsigned int*>(smem);
+        r_cnt = 0; r_slo = 0; r_qlo = 0; r_shi = 0; r_qhi = 0;
+        if constexpr (MODE == 1) {
+            p_slo = reinterpret_cast<unsigned long long*>(smem + (size_t)G * T * 4);
+            p_shi = p_slo + (size_t)G * T;
+            p_qlo = p_shi + (size_t)G * T;
+            p_qhi = p_qlo + (size_t)G * T;
+            if (tid < T)
+                for (unsigned int g = 0; g < G; ++g) {
+                    b_cnt[g * T + tid] = 0; p_slo[g * T + tid] = 0; p_shi[g * T + tid] = 0;
+                    if constexpr (MOMENTS) { p_qlo[g * T + tid] = 0; p_qhi[g * T + tid] = 0; }
+                }
+        } else if constexpr (MODE == 2) {
+            s_sum = b_cnt + G;
+            s_sq = s_sum + (size_t)G * 4;
+            for (unsigned int i = tid; i < G; i += nthreads) b_cnt[i] = 0;
+            for (unsigned int i = tid; i < G * 4; i += nthreads) { s_sum[i] = 0; if constexpr (MOMENTS) s_sq[i] = 0; }
         }
-    } else if constexpr (MODE == 2) {
-        s_sum = b_cnt + G;
-        s_sq = s_sum + (size_t)G * 4;
-        for (unsigned int i = tid; i < G; i += T) b_cnt[i] = 0;
-        for (unsigned int i = tid; i < G * 4; i += T) { s_sum[i] = 0; if constexpr (MOMENTS) s_sq[i] = 0; }
         __syncthreads();
     }
-    // MODE 0 registers
-    unsigned long long r_cnt = 0, r_slo = 0, r_qlo = 0;
-    long long r_shi = 0, r_qhi = 0;
-
-    auto consume = [&](const long long (&raw)[kSqlMaxCols]) {
-        bool pass = true;
-#pragma unroll
-        for (int c = 0; c < kSqlMaxCols; ++c)
-            if (c < a.ncols) pass = pass && sql_pass(a.cols[c], raw[c]);
-        if (!pass) return;
-        long long fx = 0, fq = 0;
-        if (a.agg_slot >= 0) {
-            long long rv = 0;
-#pragma unroll
-            for (int c = 0; c < kSqlMaxCols; ++c) if (c == a.agg_slot) rv = raw[c];
-            double d;
-            if (a.agg_kind == 0) { d = __longlong_as_double(rv); fx = __double2ll_rn(__dmul_rn(d, a.sum_scale)); }
-            else { d = (double)rv; fx = rv; }
-            if constexpr (MOMENTS) fq = __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale));
-        }
-        unsigned int g = 0;
-        if constexpr (MODE != 0) {
-            long long kv = 0;
-#pragma unroll
-            for (int c = 0; c < kSqlMaxCols; ++c) if (c == a.group_slot) kv = raw[c];
-            g = (unsigned int)(kv - a.key_min);
-            if (g >= G) return;  // cannot happen when the layout came from this table's statistics
-        }
+    __device__ __forceinline__ void add(unsigned int g, int tid, bool has_sum, long long fx, long long fq) {
         if constexpr (MODE == 0) {
             r_cnt += 1;
             r_slo += (unsigned long long)fx & 0xffffffffull; r_shi += fx >> 32;
@@ -234,12 +217,118 @@ __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
             if constexpr (MOMENTS) { p_qlo[s] += (unsigned long long)fq & 0xffffffffull; p_qhi[s] += (unsigned long long)(fq >> 32); }
         } else {
             atomicAdd(b_cnt + g, 1u);
-            if (a.agg_slot >= 0) {
+            if (has_sum) {
                 shared_add128(s_sum + g * 4, fx);
                 if constexpr (MOMENTS) shared_add128(s_sq + g * 4, fq);
             }
         }
-    };
+    }
+    // CTA totals -> global accumulators (integer atomics: order does not matter)
+    __device__ __forceinline__ void flush(unsigned long long* global_acc, int tid, int nthreads) {
+        if constexpr (MODE == 0) {
+            r_cnt = warp_reduce_u64(r_cnt);
+            r_slo = warp_reduce_u64(r_slo); r_shi = (long long)warp_reduce_u64((unsigned long long)r_shi);
+            if constexpr (MOMENTS) { r_qlo = warp_reduce_u64(r_qlo); r_qhi = (long long)warp_reduce_u64((unsigned long long)r_qhi); }
+            if ((tid & 31) == 0 && r_cnt) {
+                unsigned long long lo, hi;
+                atomicAdd(global_acc + 0, r_cnt);
+                split_to_128(r_slo, r_shi, lo, hi); global_add128(global_acc + 1, lo, hi);
+                if constexpr (MOMENTS) { split_to_128(r_qlo, r_qhi, lo, hi); global_add128(global_acc + 3, lo, hi); }
+            }
+        } else if constexpr (MODE == 1) {
+            __syncthreads();
+            const int warp = tid >> 5, lane = tid & 31;
+            if (warp < T / 32)
+                for (unsigned int g = warp; g < G; g += T / 32) {
+                    unsigned long long c = 0, sl = 0, sh = 0, ql = 0, qh = 0;
+#pragma unroll
+                    for (int k = 0; k < T / 32; ++k) {
+                        const unsigned int s = g * T + lane + 32 * k;
+                        c += b_cnt[s]; sl += p_slo[s]; sh += p_shi[s];
+                        if constexpr (MOMENTS) { ql += p_qlo[s]; qh += p_qhi[s]; }
+                    }
+                    c = warp_reduce_u64(c); sl = warp_reduce_u64(sl); sh = warp_reduce_u64(sh);
+                    if constexpr (MOMENTS) { ql = warp_reduce_u64(ql); qh = warp_reduce_u64(qh); }
+                    if (lane == 0 && c) {
+                        unsigned long long lo, hi;
+                        unsigned long long* ga = global_acc + (size_t)g * 5;
+                        atomicAdd(ga + 0, c);
+                        split_to_128(sl, (long long)sh, lo, hi); global_add128(ga + 1, lo, hi);
+                        if constexpr (MOMENTS) { split_to_128(ql, (long long)qh, lo, hi); global_add128(ga + 3, lo, hi); }
+                    }
+                }
+        } else {
+            __syncthreads();
+            for (unsigned int g = tid; g < G; g += nthreads) {
+                const unsigned int c = b_cnt[g];
+                if (!c) continue;
+                unsigned long long* ga = global_acc + (size_t)g * 5;
+                atomicAdd(ga + 0, (unsigned long long)c);
+                const unsigned int* l = s_sum + g * 4;
+                global_add128(ga + 1, ((unsigned long long)l[1] << 32) | l[0], ((unsigned long long)l[3] << 32) | l[2]);
+                if constexpr (MOMENTS) {
+                    const unsigned int* m = s_sq + g * 4;
+                    global_add128(ga + 3, ((unsigned long long)m[1] << 32) | m[0], ((unsigned long long)m[3] << 32) | m[2]);
+                }
+            }
+        }
+    }
+};
+
+// One row, row-at-a-time form (register-staged kernel and ragged tails): predicate, fixed-point conversion, bin update.
+template <int MODE, bool MOMENTS, int T>
+__device__ __forceinline__ void sql_consume(const SqlArgs& a, SqlBins<MODE, MOMENTS, T>& bins, int tid, const long long (&raw)[kSqlMaxCols]) {
+    bool pass = true;
+#pragma unroll
+    for (int c = 0; c < kSqlMaxCols; ++c)
+        if (c < a.ncols) pass = pass && sql_pass(a.cols[c], raw[c]);
+    if (!pass) return;
+    long long fx = 0, fq = 0;
+    if (a.agg_slot >= 0) {
+        long long rv = 0;
+#pragma unroll
+        for (int c = 0; c < kSqlMaxCols; ++c) if (c == a.agg_slot) rv = raw[c];
+        double d;
+        if (a.agg_kind == 0) { d = __longlong_as_double(rv); fx = __double2ll_rn(__dmul_rn(d, a.sum_scale)); }
+        else { d = (double)rv; fx = rv; }
+        if constexpr (MOMENTS) fq = __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale));
+    }
+    unsigned int g = 0;
+    if constexpr (MODE != 0) {
+        long long kv = 0;
+#pragma unroll
+        for (int c = 0; c < kSqlMaxCols; ++c) if (c == a.group_slot) kv = raw[c];
+        g = (unsigned int)(kv - a.key_min);
+        if (g >= bins.G) return;  // cannot happen when the layout came from this table's statistics
+    }
+    bins.add(g, tid, a.agg_slot >= 0, fx, fq);
+}
+
+// last CTA: publish the accumulators and re-arm them for the next launch
+__device__ __forceinline__ void sql_publish(const SqlArgs& a, int tid, int nthreads) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (unsigned int i = tid; i < a.n_groups * 5; i += nthreads) {
+        a.out[i] = __ldcg(a.global_acc + i);
+        a.global_acc[i] = 0ull;
+    }
+    if (tid == 0) *a.ticket = 0u;
+}
+
+// Register-staged visit: strided samples (rowid % step = 0 over dense ids becomes an arithmetic progression of row
+// numbers) and columns that are not vector aligned.  VEC: stride 1 from row 0, every column 32-byte aligned -> 4 rows per load.
+template <int MODE, bool MOMENTS, bool VEC>
+__global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
+    extern __shared__ __align__(16) unsigned char sql_smem[];
+    const int tid = threadIdx.x;
+    constexpr int T = kSqlThreads;
+    SqlBins<MODE, MOMENTS, T> bins;
+    bins.init(sql_smem, a.n_groups, tid, T);
 
     const uint64_t gsz = (uint64_t)gridDim.x * T;
     const uint64_t gtid = (uint64_t)blockIdx.x * T + tid;
@@ -255,7 +344,7 @@ __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
                 long long raw[kSqlMaxCols];
 #pragma unroll
                 for (int c = 0; c < kSqlMaxCols; ++c) raw[c] = c < a.ncols ? raw4[c][e] : 0;
-                consume(raw);
+                sql_consume(a, bins, tid, raw);
             }
         }
         if (gtid == 0) {
@@ -263,91 +352,236 @@ __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
                 long long raw[kSqlMaxCols];
 #pragma unroll
                 for (int c = 0; c < kSqlMaxCols; ++c) raw[c] = c < a.ncols ? sql_load_raw(a.cols[c], a.first + j) : 0;
-                consume(raw);
+                sql_consume(a, bins, tid, raw);
             }
         }
     } else {
-        // strided / unaligned visit: four independent rows in flight per thread
+        // eight independent rows in flight per thread
+        constexpr int U = 8;
         uint64_t j = gtid;
-        for (; j + 3 * gsz < a.count; j += 4 * gsz) {
-            long long raw4[4][kSqlMaxCols];
+        for (; j + (U - 1) * gsz < a.count; j += U * gsz) {
+            long long rawu[U][kSqlMaxCols];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
+            for (int e = 0; e < U; ++e)
 #pragma unroll
                 for (int c = 0; c < kSqlMaxCols; ++c)
-                    raw4[e][c] = c < a.ncols ? sql_load_raw(a.cols[c], a.first + (j + (uint64_t)e * gsz) * a.stride) : 0;
+                    rawu[e][c] = c < a.ncols ? sql_load_raw(a.cols[c], a.first + (j + (uint64_t)e * gsz) * a.stride) : 0;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) consume(raw4[e]);
+            for (int e = 0; e < U; ++e) sql_consume(a, bins, tid, rawu[e]);
         }
         for (; j < a.count; j += gsz) {
             long long raw[kSqlMaxCols];
 #pragma unroll
             for (int c = 0; c < kSqlMaxCols; ++c) raw[c] = c < a.ncols ? sql_load_raw(a.cols[c], a.first + j * a.stride) : 0;
-            consume(raw);
+            sql_consume(a, bins, tid, raw);
         }
     }
+    bins.flush(a.global_acc, tid, T);
+    sql_publish(a, tid, T);
+}
 
-    // ---- CTA totals -> global accumulators (integer atomics: order does not matter) ----
-    if constexpr (MODE == 0) {
-        r_cnt = warp_reduce_u64(r_cnt);
-        r_slo = warp_reduce_u64(r_slo); r_shi = (long long)warp_reduce_u64((unsigned long long)r_shi);
-        if constexpr (MOMENTS) { r_qlo = warp_reduce_u64(r_qlo); r_qhi = (long long)warp_reduce_u64((unsigned long long)r_qhi); }
-        if ((tid & 31) == 0 && r_cnt) {
-            unsigned long long lo, hi;
-            atomicAdd(a.global_acc + 0, r_cnt);
-            split_to_128(r_slo, r_shi, lo, hi); global_add128(a.global_acc + 1, lo, hi);
-            if constexpr (MOMENTS) { split_to_128(r_qlo, r_qhi, lo, hi); global_add128(a.global_acc + 3, lo, hi); }
-        }
-    } else if constexpr (MODE == 1) {
-        __syncthreads();
-        const int warp = tid >> 5, lane = tid & 31;
-        for (unsigned int g = warp; g < G; g += T / 32) {
-            unsigned long long c = 0, sl = 0, sh = 0, ql = 0, qh = 0;
+// TMA-staged ring (the default for full scans of aligned columns): a producer warp streams, per tile of `tile_rows`
+// rows, the matching slice of EVERY column the query reads into one shared-memory stage with 1-D bulk copies
+// (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier; 8 consumer warps work on the tile out of shared memory.
+// Bytes in flight are set by the ring, not by registers.
+//
+// The consumers run COLUMN AT A TIME over a tile: thread t owns rows t, t+256, ... (kSqlRowsPerThread of them,
+// conflict-free LDS.64 / LDS.32) and keeps one pass bit per row in a register.  Each predicate column is one tight,
+// type-specialised, fully unrolled pass over those rows (the type switch sits outside the row loop), then one pass
+// derives the group index, then one pass converts and accumulates the aggregate column.  A row-at-a-time interpreter
+// of the same query costs ~110 warp instructions per 32 rows (measured, ncu) and is issue/latency bound at 1.0 TB/s.
+// The passes are unconditional over all kSqlRowsPerThread row slots: slots beyond the tile's rows read whatever
+// follows in shared memory (the next stage, the bins, or the slack the host adds after the ring) and stay masked off.
+//
+// The reference's `rowid % step = 0` over dense ids is a filter on the row number here (no id column read) -- used
+// while step is small enough that every 32-byte sector is touched anyway; larger steps take the strided visit.
+constexpr int kSqlRowsPerThread = 8;
+
+struct SqlRingArgs {
+    SqlArgs q;
+    uint32_t tile_rows;           // multiple of 256, <= 256 * kSqlRowsPerThread
+    uint32_t col_off[kSqlMaxCols];  // byte offset of each column's slice inside a stage (multiples of 16)
+    uint32_t stage_bytes;
+    uint32_t ring_bytes;          // STAGES * stage_bytes + slack so that row slot 256 * kSqlRowsPerThread - 1 of any column is mapped
+    uint32_t samp_step;           // 0/1: every row; else row i passes iff (i + samp_phase) % samp_step == 0
+    uint32_t samp_phase;
+};
+
+template <typename T> __device__ __forceinline__ T lds_row(const unsigned char* base, uint32_t row) {
+    return *reinterpret_cast<const T*>(base + (size_t)row * sizeof(T));
+}
+
+// one predicate column over this thread's row slots of the tile: clears the pass bit of every row that fails
+template <int T> __device__ __forceinline__ uint32_t sql_pred_pass(const SqlCol& col, const unsigned char* base, int tid, uint32_t mask) {
+    constexpr int K = kSqlRowsPerThread;
+    if (col.kind == 0) {
+        const double lo = __longlong_as_double(col.lo), hi = __longlong_as_double(col.hi), ne = __longlong_as_double(col.ne);
+        const bool has_ne = col.has_ne != 0;
 #pragma unroll
-            for (int k = 0; k < T / 32; ++k) {
-                const unsigned int s = g * T + lane + 32 * k;
-                c += b_cnt[s]; sl += p_slo[s]; sh += p_shi[s];
-                if constexpr (MOMENTS) { ql += p_qlo[s]; qh += p_qhi[s]; }
-            }
-            c = warp_reduce_u64(c); sl = warp_reduce_u64(sl); sh = warp_reduce_u64(sh);
-            if constexpr (MOMENTS) { ql = warp_reduce_u64(ql); qh = warp_reduce_u64(qh); }
-            if (lane == 0 && c) {
-                unsigned long long lo, hi;
-                unsigned long long* ga = a.global_acc + (size_t)g * 5;
-                atomicAdd(ga + 0, c);
-                split_to_128(sl, (long long)sh, lo, hi); global_add128(ga + 1, lo, hi);
-                if constexpr (MOMENTS) { split_to_128(ql, (long long)qh, lo, hi); global_add128(ga + 3, lo, hi); }
+        for (int k = 0; k < K; ++k) {
+            const double v = lds_row<double>(base, tid + k * T);
+            const bool ok = v >= lo && v <= hi && !(has_ne && v == ne);
+            mask &= ~((ok ? 0u : 1u) << k);
+        }
+    } else if (col.kind == 1) {
+        const long long lo = col.has_pred ? col.lo : (long long)0x8000000000000000ull, hi = col.has_pred ? col.hi : 0x7fffffffffffffffll;
+        const bool has_ne = col.has_ne != 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const long long v = lds_row<long long>(base, tid + k * T);
+            const bool ok = v >= lo && v <= hi && !(has_ne && v == col.ne);
+            mask &= ~((ok ? 0u : 1u) << k);
+        }
+        if (col.mod_step > 0) {  // ids with gaps: rowid % step = 0 on the value itself
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if ((mask >> k) & 1u) {
+                    const long long v = lds_row<long long>(base, tid + k * T);
+                    if (v % (long long)col.mod_step != 0) mask &= ~(1u << k);
+                }
+        }
+    } else {
+        // int32 column: the int64 bounds clamp to the int32 range
+        const long long lo64 = col.lo < -2147483648ll ? -2147483648ll : col.lo, hi64 = col.hi > 2147483647ll ? 2147483647ll : col.hi;
+        if (lo64 > 2147483647ll || hi64 < -2147483648ll) return 0u;
+        const int lo = (int)lo64, hi = (int)hi64;
+        const bool has_ne = col.has_ne != 0 && col.ne >= -2147483648ll && col.ne <= 2147483647ll;
+        const int ne = (int)col.ne;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int v = lds_row<int>(base, tid + k * T);
+            const bool ok = v >= lo && v <= hi && !(has_ne && v == ne);
+            mask &= ~((ok ? 0u : 1u) << k);
+        }
+    }
+    return mask;
+}
+
+template <int MODE, bool MOMENTS, int STAGES>
+__global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra) {
+    extern __shared__ __align__(128) unsigned char sql_ring_smem[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    const SqlArgs& a = ra.q;
+    constexpr int T = kBulkConsumerWarps * 32;
+    constexpr int K = kSqlRowsPerThread;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* ring = sql_ring_smem;
+    unsigned char* bin_mem = sql_ring_smem + ra.ring_bytes;
+    SqlBins<MODE, MOMENTS, T> bins;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kBulkConsumerWarps); }
+        fence_barrier_init();
+    }
+    bins.init(bin_mem, a.n_groups, tid, kBulkThreads);  // ends with __syncthreads()
+
+    const uint64_t n_main = a.count & ~3ull;  // bulk copies move multiples of 16 bytes: 4 rows of a 4-byte column
+    const uint64_t ntiles = (n_main + ra.tile_rows - 1) / ra.tile_rows;
+    if (warp == kBulkConsumerWarps) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint64_t c = blockIdx.x; c < ntiles; c += gridDim.x, ++it) {
+                const int s = it % STAGES;
+                const uint32_t round = it / STAGES;
+                if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+                const uint64_t row0 = c * (uint64_t)ra.tile_rows;
+                const uint32_t rows = (uint32_t)((n_main - row0) < (uint64_t)ra.tile_rows ? (n_main - row0) : (uint64_t)ra.tile_rows);
+                unsigned char* stage = ring + (size_t)s * ra.stage_bytes;
+                uint32_t bytes = 0;
+                for (int k = 0; k < a.ncols; ++k) bytes += rows * (a.cols[k].kind == 2 ? 4u : 8u);
+                mbar_expect_tx(&full_bar[s], bytes);
+                for (int k = 0; k < a.ncols; ++k) {
+                    const uint32_t w = a.cols[k].kind == 2 ? 4u : 8u;
+                    bulk_g2s(stage + ra.col_off[k], static_cast<const unsigned char*>(a.cols[k].ptr) + row0 * w, rows * w, &full_bar[s]);
+                }
             }
         }
     } else {
-        __syncthreads();
-        for (unsigned int g = tid; g < G; g += T) {
-            const unsigned int c = b_cnt[g];
-            if (!c) continue;
-            unsigned long long* ga = a.global_acc + (size_t)g * 5;
-            atomicAdd(ga + 0, (unsigned long long)c);
-            const unsigned int* l = s_sum + g * 4;
-            global_add128(ga + 1, ((unsigned long long)l[1] << 32) | l[0], ((unsigned long long)l[3] << 32) | l[2]);
-            if constexpr (MOMENTS) {
-                const unsigned int* m = s_sq + g * 4;
-                global_add128(ga + 3, ((unsigned long long)m[1] << 32) | m[0], ((unsigned long long)m[3] << 32) | m[2]);
+        const int agg_slot = a.agg_slot, group_slot = a.group_slot;
+        const int agg_kind = agg_slot >= 0 ? a.cols[agg_slot].kind : -1;
+        uint32_t it = 0;
+        for (uint64_t c = blockIdx.x; c < ntiles; c += gridDim.x, ++it) {
+            const int s = it % STAGES;
+            const uint32_t round = it / STAGES;
+            mbar_wait(&full_bar[s], round & 1);
+            const uint64_t row0 = c * (uint64_t)ra.tile_rows;
+            const uint32_t rows = (uint32_t)((n_main - row0) < (uint64_t)ra.tile_rows ? (n_main - row0) : (uint64_t)ra.tile_rows);
+            const unsigned char* stage = ring + (size_t)s * ra.stage_bytes;
+            // pass bits of rows tid, tid + T, ... of this tile
+            const uint32_t nk = rows > (uint32_t)tid ? (rows - (uint32_t)tid + T - 1) / T : 0u;
+            uint32_t mask = (1u << nk) - 1u;  // nk <= K = 8
+            for (int k = 0; k < a.ncols; ++k) {
+                const SqlCol& col = a.cols[k];
+                if (col.has_pred || col.mod_step > 0) mask = sql_pred_pass<T>(col, stage + ra.col_off[k], tid, mask);
+            }
+            if (ra.samp_step > 1) {
+                uint32_t x = (uint32_t)((row0 + ra.samp_phase + (uint32_t)tid) % ra.samp_step);  // (row + phase) mod step
+                const uint32_t dt = (uint32_t)T % ra.samp_step;                                  // advanced by T mod step per owned row
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (x != 0) mask &= ~(1u << k);
+                    x += dt;
+                    if (x >= ra.samp_step) x -= ra.samp_step;
+                }
+            }
+            unsigned int g[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) g[k] = 0;
+            if constexpr (MODE != 0) {
+                const unsigned char* gb = stage + ra.col_off[group_slot];
+                if (a.cols[group_slot].kind == 2) {
+                    const int kmin = (int)a.key_min;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) g[k] = (unsigned int)(lds_row<int>(gb, tid + k * T) - kmin);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) g[k] = (unsigned int)(lds_row<long long>(gb, tid + k * T) - a.key_min);
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) if (g[k] >= bins.G) mask &= ~(1u << k);  // cannot happen for live rows with this table's own layout
+            }
+            if (agg_kind < 0) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, false, 0, 0);
+            } else if (agg_kind == 0) {
+                const unsigned char* ab = stage + ra.col_off[agg_slot];
+                long long fx[K], fq[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const double d = lds_row<double>(ab, tid + k * T);
+                    fx[k] = __double2ll_rn(__dmul_rn(d, a.sum_scale));
+                    fq[k] = MOMENTS ? __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale)) : 0;
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, true, fx[k], fq[k]);
+            } else {
+                const unsigned char* ab = stage + ra.col_off[agg_slot];
+                long long fx[K], fq[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    fx[k] = agg_kind == 2 ? (long long)lds_row<int>(ab, tid + k * T) : lds_row<long long>(ab, tid + k * T);
+                    const double d = (double)fx[k];
+                    fq[k] = MOMENTS ? __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale)) : 0;
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, true, fx[k], fq[k]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+        if (blockIdx.x == 0 && tid == 0) {  // the count % 4 tail
+            for (uint64_t j = n_main; j < a.count; ++j) {
+                long long raw[kSqlMaxCols];
+#pragma unroll
+                for (int k = 0; k < kSqlMaxCols; ++k) raw[k] = k < a.ncols ? sql_load_raw(a.cols[k], j) : 0;
+                if (ra.samp_step > 1 && (j + ra.samp_phase) % ra.samp_step != 0) continue;
+                sql_consume(a, bins, tid, raw);
             }
         }
     }
-
-    // ---- last CTA: publish and re-arm ----
-    __shared__ bool is_last;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    for (unsigned int i = tid; i < G * 5; i += T) {
-        a.out[i] = __ldcg(a.global_acc + i);
-        a.global_acc[i] = 0ull;
-    }
-    if (tid == 0) *a.ticket = 0u;
+    bins.flush(a.global_acc, tid, kBulkThreads);
+    sql_publish(a, tid, kBulkThreads);
 }
 
 }  // namespace aqe

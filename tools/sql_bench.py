@@ -1,0 +1,60 @@
+#!/usr/bin/env python3
+"""Timings of the SQL-string path (k_sql_agg) on a device-generated table: ms per query (median of reps, host wall clock
+around the synchronous C-ABI call), rows/s and achieved GB/s against the ALGORITHMIC bytes of the query (the widths of
+the distinct columns it reads x rows visited).  python tools/sql_bench.py [rows] [reps] > out.json"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import approximatequeryengine_b200 as aqe  # noqa: E402
+
+WIDTH = {"id": 8, "amount": 8, "region": 4, "product_id": 4, "timestamp": 8}
+T0 = 1700000000
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000_000
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 9
+    e = aqe.Engine(0).generate(n, seed=7)
+    cases = [
+        ("SELECT SUM(amount) FROM sales", 0, "value", ["amount"]),
+        ("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 100 AND 500", 0, "value", ["amount"]),
+        ("SELECT COUNT(amount) FROM sales WHERE amount BETWEEN 100 AND 500", 0, "value", ["amount"]),
+        ("SELECT SUM(timestamp) FROM sales WHERE region = 3", 0, "value", ["timestamp", "region"]),
+        ("SELECT SUM(amount) FROM sales GROUP BY region", 0, "value", ["amount", "region"]),
+        ("SELECT COUNT(amount) FROM sales GROUP BY region", 0, "value", ["region"]),
+        (f"SELECT AVG(amount) FROM sales WHERE timestamp BETWEEN {T0 + n // 4} AND {T0 + n // 2} GROUP BY region", 0, "value", ["amount", "region", "timestamp"]),
+        ("SELECT SUM(amount) FROM sales GROUP BY region", 0, "ci_reference", ["amount", "region"]),
+        ("SELECT SUM(amount) FROM sales GROUP BY product_id", 0, "value", ["amount", "product_id"]),
+        ("SELECT COUNT(amount) FROM sales GROUP BY product_id", 0, "value", ["product_id"]),
+        ("SELECT SUM(amount) FROM sales WHERE amount > 900 GROUP BY product_id", 0, "value", ["amount", "product_id"]),
+        ("SELECT SUM(amount) FROM sales", 50, "ci_reference", ["amount"]),
+        ("SELECT SUM(amount) FROM sales", 10, "ci_reference", ["amount"]),
+        ("SELECT SUM(amount) FROM sales", 1, "ci_reference", ["amount"]),
+        ("SELECT AVG(amount) FROM sales GROUP BY region", 10, "ci_reference", ["amount", "region"]),
+        ("SELECT SUM(amount) FROM sales GROUP BY product_id", 1, "value", ["amount", "product_id"]),
+    ]
+    out = []
+    for sql, p, mode, cols in cases:
+        e.sql(sql, p, mode)  # warm (column statistics are computed on first use)
+        ts = []
+        for _ in range(reps):
+            t = time.perf_counter()
+            rows = e.sql(sql, p, mode)
+            ts.append(time.perf_counter() - t)
+        ts.sort()
+        ms = ts[len(ts) // 2] * 1e3
+        step = 1 if p <= 0 or p >= 100 else max(1, 100 // p)
+        visited = n // step
+        # a strided visit of 8-byte values touches one 32-byte sector per row once step >= 4
+        alg = sum(WIDTH[c] for c in cols) * visited
+        out.append({"sql": sql, "p": p, "mode": mode, "ms": round(ms, 4), "rows_per_s": n / (ms / 1e3), "visited_rows": visited,
+                    "algorithmic_GB": alg / 1e9, "GBps": alg / 1e9 / (ms / 1e3), "groups": len(rows)})
+        print(f"{ms:9.3f} ms  {alg / 1e9 / (ms / 1e3):8.1f} GB/s  p={p:<3} {mode:13} {sql}", file=sys.stderr)
+    json.dump({"rows": n, "reps": reps, "cases": out}, sys.stdout, indent=1)
+
+
+if __name__ == "__main__":
+    main()
