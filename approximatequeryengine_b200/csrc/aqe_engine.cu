@@ -1681,13 +1681,15 @@ template <int MODE, bool MOMENTS> static int sql_launch_ring(const aqe_db* db, S
         const size_t smem = (size_t)ra.ring_bytes + bins;
         const int occ = sql_occupancy((const void*)kernel, kBulkThreads, smem);
         if (occ < 1) return -1;
-        int grid = (int)std::min<uint64_t>((uint64_t)db->sm_count * std::min(occ, 2), std::max<uint64_t>(ntiles, 1));
+        int grid = (int)std::min<uint64_t>((uint64_t)db->sm_count * std::min(occ, env_int("AQE_SQL_BPS", 4)), std::max<uint64_t>(ntiles, 1));
         if (grid > db->max_grid) grid = db->max_grid;
         kernel<<<grid, kBulkThreads, smem, s>>>(ra);
         LAUNCHED();
         return AQE_OK;
     };
-    int rc = go(k_sql_ring<MODE, MOMENTS, 4>, 4);
+    // 2 stages x up to 4 CTAs/SM beat 4 stages x 2 CTAs/SM on every grouped query of tools/sql_bench.py (27 instead of
+    // 18 consumer warps per SM hide the shared-memory latency of the bin updates; profiles/r1_sql_bench.json)
+    int rc = env_int("AQE_SQL_STAGES", 2) == 4 ? go(k_sql_ring<MODE, MOMENTS, 4>, 4) : -1;
     if (rc == -1) rc = go(k_sql_ring<MODE, MOMENTS, 2>, 2);
     if (rc == -1) return fail(AQE_ERR_UNSUPPORTED, "SQL path: group bins do not fit shared memory");
     return rc;
