@@ -13,7 +13,8 @@ import ctypes as C
 
 import numpy as np
 
-from . import AGG, ApproxResult, Engine, Partial, check, lib
+from . import (AGG, SQL_MOMENTS, SQL_UNSAMPLED, ApproxResult, Engine, Partial, SqlFacts, check, lib, sql_finish, sql_layout,
+               sql_merge, sql_parse)
 
 
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
@@ -44,6 +45,22 @@ def allgather_struct(obj, cls, group=None, device=None):
     dist.all_gather_into_tensor(out, mine, group=group)
     flat = out.cpu().numpy().reshape(world, words)
     return [_i64_to_struct(flat[r], cls) for r in range(world)]
+
+
+def allgather_words(arr: np.ndarray, group=None, device=None) -> np.ndarray:
+    """All-gather a fixed-length uint64 array (as int64 words) -> [world, len] in rank order."""
+    import torch
+    import torch.distributed as dist
+
+    arr = np.ascontiguousarray(arr, dtype=np.uint64)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return arr.reshape(1, -1)
+    world = dist.get_world_size(group)
+    dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    mine = torch.from_numpy(arr.view(np.int64).copy()).to(dev)
+    out = torch.empty(world * len(arr), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return out.cpu().numpy().view(np.uint64).reshape(world, len(arr))
 
 
 def merge_partials(parts, is_integer: bool = False) -> Partial:
@@ -118,6 +135,33 @@ class ShardedTable:
 
     def count(self) -> int:
         return self.total_rows
+
+    def sql(self, query: str, sample_percent: int = 0, mode: str = "value"):
+        """run_query* over the sharded table (executor.cpp:28-338): every rank scans its shard into the order-independent
+        128-bit integer accumulators of the grouped-scan kernel, the accumulators are all-gathered and added with carry
+        (exact: the result does not depend on the shard count), and every rank applies the reference's arithmetic.
+        Three tiny exchanges: the 32-byte column facts (so that all shards use one key range and one fixed-point
+        scale), the accumulators, and -- only when a group has no sampled row anywhere -- the unsampled group counts."""
+        q = sql_parse(query, sample_percent)
+        facts = allgather_struct(self.engine.sql_facts(q), SqlFacts, self.group)
+        layout = sql_layout(q, facts)
+        grouped = q.group_col >= 0
+        step = 0 if (sample_percent <= 0 or sample_percent >= 100) else max(1, 100 // sample_percent)
+        if mode == "value":
+            moments = False
+        elif grouped:
+            moments = mode == "ci_reference" or q.agg != AGG["count"]
+        else:
+            moments = q.agg != AGG["count"] and step > 0
+        acc = np.zeros(layout.n_groups * 5, dtype=np.uint64)
+        for part in allgather_words(self.engine.sql_scan(q, layout, SQL_MOMENTS if moments else 0), self.group):
+            sql_merge(acc, part)
+        exists = None
+        if grouped and step > 1 and (acc[0::5] == 0).any():   # identical on every rank: the pass below is collective
+            exists = np.zeros_like(acc)
+            for part in allgather_words(self.engine.sql_scan(q, layout, SQL_UNSAMPLED), self.group):
+                sql_merge(exists, part)
+        return sql_finish(q, layout, acc, mode, exists)
 
     def approx(self, agg="sum", error_percent=1.0, confidence_level=0.95, seed=0, **kw) -> ApproxResult:
         """Shards are strata: each rank runs its persistent CLT kernel to the same relative target with

@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-approx", action="store_true")
+    ap.add_argument("--skip-sql", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -399,6 +400,25 @@ def main():
         approx_multi = {"workload": f"BASELINE.json configs[3]: {rows * world} records sharded over {world} GPUs, APPROX SUM(amount) at 0.5% error, 95% confidence, "
                                     "block (1000-row tiles) and SRS designs, global CLT stop rule", "api": "aqe_approx_exchange (C-ABI), all ranks", **res}
 
+    # ---- secondary: the SQL-string path (run_query*) -- grouped scans over a 200 M-row table ----
+    sql = None
+    if rank == 0 and world == 1 and not args.skip_sql:
+        n_sql = min(rows, 200_000_000)
+        es = aqe.Engine(local).generate(n_sql, seed=SEED, columns=("id", "amount", "region", "product_id"))
+        sql = {"rows": n_sql, "api": "aqe_sql_run (C-ABI) -> k_sql_ring, one launch per query; ms = median host wall clock of the synchronous call", "queries": []}
+        for q, pct, mode, width in (("SELECT SUM(amount) FROM sales GROUP BY region", 0, "value", 12),
+                                    ("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 100 AND 500 GROUP BY region", 0, "ci_reference", 12),
+                                    ("SELECT AVG(amount) FROM sales GROUP BY product_id", 0, "value", 12),
+                                    ("SELECT SUM(amount) FROM sales GROUP BY region", 10, "ci_reference", 12)):
+            es.sql(q, pct, mode)
+            ts = []
+            for _ in range(9):
+                t0 = time.perf_counter(); r = es.sql(q, pct, mode); ts.append(time.perf_counter() - t0)
+            ms = statistics.median(ts) * 1e3
+            sql["queries"].append({"sql": q, "sample_percent": pct, "mode": mode, "ms": ms, "records_per_s": n_sql / (ms * 1e-3), "groups": len(r),
+                                   "algorithmic_GBps_full_scan": width * n_sql / 1e9 / (ms * 1e-3) if pct == 0 else None})
+        del es
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_reference(steps=10, warmup=2)
@@ -412,7 +432,7 @@ def main():
                              "kernel": "aqe::k_scan_ring<double, PRED=1 (amount on itself), double, STAGES=4, MOMENTS=false> (TMA bulk-copy ring, 16 KiB tiles, 2 CTAs/SM)", "kernel_ms": kms,
                              "kernel_ms_source": "timed region (a step is exactly one launch of this kernel)" if step_is_one_kernel else "kernel-only loop, same stream",
                              "kernel_ms_isolated_loop": kern_ms / args.steps, "algorithmic_bytes_per_launch": 8 * rows, "peak_source": peak_src},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clk, "approx": approx, "approx_multi_gpu": approx_multi, "exchange": ("fused in-kernel NVLink mailbox" if fused else ("nccl all_gather" if world > 1 else None)), "exchange_note": fused_note,
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clk, "approx": approx, "approx_multi_gpu": approx_multi, "sql": sql, "exchange": ("fused in-kernel NVLink mailbox" if fused else ("nccl all_gather" if world > 1 else None)), "exchange_note": fused_note,
                 "result": {"count": merged.count, "sum": merged.sum}}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -59,6 +59,36 @@ for kw in approx_cases:
         o = O.approx_sharded(rows_all, world, spec)
         assert (a.n_units, a.n_samples, a.rounds, a.status, a.population) == (o.n_units, o.n_samples, o.rounds, o.status, n_small), (rank, kw, seed, (a.n_units, a.n_samples, a.rounds, a.status), (o.n_units, o.n_samples, o.rounds, o.status))
         assert abs(a.estimate - o.estimate) <= 1e-10 * abs(o.estimate) and abs((a.ci_upper - a.ci_lower) - (o.ci_upper - o.ci_lower)) <= 1e-8 * abs(o.ci_upper - o.ci_lower + 1e-300), (kw, seed)
+# ---- SQL-string path across the GPUs: facts / integer accumulators all-gathered over NCCL, merged exactly ----
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import SqlError
+from sql_helpers import MODE_OF, REL, engine_rows, rows_close
+tq = sharded.ShardedTable.synthetic(n_small, rank, world, seed=11, device=local)
+single = aqe.Engine(local).from_rows(rows_all) if rank == 0 else None
+for sql, p, mode in (("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 100 AND 500", 10, "run_query_with_ci"),
+                     ("SELECT AVG(amount) FROM sales GROUP BY region", 0, "run_query_groupby"),
+                     ("SELECT SUM(amount) FROM sales WHERE region >= 2 GROUP BY region", 20, "run_query_groupby_with_ci"),
+                     ("SELECT COUNT(amount) FROM sales WHERE id <= 400 GROUP BY product_id", 10, "run_query_groupby"),
+                     ("SELECT SUM(amount) FROM sales GROUP BY product_id", 50, "run_query_groupby"),
+                     ("SELECT SUM(timestamp) FROM sales", 7, "run_query")):
+    try:
+        got = engine_rows(tq.sql(sql, p, MODE_OF[mode]))
+    except ValueError:
+        got = "stod"
+    try:
+        want = O.sql(rows_all, sql, p, mode) if rank == 0 else None
+    except SqlError as ex:
+        assert ex.kind == "stod" and got == "stod", (sql, ex)
+        continue
+    if rank == 0:
+        assert rows_close(got, want, REL) is None, (sql, rows_close(got, want, REL))
+        one = single.sql(sql, p, MODE_OF[mode])          # the unsharded table on one GPU: identical bits
+        assert got == [(r.key, r.value, r.ci_lower, r.ci_upper) for r in one], sql
+big_sql = {}
+for sql in ("SELECT SUM(amount) FROM sales", "SELECT SUM(amount) FROM sales WHERE timestamp > 1700000005"):
+    tq_big = t.sql(sql)            # the big table holds id, amount, timestamp
+    big_sql[sql] = tq_big[0].value
+assert big_sql["SELECT SUM(amount) FROM sales"] == ref[0].sum or abs(big_sql["SELECT SUM(amount) FROM sales"] - ref[0].sum) <= 4e-16 * ref[0].sum
 # every rank holds the identical result; latency of the fused multi-GPU estimator on the big table (configs[3])
 approx_lat = {}
 import time

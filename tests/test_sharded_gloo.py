@@ -87,3 +87,94 @@ def test_shard_ranges_tile_the_table():
             assert edges[0][0] == 0 and edges[-1][1] == n
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
             assert max(b - a for a, b in edges) - min(b - a for a, b in edges) <= 1
+
+
+class _HostShard:
+    """Stands in for an Engine on a box without a GPU: column facts and the grouped-scan accumulators of this rank's
+    rows come from numpy (tests/sql_helpers.py); everything downstream is the product's host layer."""
+
+    def __init__(self, rows):
+        self.rows = rows
+
+    def sql_facts(self, q):
+        import approximatequeryengine_b200 as aqe
+        from sql_helpers import COL_NAMES
+        f = aqe.SqlFacts()
+        f.key_min, f.key_max = (0, 0) if len(self.rows) else (0, -1)
+        if q.group_col >= 0 and len(self.rows):
+            c = self.rows[COL_NAMES[q.group_col]]
+            f.key_min, f.key_max = int(c.min()), int(c.max())
+        if q.agg_col >= 0:
+            f.agg_is_integer = int(q.agg_col != 1)
+            if len(self.rows):
+                c = self.rows[COL_NAMES[q.agg_col]]
+                f.agg_absmax = float(max(abs(float(c.min())), abs(float(c.max()))))
+        return f
+
+    def sql_scan(self, q, layout, flags=0):
+        from sql_helpers import emulate_scan
+        return emulate_scan(self.rows, q, layout, flags)
+
+
+SQL_CASES = [("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 100 AND 500", 10, "run_query_with_ci"),
+             ("SELECT AVG(amount) FROM sales GROUP BY region", 0, "run_query_groupby"),
+             ("SELECT SUM(amount) FROM sales WHERE region >= 2 GROUP BY region", 20, "run_query_groupby_with_ci"),
+             ("SELECT COUNT(amount) FROM sales WHERE id <= 400 GROUP BY product_id", 10, "run_query_groupby"),
+             ("SELECT SUM(timestamp) FROM sales", 7, "run_query")]
+
+
+def _sql_worker(rank, world, port, n, q):
+    import sys
+
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from approximatequeryengine_b200 import sharded
+    from oracle import Oracle
+    from sql_helpers import MODE_OF, engine_rows
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        a, b = sharded.shard_range(n, rank, world)
+        t = sharded.ShardedTable(_HostShard(Oracle().synth(b - a, seed=7, first_row=a)), n, a)
+        out = []
+        for sql, p, mode in SQL_CASES:
+            try:
+                out.append(engine_rows(t.sql(sql, p, MODE_OF[mode])))
+            except ValueError:
+                out.append("stod")
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_sql_over_gloo(oracle, world):
+    """SQL path across ranks: facts / accumulators / existence counts travel over gloo, every rank ends with the
+    oracle's whole-table answer and all ranks agree bit for bit."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle import SqlError
+    from sql_helpers import REL, rows_close
+    n = 20_011
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sql_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rows = oracle.synth(n, seed=7)
+    for i, (sql, p, mode) in enumerate(SQL_CASES):
+        assert all(got[r][i] == got[0][i] for r in range(world)), sql
+        try:
+            want = oracle.sql(rows, sql, p, mode)
+        except SqlError as e:
+            assert e.kind == "stod" and got[0][i] == "stod", (sql, e)
+            continue
+        assert rows_close(got[0][i], want, REL) is None, (sql, rows_close(got[0][i], want, REL))
