@@ -262,3 +262,85 @@ def test_dropin_run_query_functions(oracle, tmp_path):
     c = db.query_with_ci("SELECT SUM(amount) FROM sales", 10, correct_ci=True)
     assert c.ci_lower < math.fsum(rows2["amount"]) < c.ci_upper
     b.close_cached_tables()
+
+
+def _random_query(rng, t0, n):
+    agg = rng.choice(["SUM", "AVG", "COUNT"])
+    col = rng.choice(["amount", "amount", "region", "product_id", "timestamp", "id"])
+    terms = []
+    for _ in range(rng.integers(0, 4)):
+        c = rng.choice(["amount", "region", "product_id", "timestamp", "id"])
+        if c == "amount":
+            a, b = sorted(rng.uniform(-50, 1200, size=2))
+            terms.append(rng.choice([f"amount BETWEEN {a:.3f} AND {b:.3f}", f"amount > {a:.2f}", f"amount <= {b:.1f}", f"{a:.2f} < amount", f"amount != {a:.0f}"]))
+        elif c == "region":
+            k = int(rng.integers(-1, 9))
+            terms.append(rng.choice([f"region = {k}", f"region != {k}", f"region >= {k}", f"region < {k}.5", f"region BETWEEN 2 AND {k}", f"region <> '{k}'"]))
+        elif c == "product_id":
+            a, b = sorted(int(x) for x in rng.integers(-5, 1100, size=2))
+            terms.append(rng.choice([f"product_id BETWEEN {a} AND {b}", f"product_id < {b}", f"(product_id >= {a})", f"product_id = {a}"]))
+        elif c == "timestamp":
+            a = t0 + int(rng.integers(-10, n + 10))
+            terms.append(rng.choice([f"timestamp > {a}", f"timestamp <= {a}", f"timestamp BETWEEN {t0} AND {a}"]))
+        else:
+            a = int(rng.integers(-100, 3 * n))
+            terms.append(rng.choice([f"id > {a}", f"rowid <= {a}", f"id != {a}"]))
+    group = rng.choice([None, None, "region", "product_id", "ts_bucket"])
+    sql = f"SELECT {agg}({col}) FROM sales"
+    if terms:
+        sql += " WHERE " + " AND ".join(terms)
+    return sql, group
+
+
+def test_sql_random_queries_against_oracle(oracle):
+    """Seeded random tables (signed heavy-tailed amounts, ids with gaps, a narrow int64 GROUP BY column) x random queries
+    from the supported grammar x random sample percentages, all four entry points, against the oracle."""
+    rng = np.random.default_rng(20261018)
+    t0 = 1700000000
+    for trial in range(6):
+        n = int(rng.choice([1, 37, 1000, 4097, 30000]))
+        rows = oracle.synth(n, seed=100 + trial)
+        if trial % 2:
+            rows["amount"] = np.exp(rng.normal(2.0, 2.5, size=n)) * rng.choice([-1.0, 1.0], size=n, p=[0.2, 0.8])   # signed, 6 decades
+            rows["id"] = np.sort(rng.choice(4 * n + 10, size=n, replace=False)) - 7
+        if trial % 3 == 0:
+            rows["timestamp"] = t0 + (np.arange(n) % 40)       # int64 GROUP BY column with a narrow range
+        e = aqe.Engine(0).from_rows(rows)
+        scale = float(np.abs(rows["amount"]).sum()) or 1.0
+        for _ in range(60):
+            sql, group = _random_query(rng, t0, n)
+            if group == "ts_bucket":
+                if trial % 3:
+                    continue
+                group = "timestamp"
+            if group:
+                sql += f" GROUP BY {group}"
+            p = int(rng.choice([0, 0, 1, 5, 10, 13, 25, 50, 99, 100]))
+            for mode in (("run_query_groupby", "run_query_groupby_with_ci") if group else ("run_query", "run_query_with_ci")):
+                tag = (trial, n, sql, p, mode)
+                try:
+                    want = oracle.sql(rows, sql, p, mode)
+                except SqlError as ex:
+                    if ex.kind == "stod":
+                        with pytest.raises(ValueError):
+                            run_engine(e, sql, p, mode)
+                    elif "integer overflow" not in ex.msg:
+                        with pytest.raises(RuntimeError):
+                            run_engine(e, sql, p, mode)
+                    continue
+                try:
+                    got = run_engine(e, sql, p, mode)
+                except aqe.AqeError as ex:
+                    assert ex.code == 6 and "more than one !=" in str(ex), tag    # the one documented gap this generator can hit
+                    continue
+                assert len(got) == len(want), tag
+                for g, w in zip(got, want):
+                    assert g[0] == w[0], tag
+                    # fixed-point sums are exact to 2^-63 of the column's largest magnitude per row; with signed data the
+                    # reference's own 15-digit result can cancel, so values are compared on the scale of sum |x|
+                    tol = 1e-12 * max(abs(w[1]), scale if "amount" in sql.split("FROM")[0] else abs(w[1]))
+                    assert abs(g[1] - w[1]) <= tol or (math.isnan(g[1]) and math.isnan(w[1])) or g[1] == w[1], (tag, g, w)
+                    if math.isfinite(w[2]) and math.isfinite(w[3]) and math.isfinite(g[2]):
+                        half_w, half_g = (w[3] - w[2]) / 2, (g[3] - g[2]) / 2
+                        assert abs(half_g - half_w) <= 1e-6 * abs(half_w) + tol, (tag, g, w)
+        e.close()
