@@ -66,3 +66,57 @@ def test_scheduler_constants_match_reference(oracle):
     for p, conf in ((10.0, 0.95), (3.0, 0.90), (1.0, 0.85), (0.3, 0.80), (0.1, 0.70)):
         q = S.run(3, "SELECT SUM(amount) FROM sales", p, 4)
         assert (q.confidence_level, q.error_margin, q.samples_used) == (conf, p / 100.0, int(20000 * p / 100.0))
+
+
+# ---- SQL-string path: oracle/aqe_oracle_sql.c against the compiled executor.cpp + parser.cpp + core/db.cpp ----------------
+def test_sql_restatement_against_compiled_reference(oracle, tmp_path):
+    """Seeded random queries from the restated grammar, every entry point, random sample percentages, on a SQLite copy
+    of a seeded table (signed amounts, ids with gaps).  Grouped calls for which the restatement predicts a throw inside
+    one of the reference's worker threads are not issued: the reference process would abort."""
+    import math
+
+    import numpy as np
+
+    from oracle import RefSql, SqlError
+    if not RefSql.available():
+        pytest.skip("oracle/_ref/libaqe_refsql.so not built")
+    rng = np.random.default_rng(77)
+    n = 3000
+    rows = oracle.synth(n, seed=31)
+    rows["amount"] = np.round(np.exp(rng.normal(3.0, 2.0, size=n)) * rng.choice([-1.0, 1.0], size=n, p=[0.15, 0.85]), 6)
+    rows["id"] = np.sort(rng.choice(5 * n, size=n, replace=False)) + 1
+    db = str(tmp_path / "t.db")
+    RefSql.make_sqlite(db, rows)
+    R = RefSql(db)
+    t0 = 1700000000
+    checked = 0
+    for _ in range(150):
+        agg = rng.choice(["SUM", "AVG", "COUNT", "sum"])
+        col = rng.choice(["amount", "region", "product_id", "timestamp", "id"])
+        terms = []
+        for _k in range(rng.integers(0, 3)):
+            a, b = sorted(rng.uniform(-100, 1500, size=2))
+            k = int(rng.integers(-1, 9))
+            terms.append(rng.choice([f"amount BETWEEN {a:.2f} AND {b:.2f}", f"amount >= {a:.1f}", f"region != {k}", f"region < {k}.5", f"'{k}' = region",
+                                     f"product_id BETWEEN {int(a)} AND {int(b)}", f"timestamp > {t0 + int(a)}", f"(id <= {int(b) * 4})", f"rowid <> {int(a)}"]))
+        group = rng.choice(["", "", " GROUP BY region", " GROUP BY product_id"])
+        sql = f"SELECT {agg}({col}) FROM sales" + (" WHERE " + " AND ".join(terms) if terms else "") + group
+        p = int(rng.choice([0, 1, 4, 10, 33, 50, 99, 100]))
+        for mode in (("run_query_groupby", "run_query_groupby_with_ci") if group else ("run_query", "run_query_with_ci")):
+            try:
+                got = oracle.sql(rows, sql, p, mode)
+            except SqlError as e:
+                if group and (e.kind == "stod" or "integer overflow" in e.msg):
+                    continue
+                with pytest.raises(SqlError) as ei:
+                    R.run(sql, p, mode)
+                assert ei.value.kind == e.kind, (sql, p, mode)
+                continue
+            want = R.run(sql, p, mode)
+            assert len(got) == len(want), (sql, p, mode)
+            for g, w in zip(got, want):
+                assert g[0] == w[0]
+                for x, y in zip(g[1:], w[1:]):
+                    assert x == y or (math.isnan(x) and math.isnan(y)) or abs(x - y) <= 4e-15 * max(abs(x), abs(y)) or abs(x - y) <= 1e-9 * abs(w[1]), (sql, p, mode, g, w)
+            checked += 1
+    assert checked > 150
