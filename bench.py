@@ -231,6 +231,8 @@ def main():
         sys.exit("bench.py needs a CUDA device: this engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL writes its version banner / debug lines to stdout; stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     L = aqe.lib()

@@ -20,6 +20,7 @@ from approximatequeryengine_b200 import sharded
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for the one JSON line
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 N = int(os.environ.get("AQE_CHECK_ROWS", 1_000_000_007))
 t = sharded.ShardedTable.synthetic(N, rank, world, seed=7, device=local, columns=("id", "amount", "timestamp"))
