@@ -230,9 +230,12 @@ def main():
     if not torch.cuda.is_available():
         sys.exit("bench.py needs a CUDA device: this engine has no CPU fallback")
     torch.cuda.set_device(local)
+    # stdout carries exactly ONE JSON line (rank 0): libraries that printf to fd 1 (NCCL's version banner does) are sent
+    # to stderr for the life of the process, and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL writes its version banner / debug lines to stdout; stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     L = aqe.lib()
@@ -436,7 +439,8 @@ def main():
                              "kernel_ms_isolated_loop": kern_ms / args.steps, "algorithmic_bytes_per_launch": 8 * rows, "peak_source": peak_src},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clk, "approx": approx, "approx_multi_gpu": approx_multi, "sql": sql, "exchange": ("fused in-kernel NVLink mailbox" if fused else ("nccl all_gather" if world > 1 else None)), "exchange_note": fused_note,
                 "result": {"count": merged.count, "sum": merged.sum}}
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -20,7 +20,9 @@ from approximatequeryengine_b200 import sharded
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for the one JSON line
+sys.stdout.flush()
+real_stdout = os.fdopen(os.dup(1), "w")   # keep stdout for the one JSON line: NCCL printf()s its version banner to fd 1
+os.dup2(2, 1)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 N = int(os.environ.get("AQE_CHECK_ROWS", 1_000_000_007))
 t = sharded.ShardedTable.synthetic(N, rank, world, seed=7, device=local, columns=("id", "amount", "timestamp"))
@@ -144,6 +146,7 @@ torch.cuda.synchronize()
 f = aqe.Partial.from_buffer_copy(host[:8].numpy().tobytes())     # async form: no moments, same count / sum / comp bits
 assert (f.count, f.sum, f.comp) == (ref[1].count, ref[1].sum, ref[1].comp)
 if rank == 0:
-    print(json.dumps(res), flush=True)
+    real_stdout.write(json.dumps(res) + "\n")
+    real_stdout.flush()
 dist.barrier()
 dist.destroy_process_group()
