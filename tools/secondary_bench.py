@@ -149,4 +149,31 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
     t1 = time.perf_counter(); y = aqe.Engine(0).from_rows(rows); t_rows = time.perf_counter() - t1
     out["ingest"] = {"records": n_in, "file_bytes": 24 + 32 * n_in, "save_s": t_save, "load_s_best": min(ts), "load_GBps": 32 * n_in / min(ts) / 1e9,
                      "load_records_per_s": n_in / min(ts), "from_host_rows_GBps": 32 * len(rows) / t_rows / 1e9, "medium": os.path.dirname(path)}
+# ---- 6. SURVEY 8d (i): the reference's own CPU implementation of the CLI's calls (oracle/_ref = the unmodified reference
+#         compiled in place), 1 M rows in its B+ tree, median-free mean of `reps` calls inside C++, next to the same calls
+#         through the drop-in module on the GPU at the same size ----
+try:
+    from oracle import Oracle, Ref
+    if Ref.available():
+        O = Oracle()
+        n_ref = 1_000_000
+        rows = O.synth(n_ref, seed=7)
+        note("reference insert_batch 1M")
+        t1 = time.perf_counter(); R = Ref(rows); t_load = time.perf_counter() - t1
+        db = b.CustomBPlusDB(0)
+        db.from_array(rows)
+        ref = {"records": n_ref, "cores": os.cpu_count(), "reference_insert_batch_s": t_load, "calls": []}
+        for name, what, a, bb, reps, ours in [("sum_amount()", 0, 0.0, 0.0, 5, lambda: db.sum_amount()),
+                                              ("sum_amount_where(100,500)", 1, 100.0, 500.0, 5, lambda: db.sum_amount_where(100, 500)),
+                                              ("memory_stride_sample(1.0)", 2, 1.0, 0.0, 20, lambda: db.sample_array("memory_stride", 1.0, stats=True)["n"]),
+                                              ("clt_validated_dual_pointer_sample(20,0.95,10,4,1.0)", 3, 20.0, 1.0, 5, lambda: db.sample_array("clt_validated_dual_pointer", 20.0, max_error_percent=1.0, stats=True)["n"]),
+                                              ("block_sample(1.0,1000)", 4, 1.0, 0.0, 5, lambda: db.sample_array("block", 1.0, stats=True)["n"])]:
+            note(f"reference {name}")
+            t, v = R.time(what, reps, a, bb)
+            ms_ours, r_ours = wall(ours, reps=5)
+            ref["calls"].append({"call": name, "reference_cpu_ms": t / reps * 1e3, "reference_result": v, "gpu_ms": ms_ours, "gpu_result": r_ours,
+                                 "gpu_form": "device moments of the same sample (no list[Record])" if what >= 2 else "same call"})
+        out["reference_cpu_1M"] = ref
+except Exception as ex:  # noqa: BLE001
+    out["reference_cpu_1M"] = {"unavailable": str(ex)}
 print(json.dumps(out, indent=1))
