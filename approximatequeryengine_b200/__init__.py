@@ -490,10 +490,12 @@ class Engine:
     # ---- SQL-string path (run_query*, bindings.cpp:126-136) ----
     def sql(self, query: str, sample_percent: int = 0, mode: str = "value"):
         """List of SqlRow (one without GROUP BY), ascending key."""
-        rows = (SqlRow * SQL_MAX_GROUPS)()
+        rows = self.__dict__.get("_sql_rows")
+        if rows is None:
+            rows = self._sql_rows = (SqlRow * SQL_MAX_GROUPS)()   # reused: allocating 320 KiB per call dwarfs a small query
         n = C.c_uint32()
         check(self.L.aqe_sql_run(self.h, query.encode(), sample_percent, SQL_MODE[mode], rows, SQL_MAX_GROUPS, C.byref(n)))
-        return list(rows[: n.value])
+        return [SqlRow.from_buffer_copy(rows[i]) for i in range(n.value)]
 
     def sql_facts(self, q: SqlQuery) -> SqlFacts:
         f = SqlFacts()

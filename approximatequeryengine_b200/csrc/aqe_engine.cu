@@ -102,7 +102,7 @@ struct aqe_db {
     // SQL-string path (aqe_sql_*): lazily computed column statistics + accumulators of the grouped scan
     struct ColStat { bool valid = false; unsigned long long min_key = 0, max_key = 0; bool dense = false; long long first_id = 0; };
     ColStat col_stat[5];
-    unsigned long long* sql_acc = nullptr;       // [AQE_SQL_MAX_GROUPS][5], device, all zero between launches
+    unsigned long long* sql_acc = nullptr;       // [kSqlReplicas][n_groups][5], device, all zero between launches
     unsigned long long* sql_out_host = nullptr;  // same shape, mapped pinned: the last CTA writes it
     unsigned long long* sql_out_dev = nullptr;
     unsigned long long* sql_stat_dev = nullptr;  // [3] min key, max key, not-dense flag
@@ -1572,8 +1572,8 @@ int aqe_approx_merge(const aqe_approx_result* parts, int n, int agg, double conf
 static int sql_init(aqe_db* db) {
     if (db->sql_acc) return AQE_OK;
     const size_t bytes = sizeof(unsigned long long) * 5 * AQE_SQL_MAX_GROUPS;
-    CU(cudaMalloc(&db->sql_acc, bytes));
-    CU(cudaMemset(db->sql_acc, 0, bytes));
+    CU(cudaMalloc(&db->sql_acc, bytes * kSqlReplicas));
+    CU(cudaMemset(db->sql_acc, 0, bytes * kSqlReplicas));
     CU(cudaMalloc(&db->sql_stat_dev, 3 * sizeof(unsigned long long)));
     CU(cudaMalloc(&db->sql_ticket, sizeof(unsigned int)));
     CU(cudaMemset(db->sql_ticket, 0, sizeof(unsigned int)));

@@ -318,10 +318,10 @@ public:
         } else {
             q.group_col = AQE_COL_NONE;  // execute_query never looks at q.group_by (executor.cpp:28-58)
         }
-        std::vector<aqe_sql_row> rows(grouped ? AQE_SQL_MAX_GROUPS : 1);
+        static thread_local std::vector<aqe_sql_row> buf(AQE_SQL_MAX_GROUPS);  // reused: zero-filling 320 KiB per call costs more than a 10 M-row query
         uint32_t n = 0;
-        check(aqe_sql_execute(h_, &q, ci, rows.data(), (uint32_t)rows.size(), &n));
-        rows.resize(std::min<size_t>(n, rows.size()));
+        check(aqe_sql_execute(h_, &q, ci, buf.data(), grouped ? (uint32_t)buf.size() : 1u, &n));
+        std::vector<aqe_sql_row> rows(buf.begin(), buf.begin() + std::min<size_t>(n, grouped ? buf.size() : 1));
         for (const aqe_sql_row& r : rows)
             if (r.is_null) throw std::invalid_argument("stod");  // std::stod("NULL"), executor.cpp:46 -> ValueError
         return rows;

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(256) k_col_stats(const ColStatsArgs a) {
 constexpr int kSqlThreads = 256;
 constexpr int kSqlMaxCols = 5;          // the table has five columns; each is loaded at most once per row
 constexpr int kSqlPrivateMaxGroups = 16;
+constexpr int kSqlReplicas = 8;
 
 struct SqlCol {
     const void* ptr;
@@ -93,7 +94,9 @@ struct SqlArgs {
     double sum_scale, sq_scale;   // 2^sum_shift, 2^sq_shift
     // rows visited: i = first + j * stride for j in [0, count)
     uint64_t first, stride, count;
-    unsigned long long* global_acc;   // [n_groups][5] {count, sum_lo, sum_hi, sq_lo, sq_hi}, zero before launch, zeroed again by the last CTA
+    unsigned long long* global_acc;   // [kSqlReplicas][n_groups][5] {count, sum_lo, sum_hi, sq_lo, sq_hi}, zero before launch, zeroed again by the
+                                      // last CTA.  CTA b adds into replica b % kSqlReplicas: same-address atomics serialise in L2, and the
+                                      // replicas keep the queue on any one word at gridDim.x / kSqlReplicas deep
     unsigned long long* out;          // [n_groups][5] device-visible result
     unsigned int* ticket;
 };
@@ -226,14 +229,23 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
     // CTA totals -> global accumulators (integer atomics: order does not matter)
     __device__ __forceinline__ void flush(unsigned long long* global_acc, int tid, int nthreads) {
         if constexpr (MODE == 0) {
+            __shared__ unsigned long long part[32][5];
             r_cnt = warp_reduce_u64(r_cnt);
             r_slo = warp_reduce_u64(r_slo); r_shi = (long long)warp_reduce_u64((unsigned long long)r_shi);
             if constexpr (MOMENTS) { r_qlo = warp_reduce_u64(r_qlo); r_qhi = (long long)warp_reduce_u64((unsigned long long)r_qhi); }
-            if ((tid & 31) == 0 && r_cnt) {
-                unsigned long long lo, hi;
-                atomicAdd(global_acc + 0, r_cnt);
-                split_to_128(r_slo, r_shi, lo, hi); global_add128(global_acc + 1, lo, hi);
-                if constexpr (MOMENTS) { split_to_128(r_qlo, r_qhi, lo, hi); global_add128(global_acc + 3, lo, hi); }
+            const int warp = tid >> 5, lane = tid & 31, nw = (nthreads + 31) >> 5;
+            if (lane == 0) { part[warp][0] = r_cnt; part[warp][1] = r_slo; part[warp][2] = (unsigned long long)r_shi; part[warp][3] = r_qlo; part[warp][4] = (unsigned long long)r_qhi; }
+            __syncthreads();
+            if (warp == 0) {
+                unsigned long long v[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) v[i] = warp_reduce_u64(lane < nw ? part[lane][i] : 0ull);
+                if (lane == 0 && v[0]) {
+                    unsigned long long lo, hi;
+                    atomicAdd(global_acc + 0, v[0]);
+                    split_to_128(v[1], (long long)v[2], lo, hi); global_add128(global_acc + 1, lo, hi);
+                    if constexpr (MOMENTS) { split_to_128(v[3], (long long)v[4], lo, hi); global_add128(global_acc + 3, lo, hi); }
+                }
             }
         } else if constexpr (MODE == 1) {
             __syncthreads();
@@ -313,9 +325,24 @@ __device__ __forceinline__ void sql_publish(const SqlArgs& a, int tid, int nthre
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    for (unsigned int i = tid; i < a.n_groups * 5; i += nthreads) {
-        a.out[i] = __ldcg(a.global_acc + i);
-        a.global_acc[i] = 0ull;
+    const unsigned int words = a.n_groups * 5;
+    for (unsigned int g = tid; g < a.n_groups; g += nthreads) {
+        unsigned long long cnt = 0, lo[2] = {0, 0}, hi[2] = {0, 0};
+        for (int r = 0; r < kSqlReplicas; ++r) {
+            unsigned long long* rep = a.global_acc + (size_t)r * words + (size_t)g * 5;
+            cnt += __ldcg(rep + 0);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {  // 128-bit adds with carry
+                const unsigned long long l = __ldcg(rep + 1 + 2 * k), h = __ldcg(rep + 2 + 2 * k);
+                const unsigned long long nl = lo[k] + l;
+                hi[k] += h + (nl < lo[k] ? 1ull : 0ull);
+                lo[k] = nl;
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) rep[i] = 0ull;
+        }
+        unsigned long long* o = a.out + (size_t)g * 5;
+        o[0] = cnt; o[1] = lo[0]; o[2] = hi[0]; o[3] = lo[1]; o[4] = hi[1];
     }
     if (tid == 0) *a.ticket = 0u;
 }
@@ -376,7 +403,7 @@ __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
             sql_consume(a, bins, tid, raw);
         }
     }
-    bins.flush(a.global_acc, tid, T);
+    bins.flush(a.global_acc + (size_t)(blockIdx.x % kSqlReplicas) * a.n_groups * 5, tid, T);
     sql_publish(a, tid, T);
 }
 
@@ -513,6 +540,7 @@ __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra)
             uint32_t mask = (1u << nk) - 1u;  // nk <= K = 8
             for (int k = 0; k < a.ncols; ++k) {
                 const SqlCol& col = a.cols[k];
+                if (k == agg_slot && agg_kind == 0) continue;  // an f64 aggregate column is tested where it is converted (one LDS per row)
                 if (col.has_pred || col.mod_step > 0) mask = sql_pred_pass<T>(col, stage + ra.col_off[k], tid, mask);
             }
             if (ra.samp_step > 1) {
@@ -546,12 +574,25 @@ __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra)
                 for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, false, 0, 0);
             } else if (agg_kind == 0) {
                 const unsigned char* ab = stage + ra.col_off[agg_slot];
+                const SqlCol& ac = a.cols[agg_slot];
+                const bool has_pred = ac.has_pred != 0, has_ne = ac.has_ne != 0;
+                const double lo = __longlong_as_double(ac.lo), hi = __longlong_as_double(ac.hi), ne = __longlong_as_double(ac.ne);
                 long long fx[K], fq[K];
+                if (has_pred) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const double d = lds_row<double>(ab, tid + k * T);
-                    fx[k] = __double2ll_rn(__dmul_rn(d, a.sum_scale));
-                    fq[k] = MOMENTS ? __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale)) : 0;
+                    for (int k = 0; k < K; ++k) {
+                        const double d = lds_row<double>(ab, tid + k * T);
+                        mask &= ~(((d >= lo && d <= hi && !(has_ne && d == ne)) ? 0u : 1u) << k);
+                        fx[k] = __double2ll_rn(__dmul_rn(d, a.sum_scale));
+                        fq[k] = MOMENTS ? __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale)) : 0;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const double d = lds_row<double>(ab, tid + k * T);
+                        fx[k] = __double2ll_rn(__dmul_rn(d, a.sum_scale));
+                        fq[k] = MOMENTS ? __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale)) : 0;
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, true, fx[k], fq[k]);
@@ -580,7 +621,7 @@ __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra)
             }
         }
     }
-    bins.flush(a.global_acc, tid, kBulkThreads);
+    bins.flush(a.global_acc + (size_t)(blockIdx.x % kSqlReplicas) * a.n_groups * 5, tid, kBulkThreads);
     sql_publish(a, tid, kBulkThreads);
 }
 

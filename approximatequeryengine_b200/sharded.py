@@ -140,11 +140,16 @@ class ShardedTable:
         """run_query* over the sharded table (executor.cpp:28-338): every rank scans its shard into the order-independent
         128-bit integer accumulators of the grouped-scan kernel, the accumulators are all-gathered and added with carry
         (exact: the result does not depend on the shard count), and every rank applies the reference's arithmetic.
-        Three tiny exchanges: the 32-byte column facts (so that all shards use one key range and one fixed-point
-        scale), the accumulators, and -- only when a group has no sampled row anywhere -- the unsampled group counts."""
+        Exchanges: the 32-byte column facts (so that all shards use one key range and one fixed-point scale; once per
+        column pair, cached), the accumulators, and -- only when a group has no sampled row anywhere -- the unsampled
+        group counts."""
         q = sql_parse(query, sample_percent)
-        facts = allgather_struct(self.engine.sql_facts(q), SqlFacts, self.group)
-        layout = sql_layout(q, facts)
+        # column facts depend on (GROUP BY column, aggregate column) and the table only: exchanged once, then cached
+        cache = self.__dict__.setdefault("_sql_facts", {})
+        key = (q.group_col, q.agg_col)
+        if key not in cache:
+            cache[key] = allgather_struct(self.engine.sql_facts(q), SqlFacts, self.group)
+        layout = sql_layout(q, cache[key])
         grouped = q.group_col >= 0
         step = 0 if (sample_percent <= 0 or sample_percent >= 100) else max(1, 100 // sample_percent)
         if mode == "value":
