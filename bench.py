@@ -163,6 +163,26 @@ def cpu_reference(steps: int, warmup: int, port_too: bool = True) -> dict:
     return out
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Restrict this process to the CPUs NVML reports as local to GPU `index`, so that host buffers pinned afterwards sit
+    on that GPU's NUMA node (one rank per GPU; on a two-socket box half the GPUs otherwise pull their column across the
+    socket interconnect).  Returns a note for the JSON line; never fatal."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no CPU affinity reported for the GPU"
+        os.sched_setaffinity(0, cpus)
+        return f"process bound to the {len(cpus)} CPUs local to GPU {index}"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__}: {e})"
+
+
 def _timeit(f):
     t0 = time.perf_counter(); f(); return time.perf_counter() - t0
 
@@ -343,6 +363,8 @@ def main():
     e2e = None
     if not args.skip_e2e:
         e2e_steps = args.e2e_steps or min(args.steps, 10)
+        all_cpus = os.sched_getaffinity(0)
+        numa_note = bind_to_gpu_numa_node(local)   # the pinned column is allocated (and first touched) next to this rank's GPU
         hptr = C.c_void_p()
         aqe.check(L.aqe_host_alloc(rows * 8, C.byref(hptr)))
         eng.read_column("amount", out_ptr=hptr.value)          # device -> pinned host (setup, untimed)
@@ -365,8 +387,9 @@ def main():
         e2e = {"value": rows * world / (float(dt.item()) / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": rows * 8 * world,
                "d2h_bytes_per_step": 64 * nchunks * world, "steps": e2e_steps, "ms_per_step": float(dt.item()) / e2e_steps * 1e3,
                "api": "aqe_scan_host_column (C-ABI): pinned host amount column -> chunked H2D overlapped with k_scan -> merged partial",
-               "launches_per_step": (L.aqe_launch_count() - l0) // e2e_steps}
+               "launches_per_step": (L.aqe_launch_count() - l0) // e2e_steps, "host_numa": numa_note}
         L.aqe_host_free(hptr)
+        os.sched_setaffinity(0, all_cpus)          # the CPU baseline below uses every core
 
     clk = clocks.stop() if rank == 0 else None   # sampled over the timed region, the kernel-only loop and the e2e phase
 

@@ -195,9 +195,10 @@ def test_sql_shards_merge_bit_exactly(tables, oracle):
 
 
 def test_sql_large_table_properties():
-    """100 M rows generated on the device: linearity of the integer accumulators and agreement with the exact scan."""
-    n = 100_000_000
-    e = aqe.Engine(0).generate(n, seed=7)
+    """BASELINE.json's full size (1 B rows generated on the device; AQE_TEST_FULL_N overrides): linearity of the integer
+    accumulators, agreement with the exact scan kernel, exact counts through the strided sample."""
+    n = int(os.environ.get("AQE_TEST_FULL_N", 1_000_000_000))
+    e = aqe.Engine(0).generate(n, seed=7, columns=("id", "amount", "region", "product_id"))
     q_all = aqe.sql_parse("SELECT SUM(amount) FROM sales GROUP BY region", 0)
     layout = aqe.sql_layout(q_all, [e.sql_facts(q_all)])
     assert layout.n_groups == 8 and layout.sum_shift == 52
