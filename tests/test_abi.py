@@ -129,6 +129,10 @@ def test_no_cpu_fallback_without_device():
     assert db.insert_record(r) and db.get_total_records() == 1
     with pytest.raises(RuntimeError, match="cuda|CUDA"):
         db.sum_amount()
+    with pytest.raises(RuntimeError, match="cuda|CUDA"):
+        db.query("SELECT SUM(amount) FROM sales")           # the SQL path has no host evaluator either
+    with pytest.raises(RuntimeError, match="cuda|CUDA"):
+        db.query_groupby("SELECT COUNT(amount) FROM sales GROUP BY region")
     e = aqe.Engine(0)
     with pytest.raises(aqe.AqeError):
         e.generate(100)
