@@ -176,7 +176,8 @@ static int grid_for(const aqe_db* db, uint64_t work_items, int per_thread, int t
 // each run an independent pipeline over the chunks c = w, w+W, ... of the row range: fill a pinned buffer (pread from
 // the file / memcpy from caller memory) -> cudaMemcpyAsync -> k_aos_to_soa on the worker's own stream, two buffers
 // per worker so the next fill overlaps the previous copy.  Page-cache reads run at a few GB/s per thread, the H2D
-// link at ~55 GB/s, so several readers are needed to approach the link.  Out-of-order ids are detected inside a
+// link at ~55 GB/s, so several readers are needed to approach the link (8 readers: 30 GB/s from the page cache; copying out of
+// an mmap of the file instead of pread() measured slower, 25 GB/s).  Out-of-order ids are detected inside a
 // chunk on the device and across chunk boundaries on the host.
 struct IngestWorker {
     static const size_t kChunkRows = 1u << 19;  // 16 MiB of rows
@@ -201,6 +202,34 @@ struct IngestWorker {
     }
 };
 
+struct IngestPool {
+    static std::mutex& mu() { static std::mutex m; return m; }
+    static std::vector<IngestWorker*>& idle(int device) { static std::vector<IngestWorker*> pool[16]; return pool[device & 15]; }
+    struct Lease {
+        int device, rc = AQE_OK;
+        std::vector<IngestWorker*> workers;
+        Lease(int dev, int count) : device(dev) {
+            {
+                std::lock_guard<std::mutex> lock(mu());
+                auto& p = idle(device);
+                while ((int)workers.size() < count && !p.empty()) { workers.push_back(p.back()); p.pop_back(); }
+            }
+            while ((int)workers.size() < count) {
+                IngestWorker* w = new (std::nothrow) IngestWorker();
+                if (!w) { rc = fail(AQE_ERR_NOMEM, "out of host memory"); return; }
+                rc = w->init();
+                if (rc) { delete w; return; }
+                workers.push_back(w);
+            }
+        }
+        ~Lease() {
+            std::lock_guard<std::mutex> lock(mu());
+            auto& p = idle(device);
+            for (IngestWorker* w : workers) p.push_back(w);
+        }
+    };
+};
+
 // Feeds `n` rows obtained chunk-wise from the thread-safe `fill(dst, first, count)` into the columns.
 // *unsorted_out is set if ids were found out of order.
 template <typename Fill>
@@ -216,14 +245,18 @@ static int ingest_rows(aqe_db* db, uint64_t n, Fill fill, bool* unsorted_out) {
     unsigned int* unsorted = nullptr;
     CU(cudaMalloc(&unsorted, 4));
     CU(cudaMemset(unsorted, 0, 4));
-    std::vector<IngestWorker> workers(W);
-    for (auto& w : workers) { rc = w.init(); if (rc) { cudaFree(unsorted); return rc; } }
+    // worker resources (2 x 16 MiB pinned + 2 x 16 MiB device + a stream each) are pooled per device: allocating them costs
+    // ~15 ms per worker, a third of a 6.4 GB load when done per call
+    IngestPool::Lease lease(db->device, W);
+    if (lease.rc) { cudaFree(unsorted); return lease.rc; }
+    std::vector<IngestWorker*>& workers = lease.workers;
+    for (IngestWorker* w : workers) { w->rc = AQE_OK; w->err.clear(); }
     std::vector<int64_t> first_id(nchunks), last_id(nchunks);
     const int device = db->device;
     const MutColumns cols = db->col;
     const int sm_count = db->sm_count;
     auto body = [&](int wi) {
-        IngestWorker& w = workers[wi];
+        IngestWorker& w = *workers[wi];
         if (cudaSetDevice(device) != cudaSuccess) { w.rc = AQE_ERR_CUDA; w.err = "cudaSetDevice failed in ingest worker"; return; }
         int buf = 0;
         for (uint64_t c = (uint64_t)wi; c < nchunks; c += (uint64_t)W, buf ^= 1) {
@@ -249,8 +282,8 @@ static int ingest_rows(aqe_db* db, uint64_t n, Fill fill, bool* unsorted_out) {
     body(0);
     for (auto& t : threads) t.join();
     CU(cudaSetDevice(db->device));
-    for (auto& w : workers)
-        if (w.rc) { cudaFree(unsorted); return fail(w.rc, w.err); }
+    for (IngestWorker* w : workers)
+        if (w->rc) { cudaFree(unsorted); return fail(w->rc, w->err); }
     unsigned int flag = 0;
     CU(cudaMemcpy(&flag, unsorted, 4, cudaMemcpyDeviceToHost));
     cudaFree(unsorted);
@@ -365,18 +398,18 @@ int aqe_load_file(aqe_db* db, const char* path, uint64_t first_row, uint64_t n_r
     };
     uint64_t hdr[3];
     if (!read_at(hdr, 24, 0)) { ::close(fd); return fail(AQE_ERR_IO, std::string("short header in ") + path); }
+    int rc = db_init_cuda(db);
+    if (rc) { ::close(fd); return rc; }
     const uint64_t total = hdr[2];  // record_count; the first two words are ignored (custom_bplus_db.cpp:692-698)
     if (first_row > total) first_row = total;
     const uint64_t n = std::min<uint64_t>(n_rows, total - first_row);
-    int rc = db_init_cuda(db);
-    if (rc) { ::close(fd); return rc; }
     db->host_rows.clear(); db->host_authoritative = false;
     bool unsorted = false;
     rc = ingest_rows(db, n, [&](aqe_record* dst, uint64_t first, uint64_t cnt) { return read_at(dst, cnt * sizeof(aqe_record), 24 + (first_row + first) * 32); }, &unsorted);
     if (rc == AQE_OK && unsorted) {
         std::vector<aqe_record> rows(n);
-        if (!read_at(rows.data(), n * sizeof(aqe_record), 24 + first_row * 32)) { ::close(fd); return fail(AQE_ERR_IO, "re-read failed"); }
-        rc = upload_host_rows(db, rows.data(), n);
+        if (!read_at(rows.data(), n * sizeof(aqe_record), 24 + first_row * 32)) rc = fail(AQE_ERR_IO, "re-read failed");
+        else rc = upload_host_rows(db, rows.data(), n);
     }
     ::close(fd);
     return rc;
