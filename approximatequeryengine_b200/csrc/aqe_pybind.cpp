@@ -508,6 +508,12 @@ struct TableCache {
     void clear() { entries.clear(); }
 };
 TableCache& table_cache() { static TableCache* c = new TableCache(); return *c; }  // leaked on purpose: no CUDA calls at exit
+// parse_query runs before the database is opened (executor.cpp:29-30): a malformed query fails whatever db_path is
+CustomBPlusDB& table_for(const std::string& sql, int sample_percent, const std::string& path) {
+    aqe_sql_query q;
+    if (aqe_sql_parse(sql.c_str(), sample_percent, &q) != AQE_OK) throw std::runtime_error(aqe_last_error());
+    return table_cache().get(path);
+}
 
 }  // namespace
 
@@ -737,13 +743,13 @@ PYBIND11_MODULE(aqe_backend, m) {
 
     // bindings.cpp:126-136.  db_path names a record file (save_to_file format), not a SQLite file; num_threads is accepted
     // and ignored (one grouped-scan kernel serves every group).
-    m.def("run_query", [](const std::string& q, const std::string& path, int p) { return table_cache().get(path).query(q, p); },
+    m.def("run_query", [](const std::string& q, const std::string& path, int p) { return table_for(q, p, path).query(q, p); },
           "Execute SQL query with sampling and automatic scaling", py::arg("sql_query"), py::arg("db_path"), py::arg("sample_percent") = 0);
-    m.def("run_query_groupby", [](const std::string& q, const std::string& path, int p, int) { return table_cache().get(path).query_groupby(q, p); },
+    m.def("run_query_groupby", [](const std::string& q, const std::string& path, int p, int) { return table_for(q, p, path).query_groupby(q, p); },
           "Execute GROUP BY query with sampling", py::arg("sql_query"), py::arg("db_path"), py::arg("sample_percent") = 0, py::arg("num_threads") = 4);
-    m.def("run_query_with_ci", [](const std::string& q, const std::string& path, int p) { return table_cache().get(path).query_with_ci(q, p, false); },
+    m.def("run_query_with_ci", [](const std::string& q, const std::string& path, int p) { return table_for(q, p, path).query_with_ci(q, p, false); },
           "Execute query with confidence intervals", py::arg("sql_query"), py::arg("db_path"), py::arg("sample_percent") = 0);
-    m.def("run_query_groupby_with_ci", [](const std::string& q, const std::string& path, int p, int) { return table_cache().get(path).query_groupby_with_ci(q, p, false); },
+    m.def("run_query_groupby_with_ci", [](const std::string& q, const std::string& path, int p, int) { return table_for(q, p, path).query_groupby_with_ci(q, p, false); },
           "Execute GROUP BY query with confidence intervals", py::arg("sql_query"), py::arg("db_path"), py::arg("sample_percent") = 0, py::arg("num_threads") = 4);
     m.def("close_cached_tables", [] { table_cache().clear(); }, "drop the tables run_query* keeps resident");
     m.def("device_count", [] { int n = 0; aqe_device_count(&n); return n; });

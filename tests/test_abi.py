@@ -136,3 +136,36 @@ def test_no_cpu_fallback_without_device():
     e = aqe.Engine(0)
     with pytest.raises(aqe.AqeError):
         e.generate(100)
+
+
+def test_reference_frontend_package_runs_on_top_of_the_module(tmp_path):
+    """The reference's own Python package (src/aqe_frontend, unmodified, imported from /root/reference where that exists)
+    finds `aqe_backend`, and its run_query / run_query_groupby forward to this engine: parser errors come back as the
+    reference's RuntimeError, and without a GPU the call stops at the device boundary (no CPU evaluation)."""
+    import importlib
+    import struct
+    import sys
+    ref_root = os.environ.get("AQE_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref_root, "src", "aqe_frontend")):
+        pytest.skip("reference checkout not present")
+    b = aqe.backend()                       # puts _lib/ on sys.path: `import aqe_backend` inside runner.py resolves to it
+    sys.path.insert(0, ref_root)
+    try:
+        fe = importlib.import_module("src.aqe_frontend")
+        runner = importlib.import_module("src.aqe_frontend.runner")
+    finally:
+        sys.path.remove(ref_root)
+    assert runner.aqe_backend is b
+    path = str(tmp_path / "sales.aqe")
+    rows = aqe.synth_rows_host(1000, seed=7)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<QQQ", len(rows), 1, len(rows)) + rows.tobytes())
+    with pytest.raises(RuntimeError, match="Unsupported aggregation function"):
+        fe.run_query("SELECT MAX(amount) FROM sales", path, 0)
+    if b.device_count() == 0:
+        with pytest.raises(RuntimeError, match="cuda|CUDA"):
+            fe.run_query("SELECT SUM(amount) FROM sales", path, 10)
+    else:
+        assert fe.run_query("SELECT COUNT(amount) FROM sales", path, 0) == 1000.0
+        assert set(runner.run_query_groupby("SELECT COUNT(amount) FROM sales GROUP BY region", path, 0, 4)) == {str(k) for k in range(8)}
+    assert fe.parse_query("SELECT SUM(amount) FROM sales;") == {"agg_func": "SUM", "column": "AMOUNT", "table": "SALES"}
