@@ -495,7 +495,7 @@ class Engine:
             rows = self._sql_rows = (SqlRow * SQL_MAX_GROUPS)()   # reused: allocating 320 KiB per call dwarfs a small query
         n = C.c_uint32()
         check(self.L.aqe_sql_run(self.h, query.encode(), sample_percent, SQL_MODE[mode], rows, SQL_MAX_GROUPS, C.byref(n)))
-        return [SqlRow.from_buffer_copy(rows[i]) for i in range(n.value)]
+        return list((SqlRow * n.value).from_buffer_copy(rows))   # one copy out of the reused buffer
 
     def sql_facts(self, q: SqlQuery) -> SqlFacts:
         f = SqlFacts()

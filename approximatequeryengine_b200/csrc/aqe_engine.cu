@@ -102,7 +102,7 @@ struct aqe_db {
     // SQL-string path (aqe_sql_*): lazily computed column statistics + accumulators of the grouped scan
     struct ColStat { bool valid = false; unsigned long long min_key = 0, max_key = 0; bool dense = false; long long first_id = 0; };
     ColStat col_stat[5];
-    unsigned long long* sql_acc = nullptr;       // [kSqlReplicas][n_groups][5], device, all zero between launches
+    unsigned long long* sql_acc = nullptr;       // [n_groups][5], device, all zero between launches
     unsigned long long* sql_out_host = nullptr;  // same shape, mapped pinned: the last CTA writes it
     unsigned long long* sql_out_dev = nullptr;
     unsigned long long* sql_stat_dev = nullptr;  // [3] min key, max key, not-dense flag
@@ -1605,8 +1605,8 @@ int aqe_approx_merge(const aqe_approx_result* parts, int n, int agg, double conf
 static int sql_init(aqe_db* db) {
     if (db->sql_acc) return AQE_OK;
     const size_t bytes = sizeof(unsigned long long) * 5 * AQE_SQL_MAX_GROUPS;
-    CU(cudaMalloc(&db->sql_acc, bytes * kSqlReplicas));
-    CU(cudaMemset(db->sql_acc, 0, bytes * kSqlReplicas));
+    CU(cudaMalloc(&db->sql_acc, bytes));
+    CU(cudaMemset(db->sql_acc, 0, bytes));
     CU(cudaMalloc(&db->sql_stat_dev, 3 * sizeof(unsigned long long)));
     CU(cudaMalloc(&db->sql_ticket, sizeof(unsigned int)));
     CU(cudaMemset(db->sql_ticket, 0, sizeof(unsigned int)));
@@ -1696,36 +1696,31 @@ template <int MODE, bool MOMENTS> static int sql_launch_ring(const aqe_db* db, S
     constexpr int T = kBulkConsumerWarps * 32;
     uint32_t row_bytes = 0;
     for (int i = 0; i < ra.q.ncols; ++i) row_bytes += ra.q.cols[i].kind == K_I32 ? 4 : 8;
-    uint32_t tile = (uint32_t)(kStageBytes / row_bytes) / T * T;  // rows per stage: a multiple of 256, stage <= 16 KiB
-    if (tile < (uint32_t)T) tile = T;
-    if (tile > (uint32_t)(T * kSqlRowsPerThread)) tile = T * kSqlRowsPerThread;
+    // rows per consumer thread and tile: 8 while a stage of 2048 rows stays within 16 KiB, else 4 (1024 rows, <= 32 KiB);
+    // every row slot of a full tile is live either way
+    const int K = row_bytes <= 8 ? 8 : 4;
+    const uint32_t tile = (uint32_t)(T * K);
     ra.tile_rows = tile;
     uint32_t off = 0;
     for (int i = 0; i < ra.q.ncols; ++i) { ra.col_off[i] = off; off += tile * (ra.q.cols[i].kind == K_I32 ? 4u : 8u); }
     ra.stage_bytes = off;
-    // the consumers touch row slot T * kSqlRowsPerThread - 1 of every column whatever the tile holds: map that far
-    uint32_t reach = 0;
-    for (int i = 0; i < ra.q.ncols; ++i) reach = std::max(reach, ra.col_off[i] + (uint32_t)(T * kSqlRowsPerThread) * (ra.q.cols[i].kind == K_I32 ? 4u : 8u));
-    const uint32_t slack = reach > ra.stage_bytes ? (reach - ra.stage_bytes + 127u) & ~127u : 0u;
     const size_t bins = SqlBins<MODE, MOMENTS, T>::smem_bytes(ra.q.n_groups);
     const uint64_t ntiles = (ra.q.count + tile - 1) / tile;
-    auto go = [&](auto kernel, int stages) -> int {
-        ra.ring_bytes = (uint32_t)stages * ra.stage_bytes + (bins >= slack ? 0u : slack);  // the bins themselves serve as slack when large enough
-        const size_t smem = (size_t)ra.ring_bytes + bins;
+    // 2 stages x up to 4 CTAs/SM beat 4 stages x 2 CTAs/SM on every grouped query of tools/sql_bench.py (27 instead of
+    // 18 consumer warps per SM hide the shared-memory latency of the bin updates; profiles/r1_sql_bench.json)
+    constexpr int STAGES = 2;
+    ra.ring_bytes = (uint32_t)STAGES * ra.stage_bytes;
+    const size_t smem = (size_t)ra.ring_bytes + bins;
+    auto go = [&](auto kernel) -> int {
         const int occ = sql_occupancy((const void*)kernel, kBulkThreads, smem);
-        if (occ < 1) return -1;
+        if (occ < 1) return fail(AQE_ERR_UNSUPPORTED, "SQL path: group bins do not fit shared memory");
         int grid = (int)std::min<uint64_t>((uint64_t)db->sm_count * std::min(occ, env_int("AQE_SQL_BPS", 4)), std::max<uint64_t>(ntiles, 1));
         if (grid > db->max_grid) grid = db->max_grid;
         kernel<<<grid, kBulkThreads, smem, s>>>(ra);
         LAUNCHED();
         return AQE_OK;
     };
-    // 2 stages x up to 4 CTAs/SM beat 4 stages x 2 CTAs/SM on every grouped query of tools/sql_bench.py (27 instead of
-    // 18 consumer warps per SM hide the shared-memory latency of the bin updates; profiles/r1_sql_bench.json)
-    int rc = env_int("AQE_SQL_STAGES", 2) == 4 ? go(k_sql_ring<MODE, MOMENTS, 4>, 4) : -1;
-    if (rc == -1) rc = go(k_sql_ring<MODE, MOMENTS, 2>, 2);
-    if (rc == -1) return fail(AQE_ERR_UNSUPPORTED, "SQL path: group bins do not fit shared memory");
-    return rc;
+    return K == 8 ? go(k_sql_ring<MODE, MOMENTS, STAGES, 8>) : go(k_sql_ring<MODE, MOMENTS, STAGES, 4>);
 }
 
 static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* L, int flags, uint64_t* acc) {

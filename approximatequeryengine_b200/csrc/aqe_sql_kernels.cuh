@@ -72,7 +72,6 @@ __global__ void __launch_bounds__(256) k_col_stats(const ColStatsArgs a) {
 constexpr int kSqlThreads = 256;
 constexpr int kSqlMaxCols = 5;          // the table has five columns; each is loaded at most once per row
 constexpr int kSqlPrivateMaxGroups = 16;
-constexpr int kSqlReplicas = 8;
 
 struct SqlCol {
     const void* ptr;
@@ -94,9 +93,7 @@ struct SqlArgs {
     double sum_scale, sq_scale;   // 2^sum_shift, 2^sq_shift
     // rows visited: i = first + j * stride for j in [0, count)
     uint64_t first, stride, count;
-    unsigned long long* global_acc;   // [kSqlReplicas][n_groups][5] {count, sum_lo, sum_hi, sq_lo, sq_hi}, zero before launch, zeroed again by the
-                                      // last CTA.  CTA b adds into replica b % kSqlReplicas: same-address atomics serialise in L2, and the
-                                      // replicas keep the queue on any one word at gridDim.x / kSqlReplicas deep
+    unsigned long long* global_acc;   // [n_groups][5] {count, sum_lo, sum_hi, sq_lo, sq_hi}, zero before launch, zeroed again by the last CTA
     unsigned long long* out;          // [n_groups][5] device-visible result
     unsigned int* ticket;
 };
@@ -325,24 +322,15 @@ __device__ __forceinline__ void sql_publish(const SqlArgs& a, int tid, int nthre
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    // (replicated accumulators -- CTA b adding into copy b mod 8 to shorten the same-address atomic queues in L2 -- were
+    // tried: no gain on the scan, and summing the copies here cost 0.1-0.2 ms at 1000 groups)
     const unsigned int words = a.n_groups * 5;
-    for (unsigned int g = tid; g < a.n_groups; g += nthreads) {
-        unsigned long long cnt = 0, lo[2] = {0, 0}, hi[2] = {0, 0};
-        for (int r = 0; r < kSqlReplicas; ++r) {
-            unsigned long long* rep = a.global_acc + (size_t)r * words + (size_t)g * 5;
-            cnt += __ldcg(rep + 0);
+    for (unsigned int i0 = tid; i0 < words; i0 += 4 * nthreads) {
+        unsigned long long v[4];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {  // 128-bit adds with carry
-                const unsigned long long l = __ldcg(rep + 1 + 2 * k), h = __ldcg(rep + 2 + 2 * k);
-                const unsigned long long nl = lo[k] + l;
-                hi[k] += h + (nl < lo[k] ? 1ull : 0ull);
-                lo[k] = nl;
-            }
+        for (int u = 0; u < 4; ++u) { const unsigned int i = i0 + u * nthreads; v[u] = i < words ? __ldcg(a.global_acc + i) : 0ull; }  // 4 loads in flight
 #pragma unroll
-            for (int i = 0; i < 5; ++i) rep[i] = 0ull;
-        }
-        unsigned long long* o = a.out + (size_t)g * 5;
-        o[0] = cnt; o[1] = lo[0]; o[2] = hi[0]; o[3] = lo[1]; o[4] = hi[1];
+        for (int u = 0; u < 4; ++u) { const unsigned int i = i0 + u * nthreads; if (i < words) { a.out[i] = v[u]; a.global_acc[i] = 0ull; } }
     }
     if (tid == 0) *a.ticket = 0u;
 }
@@ -403,7 +391,7 @@ __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
             sql_consume(a, bins, tid, raw);
         }
     }
-    bins.flush(a.global_acc + (size_t)(blockIdx.x % kSqlReplicas) * a.n_groups * 5, tid, T);
+    bins.flush(a.global_acc, tid, T);
     sql_publish(a, tid, T);
 }
 
@@ -412,24 +400,25 @@ __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
 // (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier; 8 consumer warps work on the tile out of shared memory.
 // Bytes in flight are set by the ring, not by registers.
 //
-// The consumers run COLUMN AT A TIME over a tile: thread t owns rows t, t+256, ... (kSqlRowsPerThread of them,
+// The consumers run COLUMN AT A TIME over a tile: thread t owns rows t, t+256, ... (K of them,
 // conflict-free LDS.64 / LDS.32) and keeps one pass bit per row in a register.  Each predicate column is one tight,
 // type-specialised, fully unrolled pass over those rows (the type switch sits outside the row loop), then one pass
 // derives the group index, then one pass converts and accumulates the aggregate column.  A row-at-a-time interpreter
 // of the same query costs ~110 warp instructions per 32 rows (measured, ncu) and is issue/latency bound at 1.0 TB/s.
-// The passes are unconditional over all kSqlRowsPerThread row slots: slots beyond the tile's rows read whatever
-// follows in shared memory (the next stage, the bins, or the slack the host adds after the ring) and stay masked off.
+// A tile holds exactly 256 K rows (K = 8 for rows of <= 8 bytes, 4 for wider rows, so a stage stays <= 32 KiB and every
+// row slot of a full tile is live); the passes are unconditional over the K slots, and slots beyond the rows of the table's
+// last tile read stale bytes of the same stage and stay masked off.
 //
 // The reference's `rowid % step = 0` over dense ids is a filter on the row number here (no id column read) -- used
 // while step is small enough that every 32-byte sector is touched anyway; larger steps take the strided visit.
-constexpr int kSqlRowsPerThread = 8;
+constexpr int kSqlMaxRowsPerThread = 8;  // K, rows per consumer thread and tile: 8 for rows of <= 8 bytes, 4 for wider rows (stage = 256 K rows)
 
 struct SqlRingArgs {
     SqlArgs q;
-    uint32_t tile_rows;           // multiple of 256, <= 256 * kSqlRowsPerThread
+    uint32_t tile_rows;           // 256 * K
     uint32_t col_off[kSqlMaxCols];  // byte offset of each column's slice inside a stage (multiples of 16)
     uint32_t stage_bytes;
-    uint32_t ring_bytes;          // STAGES * stage_bytes + slack so that row slot 256 * kSqlRowsPerThread - 1 of any column is mapped
+    uint32_t ring_bytes;          // STAGES * stage_bytes
     uint32_t samp_step;           // 0/1: every row; else row i passes iff (i + samp_phase) % samp_step == 0
     uint32_t samp_phase;
 };
@@ -439,8 +428,7 @@ template <typename T> __device__ __forceinline__ T lds_row(const unsigned char* 
 }
 
 // one predicate column over this thread's row slots of the tile: clears the pass bit of every row that fails
-template <int T> __device__ __forceinline__ uint32_t sql_pred_pass(const SqlCol& col, const unsigned char* base, int tid, uint32_t mask) {
-    constexpr int K = kSqlRowsPerThread;
+template <int T, int K> __device__ __forceinline__ uint32_t sql_pred_pass(const SqlCol& col, const unsigned char* base, int tid, uint32_t mask) {
     if (col.kind == 0) {
         const double lo = __longlong_as_double(col.lo), hi = __longlong_as_double(col.hi), ne = __longlong_as_double(col.ne);
         const bool has_ne = col.has_ne != 0;
@@ -484,14 +472,14 @@ template <int T> __device__ __forceinline__ uint32_t sql_pred_pass(const SqlCol&
     return mask;
 }
 
-template <int MODE, bool MOMENTS, int STAGES>
+template <int MODE, bool MOMENTS, int STAGES, int K>
 __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra) {
     extern __shared__ __align__(128) unsigned char sql_ring_smem[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
     const SqlArgs& a = ra.q;
     constexpr int T = kBulkConsumerWarps * 32;
-    constexpr int K = kSqlRowsPerThread;
+    static_assert(K <= kSqlMaxRowsPerThread, "pass bits live in one register");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* ring = sql_ring_smem;
     unsigned char* bin_mem = sql_ring_smem + ra.ring_bytes;
@@ -537,11 +525,11 @@ __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra)
             const unsigned char* stage = ring + (size_t)s * ra.stage_bytes;
             // pass bits of rows tid, tid + T, ... of this tile
             const uint32_t nk = rows > (uint32_t)tid ? (rows - (uint32_t)tid + T - 1) / T : 0u;
-            uint32_t mask = (1u << nk) - 1u;  // nk <= K = 8
+            uint32_t mask = (1u << nk) - 1u;  // nk <= K
             for (int k = 0; k < a.ncols; ++k) {
                 const SqlCol& col = a.cols[k];
                 if (k == agg_slot && agg_kind == 0) continue;  // an f64 aggregate column is tested where it is converted (one LDS per row)
-                if (col.has_pred || col.mod_step > 0) mask = sql_pred_pass<T>(col, stage + ra.col_off[k], tid, mask);
+                if (col.has_pred || col.mod_step > 0) mask = sql_pred_pass<T, K>(col, stage + ra.col_off[k], tid, mask);
             }
             if (ra.samp_step > 1) {
                 uint32_t x = (uint32_t)((row0 + ra.samp_phase + (uint32_t)tid) % ra.samp_step);  // (row + phase) mod step
@@ -621,7 +609,7 @@ __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra)
             }
         }
     }
-    bins.flush(a.global_acc + (size_t)(blockIdx.x % kSqlReplicas) * a.n_groups * 5, tid, kBulkThreads);
+    bins.flush(a.global_acc, tid, kBulkThreads);
     sql_publish(a, tid, kBulkThreads);
 }
 
