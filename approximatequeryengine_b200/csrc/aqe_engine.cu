@@ -1679,15 +1679,13 @@ static int sql_occupancy(const void* kernel, int threads, size_t smem) {
     return occ;
 }
 
-template <int MODE, bool MOMENTS> static int sql_launch_regs(const aqe_db* db, const SqlArgs& a, bool vec, cudaStream_t s) {
+template <int MODE, bool MOMENTS> static int sql_launch_regs(const aqe_db* db, const SqlArgs& a, cudaStream_t s) {
     const size_t smem = SqlBins<MODE, MOMENTS, kSqlThreads>::smem_bytes(a.n_groups);
-    const void* k = vec ? (const void*)k_sql_agg<MODE, MOMENTS, true> : (const void*)k_sql_agg<MODE, MOMENTS, false>;
+    const void* k = (const void*)k_sql_agg<MODE, MOMENTS>;
     const int occ = sql_occupancy(k, kSqlThreads, smem);
     if (occ < 1) return fail(AQE_ERR_UNSUPPORTED, "SQL path: group bins do not fit shared memory");
-    const uint64_t items = vec ? (a.count + 3) / 4 : a.count;
-    const int grid = grid_for(db, items, 1, kSqlThreads, occ);
-    if (vec) k_sql_agg<MODE, MOMENTS, true><<<grid, kSqlThreads, smem, s>>>(a);
-    else k_sql_agg<MODE, MOMENTS, false><<<grid, kSqlThreads, smem, s>>>(a);
+    const int grid = grid_for(db, a.count, 1, kSqlThreads, occ);
+    k_sql_agg<MODE, MOMENTS><<<grid, kSqlThreads, smem, s>>>(a);
     LAUNCHED();
     return AQE_OK;
 }
@@ -1787,11 +1785,8 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
     a.key_min = L->key_min; a.n_groups = G;
     a.sum_scale = std::ldexp(1.0, L->sum_shift); a.sq_scale = std::ldexp(1.0, L->sq_shift);
     a.global_acc = db->sql_acc; a.out = db->sql_out_dev; a.ticket = db->sql_ticket;
-    bool aligned16 = true, aligned32 = true;
-    for (int i = 0; i < a.ncols; ++i) {
-        aligned16 = aligned16 && ((uintptr_t)a.cols[i].ptr % 16) == 0;
-        aligned32 = aligned32 && ((uintptr_t)a.cols[i].ptr % 32) == 0;
-    }
+    bool aligned16 = true;
+    for (int i = 0; i < a.ncols; ++i) aligned16 = aligned16 && ((uintptr_t)a.cols[i].ptr % 16) == 0;
     // Visit plan.  Dense ids turn the sample into an arithmetic progression of row numbers: for small steps every 32-byte
     // sector is touched anyway, so the ring streams everything and filters on the row number; from step 8 on the strided
     // gather reads less.  AQE_SQL_VARIANT: 0 auto | 1 register-staged kernel only (tools/sql_bench.py compares them).
@@ -1817,10 +1812,9 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
             a.count = a.first < db->n ? (db->n - a.first + step - 1) / step : 0;
             if (a.count == 0) return AQE_OK;
         }
-        const bool vec = a.stride == 1 && aligned32;
-        if (mode == 0) rc = moments ? sql_launch_regs<0, true>(db, a, vec, s) : sql_launch_regs<0, false>(db, a, vec, s);
-        else if (mode == 1) rc = moments ? sql_launch_regs<1, true>(db, a, vec, s) : sql_launch_regs<1, false>(db, a, vec, s);
-        else rc = moments ? sql_launch_regs<2, true>(db, a, vec, s) : sql_launch_regs<2, false>(db, a, vec, s);
+        if (mode == 0) rc = moments ? sql_launch_regs<0, true>(db, a, s) : sql_launch_regs<0, false>(db, a, s);
+        else if (mode == 1) rc = moments ? sql_launch_regs<1, true>(db, a, s) : sql_launch_regs<1, false>(db, a, s);
+        else rc = moments ? sql_launch_regs<2, true>(db, a, s) : sql_launch_regs<2, false>(db, a, s);
     }
     if (rc) return rc;
     CU(cudaGetLastError());

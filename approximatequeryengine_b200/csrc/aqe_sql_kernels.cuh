@@ -1,8 +1,9 @@
 // aqe_sql_kernels.cuh -- sm_100a kernels of the SQL-string path.
 //
 //   k_col_stats   min / max of a column as order-preserving 64-bit keys (+ "ids are first_id + row" check)
-//   k_sql_agg     the grouped scan: SELECT agg(col) FROM t [WHERE conjunction] [GROUP BY g] with the
-//                 reference's `rowid % step = 0` sampling, one launch
+//   k_sql_ring    the grouped scan: SELECT agg(col) FROM t [WHERE conjunction] [GROUP BY g] with the reference's
+//                 `rowid % step = 0` sampling, one launch, columns staged through a TMA ring
+//   k_sql_agg     the same query over a strided sample or unaligned columns (register-staged)
 //
 // What this replaces: executor.cpp:28-338 issues one SQLite statement per group (plus a SELECT DISTINCT to
 // find the groups), each a full table scan on the CPU; here every row is read once from HBM and lands in the
@@ -107,18 +108,6 @@ __device__ __forceinline__ long long sql_load_raw(const SqlCol& c, uint64_t i) {
     long long v;
     asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(static_cast<const long long*>(c.ptr) + i));
     return v;
-}
-// four consecutive rows starting at a multiple of four (columns are 32-byte aligned on this path)
-__device__ __forceinline__ void sql_load_raw4(const SqlCol& c, uint64_t i, long long (&v)[4]) {
-    if (c.kind == 2) {
-        const Vec<int32_t, 4> r = ldg_stream4(static_cast<const int32_t*>(c.ptr) + i);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = (long long)r.v[e];
-    } else {
-        const Vec<int64_t, 4> r = ldg_stream4(static_cast<const int64_t*>(c.ptr) + i);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = (long long)r.v[e];
-    }
 }
 __device__ __forceinline__ bool sql_pass(const SqlCol& c, long long raw) {
     bool ok = true;
@@ -336,8 +325,8 @@ __device__ __forceinline__ void sql_publish(const SqlArgs& a, int tid, int nthre
 }
 
 // Register-staged visit: strided samples (rowid % step = 0 over dense ids becomes an arithmetic progression of row
-// numbers) and columns that are not vector aligned.  VEC: stride 1 from row 0, every column 32-byte aligned -> 4 rows per load.
-template <int MODE, bool MOMENTS, bool VEC>
+// numbers) and columns that are not 16-byte aligned; eight independent rows in flight per thread.
+template <int MODE, bool MOMENTS>
 __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
     extern __shared__ __align__(16) unsigned char sql_smem[];
     const int tid = threadIdx.x;
@@ -346,50 +335,23 @@ __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
     bins.init(sql_smem, a.n_groups, tid, T);
 
     const uint64_t gsz = (uint64_t)gridDim.x * T;
-    const uint64_t gtid = (uint64_t)blockIdx.x * T + tid;
-    if constexpr (VEC) {
-        const uint64_t units = a.count / 4;
-        for (uint64_t u = gtid; u < units; u += gsz) {
-            long long raw4[kSqlMaxCols][4];
+    constexpr int U = 8;
+    uint64_t j = (uint64_t)blockIdx.x * T + tid;
+    for (; j + (U - 1) * gsz < a.count; j += U * gsz) {
+        long long rawu[U][kSqlMaxCols];
+#pragma unroll
+        for (int e = 0; e < U; ++e)
 #pragma unroll
             for (int c = 0; c < kSqlMaxCols; ++c)
-                if (c < a.ncols) sql_load_raw4(a.cols[c], a.first + u * 4, raw4[c]);
+                rawu[e][c] = c < a.ncols ? sql_load_raw(a.cols[c], a.first + (j + (uint64_t)e * gsz) * a.stride) : 0;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                long long raw[kSqlMaxCols];
+        for (int e = 0; e < U; ++e) sql_consume(a, bins, tid, rawu[e]);
+    }
+    for (; j < a.count; j += gsz) {
+        long long raw[kSqlMaxCols];
 #pragma unroll
-                for (int c = 0; c < kSqlMaxCols; ++c) raw[c] = c < a.ncols ? raw4[c][e] : 0;
-                sql_consume(a, bins, tid, raw);
-            }
-        }
-        if (gtid == 0) {
-            for (uint64_t j = units * 4; j < a.count; ++j) {
-                long long raw[kSqlMaxCols];
-#pragma unroll
-                for (int c = 0; c < kSqlMaxCols; ++c) raw[c] = c < a.ncols ? sql_load_raw(a.cols[c], a.first + j) : 0;
-                sql_consume(a, bins, tid, raw);
-            }
-        }
-    } else {
-        // eight independent rows in flight per thread
-        constexpr int U = 8;
-        uint64_t j = gtid;
-        for (; j + (U - 1) * gsz < a.count; j += U * gsz) {
-            long long rawu[U][kSqlMaxCols];
-#pragma unroll
-            for (int e = 0; e < U; ++e)
-#pragma unroll
-                for (int c = 0; c < kSqlMaxCols; ++c)
-                    rawu[e][c] = c < a.ncols ? sql_load_raw(a.cols[c], a.first + (j + (uint64_t)e * gsz) * a.stride) : 0;
-#pragma unroll
-            for (int e = 0; e < U; ++e) sql_consume(a, bins, tid, rawu[e]);
-        }
-        for (; j < a.count; j += gsz) {
-            long long raw[kSqlMaxCols];
-#pragma unroll
-            for (int c = 0; c < kSqlMaxCols; ++c) raw[c] = c < a.ncols ? sql_load_raw(a.cols[c], a.first + j * a.stride) : 0;
-            sql_consume(a, bins, tid, raw);
-        }
+        for (int c = 0; c < kSqlMaxCols; ++c) raw[c] = c < a.ncols ? sql_load_raw(a.cols[c], a.first + j * a.stride) : 0;
+        sql_consume(a, bins, tid, raw);
     }
     bins.flush(a.global_acc, tid, T);
     sql_publish(a, tid, T);
