@@ -752,6 +752,17 @@ static int scan_launch(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, ui
 }
 
 static int scan_sync(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, uint64_t n, bool moments, aqe_partial* out) {
+    const uint64_t kSeg = 1ull << 32;  // integer aggregates: one launch is exact up to 2^32 rows; longer shards go in segments
+    if (col_kind(spec->agg_col) > K_F64 && n > kSeg) {
+        std::vector<aqe_partial> parts;
+        for (uint64_t off = 0; off < n; off += kSeg) {
+            aqe_partial p;
+            const int rc = scan_sync(db, spec, first + off, std::min(kSeg, n - off), moments, &p);
+            if (rc) return rc;
+            parts.push_back(p);
+        }
+        return aqe_merge_partials(parts.data(), (int)parts.size(), 1, out);
+    }
     int rc = scan_launch(db, spec, first, n, moments, &db->slot_dev->partial, db->stream);
     if (rc) return rc;
     CU(cudaStreamSynchronize(db->stream));
@@ -1726,7 +1737,10 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
     if (G < 1 || G > AQE_SQL_MAX_GROUPS) return fail(AQE_ERR_INVALID, "layout: n_groups out of range");
     std::memset(acc, 0, sizeof(uint64_t) * 5 * G);
     if (q->always_false || db->n == 0) return AQE_OK;
-    if (db->n > (1ull << 32)) return fail(AQE_ERR_UNSUPPORTED, "SQL path: more than 2^32 rows per shard: split the shard");
+    // Accumulator widths: a thread sums 32-bit halves into 64-bit words (fewer than 2^32 rows per thread), a CTA counts
+    // rows per bin in 32 bits (fewer than 2^32 rows per CTA), everything above is 128-bit.  2^40 rows keeps all of that
+    // far from overflow at any grid this library launches (and is 8 TB of one 8-byte column).
+    if (db->n > (1ull << 40)) return fail(AQE_ERR_UNSUPPORTED, "SQL path: more than 2^40 rows per shard");
     int rc = sql_init(db);
     if (rc) return rc;
     const bool unsampled = (flags & AQE_SQL_UNSAMPLED) != 0;

@@ -364,3 +364,25 @@ def test_sql_register_kernel_and_ring_kernel_agree_word_for_word(tables, monkeyp
         regs = e.sql_scan(q, layout, flags)
         monkeypatch.delenv("AQE_SQL_VARIANT", raising=False)
         assert (ring == regs).all(), sql
+
+
+def test_sql_beyond_two_to_the_32_rows():
+    """4.5 B rows of one column (36 GB) on one GPU: row counts above 2^32 and the 128-bit sums stay exact."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    n = 4_500_000_000
+    if free < n * 12 + (4 << 30):
+        pytest.skip("not enough free HBM for 54 GB of columns")
+    e = aqe.Engine(0).generate(n, seed=7, columns=("amount", "region"))
+    r = e.sql("SELECT SUM(amount) FROM sales")[0]
+    p = e.scan("amount")
+    assert r.count == n == p.count and abs(r.value - p.sum) <= 4 * math.ulp(p.sum)
+    w = e.sql("SELECT COUNT(amount) FROM sales WHERE amount BETWEEN 100 AND 500")[0]
+    assert w.count == e.scan("amount", "amount", 100.0, 500.0).count and w.count > 2**30
+    a, b = e.sql("SELECT SUM(amount) FROM sales WHERE amount < 300")[0], e.sql("SELECT SUM(amount) FROM sales WHERE amount >= 300")[0]
+    assert a.count + b.count == n and abs((a.value + b.value) - r.value) <= 2 * math.ulp(r.value)
+    # integer aggregates: the exact-scan kernel goes in 2^32-row segments, the SQL kernel in one launch; same int128
+    by_region = e.sql("SELECT SUM(region) FROM sales GROUP BY region")
+    assert e.sum_int("region") == e.sql("SELECT SUM(region) FROM sales")[0].isum == sum(g.isum for g in by_region)
+    assert sum(g.count for g in by_region) == n and all(g.isum == g.key * g.count for g in by_region)
+    e.close()
