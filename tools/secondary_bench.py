@@ -176,4 +176,36 @@ try:
         out["reference_cpu_1M"] = ref
 except Exception as ex:  # noqa: BLE001
     out["reference_cpu_1M"] = {"unavailable": str(ex)}
+# ---- 7. the reference's SQL-string path (executor.cpp over SQLite, compiled unmodified: oracle/_ref/libaqe_refsql.so) on a
+#         1 M-row SQLite copy of the table, next to run_query* of the drop-in on the record file of the same rows ----
+try:
+    from oracle import Oracle, RefSql
+    if RefSql.available():
+        O = Oracle()
+        n_sql = 1_000_000
+        rows = O.synth(n_sql, seed=7)
+        with tempfile.TemporaryDirectory() as td:
+            sqlite_path, rec_path = os.path.join(td, "sales.db"), os.path.join(td, "sales.aqe")
+            note("sqlite copy of 1M rows")
+            t1 = time.perf_counter(); RefSql.make_sqlite(sqlite_path, rows); t_make = time.perf_counter() - t1
+            O.save_file(rec_path, rows)
+            R = RefSql(sqlite_path)
+            res = {"records": n_sql, "cores": os.cpu_count(), "sqlite_build_s": t_make, "queries": []}
+            for sql, p, mode, ours in [("SELECT SUM(amount) FROM sales", 0, "run_query", lambda q, pp: b.run_query(q, rec_path, pp)),
+                                       ("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 100 AND 500", 10, "run_query_with_ci", lambda q, pp: b.run_query_with_ci(q, rec_path, pp).value),
+                                       ("SELECT SUM(amount) FROM sales GROUP BY region", 0, "run_query_groupby", lambda q, pp: len(b.run_query_groupby(q, rec_path, pp, 4))),
+                                       ("SELECT AVG(amount) FROM sales GROUP BY region", 10, "run_query_groupby_with_ci", lambda q, pp: len(b.run_query_groupby_with_ci(q, rec_path, pp, 4))),
+                                       ("SELECT COUNT(amount) FROM sales WHERE product_id < 100 GROUP BY product_id", 0, "run_query_groupby", lambda q, pp: len(b.run_query_groupby(q, rec_path, pp, 4)))]:
+                note(f"reference sql {sql}")
+                ts = []
+                for _ in range(3):
+                    t1 = time.perf_counter(); r_ref = R.run(sql, p, mode); ts.append(time.perf_counter() - t1)
+                ours(sql, p)   # first call loads the record file into HBM (cached by path afterwards)
+                ms_ours, r_ours = wall(lambda: ours(sql, p), reps=7)
+                res["queries"].append({"sql": sql, "sample_percent": p, "entry_point": mode, "reference_cpu_ms": statistics.median(ts) * 1e3,
+                                       "reference_groups_or_value": len(r_ref) if "groupby" in mode else r_ref[0][1], "gpu_ms": ms_ours, "gpu_groups_or_value": r_ours})
+            b.close_cached_tables()
+        out["reference_sql_1M"] = res
+except Exception as ex:  # noqa: BLE001
+    out["reference_sql_1M"] = {"unavailable": str(ex)}
 print(json.dumps(out, indent=1))
