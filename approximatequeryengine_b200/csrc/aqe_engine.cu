@@ -1771,13 +1771,19 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
         if ((rc = need(q->group_col))) return rc;
         a.group_slot = slot_of(q->group_col);
     }
-    for (int t = 0; t < q->n_terms; ++t) {
-        const aqe_sql_term& term = q->terms[t];
-        if ((rc = need(term.col))) return rc;
-        SqlCol& c = a.cols[slot_of(term.col)];
-        c.has_pred = 1; c.has_ne = term.has_ne;
-        if (c.kind == K_F64) { std::memcpy(&c.lo, &term.lo, 8); std::memcpy(&c.hi, &term.hi, 8); std::memcpy(&c.ne, &term.ne, 8); }
-        else { c.lo = term.ilo; c.hi = term.ihi; c.ne = term.ine; }
+    if (q->n_alt < 0 || q->n_alt > AQE_SQL_MAX_ALT) return fail(AQE_ERR_INVALID, "query: n_alt out of range");
+    a.n_alt = q->n_alt;
+    for (int alt = 0; alt < q->n_alt; ++alt) {
+        if (q->n_terms[alt] < 1 || q->n_terms[alt] > 5) return fail(AQE_ERR_INVALID, "query: a WHERE branch needs 1..5 terms");
+        for (int t = 0; t < q->n_terms[alt]; ++t) {
+            const aqe_sql_term& term = q->terms[alt][t];
+            if ((rc = need(term.col))) return rc;
+            const int slot = slot_of(term.col);
+            SqlPred& c = a.cols[slot].pred[alt];
+            c.has_pred = 1; c.has_ne = term.has_ne;
+            if (a.cols[slot].kind == K_F64) { std::memcpy(&c.lo, &term.lo, 8); std::memcpy(&c.hi, &term.hi, 8); std::memcpy(&c.ne, &term.ne, 8); }
+            else { c.lo = term.ilo; c.hi = term.ihi; c.ne = term.ine; }
+        }
     }
     // ---- rowid % step = 0 (executor.cpp:38-42); rowid = id ----
     a.first = 0; a.stride = 1; a.count = db->n;

@@ -74,18 +74,24 @@ constexpr int kSqlThreads = 256;
 constexpr int kSqlMaxCols = 5;          // the table has five columns; each is loaded at most once per row
 constexpr int kSqlPrivateMaxGroups = 16;
 
+constexpr int kSqlMaxAlt = AQE_SQL_MAX_ALT;   // OR-ed conjunctions of a WHERE clause
+
+struct SqlPred {       // one conjunct on one column: closed interval [lo, hi] and optionally != ne (raw 64-bit: f64 bits or int64)
+    int has_pred;
+    int has_ne;
+    long long lo, hi, ne;
+};
 struct SqlCol {
     const void* ptr;
     int kind;          // 0 f64, 1 i64, 2 i32
-    int has_pred;      // closed interval [lo, hi] on this column (raw 64-bit: f64 bits or int64)
-    int has_ne;
     int mod_step;      // > 0: also requires value % mod_step == 0  (rowid sampling when ids are not dense)
-    long long lo, hi, ne;
+    SqlPred pred[kSqlMaxAlt];
 };
 
 struct SqlArgs {
     SqlCol cols[kSqlMaxCols];
     int ncols;
+    int n_alt;         // 0: no WHERE; else a row passes when, for some alt < n_alt, every column's pred[alt] holds
     int agg_slot;      // index into cols, -1: count only
     int group_slot;    // index into cols, -1: no GROUP BY
     int agg_kind;
@@ -109,19 +115,17 @@ __device__ __forceinline__ long long sql_load_raw(const SqlCol& c, uint64_t i) {
     asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(static_cast<const long long*>(c.ptr) + i));
     return v;
 }
-__device__ __forceinline__ bool sql_pass(const SqlCol& c, long long raw) {
-    bool ok = true;
-    if (c.has_pred) {
-        if (c.kind == 0) {
-            const double d = __longlong_as_double(raw);
-            ok = d >= __longlong_as_double(c.lo) && d <= __longlong_as_double(c.hi);
-            if (c.has_ne) ok = ok && d != __longlong_as_double(c.ne);
-        } else {
-            ok = raw >= c.lo && raw <= c.hi;
-            if (c.has_ne) ok = ok && raw != c.ne;
-        }
+__device__ __forceinline__ bool sql_pass(const SqlCol& c, const SqlPred& p, long long raw) {
+    if (!p.has_pred) return true;
+    bool ok;
+    if (c.kind == 0) {
+        const double d = __longlong_as_double(raw);
+        ok = d >= __longlong_as_double(p.lo) && d <= __longlong_as_double(p.hi);
+        if (p.has_ne) ok = ok && d != __longlong_as_double(p.ne);
+    } else {
+        ok = raw >= p.lo && raw <= p.hi;
+        if (p.has_ne) ok = ok && raw != p.ne;
     }
-    if (c.mod_step > 0) ok = ok && (raw % (long long)c.mod_step == 0);
     return ok;
 }
 
@@ -276,10 +280,17 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
 // One row, row-at-a-time form (register-staged kernel and ragged tails): predicate, fixed-point conversion, bin update.
 template <int MODE, bool MOMENTS, int T>
 __device__ __forceinline__ void sql_consume(const SqlArgs& a, SqlBins<MODE, MOMENTS, T>& bins, int tid, const long long (&raw)[kSqlMaxCols]) {
-    bool pass = true;
+    bool pass = a.n_alt == 0;
+    for (int alt = 0; alt < a.n_alt; ++alt) {
+        bool all = true;
+#pragma unroll
+        for (int c = 0; c < kSqlMaxCols; ++c)
+            if (c < a.ncols) all = all && sql_pass(a.cols[c], a.cols[c].pred[alt], raw[c]);
+        pass = pass || all;
+    }
 #pragma unroll
     for (int c = 0; c < kSqlMaxCols; ++c)
-        if (c < a.ncols) pass = pass && sql_pass(a.cols[c], raw[c]);
+        if (c < a.ncols && a.cols[c].mod_step > 0) pass = pass && (raw[c] % (long long)a.cols[c].mod_step == 0);
     if (!pass) return;
     long long fx = 0, fq = 0;
     if (a.agg_slot >= 0) {
@@ -389,11 +400,11 @@ template <typename T> __device__ __forceinline__ T lds_row(const unsigned char* 
     return *reinterpret_cast<const T*>(base + (size_t)row * sizeof(T));
 }
 
-// one predicate column over this thread's row slots of the tile: clears the pass bit of every row that fails
-template <int T, int K> __device__ __forceinline__ uint32_t sql_pred_pass(const SqlCol& col, const unsigned char* base, int tid, uint32_t mask) {
+// one conjunct of one column over this thread's row slots of the tile: clears the pass bit of every row that fails
+template <int T, int K> __device__ __forceinline__ uint32_t sql_pred_pass(const SqlCol& col, const SqlPred& p, const unsigned char* base, int tid, uint32_t mask) {
     if (col.kind == 0) {
-        const double lo = __longlong_as_double(col.lo), hi = __longlong_as_double(col.hi), ne = __longlong_as_double(col.ne);
-        const bool has_ne = col.has_ne != 0;
+        const double lo = __longlong_as_double(p.lo), hi = __longlong_as_double(p.hi), ne = __longlong_as_double(p.ne);
+        const bool has_ne = p.has_ne != 0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const double v = lds_row<double>(base, tid + k * T);
@@ -401,29 +412,20 @@ template <int T, int K> __device__ __forceinline__ uint32_t sql_pred_pass(const 
             mask &= ~((ok ? 0u : 1u) << k);
         }
     } else if (col.kind == 1) {
-        const long long lo = col.has_pred ? col.lo : (long long)0x8000000000000000ull, hi = col.has_pred ? col.hi : 0x7fffffffffffffffll;
-        const bool has_ne = col.has_ne != 0;
+        const bool has_ne = p.has_ne != 0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const long long v = lds_row<long long>(base, tid + k * T);
-            const bool ok = v >= lo && v <= hi && !(has_ne && v == col.ne);
+            const bool ok = v >= p.lo && v <= p.hi && !(has_ne && v == p.ne);
             mask &= ~((ok ? 0u : 1u) << k);
-        }
-        if (col.mod_step > 0) {  // ids with gaps: rowid % step = 0 on the value itself
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                if ((mask >> k) & 1u) {
-                    const long long v = lds_row<long long>(base, tid + k * T);
-                    if (v % (long long)col.mod_step != 0) mask &= ~(1u << k);
-                }
         }
     } else {
         // int32 column: the int64 bounds clamp to the int32 range
-        const long long lo64 = col.lo < -2147483648ll ? -2147483648ll : col.lo, hi64 = col.hi > 2147483647ll ? 2147483647ll : col.hi;
+        const long long lo64 = p.lo < -2147483648ll ? -2147483648ll : p.lo, hi64 = p.hi > 2147483647ll ? 2147483647ll : p.hi;
         if (lo64 > 2147483647ll || hi64 < -2147483648ll) return 0u;
         const int lo = (int)lo64, hi = (int)hi64;
-        const bool has_ne = col.has_ne != 0 && col.ne >= -2147483648ll && col.ne <= 2147483647ll;
-        const int ne = (int)col.ne;
+        const bool has_ne = p.has_ne != 0 && p.ne >= -2147483648ll && p.ne <= 2147483647ll;
+        const int ne = (int)p.ne;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int v = lds_row<int>(base, tid + k * T);
@@ -431,6 +433,16 @@ template <int T, int K> __device__ __forceinline__ uint32_t sql_pred_pass(const 
             mask &= ~((ok ? 0u : 1u) << k);
         }
     }
+    return mask;
+}
+// rowid % step = 0 on the id values themselves (ids with gaps)
+template <int T, int K> __device__ __forceinline__ uint32_t sql_mod_pass(const SqlCol& col, const unsigned char* base, int tid, uint32_t mask) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        if ((mask >> k) & 1u) {
+            const long long v = lds_row<long long>(base, tid + k * T);
+            if (v % (long long)col.mod_step != 0) mask &= ~(1u << k);
+        }
     return mask;
 }
 
@@ -475,8 +487,26 @@ __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra)
             }
         }
     } else {
-        const int agg_slot = a.agg_slot, group_slot = a.group_slot;
+        // per-query facts, read from the parameter bank once: which columns carry a predicate in which OR branch, where the
+        // aggregate / group columns sit in a stage (a chain of indexed constant loads per tile costs 5-15 % with this few warps)
+        const int agg_slot = a.agg_slot, group_slot = a.group_slot, n_alt = a.n_alt;
         const int agg_kind = agg_slot >= 0 ? a.cols[agg_slot].kind : -1;
+        const int group_kind = group_slot >= 0 ? a.cols[group_slot].kind : -1;
+        const uint32_t agg_off = agg_slot >= 0 ? ra.col_off[agg_slot] : 0u, group_off = group_slot >= 0 ? ra.col_off[group_slot] : 0u;
+        const bool fuse_agg_pred = n_alt == 1 && agg_kind == 0;  // an f64 aggregate column is tested where it is converted (one LDS per row)
+        uint32_t pred_cols[kSqlMaxAlt];
+        int mod_slot = -1;
+#pragma unroll
+        for (int alt = 0; alt < kSqlMaxAlt; ++alt) {
+            pred_cols[alt] = 0u;
+            for (int k = 0; k < a.ncols; ++k)
+                if (alt < n_alt && a.cols[k].pred[alt].has_pred && !(fuse_agg_pred && k == agg_slot)) pred_cols[alt] |= 1u << k;
+        }
+        for (int k = 0; k < a.ncols; ++k) if (a.cols[k].mod_step > 0) mod_slot = k;
+        const SqlPred& ap = a.cols[agg_slot >= 0 ? agg_slot : 0].pred[0];
+        const bool agg_has_pred = fuse_agg_pred && ap.has_pred != 0, agg_has_ne = ap.has_ne != 0;
+        const double agg_lo = __longlong_as_double(ap.lo), agg_hi = __longlong_as_double(ap.hi), agg_ne = __longlong_as_double(ap.ne);
+        const int kmin32 = (int)a.key_min;
         uint32_t it = 0;
         for (uint64_t c = blockIdx.x; c < ntiles; c += gridDim.x, ++it) {
             const int s = it % STAGES;
@@ -488,11 +518,26 @@ __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra)
             // pass bits of rows tid, tid + T, ... of this tile
             const uint32_t nk = rows > (uint32_t)tid ? (rows - (uint32_t)tid + T - 1) / T : 0u;
             uint32_t mask = (1u << nk) - 1u;  // nk <= K
-            for (int k = 0; k < a.ncols; ++k) {
-                const SqlCol& col = a.cols[k];
-                if (k == agg_slot && agg_kind == 0) continue;  // an f64 aggregate column is tested where it is converted (one LDS per row)
-                if (col.has_pred || col.mod_step > 0) mask = sql_pred_pass<T, K>(col, stage + ra.col_off[k], tid, mask);
+            if (n_alt == 1) {
+                for (uint32_t pc = pred_cols[0]; pc; pc &= pc - 1) {
+                    const int k = __ffs(pc) - 1;
+                    mask = sql_pred_pass<T, K>(a.cols[k], a.cols[k].pred[0], stage + ra.col_off[k], tid, mask);
+                }
+            } else if (n_alt > 1) {  // OR of conjunctions: one mask per branch
+                uint32_t any = 0u;
+#pragma unroll
+                for (int alt = 0; alt < kSqlMaxAlt; ++alt) {
+                    if (alt >= n_alt) break;
+                    uint32_t m = mask;
+                    for (uint32_t pc = pred_cols[alt]; pc; pc &= pc - 1) {
+                        const int k = __ffs(pc) - 1;
+                        m = sql_pred_pass<T, K>(a.cols[k], a.cols[k].pred[alt], stage + ra.col_off[k], tid, m);
+                    }
+                    any |= m;
+                }
+                mask = any;
             }
+            if (mod_slot >= 0) mask = sql_mod_pass<T, K>(a.cols[mod_slot], stage + ra.col_off[mod_slot], tid, mask);
             if (ra.samp_step > 1) {
                 uint32_t x = (uint32_t)((row0 + ra.samp_phase + (uint32_t)tid) % ra.samp_step);  // (row + phase) mod step
                 const uint32_t dt = (uint32_t)T % ra.samp_step;                                  // advanced by T mod step per owned row
@@ -507,11 +552,10 @@ __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra)
 #pragma unroll
             for (int k = 0; k < K; ++k) g[k] = 0;
             if constexpr (MODE != 0) {
-                const unsigned char* gb = stage + ra.col_off[group_slot];
-                if (a.cols[group_slot].kind == 2) {
-                    const int kmin = (int)a.key_min;
+                const unsigned char* gb = stage + group_off;
+                if (group_kind == 2) {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) g[k] = (unsigned int)(lds_row<int>(gb, tid + k * T) - kmin);
+                    for (int k = 0; k < K; ++k) g[k] = (unsigned int)(lds_row<int>(gb, tid + k * T) - kmin32);
                 } else {
 #pragma unroll
                     for (int k = 0; k < K; ++k) g[k] = (unsigned int)(lds_row<long long>(gb, tid + k * T) - a.key_min);
@@ -523,16 +567,13 @@ __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra)
 #pragma unroll
                 for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, false, 0, 0);
             } else if (agg_kind == 0) {
-                const unsigned char* ab = stage + ra.col_off[agg_slot];
-                const SqlCol& ac = a.cols[agg_slot];
-                const bool has_pred = ac.has_pred != 0, has_ne = ac.has_ne != 0;
-                const double lo = __longlong_as_double(ac.lo), hi = __longlong_as_double(ac.hi), ne = __longlong_as_double(ac.ne);
+                const unsigned char* ab = stage + agg_off;
                 long long fx[K], fq[K];
-                if (has_pred) {
+                if (agg_has_pred) {
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const double d = lds_row<double>(ab, tid + k * T);
-                        mask &= ~(((d >= lo && d <= hi && !(has_ne && d == ne)) ? 0u : 1u) << k);
+                        mask &= ~(((d >= agg_lo && d <= agg_hi && !(agg_has_ne && d == agg_ne)) ? 0u : 1u) << k);
                         fx[k] = __double2ll_rn(__dmul_rn(d, a.sum_scale));
                         fq[k] = MOMENTS ? __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale)) : 0;
                     }
@@ -547,7 +588,7 @@ __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra)
 #pragma unroll
                 for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, true, fx[k], fq[k]);
             } else {
-                const unsigned char* ab = stage + ra.col_off[agg_slot];
+                const unsigned char* ab = stage + agg_off;
                 long long fx[K], fq[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) {

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AQE_ABI_VERSION 2
+#define AQE_ABI_VERSION 3
 
 #if defined(AQE_BUILDING)
 #define AQE_API __attribute__((visibility("default")))
@@ -363,8 +363,8 @@ AQE_API double aqe_z_score(double confidence_level, int exact);
  * parser.cpp:20-75).  The reference turns `SELECT agg(col) FROM t [WHERE ...] [GROUP BY g]` into SQLite
  * statements over a SQLite file, sampling with `rowid % (100/p) = 0` and scaling SUM/COUNT by 100/p.
  * Here the same query runs as ONE grouped-scan kernel (k_sql_agg) over the HBM-resident columns:
- * rowid = id; WHERE = a conjunction of comparisons / BETWEENs of columns with numeric literals, compiled
- * to one closed interval (+ optional "!=" value) per column; GROUP BY on an integer column with a dense
+ * rowid = id; WHERE = AND / OR / parentheses over comparisons and BETWEENs of columns with numeric literals,
+ * compiled to at most AQE_SQL_MAX_ALT OR-ed conjunctions of one closed interval (+ optional "!=" value) per column; GROUP BY on an integer column with a dense
  * key range of at most AQE_SQL_MAX_GROUPS values.  Sums are accumulated in 128-bit fixed point
  * (order-independent, so results are bit-reproducible and shard merges are exact).
  * ---------------------------------------------------------------------------------------------- */
@@ -380,15 +380,25 @@ typedef struct aqe_sql_term {
     int64_t ine;
 } aqe_sql_term;
 
-/* Parsed + compiled query: the reference's `struct Query` (parser.h:17-24) with names resolved. */
+/* Parsed + compiled query: the reference's `struct Query` (parser.h:17-24) with names resolved.  The WHERE clause
+ * is in disjunctive normal form: up to AQE_SQL_MAX_ALT conjunctions OR-ed together, each one closed interval
+ * (+ optional "!=" value) per column. */
+#define AQE_SQL_MAX_ALT 4
 typedef struct aqe_sql_query {
     int32_t agg;              /* aqe_agg */
     int32_t agg_col;          /* aqe_column; AQE_COL_NONE for COUNT(*) */
     int32_t group_col;        /* aqe_column or AQE_COL_NONE */
     int32_t sample_percent;   /* as passed; step = 100 / p for 0 < p < 100 (executor.cpp:20-26) */
-    int32_t n_terms;          /* 0..5 */
+    int32_t n_alt;            /* 0: every row passes; else the number of OR-ed conjunctions */
     int32_t always_false;     /* WHERE is unsatisfiable */
-    aqe_sql_term terms[5];
+    int32_t top_level_or;     /* the clause text has an OR outside all parentheses.  The reference builds its statements by
+                                 pasting text around the clause -- `group = 'k' AND <where> AND rowid % step = 0`
+                                 (executor.cpp:38-42, :95-98) -- so with a top-level OR the group filter binds to the first
+                                 branch only and the sampling filter to the last.  Such queries are refused
+                                 (AQE_ERR_UNSUPPORTED) for sampled or grouped calls; write `WHERE (a OR b)`. */
+    int32_t _pad;
+    int32_t n_terms[AQE_SQL_MAX_ALT];      /* terms per conjunction, 1..5 */
+    aqe_sql_term terms[AQE_SQL_MAX_ALT][5];
     char agg_text[32], column[64], table[64], group_by[64];
     char where[512];          /* raw WHERE text as parser.cpp:36-51 extracts it */
 } aqe_sql_query;

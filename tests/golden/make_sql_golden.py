@@ -58,6 +58,12 @@ QUERIES = [
     "SELECT COUNT(amount) FROM sales WHERE id <= 90 GROUP BY product_id",
     "SELECT SUM(amount) FROM sales WHERE product_id BETWEEN 100 AND 120 GROUP BY product_id",
     "SELECT AVG(amount) FROM sales WHERE region = 5 GROUP BY region",
+    # OR / parentheses
+    "SELECT SUM(amount) FROM sales WHERE region = 1 OR region = 3",   # top-level OR: comparable for exact, ungrouped calls only
+    "SELECT SUM(amount) FROM sales WHERE (region = 1 OR region = 3)",
+    "SELECT COUNT(amount) FROM sales WHERE (region = 1 OR region = 3) AND amount > 500",
+    "SELECT AVG(amount) FROM sales WHERE (amount < 100 OR amount > 900 OR product_id = 7)",
+    "SELECT SUM(amount) FROM sales WHERE (region < 2 OR region > 5) AND (product_id < 300 OR timestamp > 1700000900) GROUP BY region",
     # what parser.cpp rejects
     "SELECT MAX(amount) FROM sales",
     "SELECT amount FROM sales",

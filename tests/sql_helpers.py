@@ -71,18 +71,21 @@ def emulate_scan(rows, q, layout, flags=0):
         return acc
     unsampled = bool(flags & aqe.SQL_UNSAMPLED)
     moments = bool(flags & aqe.SQL_MOMENTS) and not unsampled
-    mask = np.ones(len(rows), dtype=bool)
-    for t in q.terms[: q.n_terms]:
-        col = rows[COL_NAMES[t.col]]
-        if t.col == 1:
-            mask &= (col >= t.lo) & (col <= t.hi)
-            if t.has_ne:
-                mask &= col != t.ne
-        else:
-            c = col.astype(np.int64)
-            mask &= (c >= t.ilo) & (c <= t.ihi)
-            if t.has_ne:
-                mask &= c != t.ine
+    mask = np.ones(len(rows), dtype=bool) if q.n_alt == 0 else np.zeros(len(rows), dtype=bool)
+    for branch in q.branches():
+        m = np.ones(len(rows), dtype=bool)
+        for t in branch:
+            col = rows[COL_NAMES[t.col]]
+            if t.col == 1:
+                m &= (col >= t.lo) & (col <= t.hi)
+                if t.has_ne:
+                    m &= col != t.ne
+            else:
+                c = col.astype(np.int64)
+                m &= (c >= t.ilo) & (c <= t.ihi)
+                if t.has_ne:
+                    m &= c != t.ine
+        mask |= m
     p = q.sample_percent
     step = 0 if (unsampled or p <= 0 or p >= 100) else max(1, 100 // p)
     if step > 1:

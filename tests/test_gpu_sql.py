@@ -56,6 +56,8 @@ def check_case(e, c):
     except ValueError:
         return None if want_err in ("stod", "terminate") else (tag, "engine raised stod", want_err)
     except RuntimeError as ex:  # AqeError is a RuntimeError
+        if "OR outside parentheses" in str(ex):
+            return None   # refused on purpose (include/aqe_b200.h, aqe_sql_query.top_level_or)
         return None if want_err == "runtime_error" else (tag, f"engine raised {ex}", want_err)
     if want_err == "terminate" or (want_err == "runtime_error" and "integer overflow" in c.get("msg", "")):
         return None  # the reference aborts / SQLite's int64 SUM(col*col) overflows; the 128-bit accumulators do not
@@ -82,6 +84,9 @@ def test_sql_against_oracle_extra_queries(tables, oracle):
         "SELECT AVG(amount) FROM sales WHERE id > 19990 GROUP BY region",
         "SELECT SUM(timestamp) FROM sales WHERE region = 7 GROUP BY region",
         "SELECT COUNT(*) FROM sales GROUP BY product_id",
+        "SELECT SUM(amount) FROM sales WHERE (region = 1 OR region = 6) AND (amount < 50 OR amount > 950)",
+        "SELECT AVG(amount) FROM sales WHERE (product_id < 10 OR product_id >= 990 OR region = 2) GROUP BY region",
+        "SELECT COUNT(amount) FROM sales WHERE (id <= 100 OR timestamp > 1700019000) GROUP BY product_id",
         "SELECT SUM(amount) FROM sales WHERE amount < 0",
         "SELECT COUNT(amount) FROM sales WHERE amount < 0 GROUP BY region",
     ]
@@ -288,6 +293,10 @@ def _random_query(rng, t0, n):
             terms.append(rng.choice([f"id > {a}", f"rowid <= {a}", f"id != {a}"]))
     group = rng.choice([None, None, "region", "product_id", "ts_bucket"])
     sql = f"SELECT {agg}({col}) FROM sales"
+    if len(terms) >= 2 and rng.random() < 0.4:      # a parenthesised OR of the first two terms, AND-ed with the rest
+        terms = [f"({terms[0]} OR {terms[1]})"] + terms[2:]
+    if len(terms) >= 2 and rng.random() < 0.15:     # ... and sometimes the whole clause as one parenthesised OR
+        terms = ["(" + " OR ".join(terms) + ")"]
     if terms:
         sql += " WHERE " + " AND ".join(terms)
     return sql, group
@@ -332,7 +341,7 @@ def test_sql_random_queries_against_oracle(oracle):
                 try:
                     got = run_engine(e, sql, p, mode)
                 except aqe.AqeError as ex:
-                    assert ex.code == 6 and "more than one !=" in str(ex), tag    # the one documented gap this generator can hit
+                    assert ex.code == 6 and ("more than one !=" in str(ex) or "OR branches" in str(ex)), tag    # the documented gaps this generator can hit
                     continue
                 assert len(got) == len(want), tag
                 for g, w in zip(got, want):
@@ -341,7 +350,10 @@ def test_sql_random_queries_against_oracle(oracle):
                     # reference's own 15-digit result can cancel, so values are compared on the scale of sum |x|
                     tol = 1e-12 * max(abs(w[1]), scale if "amount" in sql.split("FROM")[0] else abs(w[1]))
                     assert abs(g[1] - w[1]) <= tol or (math.isnan(g[1]) and math.isnan(w[1])) or g[1] == w[1], (tag, g, w)
-                    if math.isfinite(w[2]) and math.isfinite(w[3]) and math.isfinite(g[2]):
+                    # interval widths: the reference forms sum_sq - sum^2/n from 15-digit TEXT; for timestamp / id (values ~1e9
+                    # with a tiny spread) that difference is rounding noise in the reference itself, so it is not compared there
+                    well_conditioned = not any(c in sql.split("FROM")[0] for c in ("timestamp", "(id)"))
+                    if well_conditioned and math.isfinite(w[2]) and math.isfinite(w[3]) and math.isfinite(g[2]):
                         half_w, half_g = (w[3] - w[2]) / 2, (g[3] - g[2]) / 2
                         assert abs(half_g - half_w) <= 1e-6 * abs(half_w) + tol, (tag, g, w)
         e.close()

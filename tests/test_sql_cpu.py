@@ -32,6 +32,8 @@ def test_oracle_reproduces_reference_sql_path(oracle, path):
         try:
             got = oracle.sql(rows, c["sql"], c["p"], c["mode"])
         except SqlError as e:
+            if e.kind == "unsupported" and "top-level OR" in e.msg:
+                continue   # the reference's text pasting binds its filters to one OR branch: not restated (oracle header)
             want = c.get("error")
             kind = "stod" if (e.kind == "stod" or "integer overflow" in e.msg) else e.kind
             ok = want == e.kind or (want == "terminate" and kind == "stod")
@@ -65,7 +67,8 @@ def test_engine_parser_matches_reference_parser(path):
 
 def test_engine_parser_rejections():
     for sql, code in (("SELECT MAX(amount) FROM sales", 1), ("SELECT amount FROM sales", 1), ("SUM(amount) sales", 1),
-                      ("SELECT SUM(nope) FROM sales", 1), ("SELECT SUM(amount) FROM sales WHERE region = 1 OR region = 2", 6),
+                      ("SELECT SUM(nope) FROM sales", 1), ("SELECT SUM(amount) FROM sales WHERE region = 1 OR region = 2 OR region = 3 OR region = 4 OR region = 5", 6),
+                      ("SELECT SUM(amount) FROM sales WHERE NOT region = 1", 6), ("SELECT SUM(amount) FROM sales WHERE region IN (1, 2)", 6),
                       ("SELECT SUM(amount) FROM sales WHERE nope > 1", 1), ("SELECT SUM(amount) FROM sales GROUP BY amount", 6),
                       ("SELECT SUM(amount + 1) FROM sales", 6), ("SELECT SUM(*) FROM sales", 1),
                       ("SELECT SUM(amount) FROM sales WHERE region != 1 AND region != 2", 6)):
@@ -77,7 +80,8 @@ def test_engine_parser_rejections():
 def test_where_compilation_edge_cases():
     def terms(where):
         q = aqe.sql_parse("SELECT COUNT(*) FROM t WHERE " + where, 0)
-        return q, {t.col: t for t in q.terms[: q.n_terms]}
+        assert q.n_alt <= 1
+        return q, {t.col: t for t in (q.branches()[0] if q.n_alt else [])}
     q, t = terms("region > 2.5 AND region < 5.5")
     assert (t[2].ilo, t[2].ihi) == (3, 5)
     q, t = terms("region = 2.5")
@@ -95,7 +99,7 @@ def test_where_compilation_edge_cases():
     q, t = terms("rowid >= 1e3 AND timestamp <> 5 AND product_id = 17")
     assert t[0].ilo == 1000 and t[4].has_ne and t[4].ine == 5 and (t[3].ilo, t[3].ihi) == (17, 17)
     q, t = terms("1 = 1 AND 2 BETWEEN 1 AND 3")
-    assert not q.always_false and q.n_terms == 0
+    assert not q.always_false and q.n_alt == 0
     q, t = terms("1 = 2")
     assert q.always_false
     q, t = terms("region != 9 AND region < 5")   # a != outside the interval is vacuous
@@ -122,6 +126,8 @@ def test_host_half_against_reference_golden(oracle, path):
                 bad.append((tag, "engine raised stod", want_err))
             continue
         except aqe.AqeError as e:
+            if e.code == 6 and "OR outside parentheses" in str(e):
+                continue
             if want_err != "runtime_error" or e.code != 1:
                 bad.append((tag, f"engine raised {e}", want_err))
             continue
@@ -170,3 +176,25 @@ def test_shifts():
     assert a.value == 0 and b.value == 62 - 2 * 31
     assert L.aqe_sql_shifts(float("inf"), 0, C.byref(a), C.byref(b)) == 6
     assert L.aqe_sql_shifts(float("nan"), 0, C.byref(a), C.byref(b)) == 6
+
+
+def test_where_or_and_parentheses_compile_to_dnf():
+    def branches(where):
+        q = aqe.sql_parse("SELECT COUNT(*) FROM t WHERE " + where, 0)
+        return q, [{t.col: t for t in b} for b in q.branches()]
+    q, b = branches("region = 1 OR region = 3")
+    assert q.n_alt == 2 and (b[0][2].ilo, b[0][2].ihi, b[1][2].ilo, b[1][2].ihi) == (1, 1, 3, 3)
+    q, b = branches("(region = 1 OR region = 3) AND amount > 500")          # AND distributes over OR
+    assert q.n_alt == 2 and all(x[1].lo == np.nextafter(500.0, np.inf) for x in b) and [x[2].ilo for x in b] == [1, 3]
+    q, b = branches("region = 1 AND (amount < 10 OR amount > 990) AND product_id < 5")
+    assert q.n_alt == 2 and all(x[2].ilo == 1 and x[3].ihi == 4 for x in b) and b[0][1].hi < 10 < 990 < b[1][1].lo
+    q, b = branches("region = 1 OR (region = 2 AND region = 3) OR 1 = 2")   # dead branches vanish
+    assert q.n_alt == 1 and b[0][2].ilo == 1
+    q, b = branches("region = 1 OR 1 = 1")                                   # a true branch makes the clause vacuous
+    assert q.n_alt == 0 and not q.always_false
+    q, b = branches("(region = 1 AND region = 2) OR (amount > 5 AND amount < 5)")
+    assert q.always_false
+    q, b = branches("(region < 2 OR region > 5) AND (product_id = 1 OR product_id = 2)")
+    assert q.n_alt == 4
+    with pytest.raises(aqe.AqeError):                                        # 3 x 2 = 6 branches > AQE_SQL_MAX_ALT
+        aqe.sql_parse("SELECT COUNT(*) FROM t WHERE (region = 1 OR region = 2 OR region = 3) AND (amount < 1 OR amount > 2)", 0)
