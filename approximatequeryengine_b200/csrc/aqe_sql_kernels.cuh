@@ -469,6 +469,17 @@ __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra)
     const uint64_t ntiles = (n_main + ra.tile_rows - 1) / ra.tile_rows;
     if (warp == kBulkConsumerWarps) {
         if (lane == 0) {
+            // column geometry in registers (one read of the parameter bank, not one per tile)
+            const unsigned char* cptr[kSqlMaxCols];
+            uint32_t cw[kSqlMaxCols], coff[kSqlMaxCols], row_bytes = 0;
+#pragma unroll
+            for (int k = 0; k < kSqlMaxCols; ++k) {
+                const bool live = k < a.ncols;
+                cptr[k] = live ? static_cast<const unsigned char*>(a.cols[k].ptr) : nullptr;
+                cw[k] = live ? (a.cols[k].kind == 2 ? 4u : 8u) : 0u;
+                coff[k] = live ? ra.col_off[k] : 0u;
+                row_bytes += cw[k];
+            }
             uint32_t it = 0;
             for (uint64_t c = blockIdx.x; c < ntiles; c += gridDim.x, ++it) {
                 const int s = it % STAGES;
@@ -477,13 +488,10 @@ __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra)
                 const uint64_t row0 = c * (uint64_t)ra.tile_rows;
                 const uint32_t rows = (uint32_t)((n_main - row0) < (uint64_t)ra.tile_rows ? (n_main - row0) : (uint64_t)ra.tile_rows);
                 unsigned char* stage = ring + (size_t)s * ra.stage_bytes;
-                uint32_t bytes = 0;
-                for (int k = 0; k < a.ncols; ++k) bytes += rows * (a.cols[k].kind == 2 ? 4u : 8u);
-                mbar_expect_tx(&full_bar[s], bytes);
-                for (int k = 0; k < a.ncols; ++k) {
-                    const uint32_t w = a.cols[k].kind == 2 ? 4u : 8u;
-                    bulk_g2s(stage + ra.col_off[k], static_cast<const unsigned char*>(a.cols[k].ptr) + row0 * w, rows * w, &full_bar[s]);
-                }
+                mbar_expect_tx(&full_bar[s], rows * row_bytes);
+#pragma unroll
+                for (int k = 0; k < kSqlMaxCols; ++k)
+                    if (cw[k]) bulk_g2s(stage + coff[k], cptr[k] + row0 * cw[k], rows * cw[k], &full_bar[s]);
             }
         }
     } else {
