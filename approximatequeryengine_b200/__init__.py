@@ -217,6 +217,7 @@ def lib() -> C.CDLL:
         "aqe_sql_facts_of": (i32, [vp, C.POINTER(SqlQuery), C.POINTER(SqlFacts)]),
         "aqe_sql_layout_of": (i32, [C.POINTER(SqlQuery), C.POINTER(SqlFacts), i32, C.POINTER(SqlLayout)]),
         "aqe_sql_scan": (i32, [vp, C.POINTER(SqlQuery), C.POINTER(SqlLayout), i32, vp]),
+        "aqe_sql_scan_exchange": (i32, [vp, C.POINTER(SqlQuery), C.POINTER(SqlLayout), i32, vp]),
         "aqe_sql_merge": (i32, [vp, vp, C.c_uint32]),
         "aqe_sql_finish": (i32, [C.POINTER(SqlQuery), i32, C.POINTER(SqlLayout), vp, vp, C.POINTER(SqlRow), C.c_uint32, C.POINTER(C.c_uint32)]),
         "aqe_sql_shifts": (i32, [dbl, i32, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -507,9 +508,10 @@ class Engine:
         check(self.L.aqe_sql_facts_of(self.h, C.byref(q), C.byref(f)))
         return f
 
-    def sql_scan(self, q: SqlQuery, layout: SqlLayout, flags: int = 0) -> np.ndarray:
+    def sql_scan(self, q: SqlQuery, layout: SqlLayout, flags: int = 0, exchange: bool = False) -> np.ndarray:
+        """This shard's accumulators; with exchange=True (after exchange_connect) the table-level ones, merged inside the kernel."""
         acc = np.zeros(layout.n_groups * 5, dtype=np.uint64)
-        check(self.L.aqe_sql_scan(self.h, C.byref(q), C.byref(layout), flags, _ptr(acc)))
+        check((self.L.aqe_sql_scan_exchange if exchange else self.L.aqe_sql_scan)(self.h, C.byref(q), C.byref(layout), flags, _ptr(acc)))
         return acc
 
 

@@ -96,6 +96,8 @@ struct aqe_db {
     ExSlot* ex_peers[kMaxRanks] = {nullptr};
     unsigned long long ex_seq = 0;
     unsigned long long ax_msg = 0;       // next message index of the sampled-estimate exchange (lock-step on all ranks)
+    unsigned long long sqlx_seq = 0;     // sequence number of the SQL-path exchange (lock-step on all ranks)
+    unsigned long long* sql_local = nullptr;  // [AQE_SQL_MAX_GROUPS][5]: this shard's accumulators on their way into the exchange
     uint64_t ex_total_rows = 0;          // rows of the whole table (all shards)
     bool ex_connected = false;
 
@@ -370,7 +372,7 @@ int aqe_close(aqe_db* db) {
         free_columns(db);
         cudaFree(db->scan_partials); cudaFree(db->stat_partials); cudaFree(db->approx_slots); cudaFree(db->tickets);
         cudaFree(db->gather_buf); cudaFree(db->plan_buf);
-        cudaFree(db->sql_acc); cudaFree(db->sql_stat_dev); cudaFree(db->sql_ticket);
+        cudaFree(db->sql_acc); cudaFree(db->sql_stat_dev); cudaFree(db->sql_ticket); cudaFree(db->sql_local);
         if (db->sql_out_host) cudaFreeHost(db->sql_out_host);
         for (int r = 0; r < db->ex_world; ++r)
             if (db->ex_connected && r != db->ex_rank && db->ex_peers[r]) cudaIpcCloseMemHandle(db->ex_peers[r]);
@@ -794,10 +796,11 @@ int aqe_exchange_init(aqe_db* db, int rank, int world, void* ipc_handle_out) {
     if (rc) return rc;
     if (!db->ex_mailbox) {
         // [0, 2*kMaxRanks): scan partials; [2*kMaxRanks, 4*kMaxRanks): per-look messages of the sampled estimators
-        CU(cudaMalloc(&db->ex_mailbox, sizeof(ExSlot) * kMaxRanks * 4));
+        // behind them: the sequence flags and accumulator slots of the SQL exchange (aqe_sql_kernels.cuh)
+        CU(cudaMalloc(&db->ex_mailbox, kMailboxBytes));
     }
-    CU(cudaMemset(db->ex_mailbox, 0, sizeof(ExSlot) * kMaxRanks * 4));
-    db->ex_rank = rank; db->ex_world = world; db->ex_seq = 0; db->ax_msg = 0; db->ex_connected = false;
+    CU(cudaMemset(db->ex_mailbox, 0, kMailboxBytes));
+    db->ex_rank = rank; db->ex_world = world; db->ex_seq = 0; db->ax_msg = 0; db->sqlx_seq = 0; db->ex_connected = false;
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, db->ex_mailbox));
     std::memcpy(ipc_handle_out, &h, sizeof(h));
@@ -1618,6 +1621,7 @@ static int sql_init(aqe_db* db) {
     const size_t bytes = sizeof(unsigned long long) * 5 * AQE_SQL_MAX_GROUPS;
     CU(cudaMalloc(&db->sql_acc, bytes));
     CU(cudaMemset(db->sql_acc, 0, bytes));
+    CU(cudaMalloc(&db->sql_local, bytes));
     CU(cudaMalloc(&db->sql_stat_dev, 3 * sizeof(unsigned long long)));
     CU(cudaMalloc(&db->sql_ticket, sizeof(unsigned int)));
     CU(cudaMemset(db->sql_ticket, 0, sizeof(unsigned int)));
@@ -1734,17 +1738,39 @@ template <int MODE, bool MOMENTS> static int sql_launch_ring(const aqe_db* db, S
     return K == 8 ? go(k_sql_ring<MODE, MOMENTS, STAGES, 8>) : go(k_sql_ring<MODE, MOMENTS, STAGES, 4>);
 }
 
-static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* L, int flags, uint64_t* acc) {
+static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* L, int flags, uint64_t* acc, bool exchange = false) {
     const uint32_t G = L->n_groups;
     if (G < 1 || G > AQE_SQL_MAX_GROUPS) return fail(AQE_ERR_INVALID, "layout: n_groups out of range");
     std::memset(acc, 0, sizeof(uint64_t) * 5 * G);
-    if (q->always_false || db->n == 0) return AQE_OK;
+    int rc = sql_init(db);
+    if (rc) return rc;
+    SqlExchange ex;
+    std::memset(&ex, 0, sizeof(ex));
+    if (exchange) {
+        if (!db->ex_connected) return fail(AQE_ERR_STATE, "aqe_exchange_connect has not been called");
+        ex.world = db->ex_world; ex.rank = db->ex_rank; ex.seq = ++db->sqlx_seq;
+        ex.timeout_cycles = (unsigned long long)env_int("AQE_EXCHANGE_TIMEOUT_MS", 5000) * 2000000ull;
+        for (int r = 0; r < db->ex_world; ++r) ex.peers[r] = reinterpret_cast<unsigned char*>(db->ex_peers[r]);
+        ex.status = db->tickets + 3; ex.local = db->sql_local;
+    }
+    // a shard that has nothing to scan: without an exchange the zeros (or the metadata count) are the answer; with one it still
+    // publishes them so that the other ranks' kernels are not left waiting
+    auto finish_without_scan = [&](uint64_t count0) -> int {
+        acc[0] = count0;
+        if (!exchange) return AQE_OK;
+        CU(cudaMemcpyAsync(db->sql_local, acc, sizeof(uint64_t) * 5 * G, cudaMemcpyHostToDevice, db->stream));
+        k_sql_exchange_only<<<1, 256, 0, db->stream>>>(ex, G, db->sql_out_dev);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(db->stream));
+        std::memcpy(acc, db->sql_out_host, sizeof(uint64_t) * 5 * G);
+        return aqe_exchange_check(db);
+    };
+    if (q->always_false || db->n == 0) return finish_without_scan(0);
     // Accumulator widths: a thread sums 32-bit halves into 64-bit words (fewer than 2^32 rows per thread), a CTA counts
     // rows per bin in 32 bits (fewer than 2^32 rows per CTA), everything above is 128-bit.  2^40 rows keeps all of that
     // far from overflow at any grid this library launches (and is 8 TB of one 8-byte column).
     if (db->n > (1ull << 40)) return fail(AQE_ERR_UNSUPPORTED, "SQL path: more than 2^40 rows per shard");
-    int rc = sql_init(db);
-    if (rc) return rc;
     const bool unsampled = (flags & AQE_SQL_UNSAMPLED) != 0;
     const bool moments = (flags & AQE_SQL_MOMENTS) != 0 && !unsampled;
     const bool sums = q->agg_col != AQE_COL_NONE && !unsampled && (q->agg != AQE_AGG_COUNT || moments);
@@ -1801,12 +1827,11 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
     }
     if (a.ncols == 0) {  // COUNT without WHERE / GROUP BY: metadata (0 bytes per record)
         const uint64_t first = dense ? (uint64_t)((step - phase) % step) : 0;
-        acc[0] = dense ? (first < db->n ? (db->n - first + step - 1) / step : 0) : db->n;
-        return AQE_OK;
+        return finish_without_scan(dense ? (first < db->n ? (db->n - first + step - 1) / step : 0) : db->n);
     }
     a.key_min = L->key_min; a.n_groups = G;
     a.sum_scale = std::ldexp(1.0, L->sum_shift); a.sq_scale = std::ldexp(1.0, L->sq_shift);
-    a.global_acc = db->sql_acc; a.out = db->sql_out_dev; a.ticket = db->sql_ticket;
+    a.global_acc = db->sql_acc; a.out = db->sql_out_dev; a.ticket = db->sql_ticket; a.ex = ex;
     bool aligned16 = true;
     for (int i = 0; i < a.ncols; ++i) aligned16 = aligned16 && ((uintptr_t)a.cols[i].ptr % 16) == 0;
     // Visit plan.  Dense ids turn the sample into an arithmetic progression of row numbers: for small steps every 32-byte
@@ -1817,7 +1842,7 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
     if (strided) {
         a.first = (uint64_t)((step - phase) % step); a.stride = (uint64_t)step;
         a.count = a.first < db->n ? (db->n - a.first + step - 1) / step : 0;
-        if (a.count == 0) return AQE_OK;
+        if (a.count == 0) return finish_without_scan(0);
     } else if (dense) {
         ra.samp_step = (uint32_t)step; ra.samp_phase = (uint32_t)phase;
     }
@@ -1832,7 +1857,7 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
         if (!strided && dense) {  // register kernel has no row-number filter: visit the progression
             a.first = (uint64_t)((step - phase) % step); a.stride = (uint64_t)step;
             a.count = a.first < db->n ? (db->n - a.first + step - 1) / step : 0;
-            if (a.count == 0) return AQE_OK;
+            if (a.count == 0) return finish_without_scan(0);
         }
         if (mode == 0) rc = moments ? sql_launch_regs<0, true>(db, a, s) : sql_launch_regs<0, false>(db, a, s);
         else if (mode == 1) rc = moments ? sql_launch_regs<1, true>(db, a, s) : sql_launch_regs<1, false>(db, a, s);
@@ -1842,7 +1867,7 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(db->stream));
     std::memcpy(acc, db->sql_out_host, sizeof(uint64_t) * 5 * G);
-    return AQE_OK;
+    return exchange ? aqe_exchange_check(db) : AQE_OK;
 }
 
 extern "C" {
@@ -1905,6 +1930,13 @@ int aqe_sql_scan(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* layou
     int rc = ensure_device(db);
     if (rc) return rc;
     return sql_scan_impl(db, q, layout, flags, acc);
+}
+
+int aqe_sql_scan_exchange(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* layout, int flags, uint64_t* acc) {
+    if (!db || !q || !layout || !acc) return fail(AQE_ERR_INVALID, "NULL argument");
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    return sql_scan_impl(db, q, layout, flags, acc, db->ex_world > 1);
 }
 
 int aqe_sql_merge(uint64_t* acc, const uint64_t* other, uint32_t n_groups) {

@@ -88,6 +88,31 @@ struct SqlCol {
     SqlPred pred[kSqlMaxAlt];
 };
 
+// Cross-GPU exchange fused into the grouped scan (one process per GPU, peers mapped with CUDA IPC over NVLink; same mailbox
+// allocation as the scan exchange of aqe_kernels.cuh, the SQL area sits behind its slots).  The LAST CTA of rank r stores its
+// shard's accumulators into slot [r][seq & 1] of EVERY rank's mailbox (peer stores), raises that slot's sequence flag, waits
+// until its own mailbox holds `seq` from all ranks and adds the shards' words with 128-bit carries -- integer adds commute, so
+// every rank ends with the identical table-level accumulators and no host merge, NCCL launch or staging copy is left.
+constexpr size_t kSqlxSlotWords = (size_t)AQE_SQL_MAX_GROUPS * 5;
+constexpr size_t kSqlxFlagsOffset = sizeof(ExSlot) * kMaxRanks * 4;                       // behind the scan / approx slots
+constexpr size_t kSqlxDataOffset = kSqlxFlagsOffset + sizeof(unsigned long long) * kMaxRanks * 2;
+constexpr size_t kMailboxBytes = kSqlxDataOffset + sizeof(unsigned long long) * kSqlxSlotWords * kMaxRanks * 2;
+struct SqlExchange {
+    int world;                      // 0/1 = disabled
+    int rank;
+    unsigned long long seq;
+    unsigned long long timeout_cycles;
+    unsigned char* peers[kMaxRanks];  // peers[r] = base of rank r's mailbox allocation as mapped in this process
+    unsigned int* status;             // set to 1 if a peer did not show up in time
+    unsigned long long* local;        // [n_groups][5] scratch in this GPU's memory
+};
+__device__ __forceinline__ unsigned long long* sqlx_flag(unsigned char* base, int sender, int par) {
+    return reinterpret_cast<unsigned long long*>(base + kSqlxFlagsOffset) + sender * 2 + par;
+}
+__device__ __forceinline__ unsigned long long* sqlx_data(unsigned char* base, int sender, int par) {
+    return reinterpret_cast<unsigned long long*>(base + kSqlxDataOffset) + ((size_t)sender * 2 + par) * kSqlxSlotWords;
+}
+
 struct SqlArgs {
     SqlCol cols[kSqlMaxCols];
     int ncols;
@@ -103,6 +128,7 @@ struct SqlArgs {
     unsigned long long* global_acc;   // [n_groups][5] {count, sum_lo, sum_hi, sq_lo, sq_hi}, zero before launch, zeroed again by the last CTA
     unsigned long long* out;          // [n_groups][5] device-visible result
     unsigned int* ticket;
+    SqlExchange ex;
 };
 
 __device__ __forceinline__ long long sql_load_raw(const SqlCol& c, uint64_t i) {
@@ -313,7 +339,45 @@ __device__ __forceinline__ void sql_consume(const SqlArgs& a, SqlBins<MODE, MOME
     bins.add(g, tid, a.agg_slot >= 0, fx, fq);
 }
 
-// last CTA: publish the accumulators and re-arm them for the next launch
+// The exchange proper; called by every thread of ONE CTA with this shard's accumulators in ex.local.
+__device__ __forceinline__ void sql_exchange(const SqlExchange& ex, unsigned int n_groups, unsigned long long* out, int tid, int nthreads) {
+    const unsigned int words = n_groups * 5;
+    const int par = (int)(ex.seq & 1ull);
+    for (int r = 0; r < ex.world; ++r) {   // peer stores over NVLink, coalesced
+        volatile unsigned long long* dst = sqlx_data(ex.peers[r], ex.rank, par);
+        for (unsigned int i = tid; i < words; i += nthreads) dst[i] = __ldcg(ex.local + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < ex.world) st_release_sys(sqlx_flag(ex.peers[tid], ex.rank, par), ex.seq);
+    if (tid < ex.world) {
+        const unsigned long long* flag = sqlx_flag(ex.peers[ex.rank], tid, par);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flag) != ex.seq) {
+            if ((unsigned long long)(clock64() - t0) > ex.timeout_cycles) { atomicExch(ex.status, 1u); break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    for (unsigned int g = tid; g < n_groups; g += nthreads) {   // fold the shards in rank order (any order gives the same bits)
+        unsigned long long cnt = 0, lo[2] = {0, 0}, hi[2] = {0, 0};
+        for (int r = 0; r < ex.world; ++r) {
+            const volatile unsigned long long* src = sqlx_data(ex.peers[ex.rank], r, par) + (size_t)g * 5;
+            cnt += src[0];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const unsigned long long l = src[1 + 2 * k], h = src[2 + 2 * k];
+                const unsigned long long nl = lo[k] + l;
+                hi[k] += h + (nl < lo[k] ? 1ull : 0ull);
+                lo[k] = nl;
+            }
+        }
+        unsigned long long* o = out + (size_t)g * 5;
+        o[0] = cnt; o[1] = lo[0]; o[2] = hi[0]; o[3] = lo[1]; o[4] = hi[1];
+    }
+}
+
+// last CTA: publish the accumulators (through the cross-GPU exchange when one is connected) and re-arm them for the next launch
 __device__ __forceinline__ void sql_publish(const SqlArgs& a, int tid, int nthreads) {
     __shared__ bool is_last;
     __threadfence();
@@ -325,14 +389,26 @@ __device__ __forceinline__ void sql_publish(const SqlArgs& a, int tid, int nthre
     // (replicated accumulators -- CTA b adding into copy b mod 8 to shorten the same-address atomic queues in L2 -- were
     // tried: no gain on the scan, and summing the copies here cost 0.1-0.2 ms at 1000 groups)
     const unsigned int words = a.n_groups * 5;
+    unsigned long long* dst = a.ex.world > 1 ? a.ex.local : a.out;
     for (unsigned int i0 = tid; i0 < words; i0 += 4 * nthreads) {
         unsigned long long v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) { const unsigned int i = i0 + u * nthreads; v[u] = i < words ? __ldcg(a.global_acc + i) : 0ull; }  // 4 loads in flight
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const unsigned int i = i0 + u * nthreads; if (i < words) { a.out[i] = v[u]; a.global_acc[i] = 0ull; } }
+        for (int u = 0; u < 4; ++u) { const unsigned int i = i0 + u * nthreads; if (i < words) { dst[i] = v[u]; a.global_acc[i] = 0ull; } }
     }
     if (tid == 0) *a.ticket = 0u;
+    if (a.ex.world > 1) {
+        __threadfence();
+        __syncthreads();
+        sql_exchange(a.ex, a.n_groups, a.out, tid, nthreads);
+    }
+}
+
+// A shard with nothing to scan (no rows, an unsatisfiable WHERE, COUNT(*) answered from metadata) still takes part in the exchange:
+// ex.local holds what the host computed.
+__global__ void __launch_bounds__(256) k_sql_exchange_only(const SqlExchange ex, unsigned int n_groups, unsigned long long* out) {
+    sql_exchange(ex, n_groups, out, threadIdx.x, blockDim.x);
 }
 
 // Register-staged visit: strided samples (rowid % step = 0 over dense ids becomes an arithmetic progression of row

@@ -158,14 +158,17 @@ class ShardedTable:
             moments = mode == "ci_reference" or q.agg != AGG["count"]
         else:
             moments = q.agg != AGG["count"] and step > 0
-        acc = np.zeros(layout.n_groups * 5, dtype=np.uint64)
-        for part in allgather_words(self.engine.sql_scan(q, layout, SQL_MOMENTS if moments else 0), self.group):
-            sql_merge(acc, part)
+        def table_level(flags):
+            if getattr(self, "fused", False):   # merged inside the scan kernel over the NVLink mailboxes
+                return self.engine.sql_scan(q, layout, flags, exchange=True)
+            total = np.zeros(layout.n_groups * 5, dtype=np.uint64)
+            for part in allgather_words(self.engine.sql_scan(q, layout, flags), self.group):
+                sql_merge(total, part)
+            return total
+        acc = table_level(SQL_MOMENTS if moments else 0)
         exists = None
         if grouped and step > 1 and (acc[0::5] == 0).any():   # identical on every rank: the pass below is collective
-            exists = np.zeros_like(acc)
-            for part in allgather_words(self.engine.sql_scan(q, layout, SQL_UNSAMPLED), self.group):
-                sql_merge(exists, part)
+            exists = table_level(SQL_UNSAMPLED)
         return sql_finish(q, layout, acc, mode, exists)
 
     def approx(self, agg="sum", error_percent=1.0, confidence_level=0.95, seed=0, **kw) -> ApproxResult:

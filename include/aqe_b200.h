@@ -458,6 +458,12 @@ AQE_API int aqe_sql_shifts(double agg_absmax, int agg_is_integer, int* sum_shift
 AQE_API int aqe_sql_layout_of(const aqe_sql_query* q, const aqe_sql_facts* facts, int n_shards, aqe_sql_layout* out);
 AQE_API int aqe_sql_scan(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* layout, int flags,
                          uint64_t* acc /* n_groups x 5 words, host */);
+/* Multi-GPU form (after aqe_exchange_connect on every rank; all ranks issue the same sequence of calls with the same
+ * layout): the scan kernel's last CTA stores this shard's accumulators into every rank's mailbox over NVLink, waits for
+ * all ranks and adds them with 128-bit carries inside the same kernel -- `acc` receives the TABLE-level accumulators on
+ * every rank, bit-identical to aqe_sql_merge over the per-shard results.  Replaces the all-gather + host merge. */
+AQE_API int aqe_sql_scan_exchange(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* layout, int flags,
+                                  uint64_t* acc /* n_groups x 5 words, host */);
 /* Host only: acc[i] += other[i] over the 5-word groups with 128-bit carries. */
 AQE_API int aqe_sql_merge(uint64_t* acc, const uint64_t* other, uint32_t n_groups);
 /* Host only: the arithmetic of executor.cpp on merged accumulators.  `exists` (n_groups x 5 words from an

@@ -87,6 +87,25 @@ for sql, p, mode in (("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 100 AN
         assert rows_close(got, want, REL) is None, (sql, rows_close(got, want, REL))
         one = single.sql(sql, p, MODE_OF[mode])          # the unsharded table on one GPU: identical bits
         assert got == [(r.key, r.value, r.ci_lower, r.ci_upper) for r in one], sql
+# the same queries with the accumulators exchanged INSIDE the scan kernel (NVLink mailboxes): identical bits, every rank
+plain = {}
+SQLX = (("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 100 AND 500", 10, "ci_reference"), ("SELECT AVG(amount) FROM sales GROUP BY region", 0, "value"),
+        ("SELECT SUM(amount) FROM sales WHERE region >= 2 GROUP BY region", 20, "ci_reference"), ("SELECT SUM(amount) FROM sales GROUP BY product_id", 50, "value"),
+        ("SELECT COUNT(*) FROM sales", 0, "value"), ("SELECT COUNT(amount) FROM sales WHERE amount < 0 GROUP BY region", 0, "value"),
+        ("SELECT COUNT(amount) FROM sales WHERE id <= 400 GROUP BY product_id", 10, "value"), ("SELECT SUM(timestamp) FROM sales WHERE (region = 1 OR region = 5)", 7, "value"))
+for sql, p, mode in SQLX:
+    try:
+        plain[sql] = [(r.key, r.count, r.value, r.ci_lower, r.ci_upper, r.is_null) for r in tq.sql(sql, p, mode)]
+    except Exception as ex:  # noqa: BLE001
+        plain[sql] = repr(ex)
+assert tq.enable_fused_exchange()
+for it in range(3):
+    for sql, p, mode in SQLX:
+        try:
+            got = [(r.key, r.count, r.value, r.ci_lower, r.ci_upper, r.is_null) for r in tq.sql(sql, p, mode)]
+        except Exception as ex:  # noqa: BLE001
+            got = repr(ex)
+        assert got == plain[sql] or (isinstance(got, list) and all(a[:2] == b[:2] and (a[2:] == b[2:] or a[5]) for a, b in zip(got, plain[sql]))), (rank, it, sql, got[:3], plain[sql][:3])
 big_sql = {}
 for sql in ("SELECT SUM(amount) FROM sales", "SELECT SUM(amount) FROM sales WHERE timestamp > 1700000005"):
     tq_big = t.sql(sql)            # the big table holds id, amount, timestamp
