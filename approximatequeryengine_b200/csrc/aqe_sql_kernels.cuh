@@ -412,33 +412,101 @@ __global__ void __launch_bounds__(256) k_sql_exchange_only(const SqlExchange ex,
 }
 
 // Register-staged visit: strided samples (rowid % step = 0 over dense ids becomes an arithmetic progression of row
-// numbers) and columns that are not 16-byte aligned; eight independent rows in flight per thread.
+// numbers) and columns that are not 16-byte aligned.  Same column-at-a-time shape as the ring consumer, the rows of a
+// batch coming straight from global memory: a thread owns U rows per batch, keeps one pass bit per row, runs each
+// predicate column as one pass of U independent loads, then the group column, then the aggregate column.
+template <int U> __device__ __forceinline__ uint32_t sql_pred_pass_global(const SqlCol& col, const SqlPred& p, const uint64_t (&idx)[U], uint32_t mask) {
+#pragma unroll
+    for (int e = 0; e < U; ++e) {
+        const long long raw = sql_load_raw(col, idx[e]);
+        mask &= ~((sql_pass(col, p, raw) ? 0u : 1u) << e);
+    }
+    return mask;
+}
+
 template <int MODE, bool MOMENTS>
 __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
     extern __shared__ __align__(16) unsigned char sql_smem[];
     const int tid = threadIdx.x;
     constexpr int T = kSqlThreads;
+    constexpr int U = 8;
     SqlBins<MODE, MOMENTS, T> bins;
     bins.init(sql_smem, a.n_groups, tid, T);
 
-    const uint64_t gsz = (uint64_t)gridDim.x * T;
-    constexpr int U = 8;
-    uint64_t j = (uint64_t)blockIdx.x * T + tid;
-    for (; j + (U - 1) * gsz < a.count; j += U * gsz) {
-        long long rawu[U][kSqlMaxCols];
+    // per-query facts, read from the parameter bank once
+    const int agg_slot = a.agg_slot, group_slot = a.group_slot, n_alt = a.n_alt;
+    const int agg_kind = agg_slot >= 0 ? a.cols[agg_slot].kind : -1;
+    uint32_t pred_cols[kSqlMaxAlt];
+    int mod_slot = -1;
 #pragma unroll
-        for (int e = 0; e < U; ++e)
-#pragma unroll
-            for (int c = 0; c < kSqlMaxCols; ++c)
-                rawu[e][c] = c < a.ncols ? sql_load_raw(a.cols[c], a.first + (j + (uint64_t)e * gsz) * a.stride) : 0;
-#pragma unroll
-        for (int e = 0; e < U; ++e) sql_consume(a, bins, tid, rawu[e]);
+    for (int alt = 0; alt < kSqlMaxAlt; ++alt) {
+        pred_cols[alt] = 0u;
+        for (int k = 0; k < a.ncols; ++k)
+            if (alt < n_alt && a.cols[k].pred[alt].has_pred) pred_cols[alt] |= 1u << k;
     }
-    for (; j < a.count; j += gsz) {
-        long long raw[kSqlMaxCols];
+    for (int k = 0; k < a.ncols; ++k) if (a.cols[k].mod_step > 0) mod_slot = k;
+
+    const uint64_t gsz = (uint64_t)gridDim.x * T;
+    const uint64_t last = a.count - 1;  // a.count > 0 (the host launches nothing otherwise)
+    for (uint64_t j = (uint64_t)blockIdx.x * T + tid; j < a.count; j += U * gsz) {
+        uint64_t idx[U];
+        uint32_t mask = 0u;
 #pragma unroll
-        for (int c = 0; c < kSqlMaxCols; ++c) raw[c] = c < a.ncols ? sql_load_raw(a.cols[c], a.first + j * a.stride) : 0;
-        sql_consume(a, bins, tid, raw);
+        for (int e = 0; e < U; ++e) {
+            const uint64_t je = j + (uint64_t)e * gsz;
+            if (je < a.count) mask |= 1u << e;
+            idx[e] = a.first + (je < a.count ? je : last) * a.stride;  // slots past the end re-read the last row and stay masked off
+        }
+        if (n_alt == 1) {
+            for (uint32_t pc = pred_cols[0]; pc; pc &= pc - 1) {
+                const int k = __ffs(pc) - 1;
+                mask = sql_pred_pass_global<U>(a.cols[k], a.cols[k].pred[0], idx, mask);
+            }
+        } else if (n_alt > 1) {
+            uint32_t any = 0u;
+#pragma unroll
+            for (int alt = 0; alt < kSqlMaxAlt; ++alt) {
+                if (alt >= n_alt) break;
+                uint32_t m = mask;
+                for (uint32_t pc = pred_cols[alt]; pc; pc &= pc - 1) {
+                    const int k = __ffs(pc) - 1;
+                    m = sql_pred_pass_global<U>(a.cols[k], a.cols[k].pred[alt], idx, m);
+                }
+                any |= m;
+            }
+            mask = any;
+        }
+        if (mod_slot >= 0) {
+#pragma unroll
+            for (int e = 0; e < U; ++e)
+                if ((mask >> e) & 1u) {
+                    if (sql_load_raw(a.cols[mod_slot], idx[e]) % (long long)a.cols[mod_slot].mod_step != 0) mask &= ~(1u << e);
+                }
+        }
+        unsigned int g[U];
+#pragma unroll
+        for (int e = 0; e < U; ++e) g[e] = 0;
+        if constexpr (MODE != 0) {
+#pragma unroll
+            for (int e = 0; e < U; ++e) g[e] = (unsigned int)(sql_load_raw(a.cols[group_slot], idx[e]) - a.key_min);
+#pragma unroll
+            for (int e = 0; e < U; ++e) if (g[e] >= bins.G) mask &= ~(1u << e);  // cannot happen for live rows with this table's own layout
+        }
+        long long fx[U], fq[U];
+#pragma unroll
+        for (int e = 0; e < U; ++e) { fx[e] = 0; fq[e] = 0; }
+        if (agg_kind >= 0) {
+#pragma unroll
+            for (int e = 0; e < U; ++e) {
+                const long long rv = sql_load_raw(a.cols[agg_slot], idx[e]);
+                double d;
+                if (agg_kind == 0) { d = __longlong_as_double(rv); fx[e] = __double2ll_rn(__dmul_rn(d, a.sum_scale)); }
+                else { d = (double)rv; fx[e] = rv; }
+                if constexpr (MOMENTS) fq[e] = __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale));
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < U; ++e) if ((mask >> e) & 1u) bins.add(g[e], tid, agg_kind >= 0, fx[e], fq[e]);
     }
     bins.flush(a.global_acc, tid, T);
     sql_publish(a, tid, T);
