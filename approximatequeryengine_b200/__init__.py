@@ -108,7 +108,7 @@ class SqlTerm(C.Structure):
 class SqlQuery(C.Structure):
     """Parsed + compiled query: the reference's ``struct Query`` (parser.h:17-24) with names resolved."""
     _fields_ = [("agg", C.c_int32), ("agg_col", C.c_int32), ("group_col", C.c_int32), ("sample_percent", C.c_int32),
-                ("n_alt", C.c_int32), ("always_false", C.c_int32), ("top_level_or", C.c_int32), ("_pad", C.c_int32), ("n_terms", C.c_int32 * 4), ("terms", (SqlTerm * 5) * 4),
+                ("n_alt", C.c_int32), ("always_false", C.c_int32), ("top_level_or", C.c_int32), ("_pad", C.c_int32), ("n_terms", C.c_int32 * 8), ("terms", (SqlTerm * 5) * 8),
                 ("agg_text", C.c_char * 32), ("column", C.c_char * 64), ("table", C.c_char * 64),
                 ("group_by", C.c_char * 64), ("where", C.c_char * 512)]
 
@@ -140,7 +140,7 @@ class SqlLayout(C.Structure):
 SQL_MODE = {"value": 0, "ci_reference": 1, "ci_correct": 2}
 SQL_MOMENTS, SQL_UNSAMPLED = 1, 2
 SQL_MAX_GROUPS = 4096
-SQL_MAX_ALT = 4
+SQL_MAX_ALT = 8
 
 _lib = None
 

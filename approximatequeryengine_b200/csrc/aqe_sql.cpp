@@ -57,7 +57,7 @@ bool is_identifier(const std::string& s) {
 }
 
 // ---- WHERE: tokens ---------------------------------------------------------------------------------------
-enum Tok { T_END, T_IDENT, T_NUM, T_OP, T_LP, T_RP, T_AND, T_OR, T_BETWEEN, T_OTHER };
+enum Tok { T_END, T_IDENT, T_NUM, T_OP, T_LP, T_RP, T_AND, T_OR, T_BETWEEN, T_IN, T_COMMA, T_OTHER };
 struct Token { Tok t; std::string text; bool is_int = false; int64_t i = 0; double d = 0.0; };
 
 struct Lexer {
@@ -89,7 +89,7 @@ struct Lexer {
             while (e < s.size() && (std::isalnum((unsigned char)s[e]) || s[e] == '_')) ++e;
             k.text = s.substr(p, e - p); p = e;
             const std::string u = upper(k.text);
-            k.t = u == "AND" ? T_AND : u == "OR" ? T_OR : u == "BETWEEN" ? T_BETWEEN : ((u == "NOT" || u == "IN" || u == "LIKE" || u == "IS" || u == "NULL") ? T_OTHER : T_IDENT);
+            k.t = u == "AND" ? T_AND : u == "OR" ? T_OR : u == "BETWEEN" ? T_BETWEEN : u == "IN" ? T_IN : ((u == "NOT" || u == "LIKE" || u == "IS" || u == "NULL") ? T_OTHER : T_IDENT);
             return k;
         }
         if (std::isdigit((unsigned char)c) || (c == '.' && p + 1 < s.size() && std::isdigit((unsigned char)s[p + 1]))) {
@@ -113,6 +113,7 @@ struct Lexer {
         }
         if (c == '(') { ++p; k.t = T_LP; k.text = "("; return k; }
         if (c == ')') { ++p; k.t = T_RP; k.text = ")"; return k; }
+        if (c == ',') { ++p; k.t = T_COMMA; k.text = ","; return k; }
         static const char* ops[] = {"<=", ">=", "<>", "!=", "==", "<", ">", "="};
         for (const char* o : ops) {
             const size_t n = std::strlen(o);
@@ -292,7 +293,7 @@ struct WhereCompiler {
     void advance() { cur = lx.next(); }
     bool unsupported(const std::string& what) {
         status = AQE_ERR_UNSUPPORTED;
-        err = "unsupported WHERE clause (" + what + "); supported: comparisons and BETWEEN of id|rowid|amount|region|product_id|timestamp with numeric literals, combined with AND, OR and parentheses";
+        err = "unsupported WHERE clause (" + what + "); supported: comparisons, BETWEEN and IN lists of id|rowid|amount|region|product_id|timestamp with numeric literals, combined with AND, OR and parentheses";
         return false;
     }
     bool fail_unsupported() { status = AQE_ERR_UNSUPPORTED; return false; }
@@ -340,6 +341,29 @@ struct WhereCompiler {
             if (!constrain(k.r[ca], ca, C_GE, lo, err) || !constrain(k.r[ca], ca, C_LE, hi, err)) return fail_unsupported();
             out.clear();
             if (!range_empty(k.r[ca], ca)) out.push_back(k);
+            return true;
+        }
+        if (cur.t == T_IN) {  // col IN (v1, v2, ...)  ==  col = v1 OR col = v2 OR ...
+            advance();
+            if (ca == AQE_COL_NONE) return unsupported("IN needs a column on the left");
+            if (cur.t != T_LP) return unsupported("IN without a list");
+            advance();
+            out.clear();
+            for (;;) {
+                Token v; int cv;
+                if (!operand(v, cv)) return false;
+                if (cv != AQE_COL_NONE) return unsupported("IN list entries must be literals");
+                Dnf one;
+                if (!single(ca, C_EQ, v, one)) return false;
+                bool dup = false;   // a repeated value adds nothing
+                for (const Conj& k : out) if (!one.empty() && (is_f64_col(ca) ? k.r[ca].lo == one[0].r[ca].lo : k.r[ca].ilo == one[0].r[ca].ilo)) dup = true;
+                if (!dup) out.insert(out.end(), one.begin(), one.end());
+                if (out.size() > kMaxWork) return unsupported("too many OR branches");
+                if (cur.t == T_COMMA) { advance(); continue; }
+                break;
+            }
+            if (cur.t != T_RP) return unsupported("missing ) after IN list");
+            advance();
             return true;
         }
         if (cur.t != T_OP) return unsupported(cur.t == T_END ? "comparison expected" : "near \"" + cur.text + "\"");

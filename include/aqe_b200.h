@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AQE_ABI_VERSION 3
+#define AQE_ABI_VERSION 4
 
 #if defined(AQE_BUILDING)
 #define AQE_API __attribute__((visibility("default")))
@@ -363,7 +363,7 @@ AQE_API double aqe_z_score(double confidence_level, int exact);
  * parser.cpp:20-75).  The reference turns `SELECT agg(col) FROM t [WHERE ...] [GROUP BY g]` into SQLite
  * statements over a SQLite file, sampling with `rowid % (100/p) = 0` and scaling SUM/COUNT by 100/p.
  * Here the same query runs as ONE grouped-scan kernel (k_sql_agg) over the HBM-resident columns:
- * rowid = id; WHERE = AND / OR / parentheses over comparisons and BETWEENs of columns with numeric literals,
+ * rowid = id; WHERE = AND / OR / parentheses over comparisons, BETWEENs and IN lists of columns with numeric literals,
  * compiled to at most AQE_SQL_MAX_ALT OR-ed conjunctions of one closed interval (+ optional "!=" value) per column; GROUP BY on an integer column with a dense
  * key range of at most AQE_SQL_MAX_GROUPS values.  Sums are accumulated in 128-bit fixed point
  * (order-independent, so results are bit-reproducible and shard merges are exact).
@@ -383,7 +383,7 @@ typedef struct aqe_sql_term {
 /* Parsed + compiled query: the reference's `struct Query` (parser.h:17-24) with names resolved.  The WHERE clause
  * is in disjunctive normal form: up to AQE_SQL_MAX_ALT conjunctions OR-ed together, each one closed interval
  * (+ optional "!=" value) per column. */
-#define AQE_SQL_MAX_ALT 4
+#define AQE_SQL_MAX_ALT 8
 typedef struct aqe_sql_query {
     int32_t agg;              /* aqe_agg */
     int32_t agg_col;          /* aqe_column; AQE_COL_NONE for COUNT(*) */

@@ -155,7 +155,7 @@ static val column_value(const aqe_record* r, int c) {
 
 /* ---- WHERE: AND / OR / parentheses over comparisons and BETWEENs, compiled to a postfix program ---------- */
 typedef struct operand { int col; val lit; } operand; /* col >= 0: column reference */
-typedef struct cond { operand a, b, c; int op; /* 0 = 1 != 2 < 3 <= 4 > 5 >= 6 BETWEEN */ } cond;
+typedef struct cond { operand a, b, c; int op; /* 0 = 1 != 2 < 3 <= 4 > 5 >= 6 BETWEEN 7 IN */ operand list[16]; int nlist; } cond;
 enum { W_COND = 0, W_AND = 1, W_OR = 2 };
 typedef struct where_prog { cond conds[32]; int n; struct { int kind, arg; } code[96]; int ncode; int top_level_or; } where_prog;
 
@@ -191,7 +191,7 @@ static int parse_operand(scanner* s, operand* o) {
         while (isalnum((unsigned char)*e) || *e == '_') ++e;
         o->col = column_index(p, (size_t)(e - p));
         if (o->col < 0) {
-            const int known_keyword = (e - p == 3 && !strncasecmp(p, "NOT", 3)) || (e - p == 2 && !strncasecmp(p, "IN", 2));
+            const int known_keyword = e - p == 3 && !strncasecmp(p, "NOT", 3);
             if (known_keyword) { s->status = ORC_SQL_UNSUPPORTED; return 0; }
             snprintf(s->err, sizeof(s->err), "SQL error: no such column: %.*s", (int)(e - p), p);
             s->status = ORC_SQL_RUNTIME_ERROR;
@@ -262,6 +262,25 @@ static int parse_term(scanner* s, where_prog* w) {
         c->op = 6;
         return emit(s, w, W_COND, w->n++);
     }
+    if (keyword_at(s, "IN")) {
+        s->p += 2;
+        skip_ws(s);
+        if (*s->p != '(') { s->status = ORC_SQL_UNSUPPORTED; return 0; }
+        ++s->p;
+        c->op = 7;
+        for (;;) {
+            if (c->nlist >= 16) { s->status = ORC_SQL_UNSUPPORTED; return 0; }
+            if (!parse_operand(s, &c->list[c->nlist])) return 0;
+            if (c->list[c->nlist].col >= 0) { s->status = ORC_SQL_UNSUPPORTED; return 0; }
+            ++c->nlist;
+            skip_ws(s);
+            if (*s->p == ',') { ++s->p; continue; }
+            break;
+        }
+        if (*s->p != ')') { s->status = ORC_SQL_UNSUPPORTED; return 0; }
+        ++s->p;
+        return emit(s, w, W_COND, w->n++);
+    }
     skip_ws(s);
     static const struct { const char* t; int op; } ops[] = {{"<=", 3}, {">=", 5}, {"<>", 1}, {"!=", 1}, {"==", 0}, {"<", 2}, {">", 4}, {"=", 0}};
     int op = -1;
@@ -301,7 +320,12 @@ static int compile_where(const char* text, where_prog* w, char* err, size_t errc
 }
 static val operand_value(const operand* o, const aqe_record* r) { return o->col >= 0 ? column_value(r, o->col) : o->lit; }
 static int cond_holds(const cond* c, const aqe_record* r) {
-    const val a = operand_value(&c->a, r), b = operand_value(&c->b, r);
+    const val a = operand_value(&c->a, r);
+    if (c->op == 7) {
+        for (int k = 0; k < c->nlist; ++k) if (cmp_val(a, c->list[k].lit) == 0) return 1;
+        return 0;
+    }
+    const val b = operand_value(&c->b, r);
     if (c->op == 6) return cmp_val(a, b) >= 0 && cmp_val(a, operand_value(&c->c, r)) <= 0;
     const int x = cmp_val(a, b);
     return c->op == 0 ? x == 0 : c->op == 1 ? x != 0 : c->op == 2 ? x < 0 : c->op == 3 ? x <= 0 : c->op == 4 ? x > 0 : x >= 0;

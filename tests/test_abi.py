@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(L, s), f"{s} declared in include/aqe_b200.h but not exported"
     assert set(L._signatures) == set(declared_symbols()), "ctypes table out of sync with the header"
-    assert L.aqe_abi_version() == 3
+    assert L.aqe_abi_version() == 4
 
 
 def test_struct_sizes_match_header():
@@ -40,7 +40,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(aqe.ApproxSpec) == 80
     assert C.sizeof(aqe.ApproxResult) == 96
     assert C.sizeof(aqe.SqlTerm) == 56
-    assert C.sizeof(aqe.SqlQuery) == 32 + 4 * 4 + 4 * 5 * 56 + 32 + 64 + 64 + 64 + 512
+    assert C.sizeof(aqe.SqlQuery) == 32 + 8 * 4 + 8 * 5 * 56 + 32 + 64 + 64 + 64 + 512
     assert C.sizeof(aqe.SqlRow) == 80
     assert C.sizeof(aqe.SqlFacts) == 32
     assert C.sizeof(aqe.SqlLayout) == 24

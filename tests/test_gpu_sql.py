@@ -281,7 +281,7 @@ def _random_query(rng, t0, n):
             terms.append(rng.choice([f"amount BETWEEN {a:.3f} AND {b:.3f}", f"amount > {a:.2f}", f"amount <= {b:.1f}", f"{a:.2f} < amount", f"amount != {a:.0f}"]))
         elif c == "region":
             k = int(rng.integers(-1, 9))
-            terms.append(rng.choice([f"region = {k}", f"region != {k}", f"region >= {k}", f"region < {k}.5", f"region BETWEEN 2 AND {k}", f"region <> '{k}'"]))
+            terms.append(rng.choice([f"region = {k}", f"region != {k}", f"region >= {k}", f"region < {k}.5", f"region BETWEEN 2 AND {k}", f"region <> '{k}'", f"region IN ({k}, 2, 7)"]))
         elif c == "product_id":
             a, b = sorted(int(x) for x in rng.integers(-5, 1100, size=2))
             terms.append(rng.choice([f"product_id BETWEEN {a} AND {b}", f"product_id < {b}", f"(product_id >= {a})", f"product_id = {a}"]))

@@ -67,8 +67,9 @@ def test_engine_parser_matches_reference_parser(path):
 
 def test_engine_parser_rejections():
     for sql, code in (("SELECT MAX(amount) FROM sales", 1), ("SELECT amount FROM sales", 1), ("SUM(amount) sales", 1),
-                      ("SELECT SUM(nope) FROM sales", 1), ("SELECT SUM(amount) FROM sales WHERE region = 1 OR region = 2 OR region = 3 OR region = 4 OR region = 5", 6),
-                      ("SELECT SUM(amount) FROM sales WHERE NOT region = 1", 6), ("SELECT SUM(amount) FROM sales WHERE region IN (1, 2)", 6),
+                      ("SELECT SUM(nope) FROM sales", 1), ("SELECT SUM(amount) FROM sales WHERE region IN (0, 1, 2, 3, 4, 5, 6, 7, 8)", 6),
+                      ("SELECT SUM(amount) FROM sales WHERE NOT region = 1", 6), ("SELECT SUM(amount) FROM sales WHERE region IN (1, amount)", 6),
+                      ("SELECT SUM(amount) FROM sales WHERE region NOT IN (1, 2)", 6),
                       ("SELECT SUM(amount) FROM sales WHERE nope > 1", 1), ("SELECT SUM(amount) FROM sales GROUP BY amount", 6),
                       ("SELECT SUM(amount + 1) FROM sales", 6), ("SELECT SUM(*) FROM sales", 1),
                       ("SELECT SUM(amount) FROM sales WHERE region != 1 AND region != 2", 6)):
@@ -196,5 +197,9 @@ def test_where_or_and_parentheses_compile_to_dnf():
     assert q.always_false
     q, b = branches("(region < 2 OR region > 5) AND (product_id = 1 OR product_id = 2)")
     assert q.n_alt == 4
-    with pytest.raises(aqe.AqeError):                                        # 3 x 2 = 6 branches > AQE_SQL_MAX_ALT
-        aqe.sql_parse("SELECT COUNT(*) FROM t WHERE (region = 1 OR region = 2 OR region = 3) AND (amount < 1 OR amount > 2)", 0)
+    q, b = branches("region IN (1, 3, 3, 5) AND amount > 2")                 # IN = OR of equalities, duplicates folded
+    assert q.n_alt == 3 and not q.top_level_or and [x[2].ilo for x in b] == [1, 3, 5]
+    q, b = branches("region IN (2.5, 3)")                                    # 2.5 can never equal an integer column
+    assert q.n_alt == 1 and b[0][2].ilo == 3
+    with pytest.raises(aqe.AqeError):                                        # 3 x 3 = 9 branches > AQE_SQL_MAX_ALT
+        aqe.sql_parse("SELECT COUNT(*) FROM t WHERE region IN (1, 2, 3) AND (amount < 1 OR amount > 2 OR amount = 1.5)", 0)
