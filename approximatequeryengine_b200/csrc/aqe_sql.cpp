@@ -57,7 +57,7 @@ bool is_identifier(const std::string& s) {
 }
 
 // ---- WHERE: tokens ---------------------------------------------------------------------------------------
-enum Tok { T_END, T_IDENT, T_NUM, T_OP, T_LP, T_RP, T_AND, T_OR, T_BETWEEN, T_IN, T_COMMA, T_OTHER };
+enum Tok { T_END, T_IDENT, T_NUM, T_OP, T_LP, T_RP, T_AND, T_OR, T_NOT, T_BETWEEN, T_IN, T_COMMA, T_OTHER };
 struct Token { Tok t; std::string text; bool is_int = false; int64_t i = 0; double d = 0.0; };
 
 struct Lexer {
@@ -89,7 +89,7 @@ struct Lexer {
             while (e < s.size() && (std::isalnum((unsigned char)s[e]) || s[e] == '_')) ++e;
             k.text = s.substr(p, e - p); p = e;
             const std::string u = upper(k.text);
-            k.t = u == "AND" ? T_AND : u == "OR" ? T_OR : u == "BETWEEN" ? T_BETWEEN : u == "IN" ? T_IN : ((u == "NOT" || u == "LIKE" || u == "IS" || u == "NULL") ? T_OTHER : T_IDENT);
+            k.t = u == "AND" ? T_AND : u == "OR" ? T_OR : u == "BETWEEN" ? T_BETWEEN : u == "IN" ? T_IN : u == "NOT" ? T_NOT : ((u == "LIKE" || u == "IS" || u == "NULL") ? T_OTHER : T_IDENT);
             return k;
         }
         if (std::isdigit((unsigned char)c) || (c == '.' && p + 1 < s.size() && std::isdigit((unsigned char)s[p + 1]))) {
@@ -281,6 +281,28 @@ bool conj_and(const Conj& a, const Conj& b, Conj& out, std::string& err) {
     return true;
 }
 
+// NOT of one column range: the values outside [lo, hi], plus the excluded value itself -- up to three single-range branches.
+void negate_range(const ColRange& r, int col, Dnf& out) {
+    const bool f = is_f64_col(col);
+    const double inf = std::numeric_limits<double>::infinity();
+    auto push = [&](const ColRange& x) { if (!range_empty(x, col)) { Conj k; k.r[col] = x; k.r[col].touched = true; out.push_back(k); } };
+    if (r.empty || (f ? !(r.lo <= r.hi) : r.ilo > r.ihi)) { out.push_back(Conj()); return; }  // NOT false = true
+    ColRange below, above;
+    if (f) {
+        below.hi = std::nextafter(r.lo, -inf); if (std::isinf(r.lo) && r.lo < 0) below.empty = true;
+        above.lo = std::nextafter(r.hi, inf); if (std::isinf(r.hi) && r.hi > 0) above.empty = true;
+    } else {
+        if (r.ilo == INT64_MIN) below.empty = true; else below.ihi = r.ilo - 1;
+        if (r.ihi == INT64_MAX) above.empty = true; else above.ilo = r.ihi + 1;
+    }
+    push(below); push(above);
+    if (r.has_ne && (f ? (r.ne >= r.lo && r.ne <= r.hi) : (r.ine >= r.ilo && r.ine <= r.ihi))) {
+        ColRange eq;
+        if (f) { eq.lo = eq.hi = r.ne; } else { eq.ilo = eq.ihi = r.ine; }
+        push(eq);
+    }
+}
+
 struct WhereCompiler {
     Lexer lx;
     Token cur;
@@ -293,7 +315,7 @@ struct WhereCompiler {
     void advance() { cur = lx.next(); }
     bool unsupported(const std::string& what) {
         status = AQE_ERR_UNSUPPORTED;
-        err = "unsupported WHERE clause (" + what + "); supported: comparisons, BETWEEN and IN lists of id|rowid|amount|region|product_id|timestamp with numeric literals, combined with AND, OR and parentheses";
+        err = "unsupported WHERE clause (" + what + "); supported: comparisons, BETWEEN and IN lists of id|rowid|amount|region|product_id|timestamp with numeric literals, combined with AND, OR, NOT and parentheses";
         return false;
     }
     bool fail_unsupported() { status = AQE_ERR_UNSUPPORTED; return false; }
@@ -316,7 +338,33 @@ struct WhereCompiler {
         if (!k.dead) out.push_back(k);
         return true;
     }
+    // NOT (C1 OR C2 ...) = NOT C1 AND NOT C2 ...;  NOT Ci = OR over its columns of NOT(range)
+    bool negate(const Dnf& in, Dnf& out) {
+        out = constant(true);
+        for (const Conj& k : in) {
+            Dnf nk;
+            if (k.dead) nk = constant(true);
+            else for (int c = 0; c < 5; ++c) if (k.r[c].touched) negate_range(k.r[c], c, nk);
+            // a conjunction without constraints is "true": its negation is false (nk stays empty)
+            Dnf prod;
+            for (const Conj& x : out)
+                for (const Conj& y : nk) {
+                    Conj z;
+                    if (!conj_and(x, y, z, err)) return fail_unsupported();
+                    if (!z.dead) prod.push_back(z);
+                }
+            if (prod.size() > kMaxWork) return unsupported("too many OR branches");
+            out.swap(prod);
+        }
+        return true;
+    }
     bool term(Dnf& out) {
+        if (cur.t == T_NOT) {
+            advance();
+            Dnf inner;
+            if (!term(inner)) return false;
+            return negate(inner, out);
+        }
         if (cur.t == T_LP) {
             advance();
             ++depth;
@@ -328,6 +376,16 @@ struct WhereCompiler {
         }
         Token a; int ca;
         if (!operand(a, ca)) return false;
+        if (cur.t == T_NOT) {  // col NOT BETWEEN ... / col NOT IN (...)
+            advance();
+            if (cur.t != T_BETWEEN && cur.t != T_IN) return unsupported("NOT must be followed by BETWEEN or IN here");
+            Dnf inner;
+            if (!tail(a, ca, inner)) return false;
+            return negate(inner, out);
+        }
+        return tail(a, ca, out);
+    }
+    bool tail(const Token& a, int ca, Dnf& out) {  // what follows the first operand of a comparison
         if (cur.t == T_BETWEEN) {
             advance();
             Token lo, hi; int cl, ch;

@@ -156,7 +156,7 @@ static val column_value(const aqe_record* r, int c) {
 /* ---- WHERE: AND / OR / parentheses over comparisons and BETWEENs, compiled to a postfix program ---------- */
 typedef struct operand { int col; val lit; } operand; /* col >= 0: column reference */
 typedef struct cond { operand a, b, c; int op; /* 0 = 1 != 2 < 3 <= 4 > 5 >= 6 BETWEEN 7 IN */ operand list[16]; int nlist; } cond;
-enum { W_COND = 0, W_AND = 1, W_OR = 2 };
+enum { W_COND = 0, W_AND = 1, W_OR = 2, W_NOT = 3 };
 typedef struct where_prog { cond conds[32]; int n; struct { int kind, arg; } code[96]; int ncode; int top_level_or; } where_prog;
 
 typedef struct scanner { const char* p; int status; char err[160]; int depth; } scanner;
@@ -191,8 +191,6 @@ static int parse_operand(scanner* s, operand* o) {
         while (isalnum((unsigned char)*e) || *e == '_') ++e;
         o->col = column_index(p, (size_t)(e - p));
         if (o->col < 0) {
-            const int known_keyword = e - p == 3 && !strncasecmp(p, "NOT", 3);
-            if (known_keyword) { s->status = ORC_SQL_UNSUPPORTED; return 0; }
             snprintf(s->err, sizeof(s->err), "SQL error: no such column: %.*s", (int)(e - p), p);
             s->status = ORC_SQL_RUNTIME_ERROR;
             return 0;
@@ -239,6 +237,10 @@ static int emit(scanner* s, where_prog* w, int kind, int arg) {
 static int parse_or(scanner* s, where_prog* w);
 static int parse_term(scanner* s, where_prog* w) {
     skip_ws(s);
+    if (keyword_at(s, "NOT")) { /* NOT binds tighter than AND */
+        s->p += 3;
+        return parse_term(s, w) && emit(s, w, W_NOT, 0);
+    }
     if (*s->p == '(') {
         ++s->p;
         ++s->depth;
@@ -253,6 +255,12 @@ static int parse_term(scanner* s, where_prog* w) {
     cond* c = &w->conds[w->n];
     memset(c, 0, sizeof(*c));
     if (!parse_operand(s, &c->a)) return 0;
+    int negated = 0; /* col NOT BETWEEN ... / col NOT IN (...) */
+    if (keyword_at(s, "NOT")) {
+        s->p += 3;
+        negated = 1;
+        if (!keyword_at(s, "BETWEEN") && !keyword_at(s, "IN")) { s->status = ORC_SQL_UNSUPPORTED; return 0; }
+    }
     if (keyword_at(s, "BETWEEN")) {
         s->p += 7;
         if (!parse_operand(s, &c->b)) return 0;
@@ -260,7 +268,7 @@ static int parse_term(scanner* s, where_prog* w) {
         s->p += 3;
         if (!parse_operand(s, &c->c)) return 0;
         c->op = 6;
-        return emit(s, w, W_COND, w->n++);
+        return emit(s, w, W_COND, w->n++) && (!negated || emit(s, w, W_NOT, 0));
     }
     if (keyword_at(s, "IN")) {
         s->p += 2;
@@ -279,7 +287,7 @@ static int parse_term(scanner* s, where_prog* w) {
         }
         if (*s->p != ')') { s->status = ORC_SQL_UNSUPPORTED; return 0; }
         ++s->p;
-        return emit(s, w, W_COND, w->n++);
+        return emit(s, w, W_COND, w->n++) && (!negated || emit(s, w, W_NOT, 0));
     }
     skip_ws(s);
     static const struct { const char* t; int op; } ops[] = {{"<=", 3}, {">=", 5}, {"<>", 1}, {"!=", 1}, {"==", 0}, {"<", 2}, {">", 4}, {"=", 0}};
@@ -335,6 +343,7 @@ static int row_passes(const where_prog* w, const aqe_record* r) {
     int stack[96], top = 0;
     for (int k = 0; k < w->ncode; ++k) {
         if (w->code[k].kind == W_COND) stack[top++] = cond_holds(&w->conds[w->code[k].arg], r);
+        else if (w->code[k].kind == W_NOT) stack[top - 1] = !stack[top - 1];
         else {
             const int y = stack[--top], x = stack[--top];
             stack[top++] = w->code[k].kind == W_AND ? (x && y) : (x || y);

@@ -66,6 +66,8 @@ QUERIES = [
     "SELECT SUM(amount) FROM sales WHERE (region < 2 OR region > 5) AND (product_id < 300 OR timestamp > 1700000900) GROUP BY region",
     "SELECT SUM(amount) FROM sales WHERE region IN (1, 3, 5)",
     "SELECT COUNT(amount) FROM sales WHERE product_id IN (7, 77, 777, 7) AND amount > 100 GROUP BY region",
+    "SELECT AVG(amount) FROM sales WHERE NOT (region = 1 OR amount > 500) AND product_id NOT IN (3, 4)",
+    "SELECT SUM(amount) FROM sales WHERE amount NOT BETWEEN 100 AND 900 GROUP BY region",
     # what parser.cpp rejects
     "SELECT MAX(amount) FROM sales",
     "SELECT amount FROM sales",

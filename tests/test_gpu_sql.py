@@ -293,6 +293,8 @@ def _random_query(rng, t0, n):
             terms.append(rng.choice([f"id > {a}", f"rowid <= {a}", f"id != {a}"]))
     group = rng.choice([None, None, "region", "product_id", "ts_bucket"])
     sql = f"SELECT {agg}({col}) FROM sales"
+    if terms and rng.random() < 0.2:                 # a negated first term
+        terms[0] = f"NOT ({terms[0]})"
     if len(terms) >= 2 and rng.random() < 0.4:      # a parenthesised OR of the first two terms, AND-ed with the rest
         terms = [f"({terms[0]} OR {terms[1]})"] + terms[2:]
     if len(terms) >= 2 and rng.random() < 0.15:     # ... and sometimes the whole clause as one parenthesised OR

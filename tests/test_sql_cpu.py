@@ -68,8 +68,8 @@ def test_engine_parser_matches_reference_parser(path):
 def test_engine_parser_rejections():
     for sql, code in (("SELECT MAX(amount) FROM sales", 1), ("SELECT amount FROM sales", 1), ("SUM(amount) sales", 1),
                       ("SELECT SUM(nope) FROM sales", 1), ("SELECT SUM(amount) FROM sales WHERE region IN (0, 1, 2, 3, 4, 5, 6, 7, 8)", 6),
-                      ("SELECT SUM(amount) FROM sales WHERE NOT region = 1", 6), ("SELECT SUM(amount) FROM sales WHERE region IN (1, amount)", 6),
-                      ("SELECT SUM(amount) FROM sales WHERE region NOT IN (1, 2)", 6),
+                      ("SELECT SUM(amount) FROM sales WHERE region LIKE 1", 6), ("SELECT SUM(amount) FROM sales WHERE region IN (1, amount)", 6),
+                      ("SELECT SUM(amount) FROM sales WHERE region NOT = 2", 6),
                       ("SELECT SUM(amount) FROM sales WHERE nope > 1", 1), ("SELECT SUM(amount) FROM sales GROUP BY amount", 6),
                       ("SELECT SUM(amount + 1) FROM sales", 6), ("SELECT SUM(*) FROM sales", 1),
                       ("SELECT SUM(amount) FROM sales WHERE region != 1 AND region != 2", 6)):
@@ -201,5 +201,17 @@ def test_where_or_and_parentheses_compile_to_dnf():
     assert q.n_alt == 3 and not q.top_level_or and [x[2].ilo for x in b] == [1, 3, 5]
     q, b = branches("region IN (2.5, 3)")                                    # 2.5 can never equal an integer column
     assert q.n_alt == 1 and b[0][2].ilo == 3
+    q, b = branches("NOT region = 3")                                        # negation = the complement ranges
+    assert q.n_alt == 2 and (b[0][2].ihi, b[1][2].ilo) == (2, 4)
+    q, b = branches("amount NOT BETWEEN 100 AND 500")
+    assert q.n_alt == 2 and b[0][1].hi == np.nextafter(100.0, -np.inf) and b[1][1].lo == np.nextafter(500.0, np.inf)
+    q, b = branches("region NOT IN (1, 3)")                                  # (< 1) OR (= 2) OR (> 3)
+    assert q.n_alt == 3 and [(x[2].ilo, x[2].ihi) for x in b] == [(-2**63, 0), (2, 2), (4, 2**63 - 1)]
+    q, b = branches("NOT (region = 1 OR amount > 5)")                        # De Morgan: region != 1 AND amount <= 5
+    assert q.n_alt == 2 and all(x[1].hi == 5.0 for x in b) and [(x[2].ilo, x[2].ihi) for x in b] == [(-2**63, 0), (2, 2**63 - 1)]
+    q, b = branches("NOT (region != 3)")
+    assert q.n_alt == 1 and (b[0][2].ilo, b[0][2].ihi) == (3, 3)
+    q, b = branches("NOT 1 = 1")
+    assert q.always_false
     with pytest.raises(aqe.AqeError):                                        # 3 x 3 = 9 branches > AQE_SQL_MAX_ALT
         aqe.sql_parse("SELECT COUNT(*) FROM t WHERE region IN (1, 2, 3) AND (amount < 1 OR amount > 2 OR amount = 1.5)", 0)
