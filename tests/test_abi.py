@@ -169,3 +169,14 @@ def test_reference_frontend_package_runs_on_top_of_the_module(tmp_path):
         assert fe.run_query("SELECT COUNT(amount) FROM sales", path, 0) == 1000.0
         assert set(runner.run_query_groupby("SELECT COUNT(amount) FROM sales GROUP BY region", path, 0, 4)) == {str(k) for k in range(8)}
     assert fe.parse_query("SELECT SUM(amount) FROM sales;") == {"agg_func": "SUM", "column": "AMOUNT", "table": "SALES"}
+
+
+def test_bench_refuses_to_run_without_a_gpu():
+    """bench.py's own arm has no CPU path: on a box without a device it exits non-zero with a message instead of timing anything."""
+    import subprocess
+    import sys
+    if aqe.backend().device_count() > 0:
+        pytest.skip("a GPU is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout) and not r.stdout.strip().startswith("{")
