@@ -443,8 +443,9 @@ def main():
             for _ in range(9):
                 t0 = time.perf_counter(); r = es.sql(q, pct, mode); ts.append(time.perf_counter() - t0)
             ms = statistics.median(ts) * 1e3
+            gbps = width * n_sql / 1e9 / (ms * 1e-3) if pct == 0 else None
             sql["queries"].append({"sql": q, "sample_percent": pct, "mode": mode, "ms": ms, "records_per_s": n_sql / (ms * 1e-3), "groups": len(r),
-                                   "algorithmic_GBps_full_scan": width * n_sql / 1e9 / (ms * 1e-3) if pct == 0 else None})
+                                   "algorithmic_GBps_full_scan": gbps, "frac_of_measured_hbm_peak": gbps / measured_peak()[0] if gbps else None})
         del es
 
     cpu = None
