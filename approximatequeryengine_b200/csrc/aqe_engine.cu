@@ -1832,6 +1832,8 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
     a.key_min = L->key_min; a.n_groups = G;
     a.sum_scale = std::ldexp(1.0, L->sum_shift); a.sq_scale = std::ldexp(1.0, L->sq_shift);
     a.global_acc = db->sql_acc; a.out = db->sql_out_dev; a.ticket = db->sql_ticket; a.ex = ex;
+    // 16 rows of headroom for the ragged tail rows a thread may add after its last check; AQE_SQL_DRAIN_ROWS is a test knob (drain early)
+    a.drain_rows = (unsigned int)std::min<int>(std::max(env_int("AQE_SQL_DRAIN_ROWS", (int)kSqlPackedRows), 16), (int)kSqlPackedRows - 16);
     bool aligned16 = true;
     for (int i = 0; i < a.ncols; ++i) aligned16 = aligned16 && ((uintptr_t)a.cols[i].ptr % 16) == 0;
     // Visit plan.  Dense ids turn the sample into an arithmetic progression of row numbers: for small steps every 32-byte

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) k_col_stats(const ColStatsArgs a) {
 constexpr int kSqlThreads = 256;
 constexpr int kSqlMaxCols = 5;          // the table has five columns; each is loaded at most once per row
 constexpr int kSqlPrivateMaxGroups = 16;
+constexpr unsigned int kSqlPackedRows = 65535;   // rows a thread may add to one private bin between drains (16-bit packed counter)
 
 constexpr int kSqlMaxAlt = AQE_SQL_MAX_ALT;   // OR-ed conjunctions of a WHERE clause
 
@@ -128,6 +129,7 @@ struct SqlArgs {
     unsigned long long* global_acc;   // [n_groups][5] {count, sum_lo, sum_hi, sq_lo, sq_hi}, zero before launch, zeroed again by the last CTA
     unsigned long long* out;          // [n_groups][5] device-visible result
     unsigned int* ticket;
+    unsigned int drain_rows;          // private bins (G <= 16) are drained before a thread has added this many rows to one (<= kSqlPackedRows)
     SqlExchange ex;
 };
 
@@ -188,34 +190,34 @@ __device__ __forceinline__ void shared_add128(unsigned int* limbs, long long v) 
 // T = threads that add rows (the private bins are laid out [bin][T]); every thread of the CTA must call flush().
 template <int MODE, bool MOMENTS, int T> struct SqlBins {
     unsigned int G;
-    // MODE 1: cnt[G][T] u32 | slo[G][T] u64 | shi[G][T] u64 | (qlo, qhi)
+    // MODE 1: w0[G][T] u64 = rows << 48 | sum of the values' low 32 bits   (both below their field width while a thread adds
+    //                        fewer than kSqlPackedRows rows per bin between drains: one read-modify-write chain instead of two)
+    //         w1[G][T] u64 = sum of (value >> 32) + 2^31 (biased non-negative) | (qlo, qhi: squares, split 32/32)
     // MODE 2: cnt[G] u32 | sum limbs [G][4] u32 | (sq limbs [G][4])
     unsigned int* b_cnt;
     unsigned long long *p_slo, *p_shi, *p_qlo, *p_qhi;
     unsigned int *s_sum, *s_sq;
     unsigned long long r_cnt, r_slo, r_qlo;
     long long r_shi, r_qhi;
+    bool with_sums;   // the query aggregates a column (false: COUNT only); uniform over the launch, set by the kernel after init()
 
     static size_t smem_bytes(unsigned int G) {
-        if (MODE == 1) return (size_t)G * T * (4 + 16 + (MOMENTS ? 16 : 0));
+        if (MODE == 1) return (size_t)G * T * (16 + (MOMENTS ? 16 : 0));
         if (MODE == 2) return (size_t)G * (4 + 16 + (MOMENTS ? 16 : 0));
         return 0;
     }
     // all threads of the CTA call init (it contains a barrier); tid < T owns a private column of bins
     __device__ __forceinline__ void init(unsigned char* smem, unsigned int groups, int tid, int nthreads) {
         G = groups;
+        with_sums = true;
         b_cnt = reinterpret_cast<unsigned int*>(smem);
         r_cnt = 0; r_slo = 0; r_qlo = 0; r_shi = 0; r_qhi = 0;
         if constexpr (MODE == 1) {
-            p_slo = reinterpret_cast<unsigned long long*>(smem + (size_t)G * T * 4);
+            p_slo = reinterpret_cast<unsigned long long*>(smem);
             p_shi = p_slo + (size_t)G * T;
             p_qlo = p_shi + (size_t)G * T;
             p_qhi = p_qlo + (size_t)G * T;
-            if (tid < T)
-                for (unsigned int g = 0; g < G; ++g) {
-                    b_cnt[g * T + tid] = 0; p_slo[g * T + tid] = 0; p_shi[g * T + tid] = 0;
-                    if constexpr (MOMENTS) { p_qlo[g * T + tid] = 0; p_qhi[g * T + tid] = 0; }
-                }
+            if (tid < T) zero_private(tid);
         } else if constexpr (MODE == 2) {
             s_sum = b_cnt + G;
             s_sq = s_sum + (size_t)G * 4;
@@ -231,8 +233,8 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
             if constexpr (MOMENTS) { r_qlo += (unsigned long long)fq & 0xffffffffull; r_qhi += fq >> 32; }
         } else if constexpr (MODE == 1) {
             const unsigned int s = g * T + tid;
-            b_cnt[s] += 1;
-            p_slo[s] += (unsigned long long)fx & 0xffffffffull; p_shi[s] += (unsigned long long)(fx >> 32);
+            p_slo[s] += (1ull << 48) + ((unsigned long long)fx & 0xffffffffull);
+            if (has_sum) p_shi[s] += (unsigned long long)((fx >> 32) + 0x80000000ll);   // COUNT-only queries keep one chain
             if constexpr (MOMENTS) { p_qlo[s] += (unsigned long long)fq & 0xffffffffull; p_qhi[s] += (unsigned long long)(fq >> 32); }
         } else {
             atomicAdd(b_cnt + g, 1u);
@@ -241,6 +243,42 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
                 if constexpr (MOMENTS) shared_add128(s_sq + g * 4, fq);
             }
         }
+    }
+    __device__ __forceinline__ void zero_private(int tid) {
+        for (unsigned int g = 0; g < G; ++g) {
+            p_slo[g * T + tid] = 0; p_shi[g * T + tid] = 0;
+            if constexpr (MOMENTS) { p_qlo[g * T + tid] = 0; p_qhi[g * T + tid] = 0; }
+        }
+    }
+    // MODE 1: the T bin-owning threads fold their private bins into the global accumulators and start over.  Called by exactly
+    // those T threads (a named barrier keeps the producer warp of the ring kernel out of it), at the end of the kernel and -- so
+    // that the packed row counters cannot overflow -- every time a thread may have added kSqlPackedRows rows to one bin.
+    __device__ __forceinline__ void drain(unsigned long long* global_acc, int tid) {
+        asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
+        const int warp = tid >> 5, lane = tid & 31;
+        for (unsigned int g = warp; g < G; g += T / 32) {
+            unsigned long long c = 0, sl = 0, ql = 0;
+            long long sh = 0, qh = 0;
+#pragma unroll
+            for (int k = 0; k < T / 32; ++k) {
+                const unsigned int s = g * T + lane + 32 * k;
+                const unsigned long long w0 = p_slo[s], n = w0 >> 48;
+                c += n; sl += w0 & 0xffffffffffffull;
+                if (with_sums) sh += (long long)p_shi[s] - (long long)(n << 31);   // remove the bias of the n rows
+                if constexpr (MOMENTS) { ql += p_qlo[s]; qh += (long long)p_qhi[s]; }
+            }
+            c = warp_reduce_u64(c); sl = warp_reduce_u64(sl); sh = (long long)warp_reduce_u64((unsigned long long)sh);
+            if constexpr (MOMENTS) { ql = warp_reduce_u64(ql); qh = (long long)warp_reduce_u64((unsigned long long)qh); }
+            if (lane == 0 && c) {
+                unsigned long long lo, hi;
+                unsigned long long* ga = global_acc + (size_t)g * 5;
+                atomicAdd(ga + 0, c);
+                split_to_128(sl, sh, lo, hi); global_add128(ga + 1, lo, hi);
+                if constexpr (MOMENTS) { split_to_128(ql, qh, lo, hi); global_add128(ga + 3, lo, hi); }
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
+        zero_private(tid);
     }
     // CTA totals -> global accumulators (integer atomics: order does not matter)
     __device__ __forceinline__ void flush(unsigned long long* global_acc, int tid, int nthreads) {
@@ -264,27 +302,7 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
                 }
             }
         } else if constexpr (MODE == 1) {
-            __syncthreads();
-            const int warp = tid >> 5, lane = tid & 31;
-            if (warp < T / 32)
-                for (unsigned int g = warp; g < G; g += T / 32) {
-                    unsigned long long c = 0, sl = 0, sh = 0, ql = 0, qh = 0;
-#pragma unroll
-                    for (int k = 0; k < T / 32; ++k) {
-                        const unsigned int s = g * T + lane + 32 * k;
-                        c += b_cnt[s]; sl += p_slo[s]; sh += p_shi[s];
-                        if constexpr (MOMENTS) { ql += p_qlo[s]; qh += p_qhi[s]; }
-                    }
-                    c = warp_reduce_u64(c); sl = warp_reduce_u64(sl); sh = warp_reduce_u64(sh);
-                    if constexpr (MOMENTS) { ql = warp_reduce_u64(ql); qh = warp_reduce_u64(qh); }
-                    if (lane == 0 && c) {
-                        unsigned long long lo, hi;
-                        unsigned long long* ga = global_acc + (size_t)g * 5;
-                        atomicAdd(ga + 0, c);
-                        split_to_128(sl, (long long)sh, lo, hi); global_add128(ga + 1, lo, hi);
-                        if constexpr (MOMENTS) { split_to_128(ql, (long long)qh, lo, hi); global_add128(ga + 3, lo, hi); }
-                    }
-                }
+            if (tid < T) drain(global_acc, tid);
         } else {
             __syncthreads();
             for (unsigned int g = tid; g < G; g += nthreads) {
@@ -432,6 +450,7 @@ __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
     constexpr int U = 8;
     SqlBins<MODE, MOMENTS, T> bins;
     bins.init(sql_smem, a.n_groups, tid, T);
+    bins.with_sums = a.agg_slot >= 0;
 
     // per-query facts, read from the parameter bank once
     const int agg_slot = a.agg_slot, group_slot = a.group_slot, n_alt = a.n_alt;
@@ -448,7 +467,13 @@ __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
 
     const uint64_t gsz = (uint64_t)gridDim.x * T;
     const uint64_t last = a.count - 1;  // a.count > 0 (the host launches nothing otherwise)
-    for (uint64_t j = (uint64_t)blockIdx.x * T + tid; j < a.count; j += U * gsz) {
+    unsigned int rows_since_drain = 0;
+    for (uint64_t base = (uint64_t)blockIdx.x * T; base < a.count; base += U * gsz) {   // trip count uniform over the CTA (drain() has a barrier)
+        const uint64_t j = base + tid;
+        if constexpr (MODE == 1) {
+            if (rows_since_drain + U > a.drain_rows) { bins.drain(a.global_acc, tid); rows_since_drain = 0; }
+            rows_since_drain += U;
+        }
         uint64_t idx[U];
         uint32_t mask = 0u;
 #pragma unroll
@@ -608,6 +633,7 @@ __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra)
         fence_barrier_init();
     }
     bins.init(bin_mem, a.n_groups, tid, kBulkThreads);  // ends with __syncthreads()
+    bins.with_sums = a.agg_slot >= 0;
 
     const uint64_t n_main = a.count & ~3ull;  // bulk copies move multiples of 16 bytes: 4 rows of a 4-byte column
     const uint64_t ntiles = (n_main + ra.tile_rows - 1) / ra.tile_rows;
@@ -660,7 +686,12 @@ __global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra)
         const double agg_lo = __longlong_as_double(ap.lo), agg_hi = __longlong_as_double(ap.hi), agg_ne = __longlong_as_double(ap.ne);
         const int kmin32 = (int)a.key_min;
         uint32_t it = 0;
+        unsigned int rows_since_drain = 0;
         for (uint64_t c = blockIdx.x; c < ntiles; c += gridDim.x, ++it) {
+            if constexpr (MODE == 1) {   // all consumer threads walk the same tiles: the drain's barrier is uniform over them
+                if (rows_since_drain + K > a.drain_rows) { bins.drain(a.global_acc, tid); rows_since_drain = 0; }
+                rows_since_drain += K;
+            }
             const int s = it % STAGES;
             const uint32_t round = it / STAGES;
             mbar_wait(&full_bar[s], round & 1);

@@ -378,6 +378,14 @@ def test_sql_register_kernel_and_ring_kernel_agree_word_for_word(tables, monkeyp
         regs = e.sql_scan(q, layout, flags)
         monkeypatch.delenv("AQE_SQL_VARIANT", raising=False)
         assert (ring == regs).all(), sql
+        # the packed row counters of the private bins are drained before they can overflow: force a drain at every tile / batch
+        monkeypatch.setenv("AQE_SQL_DRAIN_ROWS", "16")
+        drained_ring = e.sql_scan(q, layout, flags)
+        monkeypatch.setenv("AQE_SQL_VARIANT", "1")
+        drained_regs = e.sql_scan(q, layout, flags)
+        monkeypatch.delenv("AQE_SQL_VARIANT", raising=False)
+        monkeypatch.delenv("AQE_SQL_DRAIN_ROWS", raising=False)
+        assert (ring == drained_ring).all() and (ring == drained_regs).all(), sql
 
 
 def test_sql_beyond_two_to_the_32_rows():
