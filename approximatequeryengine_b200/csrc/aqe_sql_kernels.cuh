@@ -615,8 +615,12 @@ template <int T, int K> __device__ __forceinline__ uint32_t sql_mod_pass(const S
     return mask;
 }
 
+// CTAs per SM the register allocation must leave room for (shared memory usually sets the real limit): 4 for the plain
+// ungrouped and the shared-atomic kernels (<= 56 registers), 3 for private bins and for moments, 2 for private bins with moments.
+constexpr int sql_ring_min_ctas(int mode, bool moments) { return mode == 1 ? (moments ? 2 : 3) : (moments ? 3 : 4); }
+
 template <int MODE, bool MOMENTS, int STAGES, int K>
-__global__ void __launch_bounds__(kBulkThreads) k_sql_ring(const SqlRingArgs ra) {
+__global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)) k_sql_ring(const SqlRingArgs ra) {
     extern __shared__ __align__(128) unsigned char sql_ring_smem[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
