@@ -1709,12 +1709,19 @@ template <int MODE, bool MOMENTS> static int sql_launch_ring(const aqe_db* db, S
     constexpr int T = kBulkConsumerWarps * 32;
     uint32_t row_bytes = 0;
     for (int i = 0; i < ra.q.ncols; ++i) row_bytes += ra.q.cols[i].kind == K_I32 ? 4 : 8;
-    // Rows per consumer thread and tile (every row slot of a full tile is live either way).  8 halves the per-tile barrier and
-    // bookkeeping cost -- `SUM(timestamp) WHERE region = 3` 2.25 -> 1.72 ms, `GROUP BY region` 2.54 -> 2.41 ms on 1 B rows -- as long as
-    // two CTAs (ring + bins) still fit an SM; wide rows, the shared-atomic bins and the moment bins keep 4 and more CTAs per SM.
+    // Rows per consumer thread and tile, K (every row slot of a full tile is live either way).  A larger K halves the per-tile barrier
+    // and bookkeeping cost, more CTAs per SM hide the shared-memory latency of the bin updates; measured on 1 B rows, 12 B/row:
+    // ungrouped K = 8 / 4 CTAs 1.70 ms vs K = 4 2.25 ms; `GROUP BY region` K = 8 / 2 CTAs 2.19, K = 6 / 3 CTAs 1.95, K = 4 / 4 CTAs 2.4 ms.
+    // Rule: the largest K that still leaves three CTAs (ring + bins) on an SM, else the largest that leaves two, else 4.
     const size_t bins = SqlBins<MODE, MOMENTS, T>::smem_bytes(ra.q.n_groups);
-    const bool k8_fits = 2 * ((size_t)2 * T * 8 * row_bytes + bins + 1024) <= (size_t)227 * 1024;
-    const int K = row_bytes <= 8 || (row_bytes <= 16 && MODE != 2 && k8_fits) ? 8 : 4;
+    auto ctas_with = [&](int k) { return (size_t)(227 * 1024) / ((size_t)2 * T * k * row_bytes + bins + 1024); };
+    int K = 4;
+    for (int want : {3, 2}) {
+        bool found = false;
+        for (int k : {8, 6}) if (!found && ctas_with(k) >= (size_t)want) { K = k; found = true; }
+        if (found || ctas_with(4) >= (size_t)want) break;
+    }
+    if (row_bytes <= 8) K = 8;   // 16 KiB stages at most: always the largest tile
     const uint32_t tile = (uint32_t)(T * K);
     ra.tile_rows = tile;
     uint32_t off = 0;
@@ -1735,7 +1742,9 @@ template <int MODE, bool MOMENTS> static int sql_launch_ring(const aqe_db* db, S
         LAUNCHED();
         return AQE_OK;
     };
-    return K == 8 ? go(k_sql_ring<MODE, MOMENTS, STAGES, 8>) : go(k_sql_ring<MODE, MOMENTS, STAGES, 4>);
+    if (K == 8) return go(k_sql_ring<MODE, MOMENTS, STAGES, 8>);
+    if (K == 6) return go(k_sql_ring<MODE, MOMENTS, STAGES, 6>);
+    return go(k_sql_ring<MODE, MOMENTS, STAGES, 4>);
 }
 
 static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* L, int flags, uint64_t* acc, bool exchange = false) {
