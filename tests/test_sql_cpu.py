@@ -215,3 +215,17 @@ def test_where_or_and_parentheses_compile_to_dnf():
     assert q.always_false
     with pytest.raises(aqe.AqeError):                                        # 3 x 3 = 9 branches > AQE_SQL_MAX_ALT
         aqe.sql_parse("SELECT COUNT(*) FROM t WHERE region IN (1, 2, 3) AND (amount < 1 OR amount > 2 OR amount = 1.5)", 0)
+
+
+def test_corrected_interval_coverage_host_side(oracle):
+    """The additive corrected interval (AQE_SQL_CI_CORRECT): SUM scaled as a total, finite-population factor.  Over seeded tables it
+    covers the exact answer at about the nominal 95 % (the GPU suite repeats this through the kernels on larger tables)."""
+    import math
+    hits = 0
+    trials = 120
+    for seed in range(trials):
+        rows = oracle.synth(5000, seed=3000 + seed)
+        exact = host_execute(rows, "SELECT SUM(amount) FROM sales", 0, "value")[0].value
+        s = host_execute(rows, "SELECT SUM(amount) FROM sales", 10, "ci_correct")[0]
+        hits += s.ci_lower <= exact <= s.ci_upper
+    assert hits / trials >= 0.95 - 3 * math.sqrt(0.95 * 0.05 / trials), hits
