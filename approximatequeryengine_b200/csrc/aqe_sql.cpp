@@ -611,6 +611,21 @@ int sql_layout(const aqe_sql_query& q, const aqe_sql_facts* facts, int n, aqe_sq
         return AQE_ERR_UNSUPPORTED;
     }
     out.key_min = kmin; out.n_groups = (uint32_t)span; out.is_integer = is_int ? 1 : 0;
+    // A WHERE clause that bounds the aggregate column itself in every branch bounds the values that can reach an
+    // accumulator: scale for that bound, not for the column's, so `amount < 1e-5` on a column reaching 1e6 keeps
+    // its 62 bits.  (Rows outside are converted too, saturate, and are masked before the add.)
+    if (!is_int && q.n_alt > 0 && !q.always_false && absmax == absmax) {
+        double bound = 0.0;
+        for (int alt = 0; alt < q.n_alt && bound < absmax; ++alt) {
+            double b = INFINITY;
+            for (int t = 0; t < q.n_terms[alt]; ++t) {
+                const aqe_sql_term& term = q.terms[alt][t];
+                if (term.col == q.agg_col) b = std::max(std::fabs(term.lo), std::fabs(term.hi));
+            }
+            bound = std::max(bound, b);
+        }
+        if (bound < absmax) absmax = bound;
+    }
     return sql_shifts(absmax, is_int, out.sum_shift, out.sq_shift, err);
 }
 

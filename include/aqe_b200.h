@@ -454,7 +454,9 @@ typedef struct aqe_sql_layout {   /* agreed by all shards before the scan */
 AQE_API int aqe_sql_facts_of(aqe_db* db, const aqe_sql_query* q, aqe_sql_facts* out);
 /* Host only: fixed-point shifts for values of magnitude <= agg_absmax (|x| * 2^sum_shift < 2^62). */
 AQE_API int aqe_sql_shifts(double agg_absmax, int agg_is_integer, int* sum_shift, int* sq_shift);
-/* Host only: merge the facts of all shards into the common layout. */
+/* Host only: merge the facts of all shards into the common layout.  The scale is set for min(largest agg_absmax, the bound the
+ * WHERE clause puts on the aggregate column when every OR branch has one): `amount BETWEEN 0 AND 1e-5` keeps 62 bits below 1e-5
+ * whatever else the column holds.  Every shard must call it with the same query and the same facts. */
 AQE_API int aqe_sql_layout_of(const aqe_sql_query* q, const aqe_sql_facts* facts, int n_shards, aqe_sql_layout* out);
 AQE_API int aqe_sql_scan(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* layout, int flags,
                          uint64_t* acc /* n_groups x 5 words, host */);

@@ -160,3 +160,19 @@ def engine_rows(sql_rows):
         if r.is_null:
             raise ValueError("stod")
     return [(r.key, r.value, r.ci_lower, r.ci_upper) for r in sql_rows]
+
+
+def wide_range_rows(oracle, n=20000, seed=77):
+    """amount spans 13 decades: half the rows near 1e-6, half up to 1e6."""
+    rng = np.random.default_rng(seed)
+    rows = oracle.synth(n, seed=seed)
+    rows["amount"] = np.where(rng.random(n) < 0.5, 10.0 ** rng.uniform(-7, -5, n), 10.0 ** rng.uniform(3, 6, n))
+    return rows
+
+
+WIDE_RANGE_QUERIES = (("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 0 AND 0.00001", 0, "run_query"),
+                      ("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 0 AND 0.00001", 10, "run_query_with_ci"),
+                      ("SELECT AVG(amount) FROM sales WHERE amount > 0 AND amount <= 0.000002 GROUP BY region", 0, "run_query_groupby"),
+                      ("SELECT SUM(amount) FROM sales WHERE (amount BETWEEN 0 AND 0.000001 OR amount BETWEEN 0.000005 AND 0.00001) GROUP BY region", 20,
+                       "run_query_groupby_with_ci"))
+

@@ -16,7 +16,7 @@ import pytest
 
 import approximatequeryengine_b200 as aqe
 from oracle import SqlError
-from sql_helpers import MODE_OF, REL, engine_rows, golden_rows, load, rows_close, sql_golden_files
+from sql_helpers import MODE_OF, REL, WIDE_RANGE_QUERIES, engine_rows, golden_rows, load, rows_close, sql_golden_files, wide_range_rows
 
 pytestmark = pytest.mark.gpu
 
@@ -428,3 +428,18 @@ def test_sql_corrected_interval_covers_the_truth():
     e.close()
     sigma = math.sqrt(0.95 * 0.05 / trials)
     assert hits_sum / trials >= 0.95 - 3 * sigma and hits_avg / trials >= 0.95 - 3 * sigma, (hits_sum, hits_avg)
+
+
+def test_sql_small_values_in_a_wide_range_column(oracle):
+    """amount spans 1e-7 .. 1e6; clauses that bound amount itself set the fixed-point scale (sql_layout), so sums of the
+    1e-6-sized rows stay within 1e-12 of the reference's -- and bit-identical between the two kernels."""
+    rows = wide_range_rows(oracle, n=200003)
+    e = aqe.Engine(0).from_rows(rows)
+    for sql, p, mode in WIDE_RANGE_QUERIES + (("SELECT SUM(amount) FROM sales", 0, "run_query"),
+                                              ("SELECT AVG(amount) FROM sales WHERE amount >= 1000 GROUP BY region", 10, "run_query_groupby_with_ci")):
+        got = run_engine(e, sql, p, mode)
+        assert rows_close(got, oracle.sql(rows, sql, p, mode), REL) is None, (sql, p, rows_close(got, oracle.sql(rows, sql, p, mode), REL))
+    x = rows["amount"]
+    r = e.sql("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 0 AND 0.00001", 0)[0]
+    assert r.value == math.fsum(x[(x >= 0) & (x <= 1e-5)])   # 2^-78 grid: every selected double is on it
+    e.close()

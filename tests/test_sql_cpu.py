@@ -9,7 +9,8 @@ import pytest
 
 import approximatequeryengine_b200 as aqe
 from oracle import SqlError
-from sql_helpers import MODE_OF, REL, REL_ORACLE, engine_rows, golden_rows, host_execute, load, rows_close, sql_golden_files
+from sql_helpers import (MODE_OF, REL, REL_ORACLE, WIDE_RANGE_QUERIES, engine_rows, golden_rows, host_execute, load, rows_close, sql_golden_files,
+                         wide_range_rows)
 
 FILES = sql_golden_files()
 
@@ -229,3 +230,25 @@ def test_corrected_interval_coverage_host_side(oracle):
         s = host_execute(rows, "SELECT SUM(amount) FROM sales", 10, "ci_correct")[0]
         hits += s.ci_lower <= exact <= s.ci_upper
     assert hits / trials >= 0.95 - 3 * math.sqrt(0.95 * 0.05 / trials), hits
+
+
+def test_layout_scales_for_the_where_bound_on_the_aggregate_column(oracle):
+    """A clause that bounds the aggregate column in every branch sets the fixed-point scale: sums of 1e-6-sized values in a
+    column reaching 1e6 keep 62 significant bits (1e-12 parity would fail at the column's own scale, 2^-43 per row)."""
+    def shifts(sql, absmax=1e6):
+        f = aqe.SqlFacts()
+        f.key_min = f.key_max = 0
+        f.agg_absmax, f.agg_is_integer = absmax, 0
+        L = aqe.sql_layout(aqe.sql_parse(sql, 0), [f])
+        return L.sum_shift, L.sq_shift
+    assert shifts("SELECT SUM(amount) FROM t") == (42, 22)
+    assert shifts("SELECT SUM(amount) FROM t WHERE amount BETWEEN 0 AND 1e-5") == (78, 94)
+    assert shifts("SELECT SUM(amount) FROM t WHERE amount < 0.00001") == (42, 22)                                   # no lower bound
+    assert shifts("SELECT SUM(amount) FROM t WHERE (amount BETWEEN 0 AND 1 OR amount BETWEEN 5 AND 7)") == (59, 56)  # widest branch
+    assert shifts("SELECT SUM(amount) FROM t WHERE (amount BETWEEN 0 AND 1 OR region = 2)") == (42, 22)             # one branch unbounded
+    assert shifts("SELECT SUM(amount) FROM t WHERE amount BETWEEN 0 AND 1e9") == (42, 22)                            # never looser than the column
+    assert shifts("SELECT SUM(amount) FROM t WHERE amount = 0") == (62, 62)
+    rows = wide_range_rows(oracle)
+    for sql, p, mode in WIDE_RANGE_QUERIES:
+        got = engine_rows(host_execute(rows, sql, p, MODE_OF[mode]))
+        assert rows_close(got, oracle.sql(rows, sql, p, mode), REL) is None, (sql, p, rows_close(got, oracle.sql(rows, sql, p, mode), REL))
