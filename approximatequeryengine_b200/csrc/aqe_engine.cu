@@ -1845,11 +1845,15 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
     a.drain_rows = (unsigned int)std::min<int>(std::max(env_int("AQE_SQL_DRAIN_ROWS", (int)kSqlPackedRows), 16), (int)kSqlPackedRows - 16);
     bool aligned16 = true;
     for (int i = 0; i < a.ncols; ++i) aligned16 = aligned16 && ((uintptr_t)a.cols[i].ptr % 16) == 0;
-    // Visit plan.  Dense ids turn the sample into an arithmetic progression of row numbers: for small steps every 32-byte
-    // sector is touched anyway, so the ring streams everything and filters on the row number; from step 8 on the strided
-    // gather reads less.  AQE_SQL_VARIANT: 0 auto | 1 register-staged kernel only (tools/sql_bench.py compares them).
+    // Visit plan.  Dense ids turn the sample into an arithmetic progression of row numbers.  The ring can stream everything and
+    // filter on the row number, but it then converts and masks every row: measured at 1 B rows (tools/sql_bench.py sampled), the
+    // strided visit of the register kernel wins from step 2 on without a WHERE clause (grouped CI at p = 50: 2.11 vs 3.53 ms) and
+    // from step 4 on with one; only the predicate passes of ungrouped queries at steps 2-3 are cheaper out of the staged tile
+    // (2.07 vs 3.00 ms).  profiles/r1_sql_sampled_small_steps.json holds the table.
+    // AQE_SQL_VARIANT: 0 auto | 1 register-staged kernel only | 2 ring whenever it can run (steps < 8): tests compare them.
     const int variant = env_int("AQE_SQL_VARIANT", 0);
-    const bool strided = dense && (step >= 8 || !aligned16 || variant == 1);
+    const int ring_below = variant == 2 ? 8 : (q->n_alt > 0 && a.group_slot < 0 ? 4 : 2);
+    const bool strided = dense && (step >= ring_below || !aligned16 || variant == 1);
     if (strided) {
         a.first = (uint64_t)((step - phase) % step); a.stride = (uint64_t)step;
         a.count = a.first < db->n ? (db->n - a.first + step - 1) / step : 0;

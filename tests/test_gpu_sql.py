@@ -363,23 +363,28 @@ def test_sql_random_queries_against_oracle(oracle):
 
 def test_sql_register_kernel_and_ring_kernel_agree_word_for_word(tables, monkeypatch):
     """k_sql_agg (register-staged: strided samples, unaligned columns) forced onto full scans (AQE_SQL_VARIANT=1) leaves the
-    same integer accumulators as k_sql_ring: the fixed-point sums do not depend on which kernel, grid or order visited the rows."""
+    same integer accumulators as k_sql_ring, and so does the ring's row-number filter forced onto every small step (=2): the fixed-point sums do not depend on which kernel, grid or order visited the rows."""
     g, rows, e = [t for t in tables if t[0]["n"] == 100000][0]
     for sql, p, flags in (("SELECT SUM(amount) FROM sales WHERE amount > 250.5 AND region != 4", 0, aqe.SQL_MOMENTS),
                           ("SELECT AVG(amount) FROM sales WHERE timestamp <= 1700090000 GROUP BY region", 50, aqe.SQL_MOMENTS),
                           ("SELECT SUM(timestamp) FROM sales GROUP BY product_id", 0, 0),
                           ("SELECT COUNT(amount) FROM sales WHERE id > 77 GROUP BY product_id", 25, 0),
+                          ("SELECT SUM(amount) FROM sales GROUP BY region", 34, aqe.SQL_MOMENTS),
+                          ("SELECT AVG(amount) FROM sales", 20, aqe.SQL_MOMENTS),
                           ("SELECT SUM(amount) FROM sales GROUP BY region", 5, aqe.SQL_MOMENTS)):
         q = aqe.sql_parse(sql, p)
         layout = aqe.sql_layout(q, [e.sql_facts(q)])
         monkeypatch.delenv("AQE_SQL_VARIANT", raising=False)
-        ring = e.sql_scan(q, layout, flags)
+        auto = e.sql_scan(q, layout, flags)              # steps 2-3 with a WHERE clause: ring + row-number filter; other samples: strided visit
+        monkeypatch.setenv("AQE_SQL_VARIANT", "2")
+        ring = e.sql_scan(q, layout, flags)              # ring + row-number filter for every step below 8
         monkeypatch.setenv("AQE_SQL_VARIANT", "1")
         regs = e.sql_scan(q, layout, flags)
         monkeypatch.delenv("AQE_SQL_VARIANT", raising=False)
-        assert (ring == regs).all(), sql
+        assert (ring == regs).all() and (auto == regs).all(), sql
         # the packed row counters of the private bins are drained before they can overflow: force a drain at every tile / batch
         monkeypatch.setenv("AQE_SQL_DRAIN_ROWS", "16")
+        monkeypatch.setenv("AQE_SQL_VARIANT", "2")
         drained_ring = e.sql_scan(q, layout, flags)
         monkeypatch.setenv("AQE_SQL_VARIANT", "1")
         drained_regs = e.sql_scan(q, layout, flags)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Timings of the SQL-string path (k_sql_agg) on a device-generated table: ms per query (median of reps, host wall clock
 around the synchronous C-ABI call aqe_sql_run), rows/s and achieved GB/s against the ALGORITHMIC bytes of the query (the widths of
-the distinct columns it reads x rows visited).  python tools/sql_bench.py [rows] [reps] > out.json"""
+the distinct columns it reads x rows visited).  python tools/sql_bench.py [rows] [reps] [sampled] > out.json"""
 import json
 import os
 import sys
@@ -36,6 +36,16 @@ def main():
         ("SELECT AVG(amount) FROM sales GROUP BY region", 10, "ci_reference", ["amount", "region"]),
         ("SELECT SUM(amount) FROM sales GROUP BY product_id", 1, "value", ["amount", "product_id"]),
     ]
+    if len(sys.argv) > 3 and sys.argv[3] == "sampled":   # small steps: the ring's row-number filter vs the strided visit (AQE_SQL_VARIANT=1)
+        shapes = [("SELECT SUM(amount) FROM sales", "ci_reference", ["amount"]),
+                  ("SELECT SUM(amount) FROM sales", "value", ["amount"]),
+                  ("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 100 AND 500", "ci_reference", ["amount"]),
+                  ("SELECT SUM(timestamp) FROM sales WHERE region = 3", "value", ["timestamp", "region"]),
+                  ("SELECT AVG(amount) FROM sales GROUP BY region", "ci_reference", ["amount", "region"]),
+                  ("SELECT SUM(amount) FROM sales GROUP BY region", "value", ["amount", "region"]),
+                  (f"SELECT AVG(amount) FROM sales WHERE timestamp BETWEEN {T0 + n // 4} AND {T0 + n // 2} GROUP BY region", "value", ["amount", "region", "timestamp"]),
+                  ("SELECT SUM(amount) FROM sales GROUP BY product_id", "value", ["amount", "product_id"])]
+        cases = [(sql, p, mode, cols) for p in (50, 33, 25, 20, 15) for sql, mode, cols in shapes]
     out = []
     import ctypes as C
     buf = (aqe.SqlRow * aqe.SQL_MAX_GROUPS)()
