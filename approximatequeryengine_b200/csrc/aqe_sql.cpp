@@ -258,27 +258,46 @@ bool range_empty(const ColRange& r, int col) {
     return false;
 }
 
-// a AND b.  false when the two carry different "!=" values on one column (one value per column is all a scan tests).
-bool conj_and(const Conj& a, const Conj& b, Conj& out, std::string& err) {
-    out = a;
-    if (a.dead || b.dead) { out.dead = true; return true; }
+// a AND b, appended to `out` (nothing when unsatisfiable).  A scan tests one "!=" value per column and branch: when both
+// sides exclude a different value of one column, the range is cut at the second value into the part below and the part
+// above it -- two branches, each with one "!=" left (x != 1 AND x != 3  ==  (x < 3 AND x != 1) OR x > 3).
+void conj_and(const Conj& a, const Conj& b, Dnf& out) {
+    if (a.dead || b.dead) return;
+    Dnf work(1, a);
     for (int c = 0; c < 5; ++c) {
         const ColRange& y = b.r[c];
         if (!y.touched) continue;
-        ColRange& x = out.r[c];
-        if (!x.touched) { x = y; }
-        else {
-            x.lo = std::max(x.lo, y.lo); x.hi = std::min(x.hi, y.hi);
-            x.ilo = std::max(x.ilo, y.ilo); x.ihi = std::min(x.ihi, y.ihi);
-            x.empty = x.empty || y.empty;
-            if (y.has_ne) {
-                if (x.has_ne && (is_f64_col(c) ? x.ne != y.ne : x.ine != y.ine)) { err = "unsupported WHERE: more than one != on the same column"; return false; }
-                x.has_ne = true; x.ne = y.ne; x.ine = y.ine;
+        const bool f = is_f64_col(c);
+        Dnf next;
+        for (Conj& k : work) {
+            ColRange& x = k.r[c];
+            if (!x.touched) { x = y; }
+            else {
+                x.lo = std::max(x.lo, y.lo); x.hi = std::min(x.hi, y.hi);
+                x.ilo = std::max(x.ilo, y.ilo); x.ihi = std::min(x.ihi, y.ihi);
+                x.empty = x.empty || y.empty;
+                if (y.has_ne && x.has_ne && (f ? x.ne != y.ne : x.ine != y.ine)) {
+                    Conj below = k, above = k;
+                    ColRange& lo = below.r[c];
+                    ColRange& hi = above.r[c];
+                    if (f) {
+                        lo.hi = std::min(lo.hi, std::nextafter(y.ne, -std::numeric_limits<double>::infinity()));
+                        hi.lo = std::max(hi.lo, std::nextafter(y.ne, std::numeric_limits<double>::infinity()));
+                    } else {
+                        if (y.ine == INT64_MIN) lo.empty = true; else lo.ihi = std::min(lo.ihi, y.ine - 1);
+                        if (y.ine == INT64_MAX) hi.empty = true; else hi.ilo = std::max(hi.ilo, y.ine + 1);
+                    }
+                    if (!range_empty(lo, c)) next.push_back(below);
+                    if (!range_empty(hi, c)) next.push_back(above);
+                    continue;
+                }
+                if (y.has_ne) { x.has_ne = true; x.ne = y.ne; x.ine = y.ine; }
             }
+            if (!range_empty(x, c)) next.push_back(k);
         }
-        if (range_empty(x, c)) out.dead = true;
+        work.swap(next);
     }
-    return true;
+    out.insert(out.end(), work.begin(), work.end());
 }
 
 // NOT of one column range: the values outside [lo, hi], plus the excluded value itself -- up to three single-range branches.
@@ -349,9 +368,8 @@ struct WhereCompiler {
             Dnf prod;
             for (const Conj& x : out)
                 for (const Conj& y : nk) {
-                    Conj z;
-                    if (!conj_and(x, y, z, err)) return fail_unsupported();
-                    if (!z.dead) prod.push_back(z);
+                    conj_and(x, y, prod);
+                    if (prod.size() > kMaxWork) return unsupported("too many OR branches");
                 }
             if (prod.size() > kMaxWork) return unsupported("too many OR branches");
             out.swap(prod);
@@ -446,9 +464,8 @@ struct WhereCompiler {
             if (!term(rhs)) return false;
             for (const Conj& x : out)
                 for (const Conj& y : rhs) {
-                    Conj k;
-                    if (!conj_and(x, y, k, err)) return fail_unsupported();
-                    if (!k.dead) prod.push_back(k);
+                    conj_and(x, y, prod);
+                    if (prod.size() > kMaxWork) return unsupported("too many OR branches");
                 }
             if (prod.size() > kMaxWork) return unsupported("too many OR branches");
             out.swap(prod);

@@ -89,6 +89,8 @@ def test_sql_against_oracle_extra_queries(tables, oracle):
         "SELECT COUNT(amount) FROM sales WHERE (id <= 100 OR timestamp > 1700019000) GROUP BY product_id",
         "SELECT SUM(amount) FROM sales WHERE amount < 0",
         "SELECT COUNT(amount) FROM sales WHERE amount < 0 GROUP BY region",
+        "SELECT SUM(amount) FROM sales WHERE region != 1 AND region != 3 AND region != 6 AND product_id != 10 AND product_id != 20 GROUP BY region",
+        "SELECT AVG(amount) FROM sales WHERE region NOT IN (0, 7) AND region != 4 AND amount != 500 AND amount != 250.5",
     ]
     for sql in queries:
         for p in (0, 3, 10, 25, 50, 99):

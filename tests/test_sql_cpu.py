@@ -73,7 +73,7 @@ def test_engine_parser_rejections():
                       ("SELECT SUM(amount) FROM sales WHERE region NOT = 2", 6),
                       ("SELECT SUM(amount) FROM sales WHERE nope > 1", 1), ("SELECT SUM(amount) FROM sales GROUP BY amount", 6),
                       ("SELECT SUM(amount + 1) FROM sales", 6), ("SELECT SUM(*) FROM sales", 1),
-                      ("SELECT SUM(amount) FROM sales WHERE region != 1 AND region != 2", 6)):
+                      ("SELECT SUM(amount) FROM sales WHERE " + " AND ".join(f"product_id != {3 * k}" for k in range(17)), 6)):   # 9 pieces > AQE_SQL_MAX_ALT
         with pytest.raises(aqe.AqeError) as ei:
             aqe.sql_parse(sql, 0)
         assert ei.value.code == code, (sql, str(ei.value))
@@ -214,6 +214,16 @@ def test_where_or_and_parentheses_compile_to_dnf():
     assert q.n_alt == 1 and (b[0][2].ilo, b[0][2].ihi) == (3, 3)
     q, b = branches("NOT 1 = 1")
     assert q.always_false
+    q, b = branches("region != 1 AND region != 3")                           # a second != cuts the range: (< 3, != 1) OR (> 3)
+    assert q.n_alt == 2 and (b[0][2].ihi, b[0][2].has_ne, b[0][2].ine, b[1][2].ilo, b[1][2].has_ne) == (2, 1, 1, 4, 0)
+    q, b = branches("region != 1 AND region != 3 AND region != 1")           # the same value again adds nothing
+    assert q.n_alt == 2
+    q, b = branches("amount != 5 AND amount != 2.5 AND region >= 2 AND amount != 7")
+    assert q.n_alt == 3 and all(x[2].ilo == 2 for x in b)
+    assert sorted((x[1].lo, x[1].hi, x[1].has_ne) for x in b) == [(-np.inf, np.nextafter(2.5, -np.inf), 0), (np.nextafter(2.5, np.inf), np.nextafter(7.0, -np.inf), 1),
+                                                                   (np.nextafter(7.0, np.inf), np.inf, 0)]
+    q, b = branches("region BETWEEN 2 AND 4 AND region != 2 AND region != 4")   # cuts at the ends leave one piece
+    assert q.n_alt == 1 and (b[0][2].ilo, b[0][2].ihi) == (2, 3) and b[0][2].ine == 2
     with pytest.raises(aqe.AqeError):                                        # 3 x 3 = 9 branches > AQE_SQL_MAX_ALT
         aqe.sql_parse("SELECT COUNT(*) FROM t WHERE region IN (1, 2, 3) AND (amount < 1 OR amount > 2 OR amount = 1.5)", 0)
 
@@ -252,3 +262,14 @@ def test_layout_scales_for_the_where_bound_on_the_aggregate_column(oracle):
     for sql, p, mode in WIDE_RANGE_QUERIES:
         got = engine_rows(host_execute(rows, sql, p, MODE_OF[mode]))
         assert rows_close(got, oracle.sql(rows, sql, p, mode), REL) is None, (sql, p, rows_close(got, oracle.sql(rows, sql, p, mode), REL))
+
+
+def test_several_not_equal_values_on_one_column_against_the_oracle(oracle):
+    rows = oracle.synth(5000, seed=5)
+    a0 = float(rows["amount"][17])
+    for sql, p, mode in (("SELECT SUM(amount) FROM sales WHERE region != 1 AND region != 3 AND region != 6", 0, "run_query"),
+                         ("SELECT COUNT(amount) FROM sales WHERE region <> 0 AND region <> 7 AND product_id != 5 AND product_id != 9", 10, "run_query_with_ci"),
+                         (f"SELECT AVG(amount) FROM sales WHERE amount != {a0!r} AND amount != 500 AND id != 18 AND id != 20 GROUP BY region", 0, "run_query_groupby"),
+                         ("SELECT SUM(amount) FROM sales WHERE NOT (region = 1 OR region = 3) AND region != 5 GROUP BY region", 50, "run_query_groupby_with_ci")):
+        got = engine_rows(host_execute(rows, sql, p, MODE_OF[mode]))
+        assert rows_close(got, oracle.sql(rows, sql, p, mode), REL) is None, (sql, rows_close(got, oracle.sql(rows, sql, p, mode), REL))
