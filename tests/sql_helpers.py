@@ -176,3 +176,24 @@ WIDE_RANGE_QUERIES = (("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 0 AND
                       ("SELECT SUM(amount) FROM sales WHERE (amount BETWEEN 0 AND 0.000001 OR amount BETWEEN 0.000005 AND 0.00001) GROUP BY region", 20,
                        "run_query_groupby_with_ci"))
 
+
+
+def signed_rows(oracle, n=20000, seed=91):
+    """Negative amounts and keys: amount ~ U(-1000, 1000), product_id in -2048..2047 (exactly SQL_MAX_GROUPS keys), region in -3..4."""
+    rng = np.random.default_rng(seed)
+    rows = oracle.synth(n, seed=seed)
+    rows["amount"] = rng.uniform(-1000.0, 1000.0, n)
+    rows["product_id"] = rng.integers(-2048, 2048, n)
+    rows["product_id"][:2] = (-2048, 2047)
+    rows["region"] = rng.integers(-3, 5, n)
+    return rows
+
+
+SIGNED_QUERIES = (("SELECT SUM(amount) FROM sales", 0, "run_query"), ("SELECT AVG(amount) FROM sales WHERE amount < 0", 10, "run_query_with_ci"),
+                  ("SELECT SUM(amount) FROM sales WHERE region < 0 GROUP BY region", 0, "run_query_groupby_with_ci"),
+                  ("SELECT SUM(amount) FROM sales WHERE product_id BETWEEN -5 AND 5 GROUP BY region", 20, "run_query_groupby_with_ci"),
+                  ("SELECT SUM(amount) FROM sales GROUP BY product_id", 0, "run_query_groupby"),
+                  ("SELECT AVG(amount) FROM sales WHERE amount > -900.5 GROUP BY product_id", 50, "run_query_groupby"),
+                  ("SELECT COUNT(*) FROM sales WHERE region != -1 GROUP BY product_id", 0, "run_query_groupby"),
+                  ("SELECT SUM(product_id) FROM sales WHERE amount <= -1 GROUP BY region", 0, "run_query_groupby"),
+                  ("SELECT AVG(region) FROM sales WHERE region IN (-3, -1, 4)", 25, "run_query_with_ci"))

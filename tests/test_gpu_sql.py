@@ -450,3 +450,47 @@ def test_sql_small_values_in_a_wide_range_column(oracle):
     r = e.sql("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 0 AND 0.00001", 0)[0]
     assert r.value == math.fsum(x[(x >= 0) & (x <= 1e-5)])   # 2^-78 grid: every selected double is on it
     e.close()
+
+
+def test_sql_negative_values_and_keys_and_the_group_limit(oracle):
+    """Signed fixed point (amount ~ U(-1000, 1000)), negative group keys, exactly SQL_MAX_GROUPS keys, one more than that, and
+    groups of a single row (GROUP BY timestamp: n - 1 = 0 in the reference's variance)."""
+    from sql_helpers import SIGNED_QUERIES, signed_rows
+    rows = signed_rows(oracle)
+    e = aqe.Engine(0).from_rows(rows)
+    for sql, p, mode in SIGNED_QUERIES:
+        try:
+            want = oracle.sql(rows, sql, p, mode)
+        except SqlError as ex:
+            assert ex.kind in ("stod", "terminate"), (sql, ex)
+            with pytest.raises(ValueError):
+                run_engine(e, sql, p, mode)
+            continue
+        assert rows_close(run_engine(e, sql, p, mode), want, REL) is None, (sql, p, rows_close(run_engine(e, sql, p, mode), want, REL))
+    x = rows["amount"]
+    assert e.sql("SELECT SUM(amount) FROM sales")[0].value == math.fsum(x)                       # cancellation: still the exactly rounded sum
+    assert e.sql("SELECT SUM(amount) FROM sales WHERE amount < 0")[0].value == math.fsum(x[x < 0])
+    e.close()
+    rows["product_id"][2] = 2048
+    e = aqe.Engine(0).from_rows(rows)
+    with pytest.raises(RuntimeError, match="key range wider"):
+        e.sql("SELECT SUM(amount) FROM sales GROUP BY product_id")
+    e.close()
+    few = signed_rows(oracle, n=4096, seed=92)
+    e = aqe.Engine(0).from_rows(few)
+    for sql, p, mode in (("SELECT SUM(amount) FROM sales GROUP BY timestamp", 0, "run_query_groupby"),
+                         ("SELECT AVG(amount) FROM sales WHERE amount > -500 GROUP BY id", 0, "run_query_groupby"),
+                         ("SELECT SUM(amount) FROM sales GROUP BY timestamp", 0, "run_query_groupby_with_ci")):
+        try:
+            want = oracle.sql(few, sql, p, mode)
+        except SqlError as ex:
+            assert ex.kind in ("stod", "terminate"), (sql, ex)
+            with pytest.raises(ValueError):
+                run_engine(e, sql, p, mode)
+            continue
+        got = run_engine(e, sql, p, mode)
+        assert len(got) == len(want) and all(a[0] == b[0] and a[1] == pytest.approx(b[1], rel=REL) for a, b in zip(got, want)), sql
+        for a, b in zip(got, want):     # one row per group: the reference divides by n - 1 = 0; whatever it reports (nan / inf), the engine reports too
+            for u, v in zip(a[2:], b[2:]):
+                assert (math.isnan(u) and math.isnan(v)) or u == pytest.approx(v, rel=REL), (sql, a, b)
+    e.close()

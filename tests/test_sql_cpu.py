@@ -273,3 +273,22 @@ def test_several_not_equal_values_on_one_column_against_the_oracle(oracle):
                          ("SELECT SUM(amount) FROM sales WHERE NOT (region = 1 OR region = 3) AND region != 5 GROUP BY region", 50, "run_query_groupby_with_ci")):
         got = engine_rows(host_execute(rows, sql, p, MODE_OF[mode]))
         assert rows_close(got, oracle.sql(rows, sql, p, mode), REL) is None, (sql, rows_close(got, oracle.sql(rows, sql, p, mode), REL))
+
+
+def test_negative_values_and_keys_and_the_group_limit(oracle):
+    from sql_helpers import SIGNED_QUERIES, signed_rows
+    rows = signed_rows(oracle, n=6000)
+    for sql, p, mode in SIGNED_QUERIES:
+        try:
+            want = oracle.sql(rows, sql, p, mode)
+        except SqlError as ex:
+            assert ex.kind in ("stod", "terminate"), (sql, ex)
+            with pytest.raises(ValueError):
+                engine_rows(host_execute(rows, sql, p, MODE_OF[mode]))
+            continue
+        got = engine_rows(host_execute(rows, sql, p, MODE_OF[mode]))
+        assert rows_close(got, want, REL) is None, (sql, p, rows_close(got, want, REL))
+    rows["product_id"][2] = 2048                       # one key more than SQL_MAX_GROUPS
+    with pytest.raises(aqe.AqeError) as ei:
+        host_execute(rows, "SELECT SUM(amount) FROM sales GROUP BY product_id", 0, "value")
+    assert ei.value.code == 6 and "key range wider" in str(ei.value)
