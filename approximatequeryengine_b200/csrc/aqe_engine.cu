@@ -1711,17 +1711,25 @@ template <int MODE, bool MOMENTS> static int sql_launch_ring(const aqe_db* db, S
     for (int i = 0; i < ra.q.ncols; ++i) row_bytes += ra.q.cols[i].kind == K_I32 ? 4 : 8;
     // Rows per consumer thread and tile, K (every row slot of a full tile is live either way).  A larger K halves the per-tile barrier
     // and bookkeeping cost, more CTAs per SM hide the shared-memory latency of the bin updates; measured on 1 B rows, 12 B/row:
-    // ungrouped K = 8 / 4 CTAs 1.70 ms vs K = 4 2.25 ms; `GROUP BY region` K = 8 / 2 CTAs 2.19, K = 6 / 3 CTAs 1.95, K = 4 / 4 CTAs 2.4 ms.
-    // Rule: the largest K that still leaves three CTAs (ring + bins) on an SM, else the largest that leaves two, else 4.
+    // ungrouped K = 8 / 4 CTAs 1.70 ms vs K = 4 2.25 ms; `GROUP BY region` K = 8 / 2 CTAs 2.19, K = 6 / 3 CTAs 1.95, K = 4 / 4 CTAs 2.4 ms;
+    // the same with squares (registers allow two CTAs whatever K) K = 8 2.68, K = 6 2.94, K = 4 3.34 ms.
+    // Rule: the largest K whose kernel still runs three CTAs per SM (shared memory AND registers), else the largest that runs two, else 4.
     const size_t bins = SqlBins<MODE, MOMENTS, T>::smem_bytes(ra.q.n_groups);
-    auto ctas_with = [&](int k) { return (size_t)(227 * 1024) / ((size_t)2 * T * k * row_bytes + bins + 1024); };
+    auto ctas_with = [&](int k) -> int {
+        const size_t smem_k = (size_t)2 * T * k * row_bytes + bins;
+        if (smem_k > (size_t)(220 * 1024)) return 0;
+        return k == 8 ? sql_occupancy((const void*)k_sql_ring<MODE, MOMENTS, 2, 8>, kBulkThreads, smem_k)
+             : k == 6 ? sql_occupancy((const void*)k_sql_ring<MODE, MOMENTS, 2, 6>, kBulkThreads, smem_k)
+                      : sql_occupancy((const void*)k_sql_ring<MODE, MOMENTS, 2, 4>, kBulkThreads, smem_k);
+    };
     int K = 4;
     for (int want : {3, 2}) {
         bool found = false;
-        for (int k : {8, 6}) if (!found && ctas_with(k) >= (size_t)want) { K = k; found = true; }
-        if (found || ctas_with(4) >= (size_t)want) break;
+        for (int k : {8, 6, 4}) if (!found && ctas_with(k) >= want) { K = k; found = true; }
+        if (found) break;
     }
     if (row_bytes <= 8) K = 8;   // 16 KiB stages at most: always the largest tile
+    { const int forced = env_int("AQE_SQL_K", 0); if (forced == 4 || forced == 6 || forced == 8) K = forced; }   // experiments (tools/sql_bench.py)
     const uint32_t tile = (uint32_t)(T * K);
     ra.tile_rows = tile;
     uint32_t off = 0;
@@ -1842,7 +1850,8 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
     a.sum_scale = std::ldexp(1.0, L->sum_shift); a.sq_scale = std::ldexp(1.0, L->sq_shift);
     a.global_acc = db->sql_acc; a.out = db->sql_out_dev; a.ticket = db->sql_ticket; a.ex = ex;
     // 16 rows of headroom for the ragged tail rows a thread may add after its last check; AQE_SQL_DRAIN_ROWS is a test knob (drain early)
-    a.drain_rows = (unsigned int)std::min<int>(std::max(env_int("AQE_SQL_DRAIN_ROWS", (int)kSqlPackedRows), 16), (int)kSqlPackedRows - 16);
+    const int packed_rows = (int)(a.group_slot >= 0 && G <= (uint32_t)kSqlPrivateMaxGroups && moments ? kSqlPackedRowsMoments : kSqlPackedRows);   // SqlBins, MODE 1
+    a.drain_rows = (unsigned int)std::min<int>(std::max(env_int("AQE_SQL_DRAIN_ROWS", packed_rows), 16), packed_rows - 16);
     bool aligned16 = true;
     for (int i = 0; i < a.ncols; ++i) aligned16 = aligned16 && ((uintptr_t)a.cols[i].ptr % 16) == 0;
     // Visit plan.  Dense ids turn the sample into an arithmetic progression of row numbers.  The ring can stream everything and

@@ -74,6 +74,7 @@ constexpr int kSqlThreads = 256;
 constexpr int kSqlMaxCols = 5;          // the table has five columns; each is loaded at most once per row
 constexpr int kSqlPrivateMaxGroups = 16;
 constexpr unsigned int kSqlPackedRows = 65535;   // rows a thread may add to one private bin between drains (16-bit packed counter)
+constexpr unsigned int kSqlPackedRowsMoments = 4095;   // ... with squares: three words per bin, 12 bits of headroom per field
 
 constexpr int kSqlMaxAlt = AQE_SQL_MAX_ALT;   // OR-ed conjunctions of a WHERE clause
 
@@ -192,17 +193,20 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
     unsigned int G;
     // MODE 1: w0[G][T] u64 = rows << 48 | sum of the values' low 32 bits   (both below their field width while a thread adds
     //                        fewer than kSqlPackedRows rows per bin between drains: one read-modify-write chain instead of two)
-    //         w1[G][T] u64 = sum of (value >> 32) + 2^31 (biased non-negative) | (qlo, qhi: squares, split 32/32)
+    //         w1[G][T] u64 = sum of (value >> 32) + 2^31 (biased non-negative)
+    //         with squares, three words instead of four (16 bytes of shared-memory traffic less per row), u = value + 2^63, q = square < 2^62:
+    //         w0 = rows << 52 | sum of u[0:40)      w1 = sum of q[0:16) << 36 | sum of u[40:64)      w2 = sum of q[16:62)
+    //         -- every field has 12 spare bits: fewer than kSqlPackedRowsMoments rows per bin between drains
     // MODE 2: cnt[G] u32 | sum limbs [G][4] u32 | (sq limbs [G][4])
     unsigned int* b_cnt;
-    unsigned long long *p_slo, *p_shi, *p_qlo, *p_qhi;
+    unsigned long long *p_slo, *p_shi, *p_qlo;
     unsigned int *s_sum, *s_sq;
     unsigned long long r_cnt, r_slo, r_qlo;
     long long r_shi, r_qhi;
     bool with_sums;   // the query aggregates a column (false: COUNT only); uniform over the launch, set by the kernel after init()
 
     static size_t smem_bytes(unsigned int G) {
-        if (MODE == 1) return (size_t)G * T * (16 + (MOMENTS ? 16 : 0));
+        if (MODE == 1) return (size_t)G * T * (MOMENTS ? 24 : 16);
         if (MODE == 2) return (size_t)G * (4 + 16 + (MOMENTS ? 16 : 0));
         return 0;
     }
@@ -216,7 +220,6 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
             p_slo = reinterpret_cast<unsigned long long*>(smem);
             p_shi = p_slo + (size_t)G * T;
             p_qlo = p_shi + (size_t)G * T;
-            p_qhi = p_qlo + (size_t)G * T;
             if (tid < T) zero_private(tid);
         } else if constexpr (MODE == 2) {
             s_sum = b_cnt + G;
@@ -233,9 +236,15 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
             if constexpr (MOMENTS) { r_qlo += (unsigned long long)fq & 0xffffffffull; r_qhi += fq >> 32; }
         } else if constexpr (MODE == 1) {
             const unsigned int s = g * T + tid;
-            p_slo[s] += (1ull << 48) + ((unsigned long long)fx & 0xffffffffull);
-            if (has_sum) p_shi[s] += (unsigned long long)((fx >> 32) + 0x80000000ll);   // COUNT-only queries keep one chain
-            if constexpr (MOMENTS) { p_qlo[s] += (unsigned long long)fq & 0xffffffffull; p_qhi[s] += (unsigned long long)(fq >> 32); }
+            if constexpr (MOMENTS) {
+                const unsigned long long u = (unsigned long long)fx ^ (1ull << 63), q = (unsigned long long)fq;
+                p_slo[s] += (1ull << 52) | (u & ((1ull << 40) - 1));
+                p_shi[s] += (u >> 40) | ((q & 0xffffull) << 36);
+                p_qlo[s] += q >> 16;
+            } else {
+                p_slo[s] += (1ull << 48) + ((unsigned long long)fx & 0xffffffffull);
+                if (has_sum) p_shi[s] += (unsigned long long)((fx >> 32) + 0x80000000ll);   // COUNT-only queries keep one chain
+            }
         } else {
             atomicAdd(b_cnt + g, 1u);
             if (has_sum) {
@@ -247,7 +256,7 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
     __device__ __forceinline__ void zero_private(int tid) {
         for (unsigned int g = 0; g < G; ++g) {
             p_slo[g * T + tid] = 0; p_shi[g * T + tid] = 0;
-            if constexpr (MOMENTS) { p_qlo[g * T + tid] = 0; p_qhi[g * T + tid] = 0; }
+            if constexpr (MOMENTS) p_qlo[g * T + tid] = 0;
         }
     }
     // MODE 1: the T bin-owning threads fold their private bins into the global accumulators and start over.  Called by exactly
@@ -262,10 +271,19 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
 #pragma unroll
             for (int k = 0; k < T / 32; ++k) {
                 const unsigned int s = g * T + lane + 32 * k;
-                const unsigned long long w0 = p_slo[s], n = w0 >> 48;
-                c += n; sl += w0 & 0xffffffffffffull;
-                if (with_sums) sh += (long long)p_shi[s] - (long long)(n << 31);   // remove the bias of the n rows
-                if constexpr (MOMENTS) { ql += p_qlo[s]; qh += (long long)p_qhi[s]; }
+                if constexpr (MOMENTS) {   // value = lo + (hi << 32) for both sums, as split_to_128 takes them
+                    const unsigned long long w0 = p_slo[s], w1 = p_shi[s], w2 = p_qlo[s], n = w0 >> 52;
+                    const unsigned long long a = w0 & ((1ull << 52) - 1), b = w1 & ((1ull << 36) - 1), cq = w1 >> 36;
+                    c += n;
+                    sl += a & 0xffffffffull;
+                    sh += (long long)((a >> 32) + (b << 8)) - (long long)(n << 31);   // sum of u = a + (b << 40); the n biases of 2^63 leave as n << 31 here
+                    ql += cq + ((w2 & 0xffffull) << 16);                              // sum of q = cq + (w2 << 16)
+                    qh += (long long)(w2 >> 16);
+                } else {
+                    const unsigned long long w0 = p_slo[s], n = w0 >> 48;
+                    c += n; sl += w0 & 0xffffffffffffull;
+                    if (with_sums) sh += (long long)p_shi[s] - (long long)(n << 31);   // remove the bias of the n rows
+                }
             }
             c = warp_reduce_u64(c); sl = warp_reduce_u64(sl); sh = (long long)warp_reduce_u64((unsigned long long)sh);
             if constexpr (MOMENTS) { ql = warp_reduce_u64(ql); qh = (long long)warp_reduce_u64((unsigned long long)qh); }
