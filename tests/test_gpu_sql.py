@@ -216,6 +216,15 @@ def test_sql_large_table_properties():
     assert (e.sql_scan(q_all, layout) == whole).all()                      # run-to-run identical
     rows = aqe.sql_finish(q_all, layout, whole)
     assert sum(r.count for r in rows) == n
+    # with squares the private bins pack (rows, sum, squares) into three words and drain every ~4000 rows per thread: the count and
+    # sum words must be those of the plain scan, the squares linear over a split, and the strided visit (other kernel) must agree
+    with_sq = e.sql_scan(q_all, layout, aqe.SQL_MOMENTS)
+    assert (with_sq.reshape(-1, 5)[:, :3] == whole.reshape(-1, 5)[:, :3]).all()
+    lo_sq = e.sql_scan(aqe.sql_parse("SELECT SUM(amount) FROM sales WHERE amount < 300 GROUP BY region", 0), layout, aqe.SQL_MOMENTS)
+    hi_sq = e.sql_scan(aqe.sql_parse("SELECT SUM(amount) FROM sales WHERE amount >= 300 GROUP BY region", 0), layout, aqe.SQL_MOMENTS)
+    assert (aqe.sql_merge(lo_sq.copy(), hi_sq) == with_sq).all()
+    halves = [e.sql_scan(aqe.sql_parse(f"SELECT SUM(amount) FROM sales WHERE id {op} {n // 2} GROUP BY region", 50), layout, aqe.SQL_MOMENTS) for op in ("<=", ">")]
+    assert (aqe.sql_merge(halves[0].copy(), halves[1]) == e.sql_scan(aqe.sql_parse("SELECT SUM(amount) FROM sales GROUP BY region", 50), layout, aqe.SQL_MOMENTS)).all()
     total = e.sql("SELECT SUM(amount) FROM sales")[0]
     p = e.scan("amount")
     assert abs(total.value - p.sum) <= 4 * math.ulp(p.sum)                 # compensated scan vs exactly rounded fixed point
