@@ -79,7 +79,8 @@ constexpr unsigned int kSqlPackedRowsMoments = 4095;   // ... with squares: thre
 constexpr int kSqlMaxAlt = AQE_SQL_MAX_ALT;   // OR-ed conjunctions of a WHERE clause
 
 struct SqlPred {       // one conjunct on one column: closed interval [lo, hi] and optionally != ne (raw 64-bit: f64 bits or int64)
-    int has_pred;
+    int has_pred;      // 0 none | 1 interval | 2 membership bitmap of an integer column: bit (v - lo) of `hi`, v - lo < 64 (IN lists and
+                       //   other multi-branch clauses on a column whose values span fewer than 64 keys, folded on the host into ONE pass)
     int has_ne;
     long long lo, hi, ne;
 };
@@ -146,6 +147,10 @@ __device__ __forceinline__ long long sql_load_raw(const SqlCol& c, uint64_t i) {
 }
 __device__ __forceinline__ bool sql_pass(const SqlCol& c, const SqlPred& p, long long raw) {
     if (!p.has_pred) return true;
+    if (p.has_pred == 2) {
+        const unsigned long long d = (unsigned long long)(raw - p.lo);
+        return d < 64ull && (((unsigned long long)p.hi >> d) & 1ull) != 0ull;
+    }
     bool ok;
     if (c.kind == 0) {
         const double d = __longlong_as_double(raw);
@@ -597,6 +602,22 @@ template <int T, int K> __device__ __forceinline__ uint32_t sql_pred_pass(const 
             const double v = lds_row<double>(base, tid + k * T);
             const bool ok = v >= lo && v <= hi && !(has_ne && v == ne);
             mask &= ~((ok ? 0u : 1u) << k);
+        }
+    } else if (p.has_pred == 2) {   // membership bitmap over [lo, lo + 64)
+        const long long first = p.lo;
+        const unsigned long long bits = (unsigned long long)p.hi;
+        if (col.kind == 1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const unsigned long long d = (unsigned long long)(lds_row<long long>(base, tid + k * T) - first);
+                mask &= ~(((d < 64ull && ((bits >> d) & 1ull)) ? 0u : 1u) << k);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const unsigned long long d = (unsigned long long)((long long)lds_row<int>(base, tid + k * T) - first);
+                mask &= ~(((d < 64ull && ((bits >> d) & 1ull)) ? 0u : 1u) << k);
+            }
         }
     } else if (col.kind == 1) {
         const bool has_ne = p.has_ne != 0;

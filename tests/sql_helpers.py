@@ -196,4 +196,8 @@ SIGNED_QUERIES = (("SELECT SUM(amount) FROM sales", 0, "run_query"), ("SELECT AV
                   ("SELECT AVG(amount) FROM sales WHERE amount > -900.5 GROUP BY product_id", 50, "run_query_groupby"),
                   ("SELECT COUNT(*) FROM sales WHERE region != -1 GROUP BY product_id", 0, "run_query_groupby"),
                   ("SELECT SUM(product_id) FROM sales WHERE amount <= -1 GROUP BY region", 0, "run_query_groupby"),
-                  ("SELECT AVG(region) FROM sales WHERE region IN (-3, -1, 4)", 25, "run_query_with_ci"))
+                  ("SELECT AVG(region) FROM sales WHERE region IN (-3, -1, 4)", 25, "run_query_with_ci"),
+                  ("SELECT SUM(amount) FROM sales WHERE region IN (-3, 0, 4) AND amount > 0", 0, "run_query"),
+                  ("SELECT COUNT(amount) FROM sales WHERE region NOT IN (-1, 2) AND product_id < 100 GROUP BY region", 10, "run_query_groupby"),
+                  ("SELECT SUM(amount) FROM sales WHERE region != -3 AND region != 0 AND region != 4 AND region != 3", 34, "run_query_with_ci"),
+                  ("SELECT SUM(amount) FROM sales WHERE region IN (5, 6)", 0, "run_query_with_ci"))

@@ -91,6 +91,13 @@ def test_sql_against_oracle_extra_queries(tables, oracle):
         "SELECT COUNT(amount) FROM sales WHERE amount < 0 GROUP BY region",
         "SELECT SUM(amount) FROM sales WHERE region != 1 AND region != 3 AND region != 6 AND product_id != 10 AND product_id != 20 GROUP BY region",
         "SELECT AVG(amount) FROM sales WHERE region NOT IN (0, 7) AND region != 4 AND amount != 500 AND amount != 250.5",
+        # branches that differ in one small-domain integer column fold into one membership bitmap (aqe_engine.cu, sql_scan_impl)
+        "SELECT SUM(amount) FROM sales WHERE region IN (1, 3, 5, 7)",
+        "SELECT AVG(amount) FROM sales WHERE region IN (0, 2, 6) AND amount BETWEEN 100 AND 900 AND product_id != 17 GROUP BY region",
+        "SELECT COUNT(*) FROM sales WHERE region NOT IN (1, 2, 3) GROUP BY product_id",
+        "SELECT SUM(timestamp) FROM sales WHERE (region < 2 OR region > 5 OR region = 4)",
+        "SELECT SUM(amount) FROM sales WHERE region IN (8, 9)",
+        "SELECT SUM(amount) FROM sales WHERE product_id IN (1, 3, 5, 7) AND region = 2",      # 1000 keys: stays four branches
     ]
     for sql in queries:
         for p in (0, 3, 10, 25, 50, 99):
@@ -382,6 +389,8 @@ def test_sql_register_kernel_and_ring_kernel_agree_word_for_word(tables, monkeyp
                           ("SELECT COUNT(amount) FROM sales WHERE id > 77 GROUP BY product_id", 25, 0),
                           ("SELECT SUM(amount) FROM sales GROUP BY region", 34, aqe.SQL_MOMENTS),
                           ("SELECT AVG(amount) FROM sales", 20, aqe.SQL_MOMENTS),
+                          ("SELECT SUM(amount) FROM sales WHERE region IN (1, 4, 6) AND amount > 10 GROUP BY region", 34, aqe.SQL_MOMENTS),
+                          ("SELECT SUM(timestamp) FROM sales WHERE region NOT IN (0, 3)", 0, 0),
                           ("SELECT SUM(amount) FROM sales GROUP BY region", 5, aqe.SQL_MOMENTS)):
         q = aqe.sql_parse(sql, p)
         layout = aqe.sql_layout(q, [e.sql_facts(q)])

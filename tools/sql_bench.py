@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Timings of the SQL-string path (k_sql_agg) on a device-generated table: ms per query (median of reps, host wall clock
 around the synchronous C-ABI call aqe_sql_run), rows/s and achieved GB/s against the ALGORITHMIC bytes of the query (the widths of
-the distinct columns it reads x rows visited).  python tools/sql_bench.py [rows] [reps] [sampled] > out.json"""
+the distinct columns it reads x rows visited).  python tools/sql_bench.py [rows] [reps] [sampled|or] > out.json"""
 import json
 import os
 import sys
@@ -46,6 +46,10 @@ def main():
                   (f"SELECT AVG(amount) FROM sales WHERE timestamp BETWEEN {T0 + n // 4} AND {T0 + n // 2} GROUP BY region", "value", ["amount", "region", "timestamp"]),
                   ("SELECT SUM(amount) FROM sales GROUP BY product_id", "value", ["amount", "product_id"])]
         cases = [(sql, p, mode, cols) for p in (50, 33, 25, 20, 15) for sql, mode, cols in shapes]
+    if len(sys.argv) > 3 and sys.argv[3] == "or":   # cost of OR branches
+        cases = [(f"SELECT {agg} FROM sales WHERE {w}", 0, "value", cols) for agg, cols in (("SUM(amount)", ["amount", "region"]), ("COUNT(*)", ["region"]))
+                 for w in ("region = 1", "(region = 1 OR region = 3)", "region IN (1, 3, 5, 7)", "region IN (0, 1, 2, 3, 4, 5, 6, 7)", "region != 1 AND region != 3",
+                           "(region = 1 OR amount > 900)", "(region = 1 AND amount > 900 OR region = 3 AND amount < 100)")]
     out = []
     import ctypes as C
     buf = (aqe.SqlRow * aqe.SQL_MAX_GROUPS)()
