@@ -1820,12 +1820,13 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
     a.n_alt = q->n_alt;
     for (int alt = 0; alt < q->n_alt; ++alt)
         if (q->n_terms[alt] < 1 || q->n_terms[alt] > 5) return fail(AQE_ERR_INVALID, "query: a WHERE branch needs 1..5 terms");
-    // OR branches that differ in ONE integer column whose values span fewer than 64 keys (IN lists, NOT IN, chains of !=, with or
-    // without further AND-ed terms shared by all branches) fold into one branch: that column's test becomes a membership bitmap over
-    // [min, min + 64) built from the column's statistics -- one predicate pass instead of one per branch (measured on 1 B rows:
-    // `region IN (1, 3, 5, 7)` 3.56 ms as four branches).
+    // OR branches that differ in ONE integer column whose values span at most AQE_SQL_MAX_GROUPS keys (IN lists, NOT IN, chains of
+    // !=, with or without further AND-ed terms shared by all branches) fold into one branch: that column's test becomes a membership
+    // bitmap over [min, max] built from the column's statistics -- one predicate pass instead of one per branch (measured on 1 B
+    // rows: `region IN (1, 3, 5, 7)` 3.56 ms as four branches, 1.73 ms folded).  Fewer than 64 keys: the bitmap is one register.
     int fold_col = AQE_COL_NONE;
-    uint64_t fold_bits = 0;
+    uint64_t fold_bits = 0, fold_span = 0;
+    bool fold_any = false;
     int64_t fold_first = 0;
     if (q->n_alt > 1) {
         for (int c = 0; c < 5 && fold_col == AQE_COL_NONE; ++c) {
@@ -1847,8 +1848,9 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
             const aqe_db::ColStat* st;
             if ((rc = sql_col_stat(db, c, &st))) return rc;
             const int64_t lo = okey_to_i64(st->min_key), hi = okey_to_i64(st->max_key);
-            if (hi < lo || (uint64_t)hi - (uint64_t)lo >= 64) continue;
-            for (uint64_t d = 0; d <= (uint64_t)hi - (uint64_t)lo; ++d) {
+            if (hi < lo || (uint64_t)hi - (uint64_t)lo >= (uint64_t)AQE_SQL_MAX_GROUPS) continue;
+            fold_span = (uint64_t)hi - (uint64_t)lo + 1;
+            for (uint64_t d = 0; d < fold_span; ++d) {
                 const int64_t v = lo + (int64_t)d;
                 bool pass = false;
                 for (int alt = 0; alt < q->n_alt && !pass; ++alt)
@@ -1856,14 +1858,18 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
                         const aqe_sql_term& x = q->terms[alt][t];
                         if (x.col == c) pass = v >= x.ilo && v <= x.ihi && !(x.has_ne && v == x.ine);
                     }
-                if (pass) fold_bits |= 1ull << d;
+                if (!pass) continue;
+                fold_any = true;
+                if (fold_span <= 64) fold_bits |= 1ull << d;
+                else a.member_bits[d >> 5] |= 1u << (d & 31);
             }
             fold_col = c; fold_first = lo;
         }
     }
     if (fold_col != AQE_COL_NONE) {
-        if (fold_bits == 0) return finish_without_scan(0);   // no value the column holds passes
+        if (!fold_any) return finish_without_scan(0);   // no value the column holds passes
         a.n_alt = 1;
+        a.member_used = fold_span > 64 ? 1 : 0;
     }
     for (int alt = 0; alt < a.n_alt; ++alt) {
         for (int t = 0; t < q->n_terms[alt]; ++t) {
@@ -1871,7 +1877,11 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
             if ((rc = need(term.col))) return rc;
             const int slot = slot_of(term.col);
             SqlPred& c = a.cols[slot].pred[alt];
-            if (term.col == fold_col) { c.has_pred = 2; c.has_ne = 0; c.lo = fold_first; c.hi = (long long)fold_bits; c.ne = 0; continue; }
+            if (term.col == fold_col) {
+                c.has_ne = 0; c.ne = 0; c.lo = fold_first;
+                if (fold_span <= 64) { c.has_pred = 2; c.hi = (long long)fold_bits; } else { c.has_pred = 3; c.hi = (long long)fold_span; }
+                continue;
+            }
             c.has_pred = 1; c.has_ne = term.has_ne;
             if (a.cols[slot].kind == K_F64) { std::memcpy(&c.lo, &term.lo, 8); std::memcpy(&c.hi, &term.hi, 8); std::memcpy(&c.ne, &term.ne, 8); }
             else { c.lo = term.ilo; c.hi = term.ihi; c.ne = term.ine; }

@@ -81,6 +81,7 @@ constexpr int kSqlMaxAlt = AQE_SQL_MAX_ALT;   // OR-ed conjunctions of a WHERE c
 struct SqlPred {       // one conjunct on one column: closed interval [lo, hi] and optionally != ne (raw 64-bit: f64 bits or int64)
     int has_pred;      // 0 none | 1 interval | 2 membership bitmap of an integer column: bit (v - lo) of `hi`, v - lo < 64 (IN lists and
                        //   other multi-branch clauses on a column whose values span fewer than 64 keys, folded on the host into ONE pass)
+                       // | 3 the same for up to AQE_SQL_MAX_GROUPS keys: bit (v - lo) of SqlArgs::member_bits, v - lo < hi
     int has_ne;
     long long lo, hi, ne;
 };
@@ -131,6 +132,8 @@ struct SqlArgs {
     unsigned long long* global_acc;   // [n_groups][5] {count, sum_lo, sum_hi, sq_lo, sq_hi}, zero before launch, zeroed again by the last CTA
     unsigned long long* out;          // [n_groups][5] device-visible result
     unsigned int* ticket;
+    unsigned int member_bits[AQE_SQL_MAX_GROUPS / 32];   // has_pred == 3 (at most one predicate of a query uses it)
+    int member_used;
     unsigned int drain_rows;          // private bins (G <= 16) are drained before a thread has added this many rows to one (<= kSqlPackedRows)
     SqlExchange ex;
 };
@@ -145,12 +148,23 @@ __device__ __forceinline__ long long sql_load_raw(const SqlCol& c, uint64_t i) {
     asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(static_cast<const long long*>(c.ptr) + i));
     return v;
 }
+// membership bitmap of a folded predicate (has_pred == 3), copied from the kernel parameters by sql_member_load
+__shared__ unsigned int g_sql_member[AQE_SQL_MAX_GROUPS / 32];
+__device__ __forceinline__ void sql_member_load(const SqlArgs& a, int tid, int nthreads) {   // the caller's next __syncthreads() publishes it
+    if (a.member_used)
+        for (int i = tid; i < AQE_SQL_MAX_GROUPS / 32; i += nthreads) g_sql_member[i] = a.member_bits[i];
+}
+__device__ __forceinline__ bool sql_member(unsigned long long d, unsigned long long n) {
+    return d < n && ((g_sql_member[(unsigned int)d >> 5] >> ((unsigned int)d & 31u)) & 1u) != 0u;
+}
+
 __device__ __forceinline__ bool sql_pass(const SqlCol& c, const SqlPred& p, long long raw) {
     if (!p.has_pred) return true;
     if (p.has_pred == 2) {
         const unsigned long long d = (unsigned long long)(raw - p.lo);
         return d < 64ull && (((unsigned long long)p.hi >> d) & 1ull) != 0ull;
     }
+    if (p.has_pred == 3) return sql_member((unsigned long long)(raw - p.lo), (unsigned long long)p.hi);
     bool ok;
     if (c.kind == 0) {
         const double d = __longlong_as_double(raw);
@@ -472,6 +486,7 @@ __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
     constexpr int T = kSqlThreads;
     constexpr int U = 8;
     SqlBins<MODE, MOMENTS, T> bins;
+    sql_member_load(a, tid, T);
     bins.init(sql_smem, a.n_groups, tid, T);
     bins.with_sums = a.agg_slot >= 0;
 
@@ -603,6 +618,16 @@ template <int T, int K> __device__ __forceinline__ uint32_t sql_pred_pass(const 
             const bool ok = v >= lo && v <= hi && !(has_ne && v == ne);
             mask &= ~((ok ? 0u : 1u) << k);
         }
+    } else if (p.has_pred == 3) {   // membership bitmap in shared memory over [lo, lo + hi)
+        const long long first = p.lo;
+        const unsigned long long n = (unsigned long long)p.hi;
+        if (col.kind == 1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) mask &= ~((sql_member((unsigned long long)(lds_row<long long>(base, tid + k * T) - first), n) ? 0u : 1u) << k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) mask &= ~((sql_member((unsigned long long)((long long)lds_row<int>(base, tid + k * T) - first), n) ? 0u : 1u) << k);
+        }
     } else if (p.has_pred == 2) {   // membership bitmap over [lo, lo + 64)
         const long long first = p.lo;
         const unsigned long long bits = (unsigned long long)p.hi;
@@ -675,6 +700,7 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kBulkConsumerWarps); }
         fence_barrier_init();
     }
+    sql_member_load(a, tid, kBulkThreads);
     bins.init(bin_mem, a.n_groups, tid, kBulkThreads);  // ends with __syncthreads()
     bins.with_sums = a.agg_slot >= 0;
 

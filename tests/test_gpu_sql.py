@@ -97,7 +97,9 @@ def test_sql_against_oracle_extra_queries(tables, oracle):
         "SELECT COUNT(*) FROM sales WHERE region NOT IN (1, 2, 3) GROUP BY product_id",
         "SELECT SUM(timestamp) FROM sales WHERE (region < 2 OR region > 5 OR region = 4)",
         "SELECT SUM(amount) FROM sales WHERE region IN (8, 9)",
-        "SELECT SUM(amount) FROM sales WHERE product_id IN (1, 3, 5, 7) AND region = 2",      # 1000 keys: stays four branches
+        "SELECT SUM(amount) FROM sales WHERE product_id IN (1, 3, 5, 7) AND region = 2",      # 1000 keys: the bitmap lives in shared memory
+        "SELECT AVG(amount) FROM sales WHERE product_id NOT IN (0, 31, 32, 63, 64, 999) AND product_id != 500 GROUP BY region",
+        "SELECT COUNT(*) FROM sales WHERE (product_id < 10 OR product_id > 990 OR product_id BETWEEN 400 AND 420) GROUP BY product_id",
     ]
     for sql in queries:
         for p in (0, 3, 10, 25, 50, 99):
@@ -391,6 +393,8 @@ def test_sql_register_kernel_and_ring_kernel_agree_word_for_word(tables, monkeyp
                           ("SELECT AVG(amount) FROM sales", 20, aqe.SQL_MOMENTS),
                           ("SELECT SUM(amount) FROM sales WHERE region IN (1, 4, 6) AND amount > 10 GROUP BY region", 34, aqe.SQL_MOMENTS),
                           ("SELECT SUM(timestamp) FROM sales WHERE region NOT IN (0, 3)", 0, 0),
+                          ("SELECT SUM(amount) FROM sales WHERE product_id IN (5, 64, 65, 999) AND amount < 900 GROUP BY region", 0, aqe.SQL_MOMENTS),
+                          ("SELECT COUNT(*) FROM sales WHERE product_id NOT IN (1, 2, 3) GROUP BY product_id", 20, 0),
                           ("SELECT SUM(amount) FROM sales GROUP BY region", 5, aqe.SQL_MOMENTS)):
         q = aqe.sql_parse(sql, p)
         layout = aqe.sql_layout(q, [e.sql_facts(q)])

@@ -49,7 +49,8 @@ def main():
     if len(sys.argv) > 3 and sys.argv[3] == "or":   # cost of OR branches
         cases = [(f"SELECT {agg} FROM sales WHERE {w}", 0, "value", cols) for agg, cols in (("SUM(amount)", ["amount", "region"]), ("COUNT(*)", ["region"]))
                  for w in ("region = 1", "(region = 1 OR region = 3)", "region IN (1, 3, 5, 7)", "region IN (0, 1, 2, 3, 4, 5, 6, 7)", "region != 1 AND region != 3",
-                           "(region = 1 OR amount > 900)", "(region = 1 AND amount > 900 OR region = 3 AND amount < 100)")]
+                           "(region = 1 OR amount > 900)", "(region = 1 AND amount > 900 OR region = 3 AND amount < 100)", "product_id = 5", "product_id IN (1, 3, 5, 7)",
+                           "product_id NOT IN (1, 3, 5, 7, 9, 11)")]
     out = []
     import ctypes as C
     buf = (aqe.SqlRow * aqe.SQL_MAX_GROUPS)()
