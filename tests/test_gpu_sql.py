@@ -100,6 +100,12 @@ def test_sql_against_oracle_extra_queries(tables, oracle):
         "SELECT SUM(amount) FROM sales WHERE product_id IN (1, 3, 5, 7) AND region = 2",      # 1000 keys: the bitmap lives in shared memory
         "SELECT AVG(amount) FROM sales WHERE product_id NOT IN (0, 31, 32, 63, 64, 999) AND product_id != 500 GROUP BY region",
         "SELECT COUNT(*) FROM sales WHERE (product_id < 10 OR product_id > 990 OR product_id BETWEEN 400 AND 420) GROUP BY product_id",
+        # ... in a floating-point or wide column: one predicate pass per branch
+        "SELECT SUM(amount) FROM sales WHERE amount NOT BETWEEN 100 AND 500",
+        "SELECT AVG(amount) FROM sales WHERE (amount < 50 OR amount > 950 OR amount BETWEEN 400 AND 410) AND region >= 2 GROUP BY region",
+        "SELECT SUM(amount) FROM sales WHERE amount != 500 AND amount != 250.5 AND amount != 7 GROUP BY product_id",
+        f"SELECT SUM(region) FROM sales WHERE timestamp NOT BETWEEN {t0 + 5000} AND {t0 + 15000} AND amount < 700",
+        "SELECT COUNT(id) FROM sales WHERE (id <= 100 OR id > 19900 OR id = 5000) GROUP BY region",
     ]
     for sql in queries:
         for p in (0, 3, 10, 25, 50, 99):
@@ -395,6 +401,9 @@ def test_sql_register_kernel_and_ring_kernel_agree_word_for_word(tables, monkeyp
                           ("SELECT SUM(timestamp) FROM sales WHERE region NOT IN (0, 3)", 0, 0),
                           ("SELECT SUM(amount) FROM sales WHERE product_id IN (5, 64, 65, 999) AND amount < 900 GROUP BY region", 0, aqe.SQL_MOMENTS),
                           ("SELECT COUNT(*) FROM sales WHERE product_id NOT IN (1, 2, 3) GROUP BY product_id", 20, 0),
+                          ("SELECT SUM(amount) FROM sales WHERE amount NOT BETWEEN 200 AND 800 GROUP BY region", 0, aqe.SQL_MOMENTS),
+                          ("SELECT SUM(amount) FROM sales WHERE (amount < 10 OR amount > 990)", 50, aqe.SQL_MOMENTS),
+                          ("SELECT AVG(timestamp) FROM sales WHERE (id < 1000 OR id > 90000) AND amount > 5", 25, 0),
                           ("SELECT SUM(amount) FROM sales GROUP BY region", 5, aqe.SQL_MOMENTS)):
         q = aqe.sql_parse(sql, p)
         layout = aqe.sql_layout(q, [e.sql_facts(q)])

@@ -50,7 +50,8 @@ def main():
         cases = [(f"SELECT {agg} FROM sales WHERE {w}", 0, "value", cols) for agg, cols in (("SUM(amount)", ["amount", "region"]), ("COUNT(*)", ["region"]))
                  for w in ("region = 1", "(region = 1 OR region = 3)", "region IN (1, 3, 5, 7)", "region IN (0, 1, 2, 3, 4, 5, 6, 7)", "region != 1 AND region != 3",
                            "(region = 1 OR amount > 900)", "(region = 1 AND amount > 900 OR region = 3 AND amount < 100)", "product_id = 5", "product_id IN (1, 3, 5, 7)",
-                           "product_id NOT IN (1, 3, 5, 7, 9, 11)")]
+                           "product_id NOT IN (1, 3, 5, 7, 9, 11)", "amount NOT BETWEEN 100 AND 500", "(amount < 50 OR amount > 950 OR amount BETWEEN 400 AND 410)",
+                           f"timestamp NOT BETWEEN {T0 + n // 4} AND {T0 + n // 2}")]
     out = []
     import ctypes as C
     buf = (aqe.SqlRow * aqe.SQL_MAX_GROUPS)()
