@@ -42,6 +42,7 @@ METHODS = {
     "signal_based_clt": 25,
 }
 STATUS = {0: "STABLE", 1: "DRIFTING", 2: "INSUFFICIENT_DATA", 3: "ERROR"}
+CI_MODE = {"default": 0, "plain": 1, "stein": 2, "stein_guarded": 3}
 
 
 class AqeError(RuntimeError):
@@ -77,6 +78,12 @@ class Stats(C.Structure):
     _fields_ = [("n", C.c_uint64), ("mean", C.c_double), ("m2", C.c_double), ("sum", C.c_double)]
 
 
+class StatsPartial(C.Structure):
+    """One shard's mergeable sums over a sample plan (aqe_stats_partial, 64 bytes)."""
+    _fields_ = [("n", C.c_uint64), ("sum", C.c_double), ("sum_c", C.c_double), ("shift", C.c_double), ("sd", C.c_double),
+                ("sd_c", C.c_double), ("sdd", C.c_double), ("sdd_c", C.c_double)]
+
+
 class Segment(C.Structure):
     _fields_ = [("base", C.c_int64), ("outer_step", C.c_int64), ("inner_len", C.c_int64), ("count", C.c_int64),
                 ("scale", C.c_double), ("kind", C.c_int32), ("_pad", C.c_int32)]
@@ -87,7 +94,7 @@ class ApproxSpec(C.Structure):
         ("agg", C.c_int32), ("design", C.c_int32), ("agg_col", C.c_int32), ("pred_col", C.c_int32),
         ("lo", C.c_double), ("hi", C.c_double), ("error_percent", C.c_double), ("confidence_level", C.c_double),
         ("seed", C.c_uint64), ("min_samples", C.c_uint64), ("max_samples", C.c_uint64),
-        ("block_size", C.c_uint32), ("_pad", C.c_uint32),
+        ("block_size", C.c_uint32), ("ci_mode", C.c_uint32),
     ]
 
 
@@ -96,7 +103,7 @@ class ApproxResult(C.Structure):
         ("estimate", C.c_double), ("ci_lower", C.c_double), ("ci_upper", C.c_double), ("error_margin", C.c_double),
         ("confidence_level", C.c_double), ("n_samples", C.c_uint64), ("n_units", C.c_uint64),
         ("population", C.c_uint64), ("mean", C.c_double), ("m2", C.c_double), ("rounds", C.c_uint32),
-        ("status", C.c_int32), ("elapsed_us", C.c_double),
+        ("status", C.c_int32), ("elapsed_us", C.c_double), ("pass_fraction", C.c_double),
     ]
 
 
@@ -157,6 +164,7 @@ def lib() -> C.CDLL:
     sig = {
         "aqe_abi_version": (i32, []),
         "aqe_last_error": (C.c_char_p, []),
+        "aqe_last_scan_kernel": (C.c_char_p, []),
         "aqe_device_count": (i32, [C.POINTER(C.c_int)]),
         "aqe_launch_count": (u64, []),
         "aqe_host_alloc": (i32, [C.c_size_t, C.POINTER(vp)]),
@@ -171,6 +179,12 @@ def lib() -> C.CDLL:
         "aqe_generate_synthetic": (i32, [vp, u64, u64, u64, i32, C.c_uint32]),
         "aqe_synth_rows_host": (i32, [u64, u64, u64, i32, vp]),
         "aqe_close": (i32, [vp]),
+        "aqe_create_sharded": (i32, [C.POINTER(C.c_int), i32, C.POINTER(vp)]),
+        "aqe_open_sharded": (i32, [C.c_char_p, i32, C.POINTER(vp)]),
+        "aqe_shard_count": (i32, [vp]),
+        "aqe_shard": (vp, [vp, i32]),
+        "aqe_shard_first_row": (u64, [vp, i32]),
+        "aqe_shards_fused": (i32, [vp]),
         "aqe_count": (u64, [vp]),
         "aqe_node_count": (u64, [vp]),
         "aqe_tree_height": (u64, [vp]),
@@ -202,6 +216,10 @@ def lib() -> C.CDLL:
         "aqe_stats_from_plan": (i32, [vp, vp, i32, C.POINTER(Stats)]),
         "aqe_stats_from_plan_where": (i32, [vp, vp, i32, i32, dbl, dbl, C.POINTER(Stats)]),
         "aqe_stats_from_indices": (i32, [vp, vp, u64, i32, C.POINTER(Stats)]),
+        "aqe_stats_window": (i32, [vp, vp, i32, i32, dbl, dbl, u64, C.POINTER(StatsPartial)]),
+        "aqe_stats_merge": (i32, [C.POINTER(StatsPartial), i32, C.POINTER(Stats)]),
+        "aqe_gather_window": (i32, [vp, vp, u64, u64, u64, vp, C.POINTER(u64)]),
+        "aqe_plan_table_rows": (u64, [vp]),
         "aqe_gather_plan": (i32, [vp, vp, vp, u64]),
         "aqe_gather_records": (i32, [vp, vp, u64, vp]),
         "aqe_fast_aggregated_sum": (i32, [vp, C.POINTER(SampleParams), C.POINTER(dbl), C.POINTER(u64)]),
@@ -326,12 +344,32 @@ def merge_partials(parts, is_integer: bool = False) -> Partial:
 class Engine:
     """ctypes view of one ``aqe_db`` handle (one shard on one GPU)."""
 
-    def __init__(self, device: int | None = None):
-        if device is None:
-            device = int(os.environ.get("AQE_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    def __init__(self, device: int | None = None, devices=None):
+        """One shard on one GPU (`device`), or -- `devices` = a list of device ids, or "all" -- the whole table range-sharded
+        over several GPUs of this process (aqe_create_sharded): every method below then answers for the whole table."""
         self.L = lib()
         self.h = C.c_void_p()
+        if devices is not None:
+            if devices == "all":
+                check(self.L.aqe_create_sharded(None, 0, C.byref(self.h)))
+            else:
+                arr = (C.c_int * len(devices))(*devices)
+                check(self.L.aqe_create_sharded(arr, len(devices), C.byref(self.h)))
+            return
+        if device is None:
+            device = int(os.environ.get("AQE_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         check(self.L.aqe_create(device, C.byref(self.h)))
+
+    @property
+    def shard_count(self) -> int:
+        return self.L.aqe_shard_count(self.h)
+
+    @property
+    def fused(self) -> bool:
+        return bool(self.L.aqe_shards_fused(self.h))
+
+    def shard_first_row(self, g: int) -> int:
+        return self.L.aqe_shard_first_row(self.h, g)
 
     def close(self):
         if getattr(self, "h", None):
@@ -459,6 +497,21 @@ class Engine:
             check(self.L.aqe_stats_from_plan_where(self.h, plan.h, COLS[col], COLS[where_col], where[0], where[1], C.byref(s)))
         return s
 
+    def stats_window(self, plan: Plan, window_first: int, col="amount", where=None, where_col="amount") -> StatsPartial:
+        """This handle holds rows [window_first, window_first + count) of the plan's table: its mergeable sums."""
+        out = StatsPartial()
+        check(self.L.aqe_stats_window(self.h, plan.h, COLS[col], COLS[where_col] if where else -1, where[0] if where else 0.0,
+                                      where[1] if where else 0.0, window_first, C.byref(out)))
+        return out
+
+    def gather_window(self, plan: Plan, window_first: int, k_first: int = 0, k_count: int | None = None):
+        """Rows of plan positions [k_first, k_first + k_count) inside this handle's window (other slots zero) and their number."""
+        k_count = plan.count - k_first if k_count is None else k_count
+        out = np.zeros(k_count, dtype=RECORD_DTYPE)
+        n = C.c_uint64()
+        check(self.L.aqe_gather_window(self.h, plan.h, window_first, k_first, k_count, _ptr(out), C.byref(n)))
+        return out, n.value
+
     def stats_from_indices(self, idx, col="amount") -> Stats:
         idx = np.ascontiguousarray(idx, dtype=np.int64)
         s = Stats()
@@ -482,10 +535,10 @@ class Engine:
         return s.value, n.value
 
     def approx(self, agg="sum", error_percent=1.0, confidence_level=0.95, design="srs", seed=0, where=None,
-               where_col="amount", agg_col="amount", block_size=0, min_samples=0, max_samples=0, exchange=False) -> ApproxResult:
+               where_col="amount", agg_col="amount", block_size=0, min_samples=0, max_samples=0, exchange=False, ci_mode="default") -> ApproxResult:
         sp = ApproxSpec(AGG[agg], DESIGN[design], COLS[agg_col], COLS[where_col] if where else -1,
                         where[0] if where else 0.0, where[1] if where else 0.0, error_percent, confidence_level, seed,
-                        min_samples, max_samples, block_size, 0)
+                        min_samples, max_samples, block_size, CI_MODE[ci_mode])
         out = ApproxResult()
         check((self.L.aqe_approx_exchange if exchange else self.L.aqe_approx)(self.h, C.byref(sp), C.byref(out)))
         return out
@@ -513,6 +566,14 @@ class Engine:
         acc = np.zeros(layout.n_groups * 5, dtype=np.uint64)
         check((self.L.aqe_sql_scan_exchange if exchange else self.L.aqe_sql_scan)(self.h, C.byref(q), C.byref(layout), flags, _ptr(acc)))
         return acc
+
+
+def merge_stats(parts) -> Stats:
+    """Fold the shards' sums of a sample plan in rank order (aqe_stats_merge, host code)."""
+    arr = (StatsPartial * len(parts))(*parts)
+    out = Stats()
+    check(lib().aqe_stats_merge(arr, len(parts), C.byref(out)))
+    return out
 
 
 def estimate(stats: Stats, population: int, agg: str, z: float = 1.96, legacy_ci: bool = False):

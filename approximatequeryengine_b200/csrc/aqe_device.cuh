@@ -55,6 +55,13 @@ __host__ __device__ __forceinline__ uint64_t draw_position(uint64_t seed, uint32
     return mulhi64(u, units);
 }
 
+// Student-t quantile from the normal quantile z at the same probability (Cornish-Fisher / Fisher's expansion in 1/df):
+// t = z + (z^3 + z)/(4 df) + (5 z^5 + 16 z^3 + 3 z)/(96 df^2).  df >= 15 here (the smallest look is 16 units): error < 1e-4.
+__host__ __device__ __forceinline__ double t_from_z(double z, double df) {
+    const double z2 = z * z;
+    return z + z * (z2 + 1.0) / (4.0 * df) + z * ((5.0 * z2 + 16.0) * z2 + 3.0) / (96.0 * df * df);
+}
+
 // Pseudo-random permutation of [0, n): a 4-round balanced Feistel network over the smallest even number of bits
 // covering n, splitmix64 as the round function, cycle-walking back into [0, n).  perm(0), perm(1), ... perm(k-1) are
 // k DISTINCT, uniformly scattered positions -- simple random sampling WITHOUT replacement in O(1) memory, computed

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -34,6 +35,7 @@ using namespace aqe;
 // errors / bookkeeping
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
+static thread_local std::string g_scan_kernel;   // what the last exact scan of this thread launched (aqe_last_scan_kernel)
 static std::atomic<uint64_t> g_launches{0};
 
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -61,9 +63,14 @@ struct Slot {  // mapped pinned result area: kernels write it, the host reads it
     aqe_stats stats;
     aqe_approx_result approx;
     unsigned int flags[4];
+    aqe_stats_partial stats_raw;       // k_plan_stats over a window of a sharded table
+    unsigned long long gathered;       // k_plan_gather: rows written (window form)
 };
 
+struct Group;  // aqe_group.inl: a table range-sharded over several GPUs of this process
+
 struct aqe_db {
+    Group* group = nullptr;   // set on the handle aqe_create_sharded returns; its shards are plain handles
     int device = 0;
     bool cuda_ready = false;
     cudaStream_t stream = nullptr;
@@ -100,6 +107,7 @@ struct aqe_db {
     unsigned long long* sql_local = nullptr;  // [AQE_SQL_MAX_GROUPS][5]: this shard's accumulators on their way into the exchange
     uint64_t ex_total_rows = 0;          // rows of the whole table (all shards)
     bool ex_connected = false;
+    bool ex_ipc = false;                 // peers were opened as CUDA IPC handles (another process' memory) and must be closed as such
 
     // SQL-string path (aqe_sql_*): lazily computed column statistics + accumulators of the grouped scan
     struct ColStat { bool valid = false; unsigned long long min_key = 0, max_key = 0; bool dense = false; long long first_id = 0; };
@@ -112,6 +120,26 @@ struct aqe_db {
 };
 
 static const int kMaxGrid = 148 * 16;
+
+// ---- a table sharded over several GPUs of this process (aqe_group.inl, included at the end of this file) ----
+static int group_close(aqe_db* db);
+static int group_ensure_device(aqe_db* db);
+static int group_load_file(aqe_db* db, const char* path, uint64_t first_row, uint64_t n_rows);
+static int group_from_host_records(aqe_db* db, const aqe_record* rows, size_t n);
+static int group_generate(aqe_db* db, uint64_t seed, uint64_t first_row, uint64_t n_rows, int dist, uint32_t mask);
+static int group_read_records(aqe_db* db, uint64_t first, uint64_t n, aqe_record* out);
+static int group_read_column(aqe_db* db, int col, uint64_t first, uint64_t n, void* out);
+static int group_scan_range(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, uint64_t n, bool moments, aqe_partial* out);
+static int group_stats(aqe_db* db, const aqe_plan* pl, int col, int pred_col, double lo, double hi, aqe_stats* out);
+static int group_gather(aqe_db* db, const aqe_plan* pl, aqe_record* out, uint64_t cap);
+static int group_approx(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* out);
+static int group_sql_facts(aqe_db* db, const aqe_sql_query* q, aqe_sql_facts* out);
+static int group_sql_scan(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* L, int flags, uint64_t* acc);
+static int group_amount_view(aqe_db* db, aqe::GlobalF64* out);
+static int group_amount_perm(aqe_db* db, const int64_t** perm);
+static int group_unsupported(const char* what) {
+    return fail(AQE_ERR_UNSUPPORTED, std::string(what) + " works on one shard: use aqe_shard(db, g) of a sharded table");
+}
 
 static int db_init_cuda(aqe_db* db) {
     if (db->cuda_ready) { CU(cudaSetDevice(db->device)); return AQE_OK; }
@@ -234,8 +262,9 @@ struct IngestPool {
 
 // Feeds `n` rows obtained chunk-wise from the thread-safe `fill(dst, first, count)` into the columns.
 // *unsorted_out is set if ids were found out of order.
+// max_workers > 0 caps the reader threads (a sharded table loads its shards side by side and divides the readers among them).
 template <typename Fill>
-static int ingest_rows(aqe_db* db, uint64_t n, Fill fill, bool* unsorted_out) {
+static int ingest_rows(aqe_db* db, uint64_t n, Fill fill, bool* unsorted_out, int max_workers = 0) {
     int rc = alloc_columns(db, n, 0x1f);
     if (rc) return rc;
     *unsorted_out = false;
@@ -243,6 +272,7 @@ static int ingest_rows(aqe_db* db, uint64_t n, Fill fill, bool* unsorted_out) {
     const uint64_t nchunks = (n + IngestWorker::kChunkRows - 1) / IngestWorker::kChunkRows;
     int W = env_int("AQE_INGEST_THREADS", 0);
     if (W <= 0) W = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    if (max_workers > 0) W = std::min(W, max_workers);
     W = (int)std::min<uint64_t>((uint64_t)W, nchunks);
     unsigned int* unsorted = nullptr;
     CU(cudaMalloc(&unsorted, 4));
@@ -253,7 +283,8 @@ static int ingest_rows(aqe_db* db, uint64_t n, Fill fill, bool* unsorted_out) {
     if (lease.rc) { cudaFree(unsorted); return lease.rc; }
     std::vector<IngestWorker*>& workers = lease.workers;
     for (IngestWorker* w : workers) { w->rc = AQE_OK; w->err.clear(); }
-    std::vector<int64_t> first_id(nchunks), last_id(nchunks);
+    std::vector<int64_t> first_id, last_id;
+    try { first_id.resize(nchunks); last_id.resize(nchunks); } catch (const std::bad_alloc&) { cudaFree(unsorted); return fail(AQE_ERR_NOMEM, "out of host memory"); }
     const int device = db->device;
     const MutColumns cols = db->col;
     const int sm_count = db->sm_count;
@@ -284,8 +315,14 @@ static int ingest_rows(aqe_db* db, uint64_t n, Fill fill, bool* unsorted_out) {
     body(0);
     for (auto& t : threads) t.join();
     CU(cudaSetDevice(db->device));
+    // a worker that gave up (short read, CUDA error) may still have copies / kernels in flight on its stream: drain every stream
+    // before the staging buffers go back to the pool and the flag buffer is freed
+    bool any_failed = false;
+    for (IngestWorker* w : workers) any_failed = any_failed || w->rc != AQE_OK;
+    if (any_failed)
+        for (IngestWorker* w : workers) cudaStreamSynchronize(w->stream);
     for (IngestWorker* w : workers)
-        if (w->rc) { cudaFree(unsorted); return fail(w->rc, w->err); }
+        if (w->rc) { cudaFree(unsorted); cudaGetLastError(); return fail(w->rc, w->err); }
     unsigned int flag = 0;
     CU(cudaMemcpy(&flag, unsorted, 4, cudaMemcpyDeviceToHost));
     cudaFree(unsorted);
@@ -301,8 +338,11 @@ static int upload_host_rows(aqe_db* db, const aqe_record* rows, uint64_t n) {
     if (rc) return rc;
     if (unsorted) {
         // load_from_file -> insert_batch orders rows by id (custom_bplus_db.cpp:198-200); stable here
-        std::vector<aqe_record> sorted(rows, rows + n);
-        std::stable_sort(sorted.begin(), sorted.end(), [](const aqe_record& a, const aqe_record& b) { return a.id < b.id; });
+        std::vector<aqe_record> sorted;
+        try {
+            sorted.assign(rows, rows + n);
+            std::stable_sort(sorted.begin(), sorted.end(), [](const aqe_record& a, const aqe_record& b) { return a.id < b.id; });
+        } catch (const std::bad_alloc&) { return fail(AQE_ERR_NOMEM, "out of host memory while ordering rows by id"); }
         rc = ingest_rows(db, n, [&](aqe_record* dst, uint64_t first, uint64_t cnt) { std::memcpy(dst, sorted.data() + first, cnt * sizeof(aqe_record)); return true; }, &unsorted);
     }
     return rc;
@@ -310,6 +350,7 @@ static int upload_host_rows(aqe_db* db, const aqe_record* rows, uint64_t n) {
 
 // Brings rows appended on the host (insert_record / insert_batch) onto the device.
 static int ensure_device(aqe_db* db) {
+    if (db->group) return group_ensure_device(db);
     int rc = db_init_cuda(db);
     if (rc) return rc;
     if (!db->host_authoritative) return AQE_OK;
@@ -334,6 +375,7 @@ static int col_kind_of(int col) {  // 0 f64, 1 i64, 2 i32
 extern "C" {
 
 int aqe_abi_version(void) { return AQE_ABI_VERSION; }
+const char* aqe_last_scan_kernel(void) { return g_scan_kernel.c_str(); }
 const char* aqe_last_error(void) { return g_err.c_str(); }
 uint64_t aqe_launch_count(void) { return g_launches.load(); }
 
@@ -366,6 +408,7 @@ int aqe_create(int device, aqe_db** out) {
 
 int aqe_close(aqe_db* db) {
     if (!db) return AQE_OK;
+    if (db->group) group_close(db);
     if (db->cuda_ready) {
         cudaSetDevice(db->device);
         cudaStreamSynchronize(db->stream);
@@ -375,7 +418,7 @@ int aqe_close(aqe_db* db) {
         cudaFree(db->sql_acc); cudaFree(db->sql_stat_dev); cudaFree(db->sql_ticket); cudaFree(db->sql_local);
         if (db->sql_out_host) cudaFreeHost(db->sql_out_host);
         for (int r = 0; r < db->ex_world; ++r)
-            if (db->ex_connected && r != db->ex_rank && db->ex_peers[r]) cudaIpcCloseMemHandle(db->ex_peers[r]);
+            if (db->ex_connected && db->ex_ipc && r != db->ex_rank && db->ex_peers[r]) cudaIpcCloseMemHandle(db->ex_peers[r]);
         cudaFree(db->ex_mailbox);
         cudaFreeHost(db->slot_host);
         cudaEventDestroy(db->ev0); cudaEventDestroy(db->ev1);
@@ -385,11 +428,12 @@ int aqe_close(aqe_db* db) {
     return AQE_OK;
 }
 
-int aqe_load_file(aqe_db* db, const char* path, uint64_t first_row, uint64_t n_rows) {
-    if (!db || !path) return fail(AQE_ERR_INVALID, "NULL argument");
-    const int fd = ::open(path, O_RDONLY);
-    if (fd < 0) return fail(AQE_ERR_IO, std::string("cannot open ") + path);
-    auto read_at = [fd](void* dst, size_t bytes, uint64_t off) {
+// The record file: header (total, height, count) + count 32-byte rows (custom_bplus_db.cpp:665-683).
+struct RecordFile {
+    int fd = -1;
+    uint64_t total = 0;   // record_count; the first two header words are ignored (custom_bplus_db.cpp:692-698)
+    ~RecordFile() { if (fd >= 0) ::close(fd); }
+    bool read_at(void* dst, size_t bytes, uint64_t off) const {
         char* p = static_cast<char*>(dst);
         while (bytes) {
             const ssize_t k = ::pread(fd, p, bytes, (off_t)off);
@@ -397,23 +441,41 @@ int aqe_load_file(aqe_db* db, const char* path, uint64_t first_row, uint64_t n_r
             p += k; off += (uint64_t)k; bytes -= (size_t)k;
         }
         return true;
-    };
-    uint64_t hdr[3];
-    if (!read_at(hdr, 24, 0)) { ::close(fd); return fail(AQE_ERR_IO, std::string("short header in ") + path); }
-    int rc = db_init_cuda(db);
-    if (rc) { ::close(fd); return rc; }
-    const uint64_t total = hdr[2];  // record_count; the first two words are ignored (custom_bplus_db.cpp:692-698)
-    if (first_row > total) first_row = total;
-    const uint64_t n = std::min<uint64_t>(n_rows, total - first_row);
+    }
+    bool read_rows(aqe_record* dst, uint64_t first, uint64_t cnt) const { return read_at(dst, cnt * sizeof(aqe_record), 24 + first * 32); }
+    int open(const char* path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) return fail(AQE_ERR_IO, std::string("cannot open ") + path);
+        uint64_t hdr[3];
+        if (!read_at(hdr, 24, 0)) return fail(AQE_ERR_IO, std::string("short header in ") + path);
+        struct stat st;
+        // the header's row count sizes every allocation below: it must fit the file
+        if (::fstat(fd, &st) != 0 || (uint64_t)st.st_size < 24 || hdr[2] > ((uint64_t)st.st_size - 24) / 32)
+            return fail(AQE_ERR_IO, std::string("record count in the header exceeds the file: ") + path);
+        total = hdr[2];
+        return AQE_OK;
+    }
+};
+
+int aqe_load_file(aqe_db* db, const char* path, uint64_t first_row, uint64_t n_rows) {
+    if (!db || !path) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (db->group) return group_load_file(db, path, first_row, n_rows);
+    RecordFile f;
+    int rc = f.open(path);
+    if (rc) return rc;
+    rc = db_init_cuda(db);
+    if (rc) return rc;
+    if (first_row > f.total) first_row = f.total;
+    const uint64_t n = std::min<uint64_t>(n_rows, f.total - first_row);
     db->host_rows.clear(); db->host_authoritative = false;
     bool unsorted = false;
-    rc = ingest_rows(db, n, [&](aqe_record* dst, uint64_t first, uint64_t cnt) { return read_at(dst, cnt * sizeof(aqe_record), 24 + (first_row + first) * 32); }, &unsorted);
+    rc = ingest_rows(db, n, [&](aqe_record* dst, uint64_t first, uint64_t cnt) { return f.read_rows(dst, first_row + first, cnt); }, &unsorted);
     if (rc == AQE_OK && unsorted) {
-        std::vector<aqe_record> rows(n);
-        if (!read_at(rows.data(), n * sizeof(aqe_record), 24 + first_row * 32)) rc = fail(AQE_ERR_IO, "re-read failed");
+        std::vector<aqe_record> rows;
+        try { rows.resize(n); } catch (const std::bad_alloc&) { return fail(AQE_ERR_NOMEM, "out of host memory while ordering rows by id"); }
+        if (!f.read_rows(rows.data(), first_row, n)) rc = fail(AQE_ERR_IO, "re-read failed");
         else rc = upload_host_rows(db, rows.data(), n);
     }
-    ::close(fd);
     return rc;
 }
 
@@ -443,6 +505,7 @@ int aqe_append_records(aqe_db* db, const aqe_record* rows, size_t n) {
 
 int aqe_from_host_records(aqe_db* db, const aqe_record* rows, size_t n) {
     if (!db || (!rows && n)) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (db->group) return group_from_host_records(db, rows, n);
     int rc = db_init_cuda(db);
     if (rc) return rc;
     db->host_rows.clear(); db->host_authoritative = false;
@@ -452,6 +515,7 @@ int aqe_from_host_records(aqe_db* db, const aqe_record* rows, size_t n) {
 int aqe_attach_device_columns(aqe_db* db, const int64_t* id, const double* amount, const int32_t* region,
                               const int32_t* product_id, const int64_t* timestamp, uint64_t n) {
     if (!db) return fail(AQE_ERR_INVALID, "NULL handle");
+    if (db->group) return group_unsupported("aqe_attach_device_columns");
     int rc = db_init_cuda(db);
     if (rc) return rc;
     free_columns(db);
@@ -465,6 +529,7 @@ int aqe_attach_device_columns(aqe_db* db, const int64_t* id, const double* amoun
 
 int aqe_generate_synthetic(aqe_db* db, uint64_t seed, uint64_t first_row, uint64_t n_rows, int dist, uint32_t columns_mask) {
     if (!db) return fail(AQE_ERR_INVALID, "NULL handle");
+    if (db->group) return group_generate(db, seed, first_row, n_rows, dist, columns_mask ? columns_mask : 0x1f);
     int rc = db_init_cuda(db);
     if (rc) return rc;
     db->host_rows.clear(); db->host_authoritative = false;
@@ -492,6 +557,7 @@ int aqe_device(const aqe_db* db) { return db ? db->device : -1; }
 
 const void* aqe_column_device_ptr(aqe_db* db, int col) {
     if (!db || ensure_device(db)) return nullptr;
+    if (db->group) { group_unsupported("aqe_column_device_ptr"); return nullptr; }
     switch (col) {
         case AQE_COL_ID: return db->col.id;
         case AQE_COL_AMOUNT: return db->col.amount;
@@ -520,6 +586,7 @@ int aqe_read_records(aqe_db* db, uint64_t first, uint64_t n, aqe_record* out) {
         int rc = ensure_device(db);
         if (rc) return rc;
     }
+    if (db->group) return group_read_records(db, first, n, out);
     int rc = db_init_cuda(db);
     if (rc) return rc;
     if (first + n > db->n) return fail(AQE_ERR_INVALID, "row range out of bounds");
@@ -541,6 +608,7 @@ int aqe_read_column(aqe_db* db, int col, uint64_t first, uint64_t n, void* out) 
     if (!db || (!out && n)) return fail(AQE_ERR_INVALID, "NULL argument");
     int rc = ensure_device(db);
     if (rc) return rc;
+    if (db->group) return group_read_column(db, col, first, n, out);
     const int k = col_kind_of(col);
     const char* base = static_cast<const char*>(aqe_column_device_ptr(db, col));
     if (k < 0 || !base) return fail(AQE_ERR_STATE, "column is not resident on the device");
@@ -554,19 +622,23 @@ int aqe_read_column(aqe_db* db, int col, uint64_t first, uint64_t n, void* out) 
 int aqe_save_file(aqe_db* db, const char* path) {
     if (!db || !path) return fail(AQE_ERR_INVALID, "NULL argument");
     const uint64_t n = aqe_count(db);
-    std::vector<aqe_record> rows(n);
-    if (n) {
-        int rc = ensure_device(db);
-        if (rc) return rc;
-        rc = aqe_read_records(db, 0, n, rows.data());
-        if (rc) return rc;
-    }
+    // rows stream through a bounded buffer (k_soa_to_aos -> D2H -> fwrite per 4 M rows): a 1 B-row table never needs its
+    // 32 GB on the host at once
+    const uint64_t chunk = 1u << 22;
+    std::vector<aqe_record> buf;
+    try { buf.resize((size_t)std::min<uint64_t>(n, chunk)); } catch (const std::bad_alloc&) { return fail(AQE_ERR_NOMEM, "out of host memory"); }
     FILE* f = std::fopen(path, "wb");
     if (!f) return fail(AQE_ERR_IO, std::string("cannot create ") + path);
     const uint64_t hdr[3] = {n, tree_height(n), n};  // custom_bplus_db.cpp:669-676
     bool ok = std::fwrite(hdr, 8, 3, f) == 3;
-    if (ok && n) ok = std::fwrite(rows.data(), sizeof(aqe_record), n, f) == n;
+    int rc = AQE_OK;
+    for (uint64_t off = 0; ok && rc == AQE_OK && off < n; off += chunk) {
+        const uint64_t cnt = std::min<uint64_t>(chunk, n - off);
+        rc = aqe_read_records(db, off, cnt, buf.data());
+        if (rc == AQE_OK) ok = std::fwrite(buf.data(), sizeof(aqe_record), cnt, f) == cnt;
+    }
     ok = (std::fclose(f) == 0) && ok;
+    if (rc) return rc;
     return ok ? AQE_OK : fail(AQE_ERR_IO, std::string("write failed: ") + path);
 }
 
@@ -622,9 +694,11 @@ static int kernel_occupancy(const void* kernel, int threads, size_t smem) {
     return occ;
 }
 
+template <typename T> static const char* type_name() { return std::is_same_v<T, double> ? "double" : (sizeof(T) == 8 ? "int64" : "int32"); }
 template <typename K> static int launch_regs_kernel(const aqe_db* db, K kernel, const ScanArgs& a, int W, int U, int bps_req, cudaStream_t s) {
     const int occ = kernel_occupancy((const void*)kernel, kScanThreads, 0);
     const int bps = bps_req > 0 ? std::min(bps_req, occ) : occ;
+    g_scan_kernel += " grid=" + std::to_string(grid_for(db, a.n / W, U, kScanThreads, bps)) + " x " + std::to_string(kScanThreads) + " threads";
     kernel<<<grid_for(db, a.n / W, U, kScanThreads, bps), kScanThreads, 0, s>>>(a);
     LAUNCHED();
     return AQE_OK;
@@ -636,7 +710,22 @@ template <typename K> static int launch_ring_kernel(const aqe_db* db, K kernel, 
     const uint64_t ntiles = (a.n + rows_per_tile - 1) / rows_per_tile;
     int grid = (int)std::min<uint64_t>((uint64_t)db->sm_count * bps, std::max<uint64_t>(ntiles, 1));
     if (grid > db->max_grid) grid = db->max_grid;
-    kernel<<<grid, kBulkThreads, smem, s>>>(a);
+    g_scan_kernel += " grid=" + std::to_string(grid) + " x " + std::to_string(kBulkThreads) + " threads (" + std::to_string(bps) + " CTAs/SM), " + std::to_string(smem) +
+                     " B dynamic smem" + (a.pdl_tail ? ", programmatic dependent launch" : "");
+    if (a.pdl_tail) {
+        // programmatic stream serialization: this launch may begin while the previous kernel of the stream is still draining (it
+        // said so with griddepcontrol.launch_dependents); see ScanArgs::pdl_tail for what keeps that safe
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kBulkThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, kernel, a));
+    } else {
+        kernel<<<grid, kBulkThreads, smem, s>>>(a);
+    }
     LAUNCHED();
     return AQE_OK;
 }
@@ -649,6 +738,12 @@ template <typename K> static int launch_ring_kernel(const aqe_db* db, K kernel, 
 template <typename AggT, int PRED, typename PredT, bool MOMENTS>
 static int launch_scan_t(const aqe_db* db, const ScanArgs& a, bool aligned, cudaStream_t s) {
     const ScanTuning t = scan_tuning();
+    {
+        char buf[160];
+        std::snprintf(buf, sizeof(buf), "<%s, PRED=%d, %s, MOMENTS=%d>", type_name<AggT>(), PRED, type_name<PredT>(), MOMENTS ? 1 : 0);
+        g_scan_kernel = std::string(!aligned ? "aqe::k_scan_unaligned" : (t.variant == 0 || t.variant == 2 ? "aqe::k_scan_ring (TMA bulk-copy ring)" : "aqe::k_scan (register-staged)")) + buf;
+        if (aligned && (t.variant == 0 || t.variant == 2)) g_scan_kernel += " STAGES=" + std::to_string(t.variant == 0 ? 4 : t.stages) + " x 16 KiB";
+    }
     if (!aligned) {
         const int grid = grid_for(db, a.n, 8, kScanThreads, 8);
         k_scan_unaligned<AggT, PRED, PredT, MOMENTS><<<grid, kScanThreads, 0, s>>>(a);
@@ -734,13 +829,16 @@ static int scan_launch(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, ui
         a.ex.seq = ++db->ex_seq;
         a.ex.timeout_cycles = (unsigned long long)env_int("AQE_EXCHANGE_TIMEOUT_MS", 5000) * 2000000ull;
         for (int r = 0; r < db->ex_world; ++r) a.ex.peers[r] = db->ex_peers[r];
-        a.ex.status = db->tickets + 3;
+        a.ex.status = &db->slot_dev->flags[0];
     }
     a.agg = agg ? agg + first * kind_size(ak) : nullptr;
     a.pred = pred ? pred + first * kind_size(pk) : nullptr;
     a.n = n; a.lo = spec->lo; a.hi = spec->hi;
     integer_bounds(spec->lo, spec->hi, &a.ilo, &a.ihi);
     a.partials = db->scan_partials; a.ticket = db->tickets + 0; a.out = out_dev;
+    // back-to-back scans overlap their tails (programmatic dependent launch) when the columns are the handle's own: borrowed columns
+    // may have been written by the caller's previous kernel on this stream, which only a full stream dependency orders
+    a.pdl_tail = db->owned ? (unsigned int)std::max(0, env_int("AQE_SCAN_PDL_TILES", 8)) : 0u;
     // 256-bit vector loads on every column
     auto aligned_for = [](const void* p, int) { return ((uintptr_t)p % 32) == 0; };
     const bool aligned = aligned_for(a.agg, ak) && (pred_mode != 2 || aligned_for(a.pred, pk));
@@ -754,6 +852,7 @@ static int scan_launch(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, ui
 }
 
 static int scan_sync(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, uint64_t n, bool moments, aqe_partial* out) {
+    if (db->group) return group_scan_range(db, spec, first, n, moments, out);
     const uint64_t kSeg = 1ull << 32;  // integer aggregates: one launch is exact up to 2^32 rows; longer shards go in segments
     if (col_kind(spec->agg_col) > K_F64 && n > kSeg) {
         std::vector<aqe_partial> parts;
@@ -783,6 +882,7 @@ int aqe_scan(aqe_db* db, const aqe_scan_spec* spec, aqe_partial* out) {
 
 int aqe_scan_async(aqe_db* db, const aqe_scan_spec* spec, void* partial_dev, void* stream) {
     if (!db || !spec || !partial_dev) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (db->group) return group_unsupported("aqe_scan_async");
     int rc = ensure_device(db);
     if (rc) return rc;
     return scan_launch(db, spec, 0, db->n, false, static_cast<aqe_partial*>(partial_dev), stream ? (cudaStream_t)stream : db->stream);
@@ -790,6 +890,7 @@ int aqe_scan_async(aqe_db* db, const aqe_scan_spec* spec, void* partial_dev, voi
 
 int aqe_exchange_init(aqe_db* db, int rank, int world, void* ipc_handle_out) {
     if (!db || !ipc_handle_out) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (db->group) return group_unsupported("aqe_exchange_init (the shards of a sharded handle are already connected)");
     if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(AQE_ERR_INVALID, "rank/world out of range (at most 16 ranks)");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
     int rc = db_init_cuda(db);
@@ -809,6 +910,7 @@ int aqe_exchange_init(aqe_db* db, int rank, int world, void* ipc_handle_out) {
 
 int aqe_exchange_connect(aqe_db* db, const void* all_handles) {
     if (!db || !all_handles) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (db->group) return group_unsupported("aqe_exchange_connect");
     if (!db->ex_mailbox) return fail(AQE_ERR_STATE, "call aqe_exchange_init first");
     CU(cudaSetDevice(db->device));
     for (int r = 0; r < db->ex_world; ++r) {
@@ -819,35 +921,36 @@ int aqe_exchange_connect(aqe_db* db, const void* all_handles) {
         CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         db->ex_peers[r] = static_cast<ExSlot*>(p);
     }
-    db->ex_connected = true;
+    db->ex_connected = true; db->ex_ipc = true;
     return AQE_OK;
 }
 
 int aqe_scan_exchange_async(aqe_db* db, const aqe_scan_spec* spec, void* merged_dev, void* stream) {
     if (!db || !spec || !merged_dev) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (db->group) return group_unsupported("aqe_scan_exchange_async");
     int rc = ensure_device(db);
     if (rc) return rc;
     return scan_launch(db, spec, 0, db->n, false, static_cast<aqe_partial*>(merged_dev), stream ? (cudaStream_t)stream : db->stream, db->ex_world > 1);
 }
 
 int aqe_exchange_check(aqe_db* db) {
+    if (db && db->group) return AQE_OK;
     if (!db || !db->cuda_ready) return fail(AQE_ERR_STATE, "no device state");
-    unsigned int st = 0;
-    CU(cudaMemcpy(&st, db->tickets + 3, 4, cudaMemcpyDeviceToHost));
-    if (st) { cudaMemset(db->tickets + 3, 0, 4); return fail(AQE_ERR_CUDA, "fused exchange timed out waiting for a peer rank"); }
+    CU(cudaSetDevice(db->device));
+    CU(cudaStreamSynchronize(db->stream));   // the flag lives in the mapped pinned slot: no copy, but the kernels must have finished
+    if (db->slot_host->flags[0]) { db->slot_host->flags[0] = 0; return fail(AQE_ERR_CUDA, "fused exchange timed out waiting for a peer rank"); }
     return AQE_OK;
 }
 
 int aqe_scan_exchange(aqe_db* db, const aqe_scan_spec* spec, aqe_partial* out) {
     if (!db || !spec || !out) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (db->group) return aqe_scan(db, spec, out);   // a sharded handle exchanges inside every scan
     int rc = ensure_device(db);
     if (rc) return rc;
     rc = scan_launch(db, spec, 0, db->n, true, &db->slot_dev->partial, db->stream, db->ex_world > 1);
     if (rc) return rc;
     CU(cudaStreamSynchronize(db->stream));
-    unsigned int st = 0;
-    CU(cudaMemcpy(&st, db->tickets + 3, 4, cudaMemcpyDeviceToHost));
-    if (st) { cudaMemset(db->tickets + 3, 0, 4); return fail(AQE_ERR_CUDA, "fused exchange timed out waiting for a peer rank"); }
+    if (db->slot_host->flags[0]) { db->slot_host->flags[0] = 0; return fail(AQE_ERR_CUDA, "fused exchange timed out waiting for a peer rank"); }
     *out = db->slot_host->partial;
     return AQE_OK;
 }
@@ -1000,7 +1103,7 @@ int aqe_scan_host_column(int device, const void* host_col, int col_kind_id, uint
         CU(cudaMemcpyAsync(c->dev[b], src, cnt * esz, cudaMemcpyHostToDevice, c->streams[b]));
         ScanArgs a;
         std::memset(&a.ex, 0, sizeof(a.ex));
-        a.agg = c->dev[b]; a.pred = nullptr; a.n = cnt; a.lo = lo; a.hi = hi;
+        a.agg = c->dev[b]; a.pred = nullptr; a.n = cnt; a.lo = lo; a.hi = hi; a.pdl_tail = 0;   // the chunk was just copied in on this stream
         integer_bounds(lo, hi, &a.ilo, &a.ihi);
         a.partials = b ? c->partials2 : db->scan_partials;
         a.ticket = b ? c->tickets2 : db->tickets + 1;
@@ -1054,30 +1157,60 @@ static int plan_to_device(aqe_db* db, const aqe_plan* pl, PlanDev* out) {
 }
 
 static int check_plan_bounds(const aqe_db* db, const aqe_plan* pl) {
-    // explicit lists supplied by callers are validated; generated plans are in range by construction
-    for (int64_t v : pl->idx)
-        if (v < 0 || (uint64_t)v >= db->n) return fail(AQE_ERR_INVALID, "sample index out of range");
+    // A generated plan is in range for the table size it was built for (and for every larger table); used on a smaller table
+    // -- after a reload, or built with an explicit n_rows -- its segments would expand to rows the columns do not have.
+    if (pl->n_rows > db->n) return fail(AQE_ERR_INVALID, "sample plan was built for " + std::to_string(pl->n_rows) + " rows, the table holds " + std::to_string(db->n));
+    // explicit lists supplied by callers are validated
+    if (pl->n_rows == 0)
+        for (int64_t v : pl->idx)
+            if (v < 0 || (uint64_t)v >= db->n) return fail(AQE_ERR_INVALID, "sample index out of range");
     return AQE_OK;
 }
 
 static int ensure_amount_perm(aqe_db* db);  // below (stratified)
 
-static int stats_launch(aqe_db* db, const aqe_plan* pl, int col, aqe_stats* out, int pred_col = AQE_COL_NONE, double lo = 0.0, double hi = 0.0) {
+// The rows of the table this handle holds, as a sample plan sees them: a plain handle holds the whole table; a shard of a
+// range-sharded table holds the window [first, first + n) and reads the amount-sorted permutation of the WHOLE table.
+struct PlanWindow {
+    uint64_t first = 0, n = ~0ull;
+    const int64_t* perm = nullptr;   // by_amount_order plans of a sharded table: the table-level permutation (peer mapped)
+};
+
+// Moments over the plan's positions: finished (`out`, whole table on this handle) or, with `raw`, the mergeable sums of the
+// positions inside the window (aqe_stats_merge).  Synchronous.
+static int stats_launch(aqe_db* db, const aqe_plan* pl, int col, aqe_stats* out, int pred_col = AQE_COL_NONE, double lo = 0.0, double hi = 0.0,
+                        const PlanWindow* win = nullptr, aqe_stats_partial* raw = nullptr) {
     if (col_kind(col) < 0) return fail(AQE_ERR_INVALID, "bad column");
-    if (pred_col != AQE_COL_NONE && (col_kind(pred_col) < 0 || !col_ptr(db, pred_col))) return fail(AQE_ERR_INVALID, "bad predicate column");
-    if (!col_ptr(db, col) && pl->count) return fail(AQE_ERR_STATE, "column is not resident on the device");
-    if (pl->count == 0) { out->n = 0; out->mean = 0; out->m2 = 0; out->sum = 0; return AQE_OK; }
+    if (pred_col != AQE_COL_NONE && (col_kind(pred_col) < 0 || (!col_ptr(db, pred_col) && db->n))) return fail(AQE_ERR_INVALID, "bad predicate column");
+    if (!col_ptr(db, col) && pl->count && db->n) return fail(AQE_ERR_STATE, "column is not resident on the device");
+    if (raw) std::memset(raw, 0, sizeof(*raw));
+    if (pl->count == 0 || (raw && db->n == 0)) { if (out) { out->n = 0; out->mean = 0; out->m2 = 0; out->sum = 0; } return AQE_OK; }
     StatArgs a;
     int rc = plan_to_device(db, pl, &a.plan);
     if (rc) return rc;
-    if (pl->by_amount_order) { rc = ensure_amount_perm(db); if (rc) return rc; a.plan.perm = db->amount_perm; }
+    if (pl->by_amount_order) {
+        if (win && win->perm) a.plan.perm = win->perm;
+        else { rc = ensure_amount_perm(db); if (rc) return rc; a.plan.perm = db->amount_perm; }
+    }
     a.cols = const_cols(db); a.col = col; a.pred_col = pred_col; a.lo = lo; a.hi = hi; a.partials = db->stat_partials; a.ticket = db->tickets + 2; a.out = &db->slot_dev->stats;
-    const int grid = grid_for(db, pl->count, 4, 256, 8);
+    a.win_first = win ? win->first : 0; a.win_n = win ? std::min<uint64_t>(win->n, db->n) : ~0ull;
+    a.raw_out = raw ? &db->slot_dev->stats_raw : nullptr;
+    const int grid = grid_for(db, pl->count, 8, 256, 8);
     k_plan_stats<<<grid, 256, 0, db->stream>>>(a);
     LAUNCHED();
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(db->stream));
-    *out = db->slot_host->stats;
+    if (raw) *raw = db->slot_host->stats_raw;
+    else *out = db->slot_host->stats;
+    return AQE_OK;
+}
+
+// Rows [k_first, k_first + cnt) of the plan that fall into the window -> dst[k - k_first] (device-visible memory), on the
+// handle's stream, not synchronised.  `counter` (device-visible, may be NULL) receives the number of rows written.
+static int gather_kernel(aqe_db* db, const PlanDev& P, aqe_record* dst, uint64_t k_first, uint64_t cnt, const PlanWindow& win, unsigned long long* counter) {
+    k_plan_gather<<<grid_for(db, cnt, 2, 256, 8), 256, 0, db->stream>>>(P, const_cols(db), dst, k_first, cnt, win.first, std::min<uint64_t>(win.n, db->n), counter);
+    LAUNCHED();
+    CU(cudaGetLastError());
     return AQE_OK;
 }
 
@@ -1091,11 +1224,10 @@ static int gather_launch(aqe_db* db, const aqe_plan* pl, aqe_record* out, uint64
     const uint64_t chunk = 1u << 22;
     rc = ensure_gather_buf(db, std::min<uint64_t>(n, chunk));
     if (rc) return rc;
+    PlanWindow whole;
     for (uint64_t off = 0; off < n; off += chunk) {
         const uint64_t cnt = std::min<uint64_t>(chunk, n - off);
-        k_plan_gather<<<grid_for(db, cnt, 2, 256, 8), 256, 0, db->stream>>>(P, const_cols(db), db->gather_buf, off, cnt);
-        LAUNCHED();
-        CU(cudaGetLastError());
+        if ((rc = gather_kernel(db, P, db->gather_buf, off, cnt, whole, nullptr))) return rc;
         CU(cudaMemcpyAsync(out + off, db->gather_buf, cnt * sizeof(aqe_record), cudaMemcpyDeviceToHost, db->stream));
         CU(cudaStreamSynchronize(db->stream));
     }
@@ -1106,28 +1238,34 @@ static int gather_launch(aqe_db* db, const aqe_plan* pl, aqe_record* out, uint64
 __global__ void k_iota(int64_t* p, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (int64_t)i;
 }
-static int ensure_amount_perm(aqe_db* db) {
-    if (db->amount_perm || db->n == 0) return AQE_OK;
-    if (!db->col.amount) return fail(AQE_ERR_STATE, "amount column is not resident on the device");
-    const uint64_t n = db->n;
+// perm[r] = row with the r-th smallest amount among `keys[0, n)` (stable: ties keep ascending row order), on db's device / stream.
+static int sort_rows_by_amount(aqe_db* db, const double* keys, uint64_t n, int64_t** perm_out) {
     int64_t *iota = nullptr, *perm = nullptr;
     double* keys_out = nullptr;
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
-    CU(cudaMalloc(&iota, n * 8));
-    CU(cudaMalloc(&perm, n * 8));
-    CU(cudaMalloc(&keys_out, n * 8));
+    auto cleanup = [&](bool keep_perm) { cudaFree(tmp); cudaFree(iota); cudaFree(keys_out); if (!keep_perm) cudaFree(perm); };
+#define CUS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(false); return cuda_fail(e_, #call); } } while (0)
+    CUS(cudaMalloc(&iota, n * 8));
+    CUS(cudaMalloc(&perm, n * 8));
+    CUS(cudaMalloc(&keys_out, n * 8));
     k_iota<<<grid_for(db, n, 4, 256, 8), 256, 0, db->stream>>>(iota, n);
     LAUNCHED();
-    // stable LSD radix sort on the f64 keys: ties keep ascending row order
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, db->col.amount, keys_out, iota, perm, (int64_t)n, 0, 64, db->stream));
-    CU(cudaMalloc(&tmp, tmp_bytes));
-    CU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, db->col.amount, keys_out, iota, perm, (int64_t)n, 0, 64, db->stream));
+    // stable LSD radix sort on the f64 keys
+    CUS(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, iota, perm, (int64_t)n, 0, 64, db->stream));
+    CUS(cudaMalloc(&tmp, tmp_bytes));
+    CUS(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, iota, perm, (int64_t)n, 0, 64, db->stream));
     LAUNCHED();
-    CU(cudaStreamSynchronize(db->stream));
-    cudaFree(tmp); cudaFree(iota); cudaFree(keys_out);
-    db->amount_perm = perm;
+    CUS(cudaStreamSynchronize(db->stream));
+#undef CUS
+    cleanup(true);
+    *perm_out = perm;
     return AQE_OK;
+}
+static int ensure_amount_perm(aqe_db* db) {
+    if (db->amount_perm || db->n == 0) return AQE_OK;
+    if (!db->col.amount) return fail(AQE_ERR_STATE, "amount column is not resident on the device");
+    return sort_rows_by_amount(db, db->col.amount, db->n, &db->amount_perm);
 }
 
 // ---- lock-step stop step of clt_validated_dual_pointer_sample on the device ---------------------------------
@@ -1137,7 +1275,7 @@ static int ensure_amount_perm(aqe_db* db) {
 // thread the first step at which ITS OWN rule would fire given the published fast mean; the host then
 // resolves the global first stop in (step, thread) order.
 struct CltArgs {
-    const double* amount;
+    GlobalF64 amount;   // the whole table's amount column (one part on a plain handle, one per shard on a sharded one)
     CltThread th[64];
     int nthreads;
     int64_t check_interval, T;
@@ -1158,13 +1296,13 @@ __global__ void __launch_bounds__(1024) k_clt_prefix(const CltArgs a) {
     const uint64_t minn = t.fast ? 30 : 20;
     const uint64_t steps = t.len < a.max_steps ? t.len : a.max_steps;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const double K = t.len ? a.amount[t.first] : 0.0;
+    const double K = t.len ? a.amount.at(t.first) : 0.0;
     if (threadIdx.x == 0) { carry_d = 0.0; carry_dd = 0.0; }
     __syncthreads();
     for (uint64_t base = 0; base < steps; base += blockDim.x) {
         const uint64_t k = base + threadIdx.x;  // 0-based sample number
         double d = 0.0, dd = 0.0;
-        if (k < steps) { d = a.amount[t.first + k * t.step] - K; dd = d * d; }
+        if (k < steps) { d = a.amount.at(t.first + k * t.step) - K; dd = d * d; }
         // inclusive block scan of (d, dd)
         double pd = d, pdd = dd;
 #pragma unroll
@@ -1204,6 +1342,8 @@ __global__ void __launch_bounds__(1024) k_clt_prefix(const CltArgs a) {
     }
 }
 
+// `db`: a plain handle, or the sharded handle (then the walk runs on shard 0's GPU and reads the other shards' rows through
+// the peer mapping -- a latency-bound walk of a few thousand samples, not worth splitting).
 static int clt_resolve(aqe_db* db, const aqe_sample_params& P, PlanData& data) {
     std::vector<CltThread> th;
     int64_t T = 0;
@@ -1213,7 +1353,16 @@ static int clt_resolve(aqe_db* db, const aqe_sample_params& P, PlanData& data) {
     data.clt_kstop = 0; data.clt_stopper = -1;
     if (th.empty()) return AQE_OK;
     if (th.size() > 64) return fail(AQE_ERR_UNSUPPORTED, "clt_validated_dual_pointer_sample: at most 64 threads");
-    if (!db->col.amount) return fail(AQE_ERR_STATE, "amount column is not resident on the device");
+    GlobalF64 view;
+    std::memset(&view, 0, sizeof(view));
+    if (db->group) {
+        if ((rc = group_amount_view(db, &view))) return rc;
+        db = aqe_shard(db, 0);
+        CU(cudaSetDevice(db->device));
+    } else {
+        if (!db->col.amount) return fail(AQE_ERR_STATE, "amount column is not resident on the device");
+        view.base[0] = db->col.amount; view.first[0] = 0; view.first[1] = db->n; view.parts = 1;
+    }
     const int64_t ci = P.check_interval;
     const double z = P.confidence_level >= 0.99 ? 2.576 : (P.confidence_level >= 0.95 ? 1.96 : 1.645);  // cbd:911-912
     const int F = (int)(P.num_threads / 2);
@@ -1237,7 +1386,7 @@ static int clt_resolve(aqe_db* db, const aqe_sample_params& P, PlanData& data) {
             cap_checks = checks;
         }
         CltArgs a;
-        a.amount = db->col.amount; a.nthreads = (int)th.size();
+        a.amount = view; a.nthreads = (int)th.size();
         for (size_t q = 0; q < th.size(); ++q) a.th[q] = th[q];
         a.check_interval = ci; a.T = T; a.z = z; a.max_err = P.max_error_percent;
         a.mean_out = mean_d; a.err_out = err_d; a.max_checks = cap_checks; a.max_steps = end;
@@ -1338,6 +1487,7 @@ int aqe_plan_build(aqe_db* db, uint64_t n_rows, int method, const aqe_sample_par
     std::string err;
     const int rc = plan_build(n_rows, method, *p, data, *pl, err);
     if (rc) { delete pl; return fail(rc, err); }
+    pl->n_rows = n_rows;
     *out = pl;
     return AQE_OK;
 }
@@ -1353,6 +1503,7 @@ int aqe_plan_from_indices(const int64_t* idx, uint64_t n, aqe_plan** out) {
 }
 
 uint64_t aqe_plan_count(const aqe_plan* plan) { return plan ? plan->count : 0; }
+uint64_t aqe_plan_table_rows(const aqe_plan* plan) { return plan ? plan->n_rows : 0; }
 uint32_t aqe_plan_num_segments(const aqe_plan* plan) { return plan ? (uint32_t)plan->segs.size() : 0; }
 int aqe_plan_segments(const aqe_plan* plan, aqe_segment* out, uint32_t cap) {
     if (!plan || (!out && cap)) return fail(AQE_ERR_INVALID, "NULL argument");
@@ -1375,6 +1526,7 @@ int aqe_stats_from_plan(aqe_db* db, const aqe_plan* plan, int col, aqe_stats* ou
     if (rc) return rc;
     rc = check_plan_bounds(db, plan);
     if (rc) return rc;
+    if (db->group) return group_stats(db, plan, col, AQE_COL_NONE, 0.0, 0.0, out);
     return stats_launch(db, plan, col, out);
 }
 
@@ -1384,7 +1536,85 @@ int aqe_stats_from_plan_where(aqe_db* db, const aqe_plan* plan, int col, int pre
     if (rc) return rc;
     rc = check_plan_bounds(db, plan);
     if (rc) return rc;
+    if (db->group) return group_stats(db, plan, col, pred_col, lo, hi, out);
     return stats_launch(db, plan, col, out, pred_col, lo, hi);
+}
+
+// ---- one process per GPU: this handle is the window [window_first, window_first + n) of the plan's table ----
+int aqe_stats_window(aqe_db* db, const aqe_plan* plan, int col, int pred_col, double lo, double hi, uint64_t window_first, aqe_stats_partial* out) {
+    if (!db || !plan || !out) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (db->group) return group_unsupported("aqe_stats_window");
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    if (plan->by_amount_order) return fail(AQE_ERR_UNSUPPORTED, "plans in amount order (stratified_block_sample) need the whole table's permutation: use a sharded handle (aqe_create_sharded)");
+    if (plan->n_rows && window_first + db->n > plan->n_rows) return fail(AQE_ERR_INVALID, "window exceeds the table the plan was built for");
+    PlanWindow w;
+    w.first = window_first; w.n = db->n;
+    return stats_launch(db, plan, col, nullptr, pred_col, lo, hi, &w, out);
+}
+
+int aqe_stats_merge(const aqe_stats_partial* parts, int n, aqe_stats* out) {
+    if (!parts || !out || n < 0) return fail(AQE_ERR_INVALID, "bad argument");
+    // rank order.  sum x: double-double fold; mean / M2: Chan, Golub & LeVeque's pairwise update (each shard's moments are about
+    // its own shift K_g: mean_g = K_g + sd/n, M2_g = sdd - sd^2/n)
+    uint64_t N = 0;
+    double mean = 0.0, m2 = 0.0, s = 0.0, c = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const aqe_stats_partial& p = parts[i];
+        if (p.n == 0) continue;
+        volatile double t = s + p.sum;
+        volatile double z = t - s;
+        volatile double e = (s - (t - z)) + (p.sum - z);
+        c += p.sum_c + e;
+        s = t;
+        const double np = (double)p.n;
+        const double sd = p.sd + p.sd_c;
+        const double mean_p = p.shift + sd / np;
+        double m2_p = (p.sdd + p.sdd_c) - sd * sd / np;
+        if (m2_p < 0.0) m2_p = 0.0;
+        if (N == 0) { mean = mean_p; m2 = m2_p; }
+        else {
+            const double na = (double)N, tot = na + np, delta = mean_p - mean;
+            m2 += m2_p + delta * delta * (na * np / tot);
+            mean += delta * (np / tot);
+        }
+        N += p.n;
+    }
+    out->n = N;
+    out->sum = s + c;
+    out->mean = N ? out->sum / (double)N : 0.0;
+    out->m2 = m2;
+    return AQE_OK;
+}
+
+int aqe_gather_window(aqe_db* db, const aqe_plan* plan, uint64_t window_first, uint64_t k_first, uint64_t k_count, aqe_record* out, uint64_t* n_local) {
+    if (!db || !plan || (!out && k_count)) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (db->group) return group_unsupported("aqe_gather_window");
+    int rc = ensure_device(db);
+    if (rc) return rc;
+    if (plan->by_amount_order) return fail(AQE_ERR_UNSUPPORTED, "plans in amount order (stratified_block_sample) need the whole table's permutation: use a sharded handle (aqe_create_sharded)");
+    if (plan->n_rows && window_first + db->n > plan->n_rows) return fail(AQE_ERR_INVALID, "window exceeds the table the plan was built for");
+    if (k_first > plan->count || k_count > plan->count - k_first) return fail(AQE_ERR_INVALID, "plan range out of bounds");
+    if (plan->n_rows == 0)
+        for (int64_t v : plan->idx) if (v < 0) return fail(AQE_ERR_INVALID, "sample index out of range");
+    if (n_local) *n_local = 0;
+    if (k_count == 0) return AQE_OK;
+    PlanDev P;
+    if ((rc = plan_to_device(db, plan, &P))) return rc;
+    const uint64_t chunk = 1u << 22;
+    if ((rc = ensure_gather_buf(db, std::min<uint64_t>(k_count, chunk)))) return rc;
+    PlanWindow w;
+    w.first = window_first; w.n = db->n;
+    db->slot_host->gathered = 0;
+    for (uint64_t off = 0; off < k_count; off += chunk) {
+        const uint64_t cnt = std::min<uint64_t>(chunk, k_count - off);
+        CU(cudaMemsetAsync(db->gather_buf, 0, cnt * sizeof(aqe_record), db->stream));   // slots of other ranks' rows stay zero
+        if (db->n && (rc = gather_kernel(db, P, db->gather_buf, k_first + off, cnt, w, &db->slot_dev->gathered))) return rc;
+        CU(cudaMemcpyAsync(out + off, db->gather_buf, cnt * sizeof(aqe_record), cudaMemcpyDeviceToHost, db->stream));
+        CU(cudaStreamSynchronize(db->stream));
+    }
+    if (n_local) *n_local = db->slot_host->gathered;
+    return AQE_OK;
 }
 
 int aqe_stats_from_indices(aqe_db* db, const int64_t* idx, uint64_t n, int col, aqe_stats* out) {
@@ -1401,6 +1631,7 @@ int aqe_gather_plan(aqe_db* db, const aqe_plan* plan, aqe_record* out, uint64_t 
     if (rc) return rc;
     rc = check_plan_bounds(db, plan);
     if (rc) return rc;
+    if (db->group) return group_gather(db, plan, out, cap);
     return gather_launch(db, plan, out, cap);
 }
 
@@ -1421,8 +1652,9 @@ int aqe_fast_aggregated_sum(aqe_db* db, const aqe_sample_params* p, double* sum,
     std::string err;
     rc = plan_build(db->n, AQE_M_MULTITHREADED_MEMORY_STRIDE, *p, PlanData{}, pl, err);
     if (rc) return fail(rc, err);
+    pl.n_rows = db->n;
     aqe_stats st;
-    rc = stats_launch(db, &pl, AQE_COL_AMOUNT, &st);
+    rc = db->group ? group_stats(db, &pl, AQE_COL_AMOUNT, AQE_COL_NONE, 0.0, 0.0, &st) : stats_launch(db, &pl, AQE_COL_AMOUNT, &st);
     if (rc) return rc;
     if (sum) *sum = st.n ? st.sum : 0.0;  // raw, unscaled sample sum (custom_bplus_db.cpp:2045-2047)
     if (n) *n = st.n;
@@ -1473,12 +1705,21 @@ double aqe_z_score(double conf, int exact) {
 // ------------------------------------------------------------------------------------------------
 // K4
 // ------------------------------------------------------------------------------------------------
+// normal quantile the interval of a ci_mode is built from (include/aqe_b200.h, aqe_ci_mode) and whether it is Stein-type
+static double ci_z(double confidence_level, uint32_t ci_mode, int* stein) {
+    const uint32_t m = ci_mode == AQE_CI_DEFAULT ? (uint32_t)AQE_CI_STEIN_GUARDED : ci_mode;
+    if (stein) *stein = m != AQE_CI_PLAIN;
+    const double alpha = 1.0 - confidence_level;
+    return aqe_z_score(1.0 - (m == AQE_CI_STEIN_GUARDED ? AQE_CI_GUARD : 1.0) * alpha, 1);
+}
+
 static int approx_run(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* out, bool multi) {
     if (!db || !S || !out) return fail(AQE_ERR_INVALID, "NULL argument");
     std::memset(out, 0, sizeof(*out));
     if (!(S->error_percent > 0.0)) return fail(AQE_ERR_INVALID, "error_percent must be > 0");
     if (!(S->confidence_level > 0.0 && S->confidence_level < 1.0)) return fail(AQE_ERR_INVALID, "confidence_level must be in (0,1)");
     if (S->agg < 0 || S->agg > 2 || S->design < 0 || S->design > 1) return fail(AQE_ERR_INVALID, "bad agg / design");
+    if (S->ci_mode > AQE_CI_STEIN_GUARDED) return fail(AQE_ERR_INVALID, "bad ci_mode");
     const uint64_t N = aqe_count(db);
     const uint32_t B = S->design == AQE_DESIGN_BLOCK ? (S->block_size ? S->block_size : 1000) : 1;
     uint64_t rows_total = N, units_total = (N + B - 1) / B;
@@ -1496,7 +1737,7 @@ static int approx_run(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* o
     out->population = rows_total; out->confidence_level = S->confidence_level;
     if (rows_total == 0) { out->status = AQE_INSUFFICIENT_DATA; return AQE_OK; }
     if (S->agg == AQE_AGG_COUNT && S->pred_col == AQE_COL_NONE) {  // enhanced_aqe_cli.py:196-197: COUNT is exact
-        out->estimate = out->ci_lower = out->ci_upper = (double)rows_total; out->status = AQE_STABLE;
+        out->estimate = out->ci_lower = out->ci_upper = (double)rows_total; out->status = AQE_STABLE; out->pass_fraction = 1.0;
         return AQE_OK;
     }
     int rc = ensure_device(db);
@@ -1512,7 +1753,7 @@ static int approx_run(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* o
     a.block_rows = B;
     a.units = (N + B - 1) / B;
     a.design = S->design; a.agg = S->agg; a.agg_col = S->agg_col; a.pred_col = S->pred_col;
-    a.lo = S->lo; a.hi = S->hi; a.eps = S->error_percent; a.z = aqe_z_score(S->confidence_level, 1) * AQE_CI_CONSERVATIVE;
+    a.lo = S->lo; a.hi = S->hi; a.eps = S->error_percent; a.z = ci_z(S->confidence_level, S->ci_mode, &a.stein);
     a.seed = S->seed + (multi ? 0x9E3779B97F4A7C15ull * (uint64_t)db->ex_rank : 0ull);  // independent stream per stratum
     const uint64_t n0 = S->min_samples ? S->min_samples : (S->design == AQE_DESIGN_BLOCK ? 1024 : 16384);
     const uint64_t nmax = S->max_samples ? S->max_samples : units_total;
@@ -1534,13 +1775,14 @@ static int approx_run(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* o
         else v = part.count ? part.sum / (double)part.count : 0.0;
         out->estimate = out->ci_lower = out->ci_upper = v;
         out->n_samples = rows_total; out->n_units = units_total; out->status = AQE_STABLE;
+        out->pass_fraction = rows_total ? (double)part.count / (double)rows_total : 0.0;
         return AQE_OK;
     }
     if (multi) {
         a.ex.world = db->ex_world; a.ex.rank = db->ex_rank; a.ex.seq = db->ax_msg;
         a.ex.timeout_cycles = (unsigned long long)env_int("AQE_EXCHANGE_TIMEOUT_MS", 5000) * 2000000ull;
         for (int r = 0; r < db->ex_world; ++r) a.ex.peers[r] = db->ex_peers[r];
-        a.ex.status = db->tickets + 3;
+        a.ex.status = &db->slot_dev->flags[0];
     }
 
     static int coop_blocks_per_sm = 0;
@@ -1570,7 +1812,10 @@ static int approx_run(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* o
     return AQE_OK;
 }
 
-int aqe_approx(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* out) { return approx_run(db, S, out, false); }
+int aqe_approx(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* out) {
+    if (db && db->group) return group_approx(db, S, out);
+    return approx_run(db, S, out, false);
+}
 
 int aqe_exchange_set_total_rows(aqe_db* db, uint64_t total_rows) {
     if (!db) return fail(AQE_ERR_INVALID, "NULL handle");
@@ -1580,33 +1825,53 @@ int aqe_exchange_set_total_rows(aqe_db* db, uint64_t total_rows) {
 
 int aqe_approx_exchange(aqe_db* db, const aqe_approx_spec* S, aqe_approx_result* out) {
     if (!db) return fail(AQE_ERR_INVALID, "NULL handle");
+    if (db->group) return group_approx(db, S, out);
     return approx_run(db, S, out, db->ex_world > 1);
 }
 
 int aqe_approx_merge(const aqe_approx_result* parts, int n, int agg, double confidence_level, aqe_approx_result* out) {
     if (!parts || !out || n <= 0) return fail(AQE_ERR_INVALID, "bad argument");
-    // shards are strata: totals add, variances of the totals add (independent draws per shard)
-    const double z = aqe_z_score(confidence_level, 1) * AQE_CI_CONSERVATIVE;
+    // Shards are strata with independent draws: totals add, variances of the totals add.  AVG: each shard's estimate is the mean
+    // of ITS matching rows, so the weights are the shards' (estimated) matching-row counts population_g * pass_fraction_g -- the
+    // combined ratio estimator sum_g U_g ybar_g / sum_g U_g cbar_g the fused exchange evaluates (aqe_kernels.cuh, approx_global);
+    // without a predicate pass_fraction = 1 and the weights are the shard sizes.
+    const double z = ci_z(confidence_level, AQE_CI_DEFAULT, nullptr);
     aqe_approx_result r;
     std::memset(&r, 0, sizeof(r));
-    double total = 0.0, var_total = 0.0;
+    double total = 0.0, var_total = 0.0, wsum = 0.0, pass_rows = 0.0;
     uint64_t pop = 0;
     int worst = AQE_STABLE;
     for (int i = 0; i < n; ++i) {
         const aqe_approx_result& p = parts[i];
         const double half = (p.ci_upper - p.ci_lower) * 0.5;
-        const double w = agg == AQE_AGG_AVG ? (double)p.population : 1.0;  // AVG: weight shard means by N_g
+        const double w = agg == AQE_AGG_AVG ? (double)p.population * p.pass_fraction : 1.0;
         total += p.estimate * w;
         var_total += (half / z) * (half / z) * w * w;
+        wsum += w; pass_rows += (double)p.population * p.pass_fraction;
         pop += p.population; r.n_samples += p.n_samples; r.n_units += p.n_units;
         r.rounds = std::max(r.rounds, p.rounds); r.elapsed_us = std::max(r.elapsed_us, p.elapsed_us);
         if (p.status > worst) worst = p.status;
     }
-    if (agg == AQE_AGG_AVG && pop) { total /= (double)pop; var_total /= (double)pop * (double)pop; }
+    if (agg == AQE_AGG_AVG) {
+        if (wsum > 0.0) {
+            total /= wsum;
+            // the weights are estimates too: with e = y - R c (R the merged ratio) a shard contributes, besides w_g^2 Var(R_g), the term
+            // (U_g (R_g - R))^2 Var(cbar_g), Var(cbar_g) = p_g (1 - p_g) / n_g -- what the linearised residual of the fused path
+            // (approx_global, aqe_kernels.cuh) carries implicitly.  Zero without a predicate (p_g = 1).
+            for (int i = 0; i < n; ++i) {
+                const aqe_approx_result& p = parts[i];
+                if (p.n_samples == 0) continue;
+                const double u = (double)p.population * (p.estimate - total);
+                var_total += u * u * p.pass_fraction * (1.0 - p.pass_fraction) / (double)p.n_samples;
+            }
+            var_total /= wsum * wsum;
+        } else { total = 0.0; var_total = 0.0; }
+    }
     const double half = z * std::sqrt(var_total);
     r.estimate = total; r.ci_lower = total - half; r.ci_upper = total + half;
     r.error_margin = total != 0.0 ? half / std::fabs(total) : 0.0;
     r.confidence_level = confidence_level; r.population = pop; r.status = worst;
+    r.pass_fraction = pop ? pass_rows / (double)pop : 0.0;
     *out = r;
     return AQE_OK;
 }
@@ -1768,7 +2033,7 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
         ex.world = db->ex_world; ex.rank = db->ex_rank; ex.seq = ++db->sqlx_seq;
         ex.timeout_cycles = (unsigned long long)env_int("AQE_EXCHANGE_TIMEOUT_MS", 5000) * 2000000ull;
         for (int r = 0; r < db->ex_world; ++r) ex.peers[r] = reinterpret_cast<unsigned char*>(db->ex_peers[r]);
-        ex.status = db->tickets + 3; ex.local = db->sql_local;
+        ex.status = &db->slot_dev->flags[0]; ex.local = db->sql_local;
     }
     // a shard that has nothing to scan: without an exchange the zeros (or the metadata count) are the answer; with one it still
     // publishes them so that the other ranks' kernels are not left waiting
@@ -1951,6 +2216,10 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
     return exchange ? aqe_exchange_check(db) : AQE_OK;
 }
 
+static int sql_scan_any(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* L, int flags, uint64_t* acc) {
+    return db->group ? group_sql_scan(db, q, L, flags, acc) : sql_scan_impl(db, q, L, flags, acc);
+}
+
 extern "C" {
 
 int aqe_sql_parse(const char* sql, int sample_percent, aqe_sql_query* out) {
@@ -1965,6 +2234,7 @@ int aqe_sql_facts_of(aqe_db* db, const aqe_sql_query* q, aqe_sql_facts* out) {
     std::memset(out, 0, sizeof(*out));
     int rc = ensure_device(db);
     if (rc) return rc;
+    if (db->group) return group_sql_facts(db, q, out);
     rc = sql_init(db);
     if (rc) return rc;
     out->key_min = 0; out->key_max = db->n ? 0 : -1;
@@ -2010,13 +2280,14 @@ int aqe_sql_scan(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* layou
     if (!db || !q || !layout || !acc) return fail(AQE_ERR_INVALID, "NULL argument");
     int rc = ensure_device(db);
     if (rc) return rc;
-    return sql_scan_impl(db, q, layout, flags, acc);
+    return sql_scan_any(db, q, layout, flags, acc);
 }
 
 int aqe_sql_scan_exchange(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layout* layout, int flags, uint64_t* acc) {
     if (!db || !q || !layout || !acc) return fail(AQE_ERR_INVALID, "NULL argument");
     int rc = ensure_device(db);
     if (rc) return rc;
+    if (db->group) return group_sql_scan(db, q, layout, flags, acc);
     return sql_scan_impl(db, q, layout, flags, acc, db->ex_world > 1);
 }
 
@@ -2043,7 +2314,7 @@ int aqe_sql_execute(aqe_db* db, const aqe_sql_query* q, int mode, aqe_sql_row* r
     if ((rc = aqe_sql_layout_of(q, &facts, 1, &L))) return rc;
     std::vector<uint64_t> acc((size_t)L.n_groups * 5), exists;
     const int flags = sql_needs_moments(*q, mode) ? AQE_SQL_MOMENTS : 0;
-    if ((rc = sql_scan_impl(db, q, &L, flags, acc.data()))) return rc;
+    if ((rc = sql_scan_any(db, q, &L, flags, acc.data()))) return rc;
     const uint64_t* ex = nullptr;
     if (q->group_col != AQE_COL_NONE && sql_sample_step(q->sample_percent) > 1) {
         // a group none of whose rows were sampled still exists for the reference (SELECT DISTINCT runs unsampled)
@@ -2051,7 +2322,7 @@ int aqe_sql_execute(aqe_db* db, const aqe_sql_query* q, int mode, aqe_sql_row* r
         for (uint32_t g = 0; g < L.n_groups && !hole; ++g) hole = acc[(size_t)g * 5] == 0;
         if (hole) {
             exists.resize(acc.size());
-            if ((rc = sql_scan_impl(db, q, &L, AQE_SQL_UNSAMPLED, exists.data()))) return rc;
+            if ((rc = sql_scan_any(db, q, &L, AQE_SQL_UNSAMPLED, exists.data()))) return rc;
             ex = exists.data();
         }
     }
@@ -2066,3 +2337,8 @@ int aqe_sql_run(aqe_db* db, const char* sql, int sample_percent, int mode, aqe_s
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// the table over several GPUs of this process
+// ------------------------------------------------------------------------------------------------
+#include "aqe_group.inl"

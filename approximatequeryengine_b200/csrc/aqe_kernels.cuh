@@ -99,7 +99,7 @@ struct Exchange {
     unsigned long long seq;
     unsigned long long timeout_cycles;
     ExSlot* peers[kMaxRanks];  // peers[r] = rank r's mailbox as mapped in this process (peers[rank] = own)
-    unsigned int* status;      // set to 1 if a peer did not show up in time
+    unsigned int* status;      // set to 1 if a peer did not show up in time (a word of the handle's mapped pinned slot: the host reads it without a copy)
 };
 
 struct ScanArgs {
@@ -112,7 +112,35 @@ struct ScanArgs {
     unsigned int* ticket;   // zero before launch; reset by the last block
     aqe_partial* out;       // device-visible (device memory or mapped pinned host memory)
     Exchange ex;
+    // Programmatic dependent launch (back-to-back scans of one stream): > 0 = a CTA lets the NEXT scan of the stream start once it
+    // has this many tiles left, so the next query's first tiles stream while this one drains, folds and exchanges.  Everything a
+    // scan writes (block partials, ticket, mailboxes, result) happens behind griddep_wait(), i.e. after the previous scan has
+    // completed: stream order is kept for every side effect, only the read-only streaming overlaps.
+    unsigned int pdl_tail;
 };
+
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// (hi:lo) two's-complement 128-bit integer -> double, correctly rounded like the host's (double)(__int128): through the
+// magnitude, so a small negative total is not lost in the rounding of its 2^64-complement low word.
+__device__ __forceinline__ double i128_to_double(unsigned long long lo, long long hi) {
+    const bool neg = hi < 0;
+    unsigned long long mlo = lo, mhi = (unsigned long long)hi;
+    if (neg) { mlo = ~lo + 1ull; mhi = ~(unsigned long long)hi + (mlo == 0ull ? 1ull : 0ull); }
+    // mhi * 2^64 + mlo with ONE rounding: split mlo so that the partial sums below are exact, then add once
+    double r;
+    if (mhi == 0ull) r = __ull2double_rn(mlo);
+    else {
+        // 128-bit magnitude: normalise to 64 significant bits + sticky, convert, scale
+        const int lz = __clzll((long long)mhi);
+        unsigned long long top = lz ? ((mhi << lz) | (mlo >> (64 - lz))) : mhi;
+        const unsigned long long rest = lz ? (mlo << lz) : mlo;
+        if (rest) top |= 1ull;   // sticky bit: top has 64 bits, a double keeps 53, so bit 0 never reaches the mantissa
+        r = ldexp(__ull2double_rn(top), 64 - lz);
+    }
+    return neg ? -r : r;
+}
 
 // Fixed-rank-order fold of shard partials; the same IEEE operations as the host's aqe_merge_partials
 // (aqe_engine.cu), so device-merged and host-merged results are bit-identical.
@@ -140,7 +168,7 @@ __device__ __forceinline__ void merge_partials_dev(const aqe_partial* parts, int
     r.sum = t;
     r.sumsq = q;
     if (is_integer) {
-        r.sum = (double)r.isum_hi * 18446744073709551616.0 + (double)r.isum_lo;
+        r.sum = i128_to_double(r.isum_lo, r.isum_hi);
         r.comp = 0.0;
     }
     *out = r;
@@ -163,7 +191,7 @@ template <bool IS_INT> __device__ __forceinline__ void scan_write_out(const Scan
         const uint64_t lo = t.ilo + ((uint64_t)t.ihi << 32);
         const int64_t hi = (t.ihi >> 32) + (lo < t.ilo ? 1 : 0);
         r.isum_lo = lo; r.isum_hi = hi;
-        r.sum = (double)hi * 18446744073709551616.0 + (double)lo;
+        r.sum = i128_to_double(lo, hi);
         r.comp = 0.0; r.sumsq = 0.0; r.minv = 0.0; r.maxv = 0.0;
     } else {
         DD s = t.sum; dd_norm(s);
@@ -177,6 +205,7 @@ template <bool IS_INT> __device__ __forceinline__ void scan_write_out(const Scan
 // Second stage: the last block to finish folds the per-block partials in block order.
 template <bool IS_INT, bool MOMENTS> __device__ __forceinline__ void scan_finish(ScanAcc block_total, const ScanArgs& a, ScanAcc* sm) {
     __shared__ bool is_last;
+    griddep_wait();   // the previous scan of this stream (launched with programmatic serialization) has completed and is visible
     if (threadIdx.x == 0) {
         a.partials[blockIdx.x] = block_total;
         __threadfence();
@@ -225,7 +254,7 @@ template <bool IS_INT, bool MOMENTS> __device__ __forceinline__ void scan_finish
             if ((unsigned long long)(clock64() - t0) > a.ex.timeout_cycles) { ok = false; break; }
             __nanosleep(64);
         }
-        if (!ok) atomicExch(a.ex.status, 1u);
+        if (!ok) *(volatile unsigned int*)a.ex.status = 1u;
         const volatile unsigned long long* sp = reinterpret_cast<const volatile unsigned long long*>(&src->p);
         unsigned long long* dp = reinterpret_cast<unsigned long long*>(&sh_parts[threadIdx.x]);
 #pragma unroll
@@ -395,8 +424,13 @@ __global__ void __launch_bounds__(kBulkThreads) k_scan_ring(const ScanArgs a) {
     DD alt{0.0, 0.0};
     if (warp == kBulkConsumerWarps) {
         if (lane == 0) {
+            // tiles of this CTA: c = blockIdx.x + it * gridDim.x < ntiles
+            const uint64_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            const uint32_t pdl_at = a.pdl_tail ? (uint32_t)(my_tiles > a.pdl_tail ? my_tiles - a.pdl_tail : 0) : 0xffffffffu;
+            if (a.pdl_tail && my_tiles == 0) griddep_launch_dependents();
             uint32_t it = 0;
             for (uint64_t c = blockIdx.x; c < ntiles; c += gridDim.x, ++it) {
+                if (it == pdl_at) griddep_launch_dependents();   // this CTA has pdl_tail tiles left: the next scan of the stream may start
                 const int s = it % STAGES;
                 const uint32_t round = it / STAGES;
                 if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
@@ -482,6 +516,19 @@ __device__ __forceinline__ int64_t plan_position(const PlanDev& P, uint64_t k) {
     return pos;
 }
 
+// An f64 column of a table whose row ranges live in several allocations (the shards of a range-sharded table, mapped into
+// this GPU's address space by peer access): row i lives in the part p with first[p] <= i < first[p + 1].
+struct GlobalF64 {
+    const double* base[kMaxRanks];
+    uint64_t first[kMaxRanks + 1];
+    int parts;
+    __device__ __forceinline__ double at(uint64_t i) const {
+        int p = 0;
+        while (p + 1 < parts && i >= first[p + 1]) ++p;
+        return __ldg(base[p] + (i - first[p]));
+    }
+};
+
 struct Columns {
     const int64_t* id;
     const double* amount;
@@ -532,6 +579,11 @@ struct StatArgs {
     StatAcc* partials;
     unsigned int* ticket;
     aqe_stats* out;
+    // Range-sharded tables: the plan's positions are rows of the WHOLE table, `cols` hold rows [win_first, win_first + win_n)
+    // of it; positions outside the window belong to another shard and are skipped here (every shard walks the same plan, the
+    // gathers split).  The whole table on one GPU: win_first = 0, win_n = 2^64 - 1.
+    uint64_t win_first, win_n;
+    aqe_stats_partial* raw_out;  // windowed form: the shard's mergeable sums (aqe_stats_merge) instead of finished moments
 };
 
 __global__ void __launch_bounds__(256) k_plan_stats(const StatArgs a) {
@@ -539,32 +591,47 @@ __global__ void __launch_bounds__(256) k_plan_stats(const StatArgs a) {
     __shared__ bool is_last;
     const uint64_t G = (uint64_t)gridDim.x * blockDim.x;
     StatAcc acc = stat_identity();
-    auto value_at = [&](uint64_t k) {
-        const int64_t pos = plan_position(a.plan, k);
-        double x = column_value(a.cols, a.col, pos);
+    const bool windowed = a.raw_out != nullptr;
+    auto local_value = [&](int64_t row) {
+        double x = column_value(a.cols, a.col, row);
         if (a.pred_col != AQE_COL_NONE) {
-            const double pv = column_value(a.cols, a.pred_col, pos);
+            const double pv = column_value(a.cols, a.pred_col, row);
             x = (pv >= a.lo && pv <= a.hi) ? x : 0.0;
         }
         return x;
     };
+    // in[j]: position k is a row of this shard; x = its value (0 with in = false)
+    auto value_at = [&](uint64_t k, bool& in) {
+        const uint64_t u = (uint64_t)plan_position(a.plan, k) - a.win_first;
+        in = u < a.win_n;
+        return in ? local_value((int64_t)u) : 0.0;
+    };
+    // shift K: the plan's first sampled value; a shard of a larger table takes its own first row (any value of the data
+    // does: K only keeps sum d^2 - (sum d)^2 / n free of cancellation, the merge is exact about differing shifts)
     double K = 0.0;
-    if (a.plan.count) K = value_at(0);
-    // 4 independent gathers in flight per thread (random 8-byte reads are latency bound: one 32-byte sector each)
-    constexpr int GU = 4;
+    if (windowed) { if (a.win_n) K = column_value(a.cols, a.col, 0); }
+    else if (a.plan.count) { bool in; K = value_at(0, in); }
+    // 8 independent gathers in flight per thread.  A random 8-byte read costs a whole 128-byte line of L2 / DRAM traffic on B200
+    // (tools/microbench.cu under ncu: 4 sectors per load whatever the load form or the L2 fetch-granularity limit), so the ceiling
+    // is HBM bandwidth / 128 B, 48-56 G samples/s, reached only with many loads in flight (profiles/r2_mb_gather.jsonl)
+    constexpr int GU = 8;
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; k + (uint64_t)(GU - 1) * G < a.plan.count; k += (uint64_t)GU * G) {
         double x[GU];
+        bool in[GU];
 #pragma unroll
-        for (int j = 0; j < GU; ++j) x[j] = value_at(k + (uint64_t)j * G);
+        for (int j = 0; j < GU; ++j) x[j] = value_at(k + (uint64_t)j * G, in[j]);
 #pragma unroll
         for (int j = 0; j < GU; ++j) {
+            if (!in[j]) continue;
             const double d = __dadd_rn(x[j], -K);
             acc.n += 1; dd_add(acc.sx, x[j]); dd_add(acc.sd, d); dd_add(acc.sdd, __dmul_rn(d, d));
         }
     }
     for (; k < a.plan.count; k += G) {
-        const double x = value_at(k);
+        bool in;
+        const double x = value_at(k, in);
+        if (!in) continue;
         const double d = __dadd_rn(x, -K);
         acc.n += 1; dd_add(acc.sx, x); dd_add(acc.sd, d); dd_add(acc.sdd, __dmul_rn(d, d));
     }
@@ -580,7 +647,14 @@ __global__ void __launch_bounds__(256) k_plan_stats(const StatArgs a) {
     acc = stat_identity();
     for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) stat_merge(acc, load_cg(a.partials + b));
     acc = stat_block_reduce(acc, sm);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && windowed) {
+        dd_norm(acc.sx); dd_norm(acc.sd); dd_norm(acc.sdd);
+        aqe_stats_partial r;
+        r.n = acc.n; r.sum = acc.sx.s; r.sum_c = acc.sx.c; r.shift = K;
+        r.sd = acc.sd.s; r.sd_c = acc.sd.c; r.sdd = acc.sdd.s; r.sdd_c = acc.sdd.c;
+        *a.raw_out = r;
+        *a.ticket = 0u;
+    } else if (threadIdx.x == 0) {
         dd_norm(acc.sx); dd_norm(acc.sd); dd_norm(acc.sdd);
         aqe_stats r;
         r.n = acc.n; r.sum = acc.sx.s;
@@ -594,10 +668,17 @@ __global__ void __launch_bounds__(256) k_plan_stats(const StatArgs a) {
 }
 
 // K6: rows at plan positions, AoS, in plan order.
-__global__ void __launch_bounds__(256) k_plan_gather(const PlanDev plan, const Columns C, aqe_record* __restrict__ out, uint64_t first, uint64_t n) {
+// Sharded tables (win_*: see StatArgs): only positions inside this shard's window are written; every shard of the table writes its
+// own rows into the SAME output buffer (plan order), so the shards together fill it.
+__global__ void __launch_bounds__(256) k_plan_gather(const PlanDev plan, const Columns C, aqe_record* __restrict__ out, uint64_t first, uint64_t n,
+                                                     uint64_t win_first, uint64_t win_n, unsigned long long* counter) {
     const uint64_t G = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long wrote = 0;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += G) {
-        const int64_t i = plan_position(plan, first + k);
+        const uint64_t u = (uint64_t)plan_position(plan, first + k) - win_first;
+        if (u >= win_n) continue;
+        ++wrote;
+        const int64_t i = (int64_t)u;
         aqe_record r;
         r.id = C.id ? __ldg(C.id + i) : 0;
         r.amount = C.amount ? __ldg(C.amount + i) : 0.0;
@@ -607,6 +688,10 @@ __global__ void __launch_bounds__(256) k_plan_gather(const PlanDev plan, const C
         uint4* o = reinterpret_cast<uint4*>(out + k);
         const uint4* s = reinterpret_cast<const uint4*>(&r);
         o[0] = s[0]; o[1] = s[1];
+    }
+    if (counter) {
+        wrote = warp_reduce_u64(wrote);
+        if ((threadIdx.x & 31) == 0 && wrote) atomicAdd(counter, wrote);
     }
 }
 
@@ -692,7 +777,8 @@ struct ApproxArgs {
     uint64_t n_rows, units;
     uint32_t block_rows;  // 1 for SRS
     int design, agg, agg_col, pred_col;
-    double lo, hi, eps, z;
+    double lo, hi, eps, z;   // z: normal quantile at the (guarded) confidence level; the kernel turns it into t(df)
+    int stein;               // 1: the half width at look r uses the variance of look r-1 (include/aqe_b200.h, aqe_ci_mode)
     uint64_t seed, n0, nmax;
     ApproxAcc* slots;  // [2][gridDim.x]
     aqe_approx_result* out;
@@ -716,10 +802,14 @@ __host__ __device__ __forceinline__ uint64_t approx_share(uint64_t T, uint64_t u
 // Stratified estimate over all ranks' messages (rank order).  Returns the relative half width in percent.
 // SUM/COUNT: T = sum_g U_g mean_g, Var = sum_g U_g^2 s_g^2 / n_g.  AVG: the same over the total row count.  AVG with a
 // predicate: ratio estimator R = Num/Den with the linearised residual e = y - R c in every stratum.
-__host__ __device__ inline double approx_global(const ApproxMsg* msgs, int world, int agg, bool ratio, double z, double* est_out, double* half_out,
-                                                uint64_t* n_tot_out, uint64_t* rows_tot_out) {
+// var_io / nvar_io (per stratum; *have_prev says whether they hold the previous look): with `stein` the half width uses the
+// PREVIOUS look's stratum variances (and the t quantile at their degrees of freedom) while means and n are the current ones;
+// on return they hold the current look's.  *rel_next = the relative half width with the current variances: sizes the next look.
+__host__ __device__ inline double approx_global(const ApproxMsg* msgs, int world, int agg, bool ratio, double z, int stein, double* var_io, uint64_t* nvar_io,
+                                                bool* have_prev, double* est_out, double* half_out, uint64_t* n_tot_out, uint64_t* rows_tot_out, double* rel_next,
+                                                double* pass_fraction) {
     const double inf = HUGE_VAL;
-    double T = 0.0, V = 0.0, num = 0.0, den = 0.0, pop_rows = 0.0;
+    double T = 0.0, V = 0.0, Vcur = 0.0, num = 0.0, den = 0.0, pop_rows = 0.0, df_use = 0.0, df_cur = 0.0;
     uint64_t n_tot = 0, rows_tot = 0;
     for (int g = 0; g < world; ++g) {
         const ApproxMsg& m = msgs[g];
@@ -730,6 +820,7 @@ __host__ __device__ inline double approx_global(const ApproxMsg* msgs, int world
         num += U * (sy / n); den += U * (m.sc / n);
     }
     const double R = den > 0.0 ? num / den : 0.0;
+    const bool use_prev = stein && *have_prev;
     for (int g = 0; g < world; ++g) {
         const ApproxMsg& m = msgs[g];
         if (m.pop_units == 0 || m.n_units == 0) continue;
@@ -749,15 +840,24 @@ __host__ __device__ inline double approx_global(const ApproxMsg* msgs, int world
         } else {
             var = m.n_units > 1 ? ss / (n - 1.0) : inf;
         }
+        const double v_use = use_prev && nvar_io[g] > 1 ? var_io[g] : var;
+        df_use += use_prev && nvar_io[g] > 1 ? (double)(nvar_io[g] - 1) : n - 1.0;
+        df_cur += n - 1.0;
         T += U * mu;
-        V += U * U * var / n;
+        V += U * U * v_use / n;
+        Vcur += U * U * var / n;
+        var_io[g] = var; nvar_io[g] = m.n_units;
     }
-    double est, half;
-    if (ratio) { est = R; half = den > 0.0 ? z * sqrt(V) / den : inf; }
-    else if (agg == AQE_AGG_AVG) { est = pop_rows > 0.0 ? T / pop_rows : 0.0; half = pop_rows > 0.0 ? z * sqrt(V) / pop_rows : inf; }
-    else { est = T; half = z * sqrt(V); }
+    *have_prev = true;
+    const double tq = t_from_z(z, df_use > 4.0 ? df_use : 4.0), tq_next = t_from_z(z, df_cur > 4.0 ? df_cur : 4.0);
+    double est, half, half_next;
+    if (ratio) { est = R; half = den > 0.0 ? tq * sqrt(V) / den : inf; half_next = den > 0.0 ? tq_next * sqrt(Vcur) / den : inf; }
+    else if (agg == AQE_AGG_AVG) { est = pop_rows > 0.0 ? T / pop_rows : 0.0; half = pop_rows > 0.0 ? tq * sqrt(V) / pop_rows : inf; half_next = pop_rows > 0.0 ? tq_next * sqrt(Vcur) / pop_rows : inf; }
+    else { est = T; half = tq * sqrt(V); half_next = tq_next * sqrt(Vcur); }
     *est_out = est; *half_out = half; *n_tot_out = n_tot; *rows_tot_out = rows_tot;
-    if (ratio && !(den > 0.0)) return inf;
+    *pass_fraction = pop_rows > 0.0 ? den / pop_rows : 0.0;
+    if (ratio && !(den > 0.0)) { *rel_next = inf; return inf; }
+    *rel_next = est != 0.0 ? half_next / fabs(est) * 100.0 : inf;
     return est != 0.0 ? half / fabs(est) * 100.0 : inf;
 }
 
@@ -792,7 +892,13 @@ __global__ void __launch_bounds__(256) k_approx(const ApproxArgs a) {
     uint64_t n_prev = 0, target = multi ? approx_share(Tg, a.units, a.units_total) : a.n0;
     uint32_t rounds = 0;
     int status = AQE_DRIFTING;
-    double est = 0.0, half = 0.0, rel = 0.0, mean = 0.0, m2 = 0.0;
+    double est = 0.0, half = 0.0, rel = 0.0, rel_next = 0.0, mean = 0.0, m2 = 0.0, pass_fraction = 1.0;
+    // the previous look's variance(s): what the Stein-type interval is built from (include/aqe_b200.h, aqe_ci_mode)
+    double var_prev[kMaxRanks];
+    uint64_t nvar_prev[kMaxRanks];
+    bool have_prev = false;
+#pragma unroll
+    for (int g = 0; g < kMaxRanks; ++g) { var_prev[g] = 0.0; nvar_prev[g] = 0; }
 
     for (;;) {
         ApproxAcc acc = approx_identity();
@@ -861,7 +967,7 @@ __global__ void __launch_bounds__(256) k_approx(const ApproxArgs a) {
                 const ExSlot* src = a.ex.peers[a.ex.rank] + (2 * kMaxRanks + threadIdx.x * 2 + par);
                 const long long t0 = clock64();
                 while (ld_acquire_sys(&src->seq) != tag) {
-                    if ((unsigned long long)(clock64() - t0) > a.ex.timeout_cycles) { atomicExch(a.ex.status, 1u); break; }
+                    if ((unsigned long long)(clock64() - t0) > a.ex.timeout_cycles) { *(volatile unsigned int*)a.ex.status = 1u; break; }
                     __nanosleep(32);
                 }
                 const volatile unsigned long long* sp = reinterpret_cast<const volatile unsigned long long*>(&src->p);
@@ -870,12 +976,12 @@ __global__ void __launch_bounds__(256) k_approx(const ApproxArgs a) {
                 for (int i = 0; i < 8; ++i) dp[i] = sp[i];
             }
             __syncthreads();
-            rel = approx_global(sh_msgs, world, a.agg, ratio, a.z, &est, &half, &n_tot, &rows_tot);
+            rel = approx_global(sh_msgs, world, a.agg, ratio, a.z, a.stein, var_prev, nvar_prev, &have_prev, &est, &half, &n_tot, &rows_tot, &rel_next, &pass_fraction);
             mean = 0.0; m2 = 0.0;
             n_prev = target;
             if (rel <= a.eps) { status = AQE_STABLE; break; }
             if (Tg >= a.nmax_total) { status = AQE_DRIFTING; break; }
-            const double rn = rel / a.eps;
+            const double rn = rel_next / a.eps;
             const double want = ceil(1.1 * ((double)n_tot * rn * rn));
             const uint64_t lo_n = Tg + Tg / 4 + 1, hi_n = Tg * 8;
             uint64_t t2 = want >= (double)hi_n ? hi_n : (want <= (double)lo_n ? lo_n : (uint64_t)want);
@@ -911,13 +1017,21 @@ __global__ void __launch_bounds__(256) k_approx(const ApproxArgs a) {
             if (a.agg == AQE_AGG_AVG) { scale = (double)a.units / (double)a.n_rows; est = mu * scale; }
             else { scale = (double)a.units; est = mu * scale; }
         }
-        const double se = sqrt(var / n);
-        half = a.z * se * scale;
-        rel = est != 0.0 ? half / fabs(est) * 100.0 : __longlong_as_double(0x7ff0000000000000LL);
+        // the interval: variance of the PREVIOUS look (the one that chose this look's size) at its t quantile; the first look its own
+        const bool use_prev = a.stein && have_prev && nvar_prev[0] > 1;
+        const double v_use = use_prev ? var_prev[0] : var;
+        const double df_use = use_prev ? (double)(nvar_prev[0] - 1) : n - 1.0;
+        half = t_from_z(a.z, df_use > 4.0 ? df_use : 4.0) * sqrt(v_use / n) * scale;
+        const double half_next = t_from_z(a.z, n - 1.0 > 4.0 ? n - 1.0 : 4.0) * sqrt(var / n) * scale;
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+        rel = est != 0.0 ? half / fabs(est) * 100.0 : inf;
+        rel_next = est != 0.0 ? half_next / fabs(est) * 100.0 : inf;
+        var_prev[0] = var; nvar_prev[0] = s.units; have_prev = true;
+        pass_fraction = s.rows ? s.sc.s / (double)s.rows : 0.0;
         n_prev = target;
         if (rel <= a.eps) { status = AQE_STABLE; break; }
         if (n_prev >= a.nmax) { status = AQE_DRIFTING; break; }
-        const double rn = rel / a.eps;
+        const double rn = rel_next / a.eps;   // the next look is sized for the variance seen now: that is the one its interval will use
         const double want = ceil(1.1 * (n * rn * rn));
         const uint64_t lo_n = n_prev + n_prev / 4 + 1, hi_n = n_prev * 8;
         uint64_t t2 = want >= (double)hi_n ? hi_n : (want <= (double)lo_n ? lo_n : (uint64_t)want);
@@ -929,7 +1043,7 @@ __global__ void __launch_bounds__(256) k_approx(const ApproxArgs a) {
         r.estimate = est; r.ci_lower = est - half; r.ci_upper = est + half;
         r.error_margin = rel / 100.0; r.confidence_level = 0.0;
         r.n_samples = multi ? rows_tot : cum.rows; r.n_units = multi ? n_tot : cum.units; r.population = multi ? a.rows_total : a.n_rows;
-        r.mean = mean; r.m2 = m2; r.rounds = rounds; r.status = status; r.elapsed_us = 0.0;
+        r.mean = mean; r.m2 = m2; r.rounds = rounds; r.status = status; r.elapsed_us = 0.0; r.pass_fraction = pass_fraction;
         *a.out = r;
     }
 }

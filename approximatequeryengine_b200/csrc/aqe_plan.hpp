@@ -16,6 +16,7 @@ struct aqe_plan {
     std::vector<int64_t> idx;         // explicit positions when segs is empty
     uint64_t count = 0;
     bool by_amount_order = false;     // positions index the amount-sorted permutation (stratified)
+    uint64_t n_rows = 0;              // rows of the table the plan was built for (positions are < n_rows); 0: a caller-supplied list
     // device mirror, owned by the engine (aqe_engine.cu)
     void* d_segs = nullptr;
     void* d_start = nullptr;

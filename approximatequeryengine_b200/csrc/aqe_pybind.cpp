@@ -81,12 +81,31 @@ struct BenchmarkResults {  // custom_scheduler.hpp:68-77 (unbound in the referen
 }
 inline void check(int rc) { if (rc != AQE_OK) raise_status(rc); }
 
-int default_device() {
+// Which GPUs a CustomBPlusDB() uses.  AQE_DEVICES = "all" | a count | a comma-separated list chooses explicitly; a process that
+// is one rank of a one-process-per-GPU job (AQE_DEVICE / LOCAL_RANK set, e.g. under torchrun) keeps to its own GPU; otherwise
+// the table is range-sharded over every visible GPU (aqe_create_sharded) -- the reference's callers are single-process
+// (enhanced_aqe_cli.py:165-186), this is how they get the whole box.
+std::vector<int> default_devices() {
+    auto visible = [] { int n = 0; return aqe_device_count(&n) == AQE_OK ? n : 0; };
+    if (const char* v = std::getenv("AQE_DEVICES"); v && *v) {
+        std::vector<int> out;
+        const std::string s(v);
+        if (s == "all") { for (int g = 0; g < visible(); ++g) out.push_back(g); }
+        else if (s.find(',') == std::string::npos) { for (int g = 0; g < std::atoi(v); ++g) out.push_back(g); }
+        else {
+            size_t i = 0;
+            while (i < s.size()) { size_t j = s.find(',', i); if (j == std::string::npos) j = s.size(); if (j > i) out.push_back(std::atoi(s.substr(i, j - i).c_str())); i = j + 1; }
+        }
+        if (!out.empty()) return out;
+    }
     for (const char* name : {"AQE_DEVICE", "LOCAL_RANK"}) {
         const char* v = std::getenv(name);
-        if (v && *v) return std::atoi(v);
+        if (v && *v) return {std::atoi(v)};
     }
-    return 0;
+    std::vector<int> out;
+    for (int g = 0; g < std::min(visible(), 16); ++g) out.push_back(g);
+    if (out.empty()) out.push_back(0);   // no driver: the handle is created lazily and the first data-path call raises
+    return out;
 }
 
 int column_id(const std::string& name) {
@@ -99,8 +118,12 @@ int column_id(const std::string& name) {
 
 class CustomBPlusDB {
 public:
-    CustomBPlusDB() { check(aqe_create(default_device(), &h_)); }
-    explicit CustomBPlusDB(int device) { check(aqe_create(device, &h_)); }
+    CustomBPlusDB() : devices_(default_devices()) { open_handle(); }
+    explicit CustomBPlusDB(int device) : devices_{device} { open_handle(); }
+    explicit CustomBPlusDB(std::vector<int> devices) : devices_(std::move(devices)) {
+        if (devices_.empty()) throw py::value_error("devices: give at least one device id");
+        open_handle();
+    }
     ~CustomBPlusDB() {
         try { close_database(); } catch (...) {}
         aqe_close(h_);
@@ -305,6 +328,9 @@ public:
     }
 
     aqe_db* handle() { return h_; }
+    int shard_count() const { return aqe_shard_count(h_); }
+    bool shards_fused() const { return aqe_shards_fused(h_) != 0; }
+    std::vector<int> devices() const { return devices_; }
 
     // ---- SQL-string path on this table (the four run_query* functions of bindings.cpp:126-136 without the file) ----
     // grouped = the *_groupby forms; ci: 0 value, 1 the reference's interval (executor.cpp:177-338), 2 corrected interval
@@ -344,12 +370,16 @@ public:
     }
 
 private:
+    void open_handle() {
+        if (devices_.size() == 1) check(aqe_create(devices_[0], &h_));
+        else check(aqe_create_sharded(devices_.data(), (int)devices_.size(), &h_));
+    }
     void reset() {
-        const int dev = aqe_device(h_);
         aqe_close(h_);
         h_ = nullptr;
-        check(aqe_create(dev, &h_));
+        open_handle();
     }
+    std::vector<int> devices_;
     aqe_db* h_ = nullptr;
     py::object keep_alive_;
     std::string path_;
@@ -582,6 +612,10 @@ PYBIND11_MODULE(aqe_backend, m) {
     py::class_<DB> db(m, "CustomBPlusDB");
     db.def(py::init<>())
         .def(py::init<int>(), py::arg("device"))
+        .def(py::init<std::vector<int>>(), py::arg("devices"), "the table range-sharded over these GPUs of this process")
+        .def_property_readonly("shard_count", &DB::shard_count, "GPUs holding rows of the current table")
+        .def_property_readonly("shards_fused", &DB::shards_fused, "shard partials are exchanged inside the kernels (peer-mapped mailboxes)")
+        .def_property_readonly("devices", &DB::devices)
         .def("create_database", &DB::create_database)
         .def("open_database", &DB::open_database)
         .def("close_database", &DB::close_database)

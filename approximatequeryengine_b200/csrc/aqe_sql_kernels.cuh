@@ -409,7 +409,7 @@ __device__ __forceinline__ void sql_exchange(const SqlExchange& ex, unsigned int
         const unsigned long long* flag = sqlx_flag(ex.peers[ex.rank], tid, par);
         const long long t0 = clock64();
         while (ld_acquire_sys(flag) != ex.seq) {
-            if ((unsigned long long)(clock64() - t0) > ex.timeout_cycles) { atomicExch(ex.status, 1u); break; }
+            if ((unsigned long long)(clock64() - t0) > ex.timeout_cycles) { *(volatile unsigned int*)ex.status = 1u; break; }
             __nanosleep(64);
         }
     }

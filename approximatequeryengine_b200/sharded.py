@@ -13,8 +13,8 @@ import ctypes as C
 
 import numpy as np
 
-from . import (AGG, SQL_MOMENTS, SQL_UNSAMPLED, ApproxResult, Engine, Partial, SqlFacts, check, lib, sql_finish, sql_layout,
-               sql_merge, sql_parse)
+from . import (AGG, SQL_MOMENTS, SQL_UNSAMPLED, ApproxResult, Engine, Partial, Plan, SampleParams, SqlFacts, Stats, StatsPartial,
+               build_plan, check, lib, merge_stats, sql_finish, sql_layout, sql_merge, sql_parse)
 
 
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
@@ -170,6 +170,38 @@ class ShardedTable:
         if grouped and step > 1 and (acc[0::5] == 0).any():   # identical on every rank: the pass below is collective
             exists = table_level(SQL_UNSAMPLED)
         return sql_finish(q, layout, acc, mode, exists)
+
+    # ---- the legacy sampler families across the shards (BASELINE configs[3]: "block sampling + parallel fast/slow method") ----
+    def plan(self, method: str, params: SampleParams) -> Plan:
+        """The sampler's position list over the WHOLE table (closed-form segments; identical on every rank, nothing is
+        exchanged).  Samplers that read the table to place their samples (adaptive_block, clt_validated_dual_pointer) need the
+        whole table behind one handle: Engine(devices=...) / CustomBPlusDB(devices)."""
+        return build_plan(self.total_rows, method, params)
+
+    def stats(self, method: str | None = None, params: SampleParams | None = None, col="amount", where=None, where_col="amount",
+              plan: Plan | None = None) -> Stats:
+        """Moments of `col` over the sampler's rows.  Every rank walks the whole plan and gathers the positions inside its own
+        row range (k_plan_stats with a window), the 64-byte partial sums are all-gathered and merged in rank order
+        (aqe_stats_merge: double-double sum, Chan's update for M2) -- n and the sum are those of the one-GPU plan, bit for bit /
+        to the last ulp.  Replaces the per-thread region loops of parallel_pointer_sample (custom_bplus_db.cpp:814-854),
+        parallel_block_sample (:1218-1271), clt/optimized_clt regions (:925-926, :1046-1147), memory_stride_sample (:1526)."""
+        plan = plan or self.plan(method, params)
+        part = self.engine.stats_window(plan, self.first_row, col, where, where_col)
+        return merge_stats(allgather_struct(part, StatsPartial, self.group))
+
+    def gather(self, method: str | None = None, params: SampleParams | None = None, plan: Plan | None = None) -> np.ndarray:
+        """The sampled rows in plan order, on every rank (the list[Record] return path).  Each rank fills the slots of the
+        positions it owns and leaves the others zero; one all-reduce (sum of the 64-bit words: x + 0 + ... + 0) assembles them."""
+        import torch
+        import torch.distributed as dist
+        plan = plan or self.plan(method, params)
+        rows, _ = self.engine.gather_window(plan, self.first_row)
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return rows
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        words = torch.from_numpy(rows.view(np.int64).copy()).to(dev)
+        dist.all_reduce(words, op=dist.ReduceOp.SUM, group=self.group)
+        return words.cpu().numpy().view(rows.dtype)
 
     def approx(self, agg="sum", error_percent=1.0, confidence_level=0.95, seed=0, **kw) -> ApproxResult:
         """Shards are strata: each rank runs its persistent CLT kernel to the same relative target with

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AQE_ABI_VERSION 4
+#define AQE_ABI_VERSION 5
 
 #if defined(AQE_BUILDING)
 #define AQE_API __attribute__((visibility("default")))
@@ -99,6 +99,17 @@ typedef struct aqe_stats {
     double   sum;
 } aqe_stats;
 
+/* What ONE shard of a range-sharded table contributes to the moments of a sample plan (64 bytes, the unit exchanged
+ * between ranks): compensated sums of x, of d = x - shift and of d^2 over the plan positions that fall into the shard.
+ * aqe_stats_merge folds the shards in rank order (Chan's parallel update for mean / M2; the shifts may differ). */
+typedef struct aqe_stats_partial {
+    uint64_t n;
+    double   sum, sum_c;     /* sum x   = sum + sum_c   */
+    double   shift;          /* K of this shard */
+    double   sd, sd_c;       /* sum d   = sd + sd_c     */
+    double   sdd, sdd_c;     /* sum d^2 = sdd + sdd_c   */
+} aqe_stats_partial;
+
 /* Sampler ids: the list-returning methods of CustomBPlusDB (bindings.cpp:49-101).  Line numbers are
  * src/aqe_backend/core/custom_bplus_db.cpp. */
 typedef enum aqe_method {
@@ -166,10 +177,26 @@ typedef struct aqe_plan aqe_plan; /* opaque: a sample position list (segments or
 /* Aggregates for the fused estimators. */
 typedef enum aqe_agg { AQE_AGG_SUM = 0, AQE_AGG_AVG = 1, AQE_AGG_COUNT = 2 } aqe_agg;
 
-/* The fused estimators widen the normal-theory half width z*s/sqrt(n) by this factor (and stop on the widened
- * width).  A plain z interval has coverage ~nominal - 0.5 % under sequential stopping (measured, 4000 seeds,
- * profiles/r1_coverage_100M_4000seeds.json); "coverage >= nominal" needs a little slack.  Costs ~10 % more samples. */
-#define AQE_CI_CONSERVATIVE 1.05
+/* How the fused estimators (aqe_approx*) build the interval they stop on and report.
+ *
+ * The persistent kernel looks at cumulative sample sizes n_1 < n_2 < ... and stops at the first look whose relative half
+ * width is <= error_percent.  Stopping on the very variance estimate the interval is then built from is what biases a
+ * sequential interval (it stops when s happens to be small).  AQE_CI_STEIN removes that structurally, after Stein's
+ * two-stage procedure (1945) generalised to the looks: the half width at look r uses the variance of look r-1 -- the one
+ * that CHOSE n_r -- with the Student-t quantile at its degrees of freedom; n_r is a function of that variance alone and the
+ * sample mean is independent of it, so for normal means the coverage is exact whatever the stopping pattern (the first look
+ * uses its own variance: Stein's n = max(n_1, .) case).  Costs no samples.
+ * AQE_CI_GUARD: "coverage >= nominal" is checked over a finite number of seeds (1000 seeds: binomial sigma 0.7 %), which a
+ * procedure with exactly nominal coverage fails half the time; the default mode therefore builds the interval for
+ * alpha' = AQE_CI_GUARD * alpha (96 % when 95 % is asked; +4.8 % width, +10 % samples), a stated guard band in
+ * probability units.  tests/test_gpu_parity.py::test_coverage_sweep_config4 holds the table of all three modes. */
+#define AQE_CI_GUARD 0.8
+typedef enum aqe_ci_mode {
+    AQE_CI_DEFAULT = 0,        /* = AQE_CI_STEIN_GUARDED */
+    AQE_CI_PLAIN = 1,          /* z * s_r / sqrt(n_r) at the stopping look (the round-1 interval without its 1.05 factor) */
+    AQE_CI_STEIN = 2,          /* t(df_{r-1}) * s_{r-1} / sqrt(n_r) */
+    AQE_CI_STEIN_GUARDED = 3   /* the same at alpha' = AQE_CI_GUARD * alpha */
+} aqe_ci_mode;
 
 /* Draw designs of the persistent CLT kernel (K4). */
 typedef enum aqe_design {
@@ -189,7 +216,7 @@ typedef struct aqe_approx_spec {
     uint64_t min_samples;        /* first look; 0 = default */
     uint64_t max_samples;        /* budget; 0 = default (N) */
     uint32_t block_size;         /* AQE_DESIGN_BLOCK tile rows; 0 = 1000 (block_sample default) */
-    uint32_t _pad;
+    uint32_t ci_mode;            /* aqe_ci_mode; 0 = default */
 } aqe_approx_spec;
 
 /* status values follow CustomApproximationStatus (custom_scheduler.hpp:8-13). */
@@ -211,6 +238,8 @@ typedef struct aqe_approx_result {
     uint32_t rounds;
     int32_t  status;             /* aqe_approx_status */
     double   elapsed_us;         /* device time of the persistent kernel (CUDA events) */
+    double   pass_fraction;      /* estimated fraction of rows passing the predicate (1 without one): the weight of this shard's
+                                    AVG ... WHERE estimate when independent shard results are merged (aqe_approx_merge) */
 } aqe_approx_result;
 
 /* Synthetic "sales-shaped" generator distributions. */
@@ -222,6 +251,9 @@ typedef enum aqe_synth { AQE_SYNTH_UNIFORM = 0, AQE_SYNTH_LOGNORMAL = 1 } aqe_sy
 AQE_API int         aqe_abi_version(void);
 AQE_API const char* aqe_last_error(void);          /* thread-local, never NULL */
 AQE_API int         aqe_device_count(int* out);    /* AQE_ERR_CUDA when no driver / device */
+/* Which exact-scan kernel the calling thread's last scan launched: name, template arguments, grid, shared memory (bench.py
+ * reports it as roofline.kernel instead of a string literal).  Thread-local, never NULL. */
+AQE_API const char* aqe_last_scan_kernel(void);
 /* Number of this library's kernels launched since load (bench.py gpu_launches). */
 AQE_API uint64_t    aqe_launch_count(void);
 /* Page-locked host buffers for the host-column entry points (pageable memory also works, staged). */
@@ -256,6 +288,23 @@ AQE_API int aqe_generate_synthetic(aqe_db* db, uint64_t seed, uint64_t first_row
 /* Host twin of the generator (same bits), for files / oracles.  rows[i] = global row first_row+i. */
 AQE_API int aqe_synth_rows_host(uint64_t seed, uint64_t first_row, uint64_t n_rows, int dist, aqe_record* rows);
 AQE_API int aqe_close(aqe_db* db); /* frees device + host memory; db invalid afterwards */
+
+/* ---- the whole table over several GPUs of THIS process (aqe_open(path, n_gpus, &db); 8e: "single process,
+ * 8 devices") ----
+ * The table is cut into contiguous row ranges [N*g/G, N*(g+1)/G) (the reference's own region split,
+ * custom_bplus_db.cpp:925-926), one per device; G = min(n_devices, max(1, N / AQE_MIN_SHARD_ROWS)) so that small tables
+ * stay on one GPU (environment AQE_MIN_SHARD_ROWS, default 2^24).  Each query launches one kernel per device from one host
+ * thread per device; the 64-byte shard partials (or the SQL accumulators, or the per-look moments of the CLT kernel) are
+ * exchanged INSIDE the kernels through peer-mapped mailboxes (cudaDeviceEnablePeerAccess; NVLink stores) and folded in
+ * rank order, exactly as the one-process-per-GPU exchange does -- the same bits as aqe_merge_partials over the shards.
+ * Where the devices are not distinct peers (tests put several shards on one GPU) the shards are merged on the host.
+ * devices = NULL: devices 0 .. n_devices-1; n_devices = 0: every visible device. */
+AQE_API int aqe_create_sharded(const int* devices, int n_devices, aqe_db** out);
+AQE_API int aqe_open_sharded(const char* path, int n_gpus, aqe_db** out);   /* create_sharded(NULL, n_gpus) + load_file */
+AQE_API int aqe_shard_count(const aqe_db* db);                /* shards in use for the current contents (1 for a plain handle) */
+AQE_API aqe_db* aqe_shard(aqe_db* db, int g);                 /* borrowed handle of shard g (the handle itself for a plain one) */
+AQE_API uint64_t aqe_shard_first_row(const aqe_db* db, int g);/* first table row of shard g; g = shard_count: N */
+AQE_API int aqe_shards_fused(const aqe_db* db);               /* 1: the shards exchange inside the kernels (distinct peer devices) */
 
 AQE_API uint64_t aqe_count(const aqe_db* db);                 /* get_total_records :646 */
 AQE_API uint64_t aqe_node_count(const aqe_db* db);            /* get_node_count :654 (N/255+1) */
@@ -327,6 +376,21 @@ AQE_API int aqe_stats_from_plan_where(aqe_db* db, const aqe_plan* plan, int col,
                               aqe_stats* out);
 /* Same for a caller-supplied host index list ("same sample index list" parity, E1/E2). */
 AQE_API int aqe_stats_from_indices(aqe_db* db, const int64_t* idx, uint64_t n, int col, aqe_stats* out);
+/* Range-sharded tables, one process per GPU (sharded.ShardedTable): this handle holds rows [window_first, window_first +
+ * aqe_count(db)) of the table the plan was built for.  Every rank walks the same plan; positions outside its window belong
+ * to another rank and are skipped, so the gathers split across the GPUs and no index list is cut up or exchanged.
+ * aqe_stats_window leaves the shard's mergeable sums, aqe_stats_merge (pure host code, rank order) finishes them;
+ * aqe_gather_window writes rows [k_first, k_first + k_count) of the plan that fall into the window into out[k - k_first]
+ * and leaves the other slots untouched (the ranks' buffers, zero-filled beforehand, add up to the sample).
+ * Replaces the per-thread region loops of parallel_pointer_sample :814-854, parallel_block_sample :1218-1271,
+ * multithreaded_memory_stride_sample :1880-1960 across GPUs. */
+AQE_API int aqe_stats_window(aqe_db* db, const aqe_plan* plan, int col, int pred_col, double lo, double hi, uint64_t window_first,
+                             aqe_stats_partial* out);
+AQE_API int aqe_stats_merge(const aqe_stats_partial* parts, int n, aqe_stats* out);
+AQE_API int aqe_gather_window(aqe_db* db, const aqe_plan* plan, uint64_t window_first, uint64_t k_first, uint64_t k_count,
+                              aqe_record* out, uint64_t* n_local);
+/* Rows of the table the plan was built for (0: an explicit index list, validated against the table at use). */
+AQE_API uint64_t aqe_plan_table_rows(const aqe_plan* plan);
 /* Rows at the plan's positions, AoS, in plan order (the legacy list[Record] return path). */
 AQE_API int aqe_gather_plan(aqe_db* db, const aqe_plan* plan, aqe_record* out, uint64_t cap);
 AQE_API int aqe_gather_records(aqe_db* db, const int64_t* idx, uint64_t n, aqe_record* out);

@@ -22,6 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libaqe_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libaqe_ref.so")
 REFSQL_SO = os.path.join(HERE, "_ref", "libaqe_refsql.so")
+REFCLI_PYC = os.path.join(HERE, "_ref", "enhanced_aqe_cli.pyc")   # the reference's command line as bytecode (make refcli)
 
 RECORD_DTYPE = np.dtype(
     [("id", "<i8"), ("amount", "<f8"), ("region", "<i4"), ("product_id", "<i4"), ("timestamp", "<i8")]
@@ -70,7 +71,7 @@ class ApproxSpec(C.Structure):
         ("agg", C.c_int32), ("design", C.c_int32), ("agg_col", C.c_int32), ("pred_col", C.c_int32),
         ("lo", C.c_double), ("hi", C.c_double), ("error_percent", C.c_double), ("confidence_level", C.c_double),
         ("seed", C.c_uint64), ("min_samples", C.c_uint64), ("max_samples", C.c_uint64),
-        ("block_size", C.c_uint32), ("_pad", C.c_uint32),
+        ("block_size", C.c_uint32), ("ci_mode", C.c_uint32),
     ]
 
 
@@ -79,7 +80,7 @@ class ApproxResult(C.Structure):
         ("estimate", C.c_double), ("ci_lower", C.c_double), ("ci_upper", C.c_double), ("error_margin", C.c_double),
         ("confidence_level", C.c_double), ("n_samples", C.c_uint64), ("n_units", C.c_uint64),
         ("population", C.c_uint64), ("mean", C.c_double), ("m2", C.c_double), ("rounds", C.c_uint32),
-        ("status", C.c_int32), ("elapsed_us", C.c_double),
+        ("status", C.c_int32), ("elapsed_us", C.c_double), ("pass_fraction", C.c_double),
     ]
 
 
@@ -109,6 +110,7 @@ def build(ref: bool = True, quiet: bool = True) -> None:
         targets.append("ref")
         if any(os.path.exists(p) for p in ("/usr/lib/x86_64-linux-gnu/libsqlite3.so.0", "/usr/lib64/libsqlite3.so.0", "/usr/lib/libsqlite3.so.0")):
             targets.append("refsql")
+        targets.append("refcli")
     cmd = ["make", "-C", HERE, "-s"] + targets
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL if quiet else None)
 
@@ -178,6 +180,11 @@ class Oracle:
         L.orc_scan_mt.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                   C.POINTER(C.c_uint64)]
         L.orc_scan_mt.restype = C.c_double
+        L.orc_synth_amount_mt.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_int]
+        L.orc_sum_col_serial.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_uint64)]
+        L.orc_sum_col_serial.restype = C.c_double
+        L.orc_sum_col_exact_mt.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_uint64)]
+        L.orc_sum_col_exact_mt.restype = C.c_double
         for f in ("orc_tree_height", "orc_leaf_count", "orc_node_count"):
             getattr(L, f).argtypes = [C.c_uint64]; getattr(L, f).restype = C.c_uint64
         L.orc_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32 * 4)]
@@ -190,6 +197,25 @@ class Oracle:
         rows = np.empty(n, dtype=RECORD_DTYPE)
         self.L.orc_synth_rows(seed, first_row, n, dist, _ptr(rows))
         return rows
+
+    def synth_amount(self, n: int, seed: int = 7, first_row: int = 0, dist: int = 0, threads: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
+        """The amount column of rows [first_row, first_row + n) of the synthetic table, generated on `threads` host threads."""
+        col = np.empty(n, dtype=np.float64) if out is None else out
+        self.L.orc_synth_amount_mt(seed, first_row, n, dist, _ptr(col), threads or (os.cpu_count() or 1))
+        return col
+
+    def sum_col_serial(self, col: np.ndarray, pred=None):
+        """(sum, count) the way the reference's loops add: one double, strictly left to right (cbd:242-251, :263-274)."""
+        c = C.c_uint64()
+        s = self.L.orc_sum_col_serial(_ptr(col), len(col), int(pred is not None), pred[0] if pred else 0.0, pred[1] if pred else 0.0, C.byref(c))
+        return s, c.value
+
+    def sum_col_exact(self, col: np.ndarray, pred=None, threads: int | None = None):
+        """(sum, count) with long double Neumaier accumulation: the exactly rounded sum for all practical purposes."""
+        c = C.c_uint64()
+        s = self.L.orc_sum_col_exact_mt(_ptr(col), len(col), int(pred is not None), pred[0] if pred else 0.0, pred[1] if pred else 0.0,
+                                        threads or (os.cpu_count() or 1), C.byref(c))
+        return s, c.value
 
     def save_file(self, path: str, rows) -> None:
         rows = _rows(rows)

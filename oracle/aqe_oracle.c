@@ -967,6 +967,19 @@ ORC_API double orc_z_score(double conf, int exact) {
            ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
 }
 
+/* The interval of an aqe_ci_mode (include/aqe_b200.h): normal quantile at the (guarded) level, Student-t through Fisher's
+ * expansion, and -- Stein type -- the variance of the PREVIOUS look at its degrees of freedom. */
+static double ci_z(double conf, uint32_t ci_mode, int* stein) {
+    uint32_t m = ci_mode == AQE_CI_DEFAULT ? (uint32_t)AQE_CI_STEIN_GUARDED : ci_mode;
+    *stein = m != AQE_CI_PLAIN;
+    return orc_z_score(1.0 - (m == AQE_CI_STEIN_GUARDED ? AQE_CI_GUARD : 1.0) * (1.0 - conf), 1);
+}
+static double t_from_z(double z, double df) {
+    if (!(df > 4.0)) df = 4.0;
+    double z2 = z * z;
+    return z + z * (z2 + 1.0) / (4.0 * df) + z * ((5.0 * z2 + 16.0) * z2 + 3.0) / (96.0 * df * df);
+}
+
 static inline uint64_t draw_position(uint64_t seed, uint32_t design, uint64_t j, uint64_t units) {
     uint32_t r[4];
     uint64_t c = j >> 1;
@@ -1005,9 +1018,9 @@ ORC_API int orc_approx(const aqe_record* R, uint64_t N, const aqe_approx_spec* S
     if (N == 0) { out->status = AQE_INSUFFICIENT_DATA; return 0; }
     uint64_t B = S->design == AQE_DESIGN_BLOCK ? (S->block_size ? S->block_size : 1000) : 1;
     uint64_t units = (N + B - 1) / B;
-    double z = orc_z_score(S->confidence_level, 1) * AQE_CI_CONSERVATIVE;
+    int stein; double z = ci_z(S->confidence_level, S->ci_mode, &stein);
     if (S->agg == AQE_AGG_COUNT && S->pred_col == AQE_COL_NONE) { /* cli:197: COUNT is always exact */
-        out->estimate = out->ci_lower = out->ci_upper = (double)N; out->status = AQE_STABLE; return 0;
+        out->estimate = out->ci_lower = out->ci_upper = (double)N; out->status = AQE_STABLE; out->pass_fraction = 1.0; return 0;
     }
     uint64_t n0 = S->min_samples ? S->min_samples : (S->design == AQE_DESIGN_BLOCK ? 1024 : 16384);
     uint64_t nmax = S->max_samples ? S->max_samples : units;
@@ -1017,13 +1030,15 @@ ORC_API int orc_approx(const aqe_record* R, uint64_t N, const aqe_approx_spec* S
         orc_scan(R, N, S->agg == AQE_AGG_COUNT ? S->pred_col : S->agg_col, S->pred_col, S->lo, S->hi, &part);
         double v = S->agg == AQE_AGG_COUNT ? (double)part.count : (S->agg == AQE_AGG_SUM ? part.sum : (part.count ? part.sum / (double)part.count : 0.0));
         out->estimate = out->ci_lower = out->ci_upper = v; out->n_samples = N; out->n_units = units; out->status = AQE_STABLE;
+        out->pass_fraction = (double)part.count / (double)N;
         return 0;
     }
     int ratio = (S->agg == AQE_AGG_AVG && S->pred_col != AQE_COL_NONE);
     /* running sums in long double: the checker is allowed to be more exact than the device */
     long double sy = 0, syy = 0, sc = 0, rows = 0;
     uint64_t n = 0, target = n0; uint32_t rounds = 0;
-    double est = 0, half = 0, rel = INFINITY, mean = 0, m2 = 0;
+    double est = 0, half = 0, rel = INFINITY, rel_next = INFINITY, mean = 0, m2 = 0;
+    double var_prev = 0; uint64_t nvar_prev = 0; int have_prev = 0;
     for (;;) {
         for (; n < target; ++n) {
             uint64_t u = draw_position(S->seed, (uint32_t)S->design, n, units);
@@ -1053,12 +1068,17 @@ ORC_API int orc_approx(const aqe_record* R, uint64_t N, const aqe_approx_spec* S
             if (S->agg == AQE_AGG_AVG) { est = (double)(mu * (long double)units / (long double)N); scale = (double)units / (double)N; }
             else { est = (double)(mu * (long double)units); scale = (double)units; }
         }
-        double se = sqrt(var / (double)n);
-        half = z * se * scale;
+        int use_prev = stein && have_prev && nvar_prev > 1;
+        double v_use = use_prev ? var_prev : var;
+        double df_use = use_prev ? (double)(nvar_prev - 1) : (double)n - 1.0;
+        half = t_from_z(z, df_use) * sqrt(v_use / (double)n) * scale;
+        double half_next = t_from_z(z, (double)n - 1.0) * sqrt(var / (double)n) * scale;
         rel = est != 0 ? half / fabs(est) * 100.0 : INFINITY;
+        rel_next = est != 0 ? half_next / fabs(est) * 100.0 : INFINITY;
+        var_prev = var; nvar_prev = n; have_prev = 1;
         if (rel <= S->error_percent) { out->status = AQE_STABLE; break; }
         if (n >= nmax) { out->status = AQE_DRIFTING; break; }
-        double ratio_n = rel / S->error_percent;
+        double ratio_n = rel_next / S->error_percent;
         double nreq = (double)n * ratio_n * ratio_n;
         double want = ceil(1.1 * nreq);
         uint64_t lo_n = n + n / 4 + 1, hi_n = n * 8;
@@ -1069,6 +1089,7 @@ ORC_API int orc_approx(const aqe_record* R, uint64_t N, const aqe_approx_spec* S
     out->estimate = est; out->ci_lower = est - half; out->ci_upper = est + half;
     out->error_margin = rel / 100.0; out->n_units = n; out->n_samples = (uint64_t)rows; out->rounds = rounds;
     out->mean = mean; out->m2 = m2;
+    out->pass_fraction = rows > 0 ? (double)(sc / rows) : 0.0;
     return 0;
 }
 
@@ -1088,9 +1109,9 @@ ORC_API int orc_approx_sharded(const aqe_record* R, uint64_t N, int world, const
     if (N == 0) { out->status = AQE_INSUFFICIENT_DATA; return 0; }
     if (world < 1 || world > 16) return 1;
     uint64_t B = S->design == AQE_DESIGN_BLOCK ? (S->block_size ? S->block_size : 1000) : 1;
-    double z = orc_z_score(S->confidence_level, 1) * AQE_CI_CONSERVATIVE;
+    int stein; double z = ci_z(S->confidence_level, S->ci_mode, &stein);
     if (S->agg == AQE_AGG_COUNT && S->pred_col == AQE_COL_NONE) {
-        out->estimate = out->ci_lower = out->ci_upper = (double)N; out->status = AQE_STABLE; return 0;
+        out->estimate = out->ci_lower = out->ci_upper = (double)N; out->status = AQE_STABLE; out->pass_fraction = 1.0; return 0;
     }
     uint64_t first[16], rows[16], units[16], n[16], target[16], utot = 0;
     long double sy[16], syy[16], sc[16], nrows[16];
@@ -1112,8 +1133,10 @@ ORC_API int orc_approx_sharded(const aqe_record* R, uint64_t N, int world, const
     }
     int ratio = (S->agg == AQE_AGG_AVG && S->pred_col != AQE_COL_NONE);
     uint64_t Tg = n0; uint32_t rounds = 0;
-    double est = 0, half = 0, rel = INFINITY;
+    double est = 0, half = 0, rel = INFINITY, rel_next = INFINITY, passf = 0;
     uint64_t ntot = 0; long double rows_read = 0;
+    long double var_prev[16]; uint64_t nvar_prev[16]; int have_prev = 0;
+    for (int g = 0; g < 16; ++g) { var_prev[g] = 0; nvar_prev[g] = 0; }
     for (;;) {
         for (int g = 0; g < world; ++g) {
             uint64_t t = share_of(Tg, units[g], utot);
@@ -1128,7 +1151,9 @@ ORC_API int orc_approx_sharded(const aqe_record* R, uint64_t N, int world, const
             }
         }
         ++rounds;
-        long double T = 0, V = 0, num = 0, den = 0;
+        long double T = 0, V = 0, Vcur = 0, num = 0, den = 0;
+        double df_use = 0, df_cur = 0;
+        int use_prev = stein && have_prev;
         ntot = 0; rows_read = 0;
         for (int g = 0; g < world; ++g) {
             ntot += n[g]; rows_read += nrows[g];
@@ -1148,15 +1173,24 @@ ORC_API int orc_approx_sharded(const aqe_record* R, uint64_t N, int world, const
                 long double ss = syy[g] - sy[g] * mu; if (ss < 0) ss = 0;
                 var = n[g] > 1 ? ss / (nn - 1) : INFINITY;
             }
-            T += U * mu; V += U * U * var / nn;
+            int up = use_prev && nvar_prev[g] > 1;
+            long double v_use = up ? var_prev[g] : var;
+            df_use += up ? (double)(nvar_prev[g] - 1) : (double)n[g] - 1.0;
+            df_cur += (double)n[g] - 1.0;
+            T += U * mu; V += U * U * v_use / nn; Vcur += U * U * var / nn;
+            var_prev[g] = var; nvar_prev[g] = n[g];
         }
-        if (ratio) { est = (double)Rr; half = den > 0 ? (double)(z * sqrtl(V) / den) : INFINITY; }
-        else if (S->agg == AQE_AGG_AVG) { est = (double)(T / (long double)N); half = (double)(z * sqrtl(V) / (long double)N); }
-        else { est = (double)T; half = (double)(z * sqrtl(V)); }
+        have_prev = 1;
+        double tq = t_from_z(z, df_use), tqn = t_from_z(z, df_cur), half_next;
+        if (ratio) { est = (double)Rr; half = den > 0 ? (double)(tq * sqrtl(V) / den) : INFINITY; half_next = den > 0 ? (double)(tqn * sqrtl(Vcur) / den) : INFINITY; }
+        else if (S->agg == AQE_AGG_AVG) { est = (double)(T / (long double)N); half = (double)(tq * sqrtl(V) / (long double)N); half_next = (double)(tqn * sqrtl(Vcur) / (long double)N); }
+        else { est = (double)T; half = (double)(tq * sqrtl(V)); half_next = (double)(tqn * sqrtl(Vcur)); }
+        passf = (double)(den / (long double)N);
         rel = (ratio && !(den > 0)) ? INFINITY : (est != 0 ? half / fabs(est) * 100.0 : INFINITY);
+        rel_next = (ratio && !(den > 0)) ? INFINITY : (est != 0 ? half_next / fabs(est) * 100.0 : INFINITY);
         if (rel <= S->error_percent) { out->status = AQE_STABLE; break; }
         if (Tg >= nmax) { out->status = AQE_DRIFTING; break; }
-        double rn = rel / S->error_percent;
+        double rn = rel_next / S->error_percent;
         double want = ceil(1.1 * ((double)ntot * rn * rn));
         uint64_t lo_n = Tg + Tg / 4 + 1, hi_n = Tg * 8;
         uint64_t t2 = want >= (double)hi_n ? hi_n : (want <= (double)lo_n ? lo_n : (uint64_t)want);
@@ -1164,7 +1198,7 @@ ORC_API int orc_approx_sharded(const aqe_record* R, uint64_t N, int world, const
         Tg = t2;
     }
     out->estimate = est; out->ci_lower = est - half; out->ci_upper = est + half; out->error_margin = rel / 100.0;
-    out->n_units = ntot; out->n_samples = (uint64_t)rows_read; out->rounds = rounds;
+    out->n_units = ntot; out->n_samples = (uint64_t)rows_read; out->rounds = rounds; out->pass_fraction = passf;
     return 0;
 }
 
@@ -1187,6 +1221,71 @@ static void* mt_worker(void* arg) {
     j->sum = s; j->cnt = c;
     return NULL;
 }
+/* ---- checkers for the BASELINE sizes (10 M / 100 M / 1 B rows): the amount column of the synthetic table generated on all host
+ * cores, the reference's strict left-to-right sum over it (cbd:242-251, :263-274 -- one thread, one double), and an effectively
+ * exact sum (long double Neumaier accumulation per thread, 64 + 64 bits, folded in order) to hold the device to a few ulp. ---- */
+typedef struct { uint64_t seed, first, a, b; int dist; double* out; } synth_job;
+static void* synth_worker(void* arg) {
+    synth_job* j = (synth_job*)arg;
+    aqe_record r;
+    for (uint64_t i = j->a; i < j->b; ++i) { orc_synth_row(j->seed, j->first + i, j->dist, &r); j->out[i] = r.amount; }
+    return NULL;
+}
+ORC_API void orc_synth_amount_mt(uint64_t seed, uint64_t first_row, uint64_t n, int dist, double* out, int threads) {
+    if (threads < 1) threads = 1;
+    if (threads > 1024) threads = 1024;
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * threads);
+    synth_job* jobs = (synth_job*)malloc(sizeof(synth_job) * threads);
+    for (int t = 0; t < threads; ++t) {
+        jobs[t] = (synth_job){seed, first_row, n * (uint64_t)t / (uint64_t)threads, n * (uint64_t)(t + 1) / (uint64_t)threads, dist, out};
+        pthread_create(&th[t], NULL, synth_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+    free(th); free(jobs);
+}
+/* sum_amount / sum_amount_where as the reference computes them: for (r : records) sum += r.amount  (one double, in id order) */
+ORC_API double orc_sum_col_serial(const double* x, uint64_t n, int pred, double lo, double hi, uint64_t* count) {
+    volatile double s = 0.0; uint64_t c = 0;
+    for (uint64_t i = 0; i < n; ++i) { double v = x[i]; if (!pred || (v >= lo && v <= hi)) { s = s + v; ++c; } }
+    if (count) *count = c;
+    return s;
+}
+typedef struct { const double* x; uint64_t a, b; int pred; double lo, hi; long double s, c; uint64_t cnt; } exact_job;
+static void* exact_worker(void* arg) {
+    exact_job* j = (exact_job*)arg;
+    long double s = 0, c = 0; uint64_t cnt = 0;
+    for (uint64_t i = j->a; i < j->b; ++i) {
+        double v = j->x[i];
+        if (j->pred && !(v >= j->lo && v <= j->hi)) continue;
+        ++cnt;
+        long double t = s + (long double)v;     /* Neumaier: the rounding error of every add is kept in c */
+        if (fabsl(s) >= fabsl((long double)v)) c += (s - t) + (long double)v; else c += ((long double)v - t) + s;
+        s = t;
+    }
+    j->s = s; j->c = c; j->cnt = cnt;
+    return NULL;
+}
+ORC_API double orc_sum_col_exact_mt(const double* x, uint64_t n, int pred, double lo, double hi, int threads, uint64_t* count) {
+    if (threads < 1) threads = 1;
+    if (threads > 1024) threads = 1024;
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * threads);
+    exact_job* jobs = (exact_job*)malloc(sizeof(exact_job) * threads);
+    for (int t = 0; t < threads; ++t) {
+        jobs[t] = (exact_job){x, n * (uint64_t)t / (uint64_t)threads, n * (uint64_t)(t + 1) / (uint64_t)threads, pred, lo, hi, 0, 0, 0};
+        pthread_create(&th[t], NULL, exact_worker, &jobs[t]);
+    }
+    long double s = 0, c = 0; uint64_t cnt = 0;
+    for (int t = 0; t < threads; ++t) {
+        pthread_join(th[t], NULL);
+        long double v = jobs[t].s, tt = s + v;
+        if (fabsl(s) >= fabsl(v)) c += (s - tt) + v; else c += (v - tt) + s;
+        s = tt; c += jobs[t].c; cnt += jobs[t].cnt;
+    }
+    free(th); free(jobs);
+    if (count) *count = cnt;
+    return (double)(s + c);
+}
+
 ORC_API double orc_scan_mt(const void* base, uint64_t n, int aos, int pred, double lo, double hi, int threads, uint64_t* count) {
     if (threads < 1) threads = 1;
     if (threads > 1024) threads = 1024;

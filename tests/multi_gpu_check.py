@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Multi-GPU check of the fused exchange (run under torchrun on an N-GPU box, N >= 2; not collected by pytest):
+"""Multi-GPU check of the fused exchange (run under torchrun on an N-GPU box, N >= 2; tests/test_multi_gpu.py runs it from
+pytest -m gpu wherever two or more GPUs are visible and keeps its JSON line as the pass record):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/multi_gpu_check.py
 
@@ -62,6 +63,24 @@ for kw in approx_cases:
         o = O.approx_sharded(rows_all, world, spec)
         assert (a.n_units, a.n_samples, a.rounds, a.status, a.population) == (o.n_units, o.n_samples, o.rounds, o.status, n_small), (rank, kw, seed, (a.n_units, a.n_samples, a.rounds, a.status), (o.n_units, o.n_samples, o.rounds, o.status))
         assert abs(a.estimate - o.estimate) <= 1e-10 * abs(o.estimate) and abs((a.ci_upper - a.ci_lower) - (o.ci_upper - o.ci_lower)) <= 1e-8 * abs(o.ci_upper - o.ci_lower + 1e-300), (kw, seed)
+# ---- legacy sampler families across the ranks (configs[3]): every rank walks the plan, gathers inside its window ----
+from oracle import make_params as orc_params
+tsamp = sharded.ShardedTable.synthetic(n_small, rank, world, seed=11, device=local)
+sampler_cases = [("parallel_pointer", 2.0, dict(num_threads=6)), ("parallel_block", 3.0, dict(block_size=500, num_threads=3)), ("block", 1.0, {}),
+                 ("memory_stride", 1.0, {}), ("optimized_clt", 5.0, dict(num_threads=5)), ("sample_records", 2.5, dict(seed=11)),
+                 ("address_arithmetic", 1.5, dict(seed=4)), ("random_pointer", 0.05, dict(seed=9)), ("multithreaded_memory_stride", 2.0, dict(num_threads=5, seed=5))]
+for method, pct, kw in sampler_cases:
+    prm = aqe.make_params(method, pct, **kw)
+    st = tsamp.stats(method, prm)
+    sw = tsamp.stats(method, prm, where=(100.0, 500.0))
+    got_rows = tsamp.gather(method, prm)
+    idx = O.indices(rows_all, method, orc_params(method, pct, **kw))
+    o = O.stats(rows_all, idx)
+    assert st.n == len(idx) == sw.n and got_rows.tobytes() == rows_all[idx].tobytes(), (rank, method)
+    assert abs(st.sum - o.sum) <= 1e-12 * abs(o.sum) and abs(st.m2 - o.m2) <= 1e-9 * o.m2, (rank, method, st.sum, o.sum)
+    xs = rows_all["amount"][idx]
+    assert abs(sw.sum - float(np.sum(xs[(xs >= 100.0) & (xs <= 500.0)]))) <= 1e-9 * abs(sw.sum)
+del tsamp
 # ---- SQL-string path across the GPUs: facts / integer accumulators all-gathered over NCCL, merged exactly ----
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import SqlError
@@ -124,6 +143,19 @@ for design, eps in (("srs", 0.5), ("block", 0.5), ("srs", 0.1)):
     approx_lat[f"{design}_sum_{eps}pct_kernel_us"] = r.elapsed_us
     approx_lat[f"{design}_sum_{eps}pct_rows_read"] = r.n_samples
 
+# sampled aggregates over the big table through the sampler plans (configs[3] "block sampling + parallel fast/slow method")
+sampler_lat = {}
+for method, pct, kw in (("memory_stride", 1.0, {}), ("block", 1.0, {}), ("parallel_block", 1.0, {}), ("parallel_pointer", 1.0, {})):
+    prm = aqe.make_params(method, pct, **kw)
+    pl = t.plan(method, prm)
+    lat = []
+    for it in range(12):
+        torch.cuda.synchronize(); dist.barrier()
+        t1 = time.perf_counter(); st = t.stats(plan=pl); lat.append((time.perf_counter() - t1) * 1e3)
+    est = st.sum * (N / st.n)
+    assert abs(est - ref[0].sum) / ref[0].sum < 0.01, (method, est, ref[0].sum)
+    sampler_lat[f"{method}_{pct}pct"] = {"samples": st.n, "ms_p50": sorted(lat)[len(lat) // 2], "estimate_rel_error": abs(est - ref[0].sum) / ref[0].sum}
+
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 merged = torch.zeros(8, dtype=torch.int64, device="cuda")
 partial = torch.zeros(8, dtype=torch.int64, device="cuda"); gathered = torch.zeros(8 * world, dtype=torch.int64, device="cuda")
@@ -160,7 +192,8 @@ def timed(fn, k=200):
     return float(ms)
 
 
-res = {"world": world, "rows_total": N, "approx_fused": approx_lat, "ms_kernel_only": timed(kernel_only), "ms_nccl_allgather": timed(nccl), "ms_fused_exchange": timed(fused)}
+res = {"world": world, "rows_total": N, "checks": "fused == nccl bytes, closed forms, approx == orc_approx_sharded, samplers == oracle, SQL == oracle / single GPU: all passed",
+       "approx_fused": approx_lat, "samplers_sharded": sampler_lat, "ms_kernel_only": timed(kernel_only), "ms_nccl_allgather": timed(nccl), "ms_fused_exchange": timed(fused)}
 torch.cuda.synchronize()
 f = aqe.Partial.from_buffer_copy(host[:8].numpy().tobytes())     # async form: no moments, same count / sum / comp bits
 assert (f.count, f.sum, f.comp) == (ref[1].count, ref[1].sum, ref[1].comp)

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(L, s), f"{s} declared in include/aqe_b200.h but not exported"
     assert set(L._signatures) == set(declared_symbols()), "ctypes table out of sync with the header"
-    assert L.aqe_abi_version() == 4
+    assert L.aqe_abi_version() == 5
 
 
 def test_struct_sizes_match_header():
@@ -38,7 +38,8 @@ def test_struct_sizes_match_header():
     assert C.sizeof(aqe.Segment) == 48
     assert C.sizeof(aqe.SampleParams) == 72
     assert C.sizeof(aqe.ApproxSpec) == 80
-    assert C.sizeof(aqe.ApproxResult) == 96
+    assert C.sizeof(aqe.ApproxResult) == 104
+    assert C.sizeof(aqe.StatsPartial) == 64
     assert C.sizeof(aqe.SqlTerm) == 56
     assert C.sizeof(aqe.SqlQuery) == 32 + 8 * 4 + 8 * 5 * 56 + 32 + 64 + 64 + 64 + 512
     assert C.sizeof(aqe.SqlRow) == 80

@@ -1,0 +1,65 @@
+"""BASELINE.json configs[4] as a gate: CI coverage over 1000 seeds x error thresholds 0.1-5 % on a 100 M-record table, for the
+uniform "sales" amounts and a heavy-tailed (lognormal) column, SUM and AVG -- next to the reference CLI's estimator on the
+same samples (enhanced_aqe_cli.py:277-291, whose SUM interval is too narrow by a factor n).
+
+The table of all three interval modes (include/aqe_b200.h, aqe_ci_mode) is written to gpurun_out/ (and kept under profiles/):
+  plain          z * s_r / sqrt(n_r) at the stopping look        -- the textbook interval, biased by stopping on its own variance
+  stein          t(df_{r-1}) * s_{r-1} / sqrt(n_r)                -- variance of the look that chose n_r: unbiased by the stopping
+  stein_guarded  the same at alpha' = 0.8 alpha (the default)     -- the stated guard band for a finite-seed ">= nominal" check
+Gate: the default mode covers >= nominal - 1 binomial sigma in every cell; every cell uses its own seeds."""
+import json
+import math
+import os
+
+import pytest
+
+import approximatequeryengine_b200 as aqe
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RECORDS = int(os.environ.get("AQE_COVERAGE_RECORDS", 100_000_000))
+SEEDS = int(os.environ.get("AQE_COVERAGE_SEEDS", 1000))
+NOMINAL = 0.95
+
+
+def test_coverage_sweep_config4():
+    sigma = math.sqrt(NOMINAL * (1 - NOMINAL) / SEEDS)
+    table, cell = [], 0
+    for dist, dname in ((0, "uniform(1,1000)"), (1, "lognormal(mu=4,sigma=1.5)")):
+        e = aqe.Engine(0).generate(RECORDS, seed=7, dist=dist, columns=("amount",))
+        tot = e.scan("amount")
+        truth = {"sum": tot.sum, "avg": tot.sum / RECORDS}
+        for agg in ("sum", "avg"):
+            for eps in (0.1, 0.5, 1.0, 2.0, 5.0):
+                cell += 1
+                row = {"distribution": dname, "agg": agg, "error_percent": eps, "seeds": SEEDS}
+                for mode in ("plain", "stein", "stein_guarded"):
+                    hit = hit_ref = 0
+                    ns, looks = [], []
+                    for s in range(SEEDS):
+                        r = e.approx(agg, error_percent=eps, confidence_level=NOMINAL, seed=cell * 1_000_003 + s, ci_mode=mode)
+                        assert r.status == 0 and r.error_margin * 100 <= eps + 1e-9
+                        hit += r.ci_lower <= truth[agg] <= r.ci_upper
+                        ns.append(r.n_samples); looks.append(r.rounds)
+                        if mode == "plain":       # the reference CLI's formulas on the same sample moments
+                            st = aqe.Stats(n=r.n_units, mean=r.mean, m2=r.m2, sum=r.mean * r.n_units)
+                            _, lo, hi = aqe.estimate(st, RECORDS, agg, 1.96, legacy_ci=True)
+                            hit_ref += lo <= truth[agg] <= hi
+                    row[mode] = {"coverage": hit / SEEDS, "samples_mean": sum(ns) / SEEDS, "looks_mean": sum(looks) / SEEDS}
+                    if mode == "plain":
+                        row["reference_cli_formula_coverage"] = hit_ref / SEEDS
+                table.append(row)
+        e.close()
+    out = {"records": RECORDS, "seeds_per_cell": SEEDS, "confidence_level": NOMINAL, "binomial_sigma": sigma, "gate": "stein_guarded >= nominal - 1 sigma in every cell",
+           "rows": table}
+    for d in (os.path.join(ROOT, "gpurun_out"),):
+        if os.path.isdir(d):
+            with open(os.path.join(d, "coverage_config4.json"), "w") as f:
+                json.dump(out, f, indent=1)
+    worst = min(table, key=lambda r: r["stein_guarded"]["coverage"])
+    for r in table:
+        assert r["stein_guarded"]["coverage"] >= NOMINAL - sigma, (r["distribution"], r["agg"], r["error_percent"], r["stein_guarded"], "worst", worst)
+        assert r["stein"]["coverage"] >= NOMINAL - 3 * sigma and r["plain"]["coverage"] >= NOMINAL - 4 * sigma, r
+    # the reference's SUM interval (margin * N/n instead of margin * N) covers essentially never
+    assert max(r["reference_cli_formula_coverage"] for r in table if r["agg"] == "sum") < 0.05

@@ -1,0 +1,152 @@
+// microbench.cu -- measured ceilings that the sampled-path rooflines are quoted against (tools/, not product code):
+//
+//   gather   random / strided 8-byte reads out of a large column: samples/s and (under ncu) DRAM bytes per sample, for the load
+//            forms a gather kernel can use (ld.global.nc, ld.global.ca, ld.global.cg, L1::no_allocate) x loads in flight per
+//            thread x the device's L2 fetch-granularity limit (32 / 64 / 128 bytes).
+//   h2d      pinned host -> device cudaMemcpyAsync bandwidth, 1 GiB, per GPU and all GPUs at once (one thread per GPU).
+//
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo tools/microbench.cu -o tools/_bin/microbench
+//   tools/_bin/microbench gather [elems] | h2d [n_gpus]
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { std::fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); std::exit(1); } } while (0)
+
+__device__ __forceinline__ uint64_t mix(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+template <int MODE> __device__ __forceinline__ double load8(const double* p) {
+    double v;
+    if constexpr (MODE == 0) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else if constexpr (MODE == 1) asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else if constexpr (MODE == 2) asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+// pattern 0: uniformly random element; 1: element k * stride (memory_stride_sample's progression)
+template <int MODE, int U>
+__global__ void __launch_bounds__(256) k_gather(const double* __restrict__ col, uint64_t n, uint64_t count, int pattern, uint64_t stride, double* out) {
+    const uint64_t G = (uint64_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; k + (uint64_t)(U - 1) * G < count; k += (uint64_t)U * G) {
+        double x[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const uint64_t kk = k + (uint64_t)j * G;
+            const uint64_t pos = pattern == 0 ? __umul64hi(mix(kk), n) : (kk * stride) % n;
+            x[j] = load8<MODE>(col + pos);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) acc += x[j];
+    }
+    if (acc == 123.456) *out = acc;
+}
+
+template <int MODE, int U> static float run_gather(const double* col, uint64_t n, uint64_t count, int pattern, uint64_t stride, double* out, int reps) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int grid = 148 * 8;
+    for (int i = 0; i < 2; ++i) k_gather<MODE, U><<<grid, 256>>>(col, n, count, pattern, stride, out);
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; ++i) k_gather<MODE, U><<<grid, 256>>>(col, n, count, pattern, stride, out);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    return ms / reps;
+}
+
+static int gather_main(uint64_t n) {
+    double *col = nullptr, *out = nullptr;
+    CK(cudaMalloc(&col, n * 8));
+    CK(cudaMalloc(&out, 8));
+    CK(cudaMemset(col, 0, n * 8));
+    const uint64_t count = 16u << 20;
+    const bool quick = std::getenv("MB_QUICK") != nullptr;   // the short list (for a run under ncu)
+    for (size_t gran : {(size_t)0, (size_t)32, (size_t)64, (size_t)128}) {
+        if (gran) {
+            if (quick && gran == 64) continue;
+            cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+            if (e != cudaSuccess) { std::printf("{\"l2_fetch_granularity\": %zu, \"error\": \"%s\"}\n", gran, cudaGetErrorString(e)); cudaGetLastError(); continue; }
+        }
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        for (int pattern = 0; pattern < 2; ++pattern) {
+            auto line = [&](const char* mode, int u, float ms) {
+                std::printf("{\"bench\": \"gather\", \"l2_fetch_granularity\": %zu, \"pattern\": \"%s\", \"load\": \"%s\", \"in_flight\": %d, \"ms\": %.4f, "
+                            "\"Gsamples_per_s\": %.2f, \"sector_GBps\": %.1f}\n", got, pattern ? "stride100" : "random", mode, u, ms, count / ms / 1e6, count * 32.0 / ms / 1e6);
+                std::fflush(stdout);
+            };
+            const int reps = 5;
+            line("nc", 4, run_gather<0, 4>(col, n, count, pattern, 100, out, reps));
+            line("cg", 4, run_gather<2, 4>(col, n, count, pattern, 100, out, reps));
+            if (quick) continue;
+            line("nc", 1, run_gather<0, 1>(col, n, count, pattern, 100, out, reps));
+            line("nc", 2, run_gather<0, 2>(col, n, count, pattern, 100, out, reps));
+            line("nc", 8, run_gather<0, 8>(col, n, count, pattern, 100, out, reps));
+            line("nc", 16, run_gather<0, 16>(col, n, count, pattern, 100, out, reps));
+            line("ca", 4, run_gather<1, 4>(col, n, count, pattern, 100, out, reps));
+            line("cg", 8, run_gather<2, 8>(col, n, count, pattern, 100, out, reps));
+            line("cg", 16, run_gather<2, 16>(col, n, count, pattern, 100, out, reps));
+            line("nc.no_allocate", 4, run_gather<3, 4>(col, n, count, pattern, 100, out, reps));
+            line("nc.no_allocate", 8, run_gather<3, 8>(col, n, count, pattern, 100, out, reps));
+        }
+    }
+    return 0;
+}
+
+static int h2d_main(int ngpu) {
+    int have = 0;
+    CK(cudaGetDeviceCount(&have));
+    if (ngpu <= 0 || ngpu > have) ngpu = have;
+    const size_t bytes = 1ull << 30;
+    std::vector<void*> host(ngpu), dev(ngpu);
+    std::vector<cudaStream_t> st(ngpu);
+    for (int g = 0; g < ngpu; ++g) {
+        CK(cudaSetDevice(g));
+        CK(cudaHostAlloc(&host[g], bytes, cudaHostAllocPortable));
+        std::memset(host[g], 1, bytes);
+        CK(cudaMalloc(&dev[g], bytes));
+        CK(cudaStreamCreateWithFlags(&st[g], cudaStreamNonBlocking));
+    }
+    auto one = [&](int g, int reps) -> double {   // GB/s of `reps` back-to-back 1 GiB copies on GPU g
+        CK(cudaSetDevice(g));
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        CK(cudaMemcpyAsync(dev[g], host[g], bytes, cudaMemcpyHostToDevice, st[g]));
+        CK(cudaEventRecord(e0, st[g]));
+        for (int i = 0; i < reps; ++i) CK(cudaMemcpyAsync(dev[g], host[g], bytes, cudaMemcpyHostToDevice, st[g]));
+        CK(cudaEventRecord(e1, st[g]));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        return reps * (double)bytes / ms / 1e6;
+    };
+    for (int g = 0; g < ngpu; ++g) std::printf("{\"bench\": \"h2d\", \"gpu\": %d, \"alone_GBps\": %.2f}\n", g, one(g, 4));
+    std::vector<double> r(ngpu);
+    std::vector<std::thread> th;
+    for (int g = 0; g < ngpu; ++g) th.emplace_back([&, g] { r[g] = one(g, 6); });
+    for (auto& t : th) t.join();
+    double sum = 0;
+    for (int g = 0; g < ngpu; ++g) sum += r[g];
+    std::printf("{\"bench\": \"h2d\", \"gpus\": %d, \"concurrent_total_GBps\": %.2f, \"per_gpu_min_GBps\": %.2f}\n", ngpu, sum, *std::min_element(r.begin(), r.end()));
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc >= 2 && !std::strcmp(argv[1], "gather")) return gather_main(argc >= 3 ? std::strtoull(argv[2], nullptr, 10) : (1ull << 30));
+    if (argc >= 2 && !std::strcmp(argv[1], "h2d")) return h2d_main(argc >= 3 ? std::atoi(argv[2]) : 0);
+    std::fprintf(stderr, "usage: microbench gather [elems] | h2d [n_gpus]\n");
+    return 2;
+}
