@@ -679,18 +679,19 @@ static ScanTuning scan_tuning() {
 
 // occupancy (and the one-time dynamic-smem opt-in) per kernel, looked up once
 static int kernel_occupancy(const void* kernel, int threads, size_t smem) {
-    struct Key { const void* k; int dev; int occ; };
+    struct Key { const void* k; int dev; size_t smem; int occ; };
     static std::mutex mu;
     static std::vector<Key> cache;
     int dev = 0;
     cudaGetDevice(&dev);  // function attributes are per device
     std::lock_guard<std::mutex> lock(mu);
-    for (auto& e : cache) if (e.k == kernel && e.dev == dev) return e.occ;
-    if (smem) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t opted = 0;
+    for (auto& e : cache) if (e.k == kernel && e.dev == dev) { if (e.smem == smem) return e.occ; opted = std::max(opted, e.smem); }
+    if (smem > opted) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
     occ = std::max(occ, 1);
-    cache.push_back(Key{kernel, dev, occ});
+    cache.push_back(Key{kernel, dev, smem, occ});
     return occ;
 }
 
@@ -704,7 +705,9 @@ template <typename K> static int launch_regs_kernel(const aqe_db* db, K kernel, 
     return AQE_OK;
 }
 template <typename K> static int launch_ring_kernel(const aqe_db* db, K kernel, const ScanArgs& a, int stages, int rows_per_tile, int bps_req, cudaStream_t s) {
-    const size_t smem = (size_t)stages * kStageBytes;
+    size_t smem = (size_t)stages * kStageBytes;
+    // programmatic dependent launch: exactly two CTAs fit an SM (3 x 76 KiB > 227 KiB), see ScanArgs::pdl_tail
+    if (a.pdl_tail && (bps_req == 0 || bps_req == 2)) smem = std::max<size_t>(smem, 76 * 1024);
     const int occ = kernel_occupancy((const void*)kernel, kBulkThreads, smem);
     const int bps = bps_req > 0 ? std::min(bps_req, occ) : occ;
     const uint64_t ntiles = (a.n + rows_per_tile - 1) / rows_per_tile;
@@ -838,7 +841,7 @@ static int scan_launch(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, ui
     a.partials = db->scan_partials; a.ticket = db->tickets + 0; a.out = out_dev;
     // back-to-back scans overlap their tails (programmatic dependent launch) when the columns are the handle's own: borrowed columns
     // may have been written by the caller's previous kernel on this stream, which only a full stream dependency orders
-    a.pdl_tail = db->owned ? (unsigned int)std::max(0, env_int("AQE_SCAN_PDL_TILES", 8)) : 0u;
+    a.pdl_tail = db->owned && env_int("AQE_SCAN_PDL", 1) != 0 ? 1u : 0u;
     // 256-bit vector loads on every column
     auto aligned_for = [](const void* p, int) { return ((uintptr_t)p % 32) == 0; };
     const bool aligned = aligned_for(a.agg, ak) && (pred_mode != 2 || aligned_for(a.pred, pk));

@@ -112,10 +112,13 @@ struct ScanArgs {
     unsigned int* ticket;   // zero before launch; reset by the last block
     aqe_partial* out;       // device-visible (device memory or mapped pinned host memory)
     Exchange ex;
-    // Programmatic dependent launch (back-to-back scans of one stream): > 0 = a CTA lets the NEXT scan of the stream start once it
-    // has this many tiles left, so the next query's first tiles stream while this one drains, folds and exchanges.  Everything a
-    // scan writes (block partials, ticket, mailboxes, result) happens behind griddep_wait(), i.e. after the previous scan has
-    // completed: stream order is kept for every side effect, only the read-only streaming overlaps.
+    // Programmatic dependent launch (back-to-back scans of one stream): != 0 = every CTA says at its start that the NEXT scan of the
+    // stream may be launched.  The ring kernel is launched with exactly as many CTAs as the GPU holds (2 per SM, shared memory padded
+    // so that a third cannot fit), so the next scan's CTAs wait for slots and take them one by one as this scan's CTAs exit: no idle
+    // tail, no launch gap, still two CTAs on every SM (a first version that let a third CTA squeeze in next to a draining scan left
+    // the next scan's CTAs unevenly spread over the SMs and ran 10-25 % SLOWER, profiles/r2_pdl_ab.jsonl).  Everything a scan writes
+    // (block partials, ticket, mailboxes, result) happens behind griddep_wait(), i.e. after the previous scan has completed:
+    // stream order is kept for every side effect, only the read-only streaming overlaps the previous scan's fold and exchange.
     unsigned int pdl_tail;
 };
 
@@ -419,18 +422,14 @@ __global__ void __launch_bounds__(kBulkThreads) k_scan_ring(const ScanArgs a) {
         fence_barrier_init();
     }
     __syncthreads();
+    if (a.pdl_tail) griddep_launch_dependents();
 
     ScanAcc acc = scan_identity();
     DD alt{0.0, 0.0};
     if (warp == kBulkConsumerWarps) {
         if (lane == 0) {
-            // tiles of this CTA: c = blockIdx.x + it * gridDim.x < ntiles
-            const uint64_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-            const uint32_t pdl_at = a.pdl_tail ? (uint32_t)(my_tiles > a.pdl_tail ? my_tiles - a.pdl_tail : 0) : 0xffffffffu;
-            if (a.pdl_tail && my_tiles == 0) griddep_launch_dependents();
             uint32_t it = 0;
             for (uint64_t c = blockIdx.x; c < ntiles; c += gridDim.x, ++it) {
-                if (it == pdl_at) griddep_launch_dependents();   // this CTA has pdl_tail tiles left: the next scan of the stream may start
                 const int s = it % STAGES;
                 const uint32_t round = it / STAGES;
                 if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
@@ -453,14 +452,45 @@ __global__ void __launch_bounds__(kBulkThreads) k_scan_ring(const ScanArgs a) {
             const uint32_t rows = (uint32_t)((n_main - row0) < (uint64_t)G::kRows ? (n_main - row0) : (uint64_t)G::kRows);
             const unsigned char* stage = smem_raw + (size_t)s * kStageBytes;
             const uint32_t nunits = rows / U;
+            if constexpr (!IS_INT && !MOMENTS) {
+                // f64 sums: the (at most 8) values a thread takes from one tile are added in plain double -- two independent chains --
+                // and only the tile's subtotal enters the compensated (TwoSum) accumulator: 1 + 7/8 FP64 adds per value instead of 7.
+                // The FP64 pipe was 48 % busy with the per-value TwoSum and held the board at its 1 kW power cap in sustained loops
+                // (SM clock 1.71 GHz, 5.6 TB/s; profiles/r2_bench_n1_a.json).  Error: a subtotal of <= 8 same-sign values is off by
+                // <= 3 ulp of ITSELF, the compensated sum of the subtotals adds nothing to that: <= 2 ulp of the total in the worst case,
+                // ~1e-20 relative in practice (the subtotals' errors are independent); the reference's serial sum is off by ~5e-13 at 1 B rows.
+                double b0 = 0.0, b1 = 0.0;
+                uint32_t passed = 0;
 #pragma unroll 4
-            for (uint32_t i = ct; i < nunits; i += kBulkConsumerWarps * 32) {
-                const Vec<AggT, U> av = lds_vec<AggT, U>(stage, i);
-                Vec<PredT, U> pv;
-                if constexpr (PRED == 2) pv = lds_vec<PredT, U>(stage + G::kAggBytes, i);
+                for (uint32_t i = ct; i < nunits; i += kBulkConsumerWarps * 32) {
+                    const Vec<AggT, U> av = lds_vec<AggT, U>(stage, i);
+                    Vec<PredT, U> pv;
+                    if constexpr (PRED == 2) pv = lds_vec<PredT, U>(stage + G::kAggBytes, i);
 #pragma unroll
-                for (int e = 0; e < U; ++e)
-                    scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, av.v[e], PRED == 2 ? pv.v[e] : PredT(0), a, e & 1);
+                    for (int e = 0; e < U; ++e) {
+                        bool pass = true;
+                        if constexpr (PRED == 1) pass = (av.v[e] >= a.lo) && (av.v[e] <= a.hi);
+                        if constexpr (PRED == 2) {
+                            if constexpr (std::is_integral_v<PredT>) pass = ((long long)pv.v[e] >= a.ilo) && ((long long)pv.v[e] <= a.ihi);
+                            else { const double d = as_f64(pv.v[e]); pass = (d >= a.lo) && (d <= a.hi); }
+                        }
+                        passed += pass ? 1u : 0u;
+                        const double x = pass ? (double)av.v[e] : 0.0;
+                        if (e & 1) b1 = __dadd_rn(b1, x); else b0 = __dadd_rn(b0, x);
+                    }
+                }
+                acc.count += passed;
+                dd_add(acc.sum, __dadd_rn(b0, b1));
+            } else {
+#pragma unroll 4
+                for (uint32_t i = ct; i < nunits; i += kBulkConsumerWarps * 32) {
+                    const Vec<AggT, U> av = lds_vec<AggT, U>(stage, i);
+                    Vec<PredT, U> pv;
+                    if constexpr (PRED == 2) pv = lds_vec<PredT, U>(stage + G::kAggBytes, i);
+#pragma unroll
+                    for (int e = 0; e < U; ++e)
+                        scan_consume<AggT, PRED, PredT, MOMENTS>(acc, alt, av.v[e], PRED == 2 ? pv.v[e] : PredT(0), a, e & 1);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);

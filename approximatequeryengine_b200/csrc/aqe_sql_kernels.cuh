@@ -197,12 +197,15 @@ __device__ __forceinline__ unsigned int limb_add(unsigned int* limb, unsigned in
     if (s) { const unsigned int old = atomicAdd(limb, s); carry |= (old + s < old) ? 1u : 0u; }
     return carry;
 }
-__device__ __forceinline__ void shared_add128(unsigned int* limbs, long long v) {
+// The four limbs of bin g live G words apart (limb-major: word l * G + g), so that the 32 lanes of a warp, each with its own
+// group key, spread over all 32 banks.  (Group-major [g][4] put limb l of every bin into the 8 banks l, l + 4, ...: the lanes of a
+// warp queued ~7 deep on them instead of ~3.5, and the ATOMS wavefronts are what bounds this kernel.)
+__device__ __forceinline__ void shared_add128(unsigned int* limbs, unsigned int G, unsigned int g, long long v) {
     const unsigned int sign = v < 0 ? 0xffffffffu : 0u;
-    unsigned int c = limb_add(limbs + 0, (unsigned int)v, 0u);
-    c = limb_add(limbs + 1, (unsigned int)((unsigned long long)v >> 32), c);
-    c = limb_add(limbs + 2, sign, c);
-    limb_add(limbs + 3, sign, c);
+    unsigned int c = limb_add(limbs + g, (unsigned int)v, 0u);
+    c = limb_add(limbs + G + g, (unsigned int)((unsigned long long)v >> 32), c);
+    c = limb_add(limbs + 2 * G + g, sign, c);
+    limb_add(limbs + 3 * G + g, sign, c);
 }
 
 // ---- bins: where a row's (count, value, value^2) lands ------------------------------------------------------
@@ -216,7 +219,7 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
     //         with squares, three words instead of four (16 bytes of shared-memory traffic less per row), u = value + 2^63, q = square < 2^62:
     //         w0 = rows << 52 | sum of u[0:40)      w1 = sum of q[0:16) << 36 | sum of u[40:64)      w2 = sum of q[16:62)
     //         -- every field has 12 spare bits: fewer than kSqlPackedRowsMoments rows per bin between drains
-    // MODE 2: cnt[G] u32 | sum limbs [G][4] u32 | (sq limbs [G][4])
+    // MODE 2: cnt[G] u32 | sum limbs [4][G] u32 | (sq limbs [4][G])
     unsigned int* b_cnt;
     unsigned long long *p_slo, *p_shi, *p_qlo;
     unsigned int *s_sum, *s_sq;
@@ -267,8 +270,8 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
         } else {
             atomicAdd(b_cnt + g, 1u);
             if (has_sum) {
-                shared_add128(s_sum + g * 4, fx);
-                if constexpr (MOMENTS) shared_add128(s_sq + g * 4, fq);
+                shared_add128(s_sum, G, g, fx);
+                if constexpr (MOMENTS) shared_add128(s_sq, G, g, fq);
             }
         }
     }
@@ -347,11 +350,11 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
                 if (!c) continue;
                 unsigned long long* ga = global_acc + (size_t)g * 5;
                 atomicAdd(ga + 0, (unsigned long long)c);
-                const unsigned int* l = s_sum + g * 4;
-                global_add128(ga + 1, ((unsigned long long)l[1] << 32) | l[0], ((unsigned long long)l[3] << 32) | l[2]);
+                const unsigned int* l = s_sum + g;
+                global_add128(ga + 1, ((unsigned long long)l[G] << 32) | l[0], ((unsigned long long)l[3 * G] << 32) | l[2 * G]);
                 if constexpr (MOMENTS) {
-                    const unsigned int* m = s_sq + g * 4;
-                    global_add128(ga + 3, ((unsigned long long)m[1] << 32) | m[0], ((unsigned long long)m[3] << 32) | m[2]);
+                    const unsigned int* m = s_sq + g;
+                    global_add128(ga + 3, ((unsigned long long)m[G] << 32) | m[0], ((unsigned long long)m[3 * G] << 32) | m[2 * G]);
                 }
             }
         }
