@@ -573,9 +573,14 @@ def main():
     # ---- secondary, N > 1: the whole box behind ONE CustomBPlusDB of ONE process (rank 0; the other ranks wait on the CPU) ----
     single = None
     if world > 1 and not args.skip_single_process:
-        store = dist.distributed_c10d._get_default_store()
+        try:
+            store = dist.distributed_c10d._get_default_store()
+        except Exception:  # noqa: BLE001
+            store = None
         sync_all()
-        if rank == 0:
+        if store is None:
+            single = {"skipped": "no c10d store to park the other ranks on"}
+        elif rank == 0:
             try:
                 b = aqe.backend()
                 sp = b.CustomBPlusDB(list(range(world)))
@@ -598,7 +603,7 @@ def main():
                 single = {"error": repr(ex)}
             store.set("aqe_single_process_done", "1")
         else:
-            store.wait(["aqe_single_process_done"])
+            store.wait(["aqe_single_process_done"])      # on the CPU: no kernel of this rank runs while rank 0 uses every GPU
         sync_all()
 
     # ---- secondary, N > 1: the weak-scaling figure (1 B records per GPU), kept next to the strong headline ----

@@ -11,11 +11,15 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cerrno>
 #include <cstring>
 #include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { std::fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); std::exit(1); } } while (0)
 
@@ -144,9 +148,75 @@ static int h2d_main(int ngpu) {
     return 0;
 }
 
+// h2dnuma: does the placement of the pinned host buffers limit the all-GPUs-at-once rate?  Buffers are mmap'ed, given a NUMA
+// policy with mbind(2) (default / interleaved over all nodes / bound to node k), touched, registered with CUDA and copied from on
+// all GPUs at once.  Prints what the kernel allows (nodes online, this process' allowed memory nodes).
+static int h2dnuma_main(int ngpu) {
+    int have = 0;
+    CK(cudaGetDeviceCount(&have));
+    if (ngpu <= 0 || ngpu > have) ngpu = have;
+    int nodes = 0;
+    for (int k = 0; k < 64; ++k) { char path[64]; std::snprintf(path, sizeof(path), "/sys/devices/system/node/node%d", k); if (access(path, F_OK) == 0) nodes = k + 1; }
+    if (nodes < 1) nodes = 1;
+    {
+        FILE* f = std::fopen("/proc/self/status", "r");
+        char line[512];
+        while (f && std::fgets(line, sizeof(line), f))
+            if (!std::strncmp(line, "Mems_allowed_list", 17) || !std::strncmp(line, "Cpus_allowed_list", 17)) { line[std::strcspn(line, "\n")] = 0; std::printf("{\"bench\": \"h2dnuma\", \"status\": \"%s\"}\n", line); }
+        if (f) std::fclose(f);
+    }
+    const size_t bytes = 1ull << 30;
+    std::vector<void*> dev(ngpu);
+    std::vector<cudaStream_t> st(ngpu);
+    for (int g = 0; g < ngpu; ++g) { CK(cudaSetDevice(g)); CK(cudaMalloc(&dev[g], bytes)); CK(cudaStreamCreateWithFlags(&st[g], cudaStreamNonBlocking)); }
+    for (int policy = -2; policy < nodes; ++policy) {   // -2 default, -1 interleave over all nodes, k >= 0 bind to node k
+        std::vector<void*> host(ngpu, nullptr);
+        bool ok = true;
+        for (int g = 0; g < ngpu && ok; ++g) {
+            void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+            if (p == MAP_FAILED) { ok = false; break; }
+            host[g] = p;
+            if (policy != -2) {
+                unsigned long mask = policy == -1 ? ((nodes >= 64 ? ~0ul : ((1ul << nodes) - 1))) : (1ul << policy);
+                const long rc = syscall(SYS_mbind, p, bytes, policy == -1 ? 3 /* MPOL_INTERLEAVE */ : 2 /* MPOL_BIND */, &mask, (unsigned long)(nodes + 1), 0u);
+                if (rc != 0) { std::printf("{\"bench\": \"h2dnuma\", \"policy\": %d, \"error\": \"mbind failed (errno %d)\"}\n", policy, errno); ok = false; }
+            }
+            if (ok) { std::memset(p, 1, bytes); CK(cudaSetDevice(g)); if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); ok = false; } }
+        }
+        if (ok) {
+            std::vector<double> r(ngpu);
+            std::vector<std::thread> th;
+            for (int g = 0; g < ngpu; ++g)
+                th.emplace_back([&, g] {
+                    CK(cudaSetDevice(g));
+                    cudaEvent_t e0, e1;
+                    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+                    CK(cudaMemcpyAsync(dev[g], host[g], bytes, cudaMemcpyHostToDevice, st[g]));
+                    CK(cudaEventRecord(e0, st[g]));
+                    for (int i = 0; i < 6; ++i) CK(cudaMemcpyAsync(dev[g], host[g], bytes, cudaMemcpyHostToDevice, st[g]));
+                    CK(cudaEventRecord(e1, st[g]));
+                    CK(cudaEventSynchronize(e1));
+                    float ms = 0;
+                    CK(cudaEventElapsedTime(&ms, e0, e1));
+                    r[g] = 6.0 * (double)bytes / ms / 1e6;
+                });
+            for (auto& t : th) t.join();
+            double sum = 0;
+            for (double v : r) sum += v;
+            std::printf("{\"bench\": \"h2dnuma\", \"gpus\": %d, \"numa_nodes\": %d, \"policy\": \"%s%d\", \"concurrent_total_GBps\": %.2f, \"per_gpu_min_GBps\": %.2f, \"per_gpu_max_GBps\": %.2f}\n",
+                        ngpu, nodes, policy == -2 ? "default" : (policy == -1 ? "interleave" : "bind node "), policy < 0 ? 0 : policy, sum,
+                        *std::min_element(r.begin(), r.end()), *std::max_element(r.begin(), r.end()));
+            std::fflush(stdout);
+        }
+        for (int g = 0; g < ngpu; ++g) if (host[g]) { cudaHostUnregister(host[g]); cudaGetLastError(); munmap(host[g], bytes); }
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && !std::strcmp(argv[1], "h2dnuma")) return h2dnuma_main(argc >= 3 ? std::atoi(argv[2]) : 0);
     if (argc >= 2 && !std::strcmp(argv[1], "gather")) return gather_main(argc >= 3 ? std::strtoull(argv[2], nullptr, 10) : (1ull << 30));
     if (argc >= 2 && !std::strcmp(argv[1], "h2d")) return h2d_main(argc >= 3 ? std::atoi(argv[2]) : 0);
-    std::fprintf(stderr, "usage: microbench gather [elems] | h2d [n_gpus]\n");
+    std::fprintf(stderr, "usage: microbench gather [elems] | h2d [n_gpus] | h2dnuma [n_gpus]\n");
     return 2;
 }
