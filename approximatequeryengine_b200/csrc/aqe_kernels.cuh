@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(kBulkThreads) k_scan_ring(const ScanArgs a) {
             const uint32_t rows = (uint32_t)((n_main - row0) < (uint64_t)G::kRows ? (n_main - row0) : (uint64_t)G::kRows);
             const unsigned char* stage = smem_raw + (size_t)s * kStageBytes;
             const uint32_t nunits = rows / U;
-            if constexpr (!IS_INT && !MOMENTS) {
+            if constexpr (!IS_INT) {
                 // f64 sums: the (at most 8) values a thread takes from one tile are added in plain double -- two independent chains --
                 // and only the tile's subtotal enters the compensated (TwoSum) accumulator: 1 + 7/8 FP64 adds per value instead of 7.
                 // The FP64 pipe was 48 % busy with the per-value TwoSum and held the board at its 1 kW power cap in sustained loops
@@ -477,6 +477,11 @@ __global__ void __launch_bounds__(kBulkThreads) k_scan_ring(const ScanArgs a) {
                         passed += pass ? 1u : 0u;
                         const double x = pass ? (double)av.v[e] : 0.0;
                         if (e & 1) b1 = __dadd_rn(b1, x); else b0 = __dadd_rn(b0, x);
+                        if constexpr (MOMENTS) {   // the synchronous API also reports sum of squares / min / max; count, sum, comp are the same bits
+                            acc.sq.s = fma(x, x, acc.sq.s);
+                            acc.mn = fmin(acc.mn, pass ? (double)av.v[e] : acc.mn);
+                            acc.mx = fmax(acc.mx, pass ? (double)av.v[e] : acc.mx);
+                        }
                     }
                 }
                 acc.count += passed;

@@ -180,7 +180,14 @@ public:
     void generate_synthetic(uint64_t n_rows, uint64_t seed, uint64_t first_row, int dist, uint32_t columns_mask) {
         check(aqe_generate_synthetic(h_, seed, first_row, n_rows, dist, columns_mask));
     }
+    // borrowed columns live on ONE GPU: a handle that was going to shard over several becomes a handle on `device`
+    void single_device(int device) {
+        if (devices_.size() == 1 && devices_[0] == device) return;
+        devices_.assign(1, device);
+        reset();
+    }
     void attach_columns(uintptr_t id, uintptr_t amount, uintptr_t region, uintptr_t product_id, uintptr_t timestamp, uint64_t n) {
+        if (devices_.size() > 1) single_device(devices_[0]);
         check(aqe_attach_device_columns(h_, reinterpret_cast<const int64_t*>(id), reinterpret_cast<const double*>(amount),
                                         reinterpret_cast<const int32_t*>(region), reinterpret_cast<const int32_t*>(product_id),
                                         reinterpret_cast<const int64_t*>(timestamp), n));
@@ -189,6 +196,7 @@ public:
     void from_torch(py::object id, py::object amount, py::object region, py::object product_id, py::object timestamp) {
         uint64_t n = 0;
         bool have_n = false;
+        int tensor_device = 0;
         auto ptr_of = [&](py::object t, const char* name, const char* want) -> uintptr_t {
             if (t.is_none()) return 0;
             if (!py::hasattr(t, "data_ptr")) throw py::value_error(std::string(name) + ": expected a CUDA tensor");
@@ -198,12 +206,17 @@ public:
             if (dt != want) throw py::value_error(std::string(name) + ": dtype must be " + want + ", got " + dt);
             const uint64_t m = t.attr("numel")().cast<uint64_t>();
             if (have_n && m != n) throw py::value_error("all columns must have the same length");
+            const py::object index = t.attr("device").attr("index");
+            const int dev = index.is_none() ? 0 : index.cast<int>();
+            if (have_n && dev != tensor_device) throw py::value_error("all columns must live on the same GPU");
+            tensor_device = dev;
             n = m; have_n = true;
             return t.attr("data_ptr")().cast<uintptr_t>();
         };
         const uintptr_t a = ptr_of(id, "id", "torch.int64"), b = ptr_of(amount, "amount", "torch.float64"), c = ptr_of(region, "region", "torch.int32"),
                         d = ptr_of(product_id, "product_id", "torch.int32"), e = ptr_of(timestamp, "timestamp", "torch.int64");
         if (!have_n) throw py::value_error("from_torch: give at least one column");
+        single_device(tensor_device);
         attach_columns(a, b, c, d, e, n);
         keep_alive_ = py::make_tuple(id, amount, region, product_id, timestamp);  // the engine borrows the memory
     }

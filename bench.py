@@ -596,8 +596,17 @@ def main():
                           "gpus": sp.shard_count, "fused": sp.shards_fused, "records": total, "ms_per_query_p50": ms, "ms_per_query_min": min(ts) * 1e3,
                           "records_per_s": total / (ms * 1e-3), "sum": v, "bits_equal_to_process_per_gpu_result": v == merged.sum and v2 == v,
                           "timing": "host wall clock of the synchronous call, the other ranks' processes idle"}
-                r = sp.approx_sum(error_percent=0.5, seed=3, design="block")
-                single["approx_sum_0.5pct_block"] = {"status": str(r.status), "kernel_us": r.kernel_us, "rel_err_percent": abs(r.value - 500.5 * total) / (500.5 * total) * 100}
+                lat = []
+                for sd in range(30):
+                    t0 = time.perf_counter(); r = sp.approx_sum(error_percent=0.5, seed=sd, design="block"); lat.append((time.perf_counter() - t0) * 1e6)
+                single["approx_sum_0.5pct_block"] = {"status": str(r.status), "latency_us_p50": statistics.median(lat[5:]), "kernel_us": r.kernel_us,
+                                                     "rel_err_percent": abs(r.value - 500.5 * total) / (500.5 * total) * 100}
+                st = sp.sample_array("parallel_block", 1.0, stats=True)
+                ts2 = []
+                for _ in range(8):
+                    t0 = time.perf_counter(); st = sp.sample_array("parallel_block", 1.0, stats=True); ts2.append(time.perf_counter() - t0)
+                single["parallel_block_1pct_stats"] = {"samples": st["n"], "ms_p50": statistics.median(ts2) * 1e3,
+                                                       "estimate_rel_error_percent": abs(st["sum"] * (total / st["n"]) - 500.5 * total) / (500.5 * total) * 100}
                 del sp
             except Exception as ex:  # noqa: BLE001
                 single = {"error": repr(ex)}
