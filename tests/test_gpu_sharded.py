@@ -160,8 +160,8 @@ def test_approx_over_shards(world):
                 assert r.status == 0 and r.population == N and r.error_margin <= 0.0100001, (name, agg, where)
                 hit += r.ci_lower <= want <= r.ci_upper
             assert hit >= 34, (name, agg, where, hit)
-        r = g.approx("sum", design="block", block_size=500, min_samples=64, seed=1)
-        assert r.status == 0 and abs(r.estimate - truth) / truth < 0.03
+        r = g.approx("sum", design="block", block_size=500, min_samples=64, seed=1)      # 600 tiles in all: the budget may run out (DRIFTING)
+        assert r.status in (0, 1) and abs(r.estimate - truth) / truth < 0.03 and r.ci_lower <= r.estimate <= r.ci_upper
 
 
 def test_files_appends_and_reload(world, oracle, tmp_path):
