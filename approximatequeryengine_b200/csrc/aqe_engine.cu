@@ -829,6 +829,7 @@ static int scan_launch(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, ui
     if (exchange) {
         if (!db->ex_connected) return fail(AQE_ERR_STATE, "aqe_exchange_connect has not been called");
         a.ex.world = db->ex_world; a.ex.rank = db->ex_rank; a.ex.is_integer = ak != K_F64;
+        a.ex.split = env_int("AQE_EXCHANGE_SPLIT", 1) != 0 ? 1 : 0;
         a.ex.seq = ++db->ex_seq;
         a.ex.timeout_cycles = (unsigned long long)env_int("AQE_EXCHANGE_TIMEOUT_MS", 5000) * 2000000ull;
         for (int r = 0; r < db->ex_world; ++r) a.ex.peers[r] = db->ex_peers[r];
@@ -851,6 +852,18 @@ static int scan_launch(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, ui
     else rc = launch_scan_pred<int32_t, false>(db, a, pred_mode, pk, aligned, s);
     if (rc) return rc;
     CU(cudaGetLastError());
+    if (exchange && a.ex.split) {
+        // the wait for the peers + the rank-order fold: one warp, right behind the scan (k_scan_merge, aqe_kernels.cuh)
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(1); cfg.blockDim = dim3(32); cfg.stream = s;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr; cfg.numAttrs = a.pdl_tail ? 1 : 0;
+        CU(cudaLaunchKernelEx(&cfg, k_scan_merge, a.ex, out_dev));
+        LAUNCHED();
+    }
     return AQE_OK;
 }
 

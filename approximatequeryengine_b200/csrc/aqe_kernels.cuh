@@ -95,7 +95,7 @@ struct Exchange {
     int world;                 // 0/1 = disabled
     int rank;
     int is_integer;
-    int pad;
+    int split;                 // 1: the scan kernel only PUBLISHES its partial; k_scan_merge (next in the stream) waits for the peers and folds
     unsigned long long seq;
     unsigned long long timeout_cycles;
     ExSlot* peers[kMaxRanks];  // peers[r] = rank r's mailbox as mapped in this process (peers[rank] = own)
@@ -248,6 +248,7 @@ template <bool IS_INT, bool MOMENTS> __device__ __forceinline__ void scan_finish
         __threadfence_system();
         st_release_sys(&dst->seq, a.ex.seq);
     }
+    if (a.ex.split) return;   // the wait for the peers must not hold an SM slot of this grid: the next scan's CTA is queued for it
     __syncthreads();
     if ((int)threadIdx.x < world) {
         const ExSlot* src = a.ex.peers[a.ex.rank] + (threadIdx.x * 2 + par);
@@ -265,6 +266,33 @@ template <bool IS_INT, bool MOMENTS> __device__ __forceinline__ void scan_finish
     }
     __syncthreads();
     if (threadIdx.x == 0) merge_partials_dev(sh_parts, world, a.ex.is_integer != 0, a.out);
+}
+
+// Second half of the fused exchange as its own one-warp kernel, launched right behind the scan on the same stream: waits until
+// this rank's mailbox holds `seq` from every rank, folds the partials in rank order and writes the table-level result.  Keeping
+// the wait out of the scan grid matters for back-to-back queries: a scan CTA that sits on an SM waiting for a slower GPU keeps the
+// next scan's CTA (queued for exactly that slot, static tile assignment) from starting, and the whole next query ends that much
+// later (measured at 8 GPUs: 148 us per query with the wait inside the scan, 140 us for the scan alone).  One warp, no shared-memory
+// ring: it fits next to the two scan CTAs of any SM.
+__global__ void __launch_bounds__(32) k_scan_merge(const Exchange ex, aqe_partial* out) {
+    __shared__ aqe_partial sh_parts[kMaxRanks];
+    griddep_launch_dependents();   // the next scan of the stream may be launched (its CTAs queue for SM slots)
+    griddep_wait();                // this rank's scan has completed: its partial is in every mailbox
+    const int world = ex.world, par = (int)(ex.seq & 1ull);
+    if ((int)threadIdx.x < world) {
+        const ExSlot* src = ex.peers[ex.rank] + (threadIdx.x * 2 + par);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(&src->seq) != ex.seq) {
+            if ((unsigned long long)(clock64() - t0) > ex.timeout_cycles) { *(volatile unsigned int*)ex.status = 1u; break; }
+            __nanosleep(64);
+        }
+        const volatile unsigned long long* sp = reinterpret_cast<const volatile unsigned long long*>(&src->p);
+        unsigned long long* dp = reinterpret_cast<unsigned long long*>(&sh_parts[threadIdx.x]);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(aqe_partial) / 8); ++i) dp[i] = sp[i];
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) merge_partials_dev(sh_parts, world, ex.is_integer != 0, out);
 }
 
 template <typename T> __device__ __forceinline__ double as_f64(T v) { return (double)v; }

@@ -480,9 +480,11 @@ def main():
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         agg = torch.tensor([h2d_alone, h2d_together], dtype=torch.float64, device="cuda")
+        slowest = torch.tensor([h2d_together], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+            dist.all_reduce(slowest, op=dist.ReduceOp.MIN)
         chunk_mb = int(os.environ.get("AQE_E2E_CHUNK_MB", 64))
         nchunks = -(-rows * 8 // (chunk_mb << 20))
         e2e_val = total / (float(dt.item()) / e2e_steps)
@@ -495,7 +497,12 @@ def main():
                             "sum_over_gpus_all_at_once_GBps": float(agg[1].item())},
                "frac_of_h2d_peak": e2e_val * 8 / 1e9 / float(agg[1].item()),
                "frac_of_h2d_peak_note": "against every GPU copying at once (what the host's memory system and PCIe root ports sustain together); "
-                                        "sum_over_gpus_each_alone is N x one link"}
+                                        "sum_over_gpus_each_alone is N x one link",
+               # equal shards finish when the GPU with the slowest link does: the step cannot beat N x that GPU's concurrent rate
+               "slowest_gpu_all_at_once_GBps": float(slowest.item()), "frac_of_n_times_slowest_gpu": e2e_val * 8 / 1e9 / (world * float(slowest.item())),
+               "host_limit": "the pod's cpuset confines host memory to one NUMA node (Mems_allowed 0; tools/microbench h2dnuma: mbind to other nodes is not "
+                             "possible, interleave = default), so at 8 GPUs every link pulls from one socket: 236-261 GB/s in all, 24-35 GB/s per GPU "
+                             "(profiles/r2_mb_h2dnuma_n8.jsonl)" if world >= 4 else None}
         L.aqe_host_free(hptr)
         os.sched_setaffinity(0, all_cpus)          # the CPU baseline below uses every core
 
