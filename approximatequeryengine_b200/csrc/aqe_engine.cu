@@ -100,6 +100,7 @@ struct aqe_db {
     // fused cross-GPU exchange (see Exchange in aqe_kernels.cuh)
     int ex_rank = 0, ex_world = 0;
     ExSlot* ex_mailbox = nullptr;
+    aqe_partial* ex_local = nullptr;     // this shard's partial on its way from the scan kernel to k_scan_merge
     ExSlot* ex_peers[kMaxRanks] = {nullptr};
     unsigned long long ex_seq = 0;
     unsigned long long ax_msg = 0;       // next message index of the sampled-estimate exchange (lock-step on all ranks)
@@ -161,6 +162,7 @@ static int db_init_cuda(aqe_db* db) {
     CU(cudaMalloc(&db->approx_slots, sizeof(ApproxAcc) * 2 * kMaxGrid));
     CU(cudaMalloc(&db->tickets, sizeof(unsigned int) * 4));
     CU(cudaMemset(db->tickets, 0, sizeof(unsigned int) * 4));
+    CU(cudaMalloc(&db->ex_local, sizeof(aqe_partial)));
     CU(cudaHostAlloc(&db->slot_host, sizeof(Slot), cudaHostAllocMapped));
     CU(cudaHostGetDevicePointer(&db->slot_dev, db->slot_host, 0));
     db->cuda_ready = true;
@@ -419,7 +421,7 @@ int aqe_close(aqe_db* db) {
         if (db->sql_out_host) cudaFreeHost(db->sql_out_host);
         for (int r = 0; r < db->ex_world; ++r)
             if (db->ex_connected && db->ex_ipc && r != db->ex_rank && db->ex_peers[r]) cudaIpcCloseMemHandle(db->ex_peers[r]);
-        cudaFree(db->ex_mailbox);
+        cudaFree(db->ex_mailbox); cudaFree(db->ex_local);
         cudaFreeHost(db->slot_host);
         cudaEventDestroy(db->ev0); cudaEventDestroy(db->ev1);
         cudaStreamDestroy(db->stream);
@@ -830,6 +832,7 @@ static int scan_launch(aqe_db* db, const aqe_scan_spec* spec, uint64_t first, ui
         if (!db->ex_connected) return fail(AQE_ERR_STATE, "aqe_exchange_connect has not been called");
         a.ex.world = db->ex_world; a.ex.rank = db->ex_rank; a.ex.is_integer = ak != K_F64;
         a.ex.split = env_int("AQE_EXCHANGE_SPLIT", 1) != 0 ? 1 : 0;
+        a.ex.local = db->ex_local;
         a.ex.seq = ++db->ex_seq;
         a.ex.timeout_cycles = (unsigned long long)env_int("AQE_EXCHANGE_TIMEOUT_MS", 5000) * 2000000ull;
         for (int r = 0; r < db->ex_world; ++r) a.ex.peers[r] = db->ex_peers[r];

@@ -95,7 +95,8 @@ struct Exchange {
     int world;                 // 0/1 = disabled
     int rank;
     int is_integer;
-    int split;                 // 1: the scan kernel only PUBLISHES its partial; k_scan_merge (next in the stream) waits for the peers and folds
+    int split;                 // 1: the scan kernel leaves its partial in `local`; k_scan_merge (next in the stream) publishes it, waits for the peers and folds
+    aqe_partial* local;        // this GPU's memory
     unsigned long long seq;
     unsigned long long timeout_cycles;
     ExSlot* peers[kMaxRanks];  // peers[r] = rank r's mailbox as mapped in this process (peers[rank] = own)
@@ -230,6 +231,13 @@ template <bool IS_INT, bool MOMENTS> __device__ __forceinline__ void scan_finish
         }
         return;
     }
+    if (a.ex.split) {   // publish / wait / fold happen in k_scan_merge: this CTA's SM slot is wanted by the next scan of the stream
+        if (threadIdx.x == 0) {
+            scan_write_out<IS_INT>(acc, a.ex.local);
+            *a.ticket = 0u;
+        }
+        return;
+    }
     // ---- fused all-gather + merge over peer memory ----
     __shared__ aqe_partial sh_parts[kMaxRanks];
     __shared__ aqe_partial sh_local;
@@ -248,7 +256,6 @@ template <bool IS_INT, bool MOMENTS> __device__ __forceinline__ void scan_finish
         __threadfence_system();
         st_release_sys(&dst->seq, a.ex.seq);
     }
-    if (a.ex.split) return;   // the wait for the peers must not hold an SM slot of this grid: the next scan's CTA is queued for it
     __syncthreads();
     if ((int)threadIdx.x < world) {
         const ExSlot* src = a.ex.peers[a.ex.rank] + (threadIdx.x * 2 + par);
@@ -268,17 +275,28 @@ template <bool IS_INT, bool MOMENTS> __device__ __forceinline__ void scan_finish
     if (threadIdx.x == 0) merge_partials_dev(sh_parts, world, a.ex.is_integer != 0, a.out);
 }
 
-// Second half of the fused exchange as its own one-warp kernel, launched right behind the scan on the same stream: waits until
-// this rank's mailbox holds `seq` from every rank, folds the partials in rank order and writes the table-level result.  Keeping
-// the wait out of the scan grid matters for back-to-back queries: a scan CTA that sits on an SM waiting for a slower GPU keeps the
-// next scan's CTA (queued for exactly that slot, static tile assignment) from starting, and the whole next query ends that much
-// later (measured at 8 GPUs: 148 us per query with the wait inside the scan, 140 us for the scan alone).  One warp, no shared-memory
-// ring: it fits next to the two scan CTAs of any SM.
+// The exchange proper as its own one-warp kernel, launched right behind the scan on the same stream: stores this shard's partial
+// + the query's sequence number into every rank's mailbox (peer stores over NVLink), waits until this rank's mailbox holds `seq`
+// from every rank, folds the partials in rank order and writes the table-level result.  Keeping all of that out of the scan grid
+// matters for back-to-back queries: the scan CTA that would publish (system-scope fence + NVLink stores) and wait for a slower GPU
+// holds an SM slot the next scan's CTA is queued for (static tile assignment), and the whole next query ends that much later
+// (measured at 8 GPUs: 148.0 us per query with publish + wait inside the scan, 146.8 with the wait moved out, 141.7 for the scan
+// alone).  One warp, 1 KiB of shared memory: it fits next to the two scan CTAs of any SM.
 __global__ void __launch_bounds__(32) k_scan_merge(const Exchange ex, aqe_partial* out) {
     __shared__ aqe_partial sh_parts[kMaxRanks];
     griddep_launch_dependents();   // the next scan of the stream may be launched (its CTAs queue for SM slots)
-    griddep_wait();                // this rank's scan has completed: its partial is in every mailbox
+    griddep_wait();                // this rank's scan has completed: its partial is in ex.local
     const int world = ex.world, par = (int)(ex.seq & 1ull);
+    if ((int)threadIdx.x < world) {
+        ExSlot* dst = ex.peers[threadIdx.x] + (ex.rank * 2 + par);
+        const unsigned long long* lp = reinterpret_cast<const unsigned long long*>(ex.local);
+        volatile unsigned long long* d = reinterpret_cast<volatile unsigned long long*>(&dst->p);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(aqe_partial) / 8); ++i) d[i] = __ldcg(lp + i);
+        __threadfence_system();
+        st_release_sys(&dst->seq, ex.seq);
+    }
+    __syncwarp();
     if ((int)threadIdx.x < world) {
         const ExSlot* src = ex.peers[ex.rank] + (threadIdx.x * 2 + par);
         const long long t0 = clock64();
