@@ -706,7 +706,8 @@ template <typename K> static int launch_regs_kernel(const aqe_db* db, K kernel, 
     LAUNCHED();
     return AQE_OK;
 }
-template <typename K> static int launch_ring_kernel(const aqe_db* db, K kernel, const ScanArgs& a, int stages, int rows_per_tile, int bps_req, cudaStream_t s) {
+template <typename K> static int launch_ring_kernel(const aqe_db* db, K kernel, const ScanArgs& a_in, int stages, int rows_per_tile, int bps_req, cudaStream_t s) {
+    ScanArgs a = a_in;
     size_t smem = (size_t)stages * kStageBytes;
     // programmatic dependent launch: exactly two CTAs fit an SM (3 x 76 KiB > 227 KiB), see ScanArgs::pdl_tail
     if (a.pdl_tail && (bps_req == 0 || bps_req == 2)) smem = std::max<size_t>(smem, 76 * 1024);
@@ -715,6 +716,18 @@ template <typename K> static int launch_ring_kernel(const aqe_db* db, K kernel, 
     const uint64_t ntiles = (a.n + rows_per_tile - 1) / rows_per_tile;
     int grid = (int)std::min<uint64_t>((uint64_t)db->sm_count * bps, std::max<uint64_t>(ntiles, 1));
     if (grid > db->max_grid) grid = db->max_grid;
+    // tile schedule (ScanArgs::even_rounds): plain round-robin, or -- two CTAs per SM, back-to-back scans -- the first half of the grid
+    // takes `skew` more tiles than the second so that the two CTAs of an SM do not hand over to the next scan at the same time
+    const uint64_t n_main_tiles = ((a.n & ~3ull) + rows_per_tile - 1) / rows_per_tile;
+    a.even_rounds = ~0ull; a.long_ctas = (unsigned)grid;
+    // 16 tiles apart (~10 us of streaming): measured at 125 M rows, back to back: 0.1396 ms per scan without skew, 0.1379 with 6,
+    // 0.1349 with 16, 0.1347 with 24 (profiles/r2_pdl_ab.jsonl) -- the 1 B-row rate; shorter tables take a proportional skew
+    uint64_t skew = (uint64_t)std::max(0, env_int("AQE_SCAN_SKEW", 16));
+    skew = std::min<uint64_t>(skew, n_main_tiles / ((uint64_t)grid * 4));
+    if (a.pdl_tail && skew && bps == 2 && grid == 2 * db->sm_count) {
+        a.long_ctas = (unsigned)(grid / 2);
+        a.even_rounds = (n_main_tiles - (uint64_t)a.long_ctas * skew) / (uint64_t)grid;
+    }
     g_scan_kernel += " grid=" + std::to_string(grid) + " x " + std::to_string(kBulkThreads) + " threads (" + std::to_string(bps) + " CTAs/SM), " + std::to_string(smem) +
                      " B dynamic smem" + (a.pdl_tail ? ", programmatic dependent launch" : "");
     if (a.pdl_tail) {

@@ -121,7 +121,21 @@ struct ScanArgs {
     // (block partials, ticket, mailboxes, result) happens behind griddep_wait(), i.e. after the previous scan has completed:
     // stream order is kept for every side effect, only the read-only streaming overlaps the previous scan's fold and exchange.
     unsigned int pdl_tail;
+    // Static tile schedule of the ring kernel.  Rounds [0, even_rounds) deal tiles round-robin to all CTAs (tile = round * grid +
+    // block); the remaining tiles go round-robin to the first `long_ctas` CTAs only (long_ctas = grid: the plain schedule).  With two
+    // CTAs per SM and long_ctas = half the grid, the two CTAs of an SM finish a few tiles apart, so that in a stream of back-to-back
+    // scans (programmatic dependent launch) one of them is always streaming while the other folds its partial and the next scan's CTA
+    // fills its pipeline -- otherwise both slots of every SM go through that ~4 us hand-over at the same time.
+    unsigned long long even_rounds;
+    unsigned int long_ctas;
 };
+
+// it-th tile of CTA `block` under the schedule above (>= ntiles: the CTA is done)
+__device__ __forceinline__ uint64_t scan_tile_of(const ScanArgs& a, uint64_t it, unsigned int block, unsigned int grid, uint64_t ntiles) {
+    if (it < a.even_rounds) return it * grid + block;
+    if (block >= a.long_ctas) return ntiles;
+    return a.even_rounds * grid + (it - a.even_rounds) * a.long_ctas + block;
+}
 
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -475,7 +489,7 @@ __global__ void __launch_bounds__(kBulkThreads) k_scan_ring(const ScanArgs a) {
     if (warp == kBulkConsumerWarps) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (uint64_t c = blockIdx.x; c < ntiles; c += gridDim.x, ++it) {
+            for (uint64_t c; (c = scan_tile_of(a, it, blockIdx.x, gridDim.x, ntiles)) < ntiles; ++it) {
                 const int s = it % STAGES;
                 const uint32_t round = it / STAGES;
                 if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
@@ -490,7 +504,7 @@ __global__ void __launch_bounds__(kBulkThreads) k_scan_ring(const ScanArgs a) {
     } else {
         const uint32_t ct = threadIdx.x;  // 0 .. 255
         uint32_t it = 0;
-        for (uint64_t c = blockIdx.x; c < ntiles; c += gridDim.x, ++it) {
+        for (uint64_t c; (c = scan_tile_of(a, it, blockIdx.x, gridDim.x, ntiles)) < ntiles; ++it) {
             const int s = it % STAGES;
             const uint32_t round = it / STAGES;
             mbar_wait(&full_bar[s], round & 1);

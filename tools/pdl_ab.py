@@ -45,4 +45,14 @@ for n in (125_000_000, 1_000_000_000):
                           "sustained_2s_ms_per_query": round(sustained, 5), "sustained_GBps": round(8 * n / sustained / 1e6, 1),
                           "sm_mhz_under_load": c.get("sm_mhz"), "power_w_max": c.get("power_w_max"), "reasons": c.get("reasons"),
                           "kernel": aqe.lib().aqe_last_scan_kernel().decode()}), flush=True)
+    if n < 500_000_000:   # the skewed tile schedule (ScanArgs::even_rounds, AQE_SCAN_SKEW) at the strong-scaling shard size
+        os.environ["AQE_SCAN_PDL"] = "1"
+        for skew in (0, 2, 4, 6, 8, 12, 16, 24, 0, 6):
+            os.environ["AQE_SCAN_SKEW"] = str(skew)
+            loop(eng, 5)
+            burst = min(loop(eng, 300) for _ in range(3))
+            p = aqe.Partial.from_buffer_copy(host_out.numpy().tobytes())
+            assert (p.count, p.sum) == (ref.count, ref.sum), (skew, p.count, ref.count, p.sum, ref.sum)
+            print(json.dumps({"rows": n, "pdl": 1, "skew_tiles": skew, "burst_ms_per_query": round(burst, 5), "burst_GBps": round(8 * n / burst / 1e6, 1)}), flush=True)
+        os.environ.pop("AQE_SCAN_SKEW", None)
     eng.close()
