@@ -1227,8 +1227,12 @@ static int stats_launch(aqe_db* db, const aqe_plan* pl, int col, aqe_stats* out,
     a.cols = const_cols(db); a.col = col; a.pred_col = pred_col; a.lo = lo; a.hi = hi; a.partials = db->stat_partials; a.ticket = db->tickets + 2; a.out = &db->slot_dev->stats;
     a.win_first = win ? win->first : 0; a.win_n = win ? std::min<uint64_t>(win->n, db->n) : ~0ull;
     a.raw_out = raw ? &db->slot_dev->stats_raw : nullptr;
-    const int grid = grid_for(db, pl->count, 8, 256, 8);
-    k_plan_stats<<<grid, 256, 0, db->stream>>>(a);
+    bool tiles = !pl->segs.empty();   // every segment a run of contiguous rows?
+    for (const aqe_segment& sg : pl->segs) tiles = tiles && sg.kind == 0 && sg.inner_len >= 32;
+    if (pl->by_amount_order) tiles = false;
+    const int grid = grid_for(db, pl->count, tiles ? 4 : 8, 256, 8);
+    if (tiles) k_plan_stats<4><<<grid, 256, 0, db->stream>>>(a);
+    else k_plan_stats<8><<<grid, 256, 0, db->stream>>>(a);
     LAUNCHED();
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(db->stream));

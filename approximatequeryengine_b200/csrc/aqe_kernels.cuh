@@ -681,7 +681,9 @@ struct StatArgs {
     aqe_stats_partial* raw_out;  // windowed form: the shard's mergeable sums (aqe_stats_merge) instead of finished moments
 };
 
-__global__ void __launch_bounds__(256) k_plan_stats(const StatArgs a) {
+// GU = independent gathers in flight per thread: 8 for scattered positions (stride / permutation / index-list plans), 4 for plans of
+// contiguous tiles (coalesced already; the 16 extra registers of GU = 8 cost them occupancy: 44.9 -> 63.8 us under ncu, 400 M rows).
+template <int GU> __global__ void __launch_bounds__(256) k_plan_stats(const StatArgs a) {
     __shared__ StatAcc sm[32];
     __shared__ bool is_last;
     const uint64_t G = (uint64_t)gridDim.x * blockDim.x;
@@ -709,7 +711,6 @@ __global__ void __launch_bounds__(256) k_plan_stats(const StatArgs a) {
     // 8 independent gathers in flight per thread.  A random 8-byte read costs a whole 128-byte line of L2 / DRAM traffic on B200
     // (tools/microbench.cu under ncu: 4 sectors per load whatever the load form or the L2 fetch-granularity limit), so the ceiling
     // is HBM bandwidth / 128 B, 48-56 G samples/s, reached only with many loads in flight (profiles/r2_mb_gather.jsonl)
-    constexpr int GU = 8;
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; k + (uint64_t)(GU - 1) * G < a.plan.count; k += (uint64_t)GU * G) {
         double x[GU];
