@@ -31,9 +31,9 @@
 
 #include "aqe_b200.h"
 
-namespace py = pybind11;
+#include <structmember.h>
 
-namespace {
+namespace py = pybind11;
 
 struct Record {  // custom_bplus_db.hpp:17-27
     int64_t id = 0;
@@ -43,6 +43,66 @@ struct Record {  // custom_bplus_db.hpp:17-27
     int64_t timestamp = 0;
 };
 static_assert(sizeof(Record) == sizeof(aqe_record), "Record is the 32-byte row");
+
+// `Record` as a plain CPython type (five C members, default constructor, read/write attributes -- bindings.cpp:14-20) instead of a
+// pybind11 class: every sampler returns list[Record] BY VALUE and the reference's callers loop over the objects in Python
+// (enhanced_aqe_cli.py:188-200), so creating them is the cost of a sampled query (round 1: 100 k records 23.7 ms, 99 % of it pybind11
+// instance bookkeeping at ~230 ns per object).  A type without a __dict__, GC header or holder costs one small allocation.
+struct RecordObject {
+    PyObject_HEAD
+    Record r;
+};
+static PyTypeObject* g_record_type = nullptr;
+
+static PyObject* record_new(PyTypeObject* type, PyObject*, PyObject*) {
+    RecordObject* o = reinterpret_cast<RecordObject*>(type->tp_alloc(type, 0));
+    if (o) o->r = Record{};
+    return reinterpret_cast<PyObject*>(o);
+}
+static int record_init(PyObject*, PyObject* args, PyObject* kwargs) {
+    if (PyTuple_GET_SIZE(args) != 0 || (kwargs && PyDict_Size(kwargs) != 0)) {
+        PyErr_SetString(PyExc_TypeError, "Record() takes no arguments");   // bindings.cpp:15: py::init<>()
+        return -1;
+    }
+    return 0;
+}
+static PyObject* record_repr(PyObject* self) {
+    const Record& r = reinterpret_cast<RecordObject*>(self)->r;
+    const std::string t = "Record(id=" + std::to_string(r.id) + ", amount=" + std::to_string(r.amount) + ", region=" + std::to_string(r.region) +
+                          ", product_id=" + std::to_string(r.product_id) + ", timestamp=" + std::to_string(r.timestamp) + ")";
+    return PyUnicode_FromStringAndSize(t.data(), (Py_ssize_t)t.size());
+}
+static PyMemberDef record_members[] = {
+    {"id", T_LONGLONG, offsetof(RecordObject, r) + offsetof(Record, id), 0, nullptr},
+    {"amount", T_DOUBLE, offsetof(RecordObject, r) + offsetof(Record, amount), 0, nullptr},
+    {"region", T_INT, offsetof(RecordObject, r) + offsetof(Record, region), 0, nullptr},
+    {"product_id", T_INT, offsetof(RecordObject, r) + offsetof(Record, product_id), 0, nullptr},
+    {"timestamp", T_LONGLONG, offsetof(RecordObject, r) + offsetof(Record, timestamp), 0, nullptr},
+    {nullptr, 0, 0, 0, nullptr}};
+static PyType_Slot record_slots[] = {{Py_tp_new, reinterpret_cast<void*>(record_new)},   {Py_tp_init, reinterpret_cast<void*>(record_init)},
+                                     {Py_tp_repr, reinterpret_cast<void*>(record_repr)}, {Py_tp_members, record_members},
+                                     {Py_tp_doc, const_cast<char*>("fixed-width row {id, amount, region, product_id, timestamp} (custom_bplus_db.hpp:17-27)")},
+                                     {0, nullptr}};
+static PyType_Spec record_spec = {"aqe_backend.Record", (int)sizeof(RecordObject), 0, Py_TPFLAGS_DEFAULT, record_slots};
+
+namespace pybind11 { namespace detail {
+template <> struct type_caster<Record> {
+    PYBIND11_TYPE_CASTER(Record, const_name("Record"));
+    bool load(handle src, bool) {
+        if (!src || !g_record_type || !PyObject_TypeCheck(src.ptr(), g_record_type)) return false;
+        value = reinterpret_cast<RecordObject*>(src.ptr())->r;
+        return true;
+    }
+    static handle cast(const Record& r, return_value_policy, handle) {
+        RecordObject* o = reinterpret_cast<RecordObject*>(g_record_type->tp_alloc(g_record_type, 0));
+        if (!o) throw error_already_set();
+        o->r = r;
+        return reinterpret_cast<PyObject*>(o);
+    }
+};
+}}  // namespace pybind11::detail
+
+namespace {
 
 enum class CustomApproximationStatus { STABLE, DRIFTING, INSUFFICIENT_DATA, ERROR };  // custom_scheduler.hpp:8-13
 
@@ -565,17 +625,13 @@ PYBIND11_MODULE(aqe_backend, m) {
     m.attr("__engine__") = "aqe_b200";
     m.attr("abi_version") = aqe_abi_version();
 
-    py::class_<Record>(m, "Record")
-        .def(py::init<>())
-        .def_readwrite("id", &Record::id)
-        .def_readwrite("amount", &Record::amount)
-        .def_readwrite("region", &Record::region)
-        .def_readwrite("product_id", &Record::product_id)
-        .def_readwrite("timestamp", &Record::timestamp)
-        .def("__repr__", [](const Record& r) {
-            return "Record(id=" + std::to_string(r.id) + ", amount=" + std::to_string(r.amount) + ", region=" + std::to_string(r.region) +
-                   ", product_id=" + std::to_string(r.product_id) + ", timestamp=" + std::to_string(r.timestamp) + ")";
-        });
+    {   // class Record (bindings.cpp:14-20) as a plain CPython type: see RecordObject above
+        PyObject* t = PyType_FromSpec(&record_spec);
+        if (!t) throw py::error_already_set();
+        g_record_type = reinterpret_cast<PyTypeObject*>(t);
+        m.add_object("Record", py::reinterpret_steal<py::object>(t));
+        Py_INCREF(t);   // g_record_type keeps its own reference for the life of the process
+    }
 
     py::enum_<CustomApproximationStatus>(m, "CustomApproximationStatus")
         .value("STABLE", CustomApproximationStatus::STABLE)

@@ -546,6 +546,16 @@ def main():
                               "frac": g["Gsamples_per_s"] / ceil["stride100_Gsamples_per_s"] if ceil.get("stride100_Gsamples_per_s") else None,
                               "ceiling_source": "static, profiles/r2_gather_ceiling.json (tools/microbench.cu, 16 loads in flight)", "includes": "host wall clock of the synchronous call (launch + sync)"}
         approx["gather"] = gather
+        # the legacy return path the unmodified CLI uses (enhanced_aqe_cli.py:179-200): list[Record] by value, then a Python loop
+        ts, ts_arr, ts_loop = [], [], []
+        for _ in range(7):
+            t0 = time.perf_counter(); recs = db.memory_stride_sample(1.0, 0); t1 = time.perf_counter()
+            tot = sum(r.amount for r in recs); t2 = time.perf_counter()
+            arr = db.sample_array("memory_stride", 1.0); t3 = time.perf_counter()
+            ts.append(t1 - t0); ts_loop.append(t2 - t1); ts_arr.append(t3 - t2)
+        approx["list_record_path"] = {"records": len(recs), "memory_stride_sample_ms": statistics.median(ts) * 1e3, "python_sum_loop_ms": statistics.median(ts_loop) * 1e3,
+                                      "sample_array_ms": statistics.median(ts_arr) * 1e3, "ns_per_record_object": statistics.median(ts) / max(len(recs), 1) * 1e9,
+                                      "note": "Record is a plain CPython type (csrc/aqe_pybind.cpp); round 1 (pybind11 class): 23.7 ms for the same 100 k records"}
         del db
 
     # ---- secondary, N > 1: BASELINE.json configs[3] -- block sampling, APPROX SUM at 0.5 % over the sharded table, one global
