@@ -104,16 +104,43 @@ struct Group {
     int active = 1;                // shards holding rows: ranks 0 .. active-1
     std::vector<uint64_t> first;   // active + 1 row offsets into the table
     bool peer = false;             // distinct devices, peer access on: exchanges run inside the kernels
+    int ready = 0;                 // shards whose GPU has been set up (context, scratch, peer access, mailbox): done on demand, so a
+                                   // handle over 8 GPUs that only ever holds a small table touches one GPU
     int64_t* perm = nullptr;       // rows of the WHOLE table ordered by amount (stratified_block_sample), on shard 0's device
     std::unique_ptr<Workers> pool;
     uint64_t rows_of(int g) const { return first[g + 1] - first[g]; }
 };
 
 // ---- exchange state: fresh mailboxes and sequence numbers for `active` ranks (after every layout change or failed exchange) ----
+// Sets up the GPUs of shards [ready, want): CUDA state of the handle, peer access to and from every shard already set up, the mailbox.
+static int group_prepare(aqe_db* gdb, int want) {
+    Group* G = gdb->group;
+    for (int g = G->ready; g < want; ++g) {
+        aqe_db* c = G->shards[g];
+        int rc = db_init_cuda(c);
+        if (rc) return rc;
+        if (G->peer) {
+            for (int h = 0; h < g; ++h) {
+                for (int dir = 0; dir < 2; ++dir) {
+                    const int from = dir ? G->shards[h]->device : c->device, to = dir ? c->device : G->shards[h]->device;
+                    CU(cudaSetDevice(from));
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                    else if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+                }
+            }
+            CU(cudaSetDevice(c->device));
+            if (!c->ex_mailbox) CU(cudaMalloc(&c->ex_mailbox, kMailboxBytes));
+        }
+        G->ready = g + 1;
+    }
+    return AQE_OK;
+}
+
 static int group_reset_exchange(aqe_db* gdb) {
     Group* G = gdb->group;
     if (!G->peer) return AQE_OK;
-    for (size_t g = 0; g < G->shards.size(); ++g) {
+    for (int g = 0; g < G->ready; ++g) {
         aqe_db* c = G->shards[g];
         CU(cudaSetDevice(c->device));
         CU(cudaStreamSynchronize(c->stream));
@@ -122,7 +149,7 @@ static int group_reset_exchange(aqe_db* gdb) {
         c->ex_rank = (int)g; c->ex_world = G->active; c->ex_seq = 0; c->ax_msg = 0; c->sqlx_seq = 0;
         c->ex_total_rows = gdb->n;
         c->ex_connected = (int)g < G->active && G->active > 1;
-        for (int r = 0; r < kMaxRanks; ++r) c->ex_peers[r] = r < (int)G->shards.size() ? G->shards[r]->ex_mailbox : nullptr;
+        for (int r = 0; r < kMaxRanks; ++r) c->ex_peers[r] = r < G->ready ? G->shards[r]->ex_mailbox : nullptr;
     }
     return AQE_OK;
 }
@@ -136,6 +163,8 @@ static int group_set_layout(aqe_db* gdb, uint64_t n) {
     G->first.assign((size_t)G->active + 1, 0);
     for (int g = 0; g <= G->active; ++g) G->first[g] = shard_edge(n, g, G->active);
     gdb->n = n;
+    int rc0 = group_prepare(gdb, G->active);
+    if (rc0) return rc0;
     if (G->perm) { cudaSetDevice(G->shards[0]->device); cudaFree(G->perm); G->perm = nullptr; }
     for (size_t g = (size_t)G->active; g < G->shards.size(); ++g) {   // shards left without rows give their memory back
         aqe_db* c = G->shards[g];
@@ -207,7 +236,7 @@ static int group_from_host_records(aqe_db* gdb, const aqe_record* rows, size_t n
 }
 
 static int group_ensure_device(aqe_db* gdb) {
-    if (!gdb->host_authoritative) return AQE_OK;
+    if (!gdb->host_authoritative) return group_prepare(gdb, gdb->group->active);
     const int rc = group_upload(gdb, gdb->host_rows.data(), gdb->host_rows.size());
     if (rc) return rc;
     gdb->host_authoritative = false;
@@ -530,26 +559,14 @@ int aqe_create_sharded(const int* devices, int n_devices, aqe_db** out) {
     gdb->group = G; gdb->device = dev[0];
     G->peer = distinct;
     auto bail = [&](int rc) { const std::string keep = g_err; aqe_close(gdb); g_err = keep; return rc; };
-    for (int g = 0; g < n_devices; ++g) {
+    for (int g = 0; g < n_devices; ++g) {   // plain handles; their GPUs are set up when a table is large enough to reach them (group_prepare)
         aqe_db* c = nullptr;
-        int rc = aqe_create(dev[g], &c);
+        const int rc = aqe_create(dev[g], &c);
         if (rc) return bail(rc);
         G->shards.push_back(c);
-        if ((rc = db_init_cuda(c))) return bail(rc);
-        if (distinct) {
-            for (int b = 0; b < n_devices; ++b)
-                if (b != g) {
-                    e = cudaDeviceEnablePeerAccess(dev[b], 0);
-                    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-                    else if (e != cudaSuccess) return bail(cuda_fail(e, "cudaDeviceEnablePeerAccess"));
-                }
-            e = cudaMalloc(&c->ex_mailbox, kMailboxBytes);
-            if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc (mailbox)"));
-        }
     }
     G->pool.reset(new Workers(n_devices));
-    const int rc = group_set_layout(gdb, 0);
-    if (rc) return bail(rc);
+    G->active = 1; G->first.assign(2, 0);   // an empty table on shard 0; no CUDA call until rows arrive or a query runs (like aqe_create)
     *out = gdb;
     return AQE_OK;
 }
