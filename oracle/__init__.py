@@ -22,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libaqe_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libaqe_ref.so")
 REFSQL_SO = os.path.join(HERE, "_ref", "libaqe_refsql.so")
-REFCLI_PYC = os.path.join(HERE, "_ref", "enhanced_aqe_cli.pyc")   # the reference's command line as bytecode (make refcli)
+REFCLI_PYC = os.path.join(HERE, "_ref", "enhanced_aqe_cli.bytecode")   # the reference's command line as bytecode (make refcli)
 
 RECORD_DTYPE = np.dtype(
     [("id", "<i8"), ("amount", "<f8"), ("region", "<i4"), ("product_id", "<i4"), ("timestamp", "<i8")]

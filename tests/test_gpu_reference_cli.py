@@ -2,7 +2,7 @@
 reference's own files, unmodified, as acceptance callers").
 
 `make -C oracle refcli` compiles /root/reference/enhanced_aqe_cli.py to CPython bytecode where it lies (oracle/_ref/
-enhanced_aqe_cli.pyc: a compiled artefact like the .so files next to it, git-ignored, shipped with the snapshot; no reference
+enhanced_aqe_cli.bytecode: a compiled artefact like the .so files next to it, git-ignored, shipped with the snapshot; no reference
 source enters the repo).  The CLI looks for its backend in <its directory>/build/src/aqe_backend (enhanced_aqe_cli.py:24-26):
 the test gives it a directory where that path is a link to approximatequeryengine_b200/_lib and
 runs it as a subprocess for the query forms it supports -- exact SUM / AVG / COUNT (:320-370), `APPROX(...)` routed to the
@@ -27,18 +27,18 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def cli_dir(tmp_path_factory):
     if not os.path.exists(REFCLI_PYC):
-        pytest.skip("oracle/_ref/enhanced_aqe_cli.pyc not built (make -C oracle refcli needs /root/reference)")
+        pytest.skip("oracle/_ref/enhanced_aqe_cli.bytecode not built (make -C oracle refcli needs /root/reference)")
     d = tmp_path_factory.mktemp("refcli")
     os.makedirs(d / "build" / "src")
     os.symlink(aqe.LIB_DIR, d / "build" / "src" / "aqe_backend")
-    os.symlink(REFCLI_PYC, d / "enhanced_aqe_cli.pyc")
+    os.symlink(REFCLI_PYC, d / "enhanced_aqe_cli.bytecode")
     return d
 
 
 def run_cli(cli_dir, *argv):
     env = dict(os.environ, PYTHONIOENCODING="utf-8", AQE_DEVICE="0")
     env.pop("AQE_DEVICES", None)
-    r = subprocess.run([sys.executable, str(cli_dir / "enhanced_aqe_cli.pyc"), *argv], cwd=cli_dir, env=env, capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, str(cli_dir / "enhanced_aqe_cli.bytecode"), *argv], cwd=cli_dir, env=env, capture_output=True, text=True, timeout=300)
     return r.returncode, r.stdout + r.stderr
 
 
