@@ -211,8 +211,14 @@ static int grid_for(const aqe_db* db, uint64_t work_items, int per_thread, int t
 // link at ~55 GB/s, so several readers are needed to approach the link (8 readers: 30 GB/s from the page cache; copying out of
 // an mmap of the file instead of pread() measured slower, 25 GB/s).  Out-of-order ids are detected inside a
 // chunk on the device and across chunk boundaries on the host.
+// rows per ingest chunk (AQE_INGEST_CHUNK_MB, read once: the pooled staging buffers have this size), default 16 MiB of rows
+static size_t ingest_chunk_rows() {
+    static const size_t rows = (size_t)std::min(64, std::max(1, env_int("AQE_INGEST_CHUNK_MB", 16))) << 15;
+    return rows;
+}
+
 struct IngestWorker {
-    static const size_t kChunkRows = 1u << 19;  // 16 MiB of rows
+    bool ready = false;   // staging allocated (by the worker's own thread, so that the workers of a first load allocate side by side)
     aqe_record* pinned[2] = {nullptr, nullptr};
     aqe_record* dev[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
@@ -220,12 +226,14 @@ struct IngestWorker {
     int rc = AQE_OK;
     std::string err;
     int init() {
+        if (ready) return AQE_OK;
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
-            CU(cudaHostAlloc(&pinned[i], kChunkRows * sizeof(aqe_record), cudaHostAllocDefault));
-            CU(cudaMalloc(&dev[i], kChunkRows * sizeof(aqe_record)));
+            CU(cudaHostAlloc(&pinned[i], ingest_chunk_rows() * sizeof(aqe_record), cudaHostAllocDefault));
+            CU(cudaMalloc(&dev[i], ingest_chunk_rows() * sizeof(aqe_record)));
             CU(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
         }
+        ready = true;
         return AQE_OK;
     }
     ~IngestWorker() {
@@ -249,9 +257,7 @@ struct IngestPool {
             while ((int)workers.size() < count) {
                 IngestWorker* w = new (std::nothrow) IngestWorker();
                 if (!w) { rc = fail(AQE_ERR_NOMEM, "out of host memory"); return; }
-                rc = w->init();
-                if (rc) { delete w; return; }
-                workers.push_back(w);
+                workers.push_back(w);   // its staging is allocated by the thread that will use it (IngestWorker::init in ingest_rows)
             }
         }
         ~Lease() {
@@ -271,7 +277,8 @@ static int ingest_rows(aqe_db* db, uint64_t n, Fill fill, bool* unsorted_out, in
     if (rc) return rc;
     *unsorted_out = false;
     if (n == 0) return AQE_OK;
-    const uint64_t nchunks = (n + IngestWorker::kChunkRows - 1) / IngestWorker::kChunkRows;
+    const uint64_t chunk_rows = ingest_chunk_rows();
+    const uint64_t nchunks = (n + chunk_rows - 1) / chunk_rows;
     int W = env_int("AQE_INGEST_THREADS", 0);
     if (W <= 0) W = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
     if (max_workers > 0) W = std::min(W, max_workers);
@@ -293,9 +300,10 @@ static int ingest_rows(aqe_db* db, uint64_t n, Fill fill, bool* unsorted_out, in
     auto body = [&](int wi) {
         IngestWorker& w = *workers[wi];
         if (cudaSetDevice(device) != cudaSuccess) { w.rc = AQE_ERR_CUDA; w.err = "cudaSetDevice failed in ingest worker"; return; }
+        if (!w.ready && w.init() != AQE_OK) { w.rc = AQE_ERR_NOMEM; w.err = "ingest worker: cannot allocate staging buffers: " + g_err; return; }
         int buf = 0;
         for (uint64_t c = (uint64_t)wi; c < nchunks; c += (uint64_t)W, buf ^= 1) {
-            const uint64_t first = c * IngestWorker::kChunkRows, cnt = std::min<uint64_t>(IngestWorker::kChunkRows, n - first);
+            const uint64_t first = c * chunk_rows, cnt = std::min<uint64_t>(chunk_rows, n - first);
             cudaError_t e = cudaEventSynchronize(w.done[buf]);  // the pinned buffer is free again
             if (e == cudaSuccess && !fill(w.pinned[buf], first, cnt)) { w.rc = AQE_ERR_IO; w.err = "short read while loading rows"; return; }
             first_id[c] = w.pinned[buf][0].id; last_id[c] = w.pinned[buf][cnt - 1].id;
