@@ -208,12 +208,14 @@ static int grid_for(const aqe_db* db, uint64_t work_items, int per_thread, int t
 // each run an independent pipeline over the chunks c = w, w+W, ... of the row range: fill a pinned buffer (pread from
 // the file / memcpy from caller memory) -> cudaMemcpyAsync -> k_aos_to_soa on the worker's own stream, two buffers
 // per worker so the next fill overlaps the previous copy.  Page-cache reads run at a few GB/s per thread, the H2D
-// link at ~55 GB/s, so several readers are needed to approach the link (8 readers: 30 GB/s from the page cache; copying out of
+// link at ~55 GB/s, so several readers are needed to approach the link (8 readers: 44 GB/s from the page cache with 4 MiB chunks; copying out of
 // an mmap of the file instead of pread() measured slower, 25 GB/s).  Out-of-order ids are detected inside a
 // chunk on the device and across chunk boundaries on the host.
-// rows per ingest chunk (AQE_INGEST_CHUNK_MB, read once: the pooled staging buffers have this size), default 16 MiB of rows
+// rows per ingest chunk (AQE_INGEST_CHUNK_MB, read once: the pooled staging buffers have this size).  4 MiB: a 3.2 GB file from the
+// page cache loads at 44 GB/s with 8 readers (16 MiB chunks: 32 GB/s, 8: 38, 2: 29-44) and a first load in a fresh process allocates
+// 64 MB instead of 256 MB of pinned staging (profiles/r2_ingest_cold.json)
 static size_t ingest_chunk_rows() {
-    static const size_t rows = (size_t)std::min(64, std::max(1, env_int("AQE_INGEST_CHUNK_MB", 16))) << 15;
+    static const size_t rows = (size_t)std::min(64, std::max(1, env_int("AQE_INGEST_CHUNK_MB", 4))) << 15;
     return rows;
 }
 
