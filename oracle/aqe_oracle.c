@@ -1068,7 +1068,7 @@ ORC_API int orc_approx(const aqe_record* R, uint64_t N, const aqe_approx_spec* S
             if (S->agg == AQE_AGG_AVG) { est = (double)(mu * (long double)units / (long double)N); scale = (double)units / (double)N; }
             else { est = (double)(mu * (long double)units); scale = (double)units; }
         }
-        int use_prev = stein && have_prev && nvar_prev > 1;
+        int use_prev = stein && have_prev && nvar_prev > 1 && var_prev > var;   /* the larger of the two variances */
         double v_use = use_prev ? var_prev : var;
         double df_use = use_prev ? (double)(nvar_prev - 1) : (double)n - 1.0;
         half = t_from_z(z, df_use) * sqrt(v_use / (double)n) * scale;
@@ -1173,7 +1173,7 @@ ORC_API int orc_approx_sharded(const aqe_record* R, uint64_t N, int world, const
                 long double ss = syy[g] - sy[g] * mu; if (ss < 0) ss = 0;
                 var = n[g] > 1 ? ss / (nn - 1) : INFINITY;
             }
-            int up = use_prev && nvar_prev[g] > 1;
+            int up = use_prev && nvar_prev[g] > 1 && var_prev[g] > var;
             long double v_use = up ? var_prev[g] : var;
             df_use += up ? (double)(nvar_prev[g] - 1) : (double)n[g] - 1.0;
             df_cur += (double)n[g] - 1.0;
