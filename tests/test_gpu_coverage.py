@@ -4,7 +4,7 @@ same samples (enhanced_aqe_cli.py:277-291, whose SUM interval is too narrow by a
 
 The table of all three interval modes (include/aqe_b200.h, aqe_ci_mode) is written to gpurun_out/ (and kept under profiles/):
   plain          z * s_r / sqrt(n_r) at the stopping look        -- the textbook interval, biased by stopping on its own variance
-  stein          t(df_{r-1}) * s_{r-1} / sqrt(n_r)                -- variance of the look that chose n_r: unbiased by the stopping
+  stein          t(df) * max(s_{r-1}, s_r) / sqrt(n_r)            -- the variance that chose n_r cannot be undercut by a lucky s_r
   stein_guarded  the same at alpha' = 0.8 alpha (the default)     -- the stated guard band for a finite-seed ">= nominal" check
 Gate: the default mode covers >= nominal - 1 binomial sigma in every cell; every cell uses its own seeds."""
 import json
