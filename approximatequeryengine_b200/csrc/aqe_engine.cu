@@ -2215,6 +2215,7 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
         return finish_without_scan(dense ? (first < db->n ? (db->n - first + step - 1) / step : 0) : db->n);
     }
     a.key_min = L->key_min; a.n_groups = G;
+    a.pair_bins = env_int("AQE_SQL_PAIR_BINS", 1);
     a.sum_scale = std::ldexp(1.0, L->sum_shift); a.sq_scale = std::ldexp(1.0, L->sq_shift);
     a.global_acc = db->sql_acc; a.out = db->sql_out_dev; a.ticket = db->sql_ticket; a.ex = ex;
     // 16 rows of headroom for the ragged tail rows a thread may add after its last check; AQE_SQL_DRAIN_ROWS is a test knob (drain early)

@@ -135,6 +135,7 @@ struct SqlArgs {
     unsigned int member_bits[AQE_SQL_MAX_GROUPS / 32];   // has_pred == 3 (at most one predicate of a query uses it)
     int member_used;
     unsigned int drain_rows;          // private bins (G <= 16) are drained before a thread has added this many rows to one (<= kSqlPackedRows)
+    int pair_bins;                    // private bins: words 0 and 1 of a bin sit side by side and are updated with ONE 128-bit load / store
     SqlExchange ex;
 };
 
@@ -226,6 +227,8 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
     unsigned long long r_cnt, r_slo, r_qlo;
     long long r_shi, r_qhi;
     bool with_sums;   // the query aggregates a column (false: COUNT only); uniform over the launch, set by the kernel after init()
+    bool paired;      // MODE 1: words 0 and 1 interleaved as [bin][thread] 16-byte pairs (one LDS.128 + one STS.128 per row instead of
+                      // two 64-bit chains); set by the kernel after init(), uniform over the launch.  p_slo then addresses the pairs.
 
     static size_t smem_bytes(unsigned int G) {
         if (MODE == 1) return (size_t)G * T * (MOMENTS ? 24 : 16);
@@ -235,7 +238,7 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
     // all threads of the CTA call init (it contains a barrier); tid < T owns a private column of bins
     __device__ __forceinline__ void init(unsigned char* smem, unsigned int groups, int tid, int nthreads) {
         G = groups;
-        with_sums = true;
+        with_sums = true; paired = false;
         b_cnt = reinterpret_cast<unsigned int*>(smem);
         r_cnt = 0; r_slo = 0; r_qlo = 0; r_shi = 0; r_qhi = 0;
         if constexpr (MODE == 1) {
@@ -260,9 +263,23 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
             const unsigned int s = g * T + tid;
             if constexpr (MOMENTS) {
                 const unsigned long long u = (unsigned long long)fx ^ (1ull << 63), q = (unsigned long long)fq;
-                p_slo[s] += (1ull << 52) | (u & ((1ull << 40) - 1));
-                p_shi[s] += (u >> 40) | ((q & 0xffffull) << 36);
+                if (paired) {
+                    ulonglong2* pp = reinterpret_cast<ulonglong2*>(p_slo) + s;
+                    ulonglong2 v = *pp;
+                    v.x += (1ull << 52) | (u & ((1ull << 40) - 1));
+                    v.y += (u >> 40) | ((q & 0xffffull) << 36);
+                    *pp = v;
+                } else {
+                    p_slo[s] += (1ull << 52) | (u & ((1ull << 40) - 1));
+                    p_shi[s] += (u >> 40) | ((q & 0xffffull) << 36);
+                }
                 p_qlo[s] += q >> 16;
+            } else if (paired) {   // (implies has_sum)
+                ulonglong2* pp = reinterpret_cast<ulonglong2*>(p_slo) + s;
+                ulonglong2 v = *pp;
+                v.x += (1ull << 48) + ((unsigned long long)fx & 0xffffffffull);
+                v.y += (unsigned long long)((fx >> 32) + 0x80000000ll);
+                *pp = v;
             } else {
                 p_slo[s] += (1ull << 48) + ((unsigned long long)fx & 0xffffffffull);
                 if (has_sum) p_shi[s] += (unsigned long long)((fx >> 32) + 0x80000000ll);   // COUNT-only queries keep one chain
@@ -277,7 +294,9 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
     }
     __device__ __forceinline__ void zero_private(int tid) {
         for (unsigned int g = 0; g < G; ++g) {
-            p_slo[g * T + tid] = 0; p_shi[g * T + tid] = 0;
+            // a thread clears ITS OWN bins (after a drain the others are already adding to theirs)
+            if (paired) reinterpret_cast<ulonglong2*>(p_slo)[g * T + tid] = make_ulonglong2(0ull, 0ull);
+            else { p_slo[g * T + tid] = 0; p_shi[g * T + tid] = 0; }
             if constexpr (MOMENTS) p_qlo[g * T + tid] = 0;
         }
     }
@@ -294,7 +313,7 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
             for (int k = 0; k < T / 32; ++k) {
                 const unsigned int s = g * T + lane + 32 * k;
                 if constexpr (MOMENTS) {   // value = lo + (hi << 32) for both sums, as split_to_128 takes them
-                    const unsigned long long w0 = p_slo[s], w1 = p_shi[s], w2 = p_qlo[s], n = w0 >> 52;
+                    const unsigned long long w0 = paired ? p_slo[2 * s] : p_slo[s], w1 = paired ? p_slo[2 * s + 1] : p_shi[s], w2 = p_qlo[s], n = w0 >> 52;
                     const unsigned long long a = w0 & ((1ull << 52) - 1), b = w1 & ((1ull << 36) - 1), cq = w1 >> 36;
                     c += n;
                     sl += a & 0xffffffffull;
@@ -302,9 +321,9 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
                     ql += cq + ((w2 & 0xffffull) << 16);                              // sum of q = cq + (w2 << 16)
                     qh += (long long)(w2 >> 16);
                 } else {
-                    const unsigned long long w0 = p_slo[s], n = w0 >> 48;
+                    const unsigned long long w0 = paired ? p_slo[2 * s] : p_slo[s], n = w0 >> 48;
                     c += n; sl += w0 & 0xffffffffffffull;
-                    if (with_sums) sh += (long long)p_shi[s] - (long long)(n << 31);   // remove the bias of the n rows
+                    if (with_sums) sh += (long long)(paired ? p_slo[2 * s + 1] : p_shi[s]) - (long long)(n << 31);   // remove the bias of the n rows
                 }
             }
             c = warp_reduce_u64(c); sl = warp_reduce_u64(sl); sh = (long long)warp_reduce_u64((unsigned long long)sh);
@@ -492,6 +511,7 @@ __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
     sql_member_load(a, tid, T);
     bins.init(sql_smem, a.n_groups, tid, T);
     bins.with_sums = a.agg_slot >= 0;
+    bins.paired = MODE == 1 && a.pair_bins != 0 && a.agg_slot >= 0;
 
     // per-query facts, read from the parameter bank once
     const int agg_slot = a.agg_slot, group_slot = a.group_slot, n_alt = a.n_alt;
@@ -706,6 +726,7 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
     sql_member_load(a, tid, kBulkThreads);
     bins.init(bin_mem, a.n_groups, tid, kBulkThreads);  // ends with __syncthreads()
     bins.with_sums = a.agg_slot >= 0;
+    bins.paired = MODE == 1 && a.pair_bins != 0 && a.agg_slot >= 0;
 
     const uint64_t n_main = a.count & ~3ull;  // bulk copies move multiples of 16 bytes: 4 rows of a 4-byte column
     const uint64_t ntiles = (n_main + ra.tile_rows - 1) / ra.tile_rows;
