@@ -2240,12 +2240,32 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
         ra.samp_step = (uint32_t)step; ra.samp_phase = (uint32_t)phase;
     }
     const bool ring = !strided && aligned16 && variant != 1;
-    const int mode = a.group_slot < 0 ? 0 : (G <= (uint32_t)kSqlPrivateMaxGroups ? 1 : 2);
+    int mode = a.group_slot < 0 ? 0 : (G <= (uint32_t)kSqlPrivateMaxGroups ? 1 : 2);
+    if (mode == 2 && a.agg_slot >= 0 && env_int("AQE_SQL_PACKED", 1)) {
+        // Packed shared bins (SqlBins MODE 3, three atomics per row) hold sums of u = fx - bias with 0 <= u < 2^62: usable whenever the
+        // fixed-point values of the aggregate column span fewer than 2^62 steps -- every floating-point column scaled for its own
+        // magnitude and every integer column narrower than that.  The range comes from the cached column statistics; a WHERE-bounded
+        // scale (sql_layout) under which the column's extremes saturate keeps the general form.
+        const aqe_db::ColStat* st;
+        if ((rc = sql_col_stat(db, q->agg_col, &st))) return rc;
+        __int128 flo, fhi;
+        bool fits = true;
+        if (a.agg_kind == K_F64) {
+            const double lo = okey_f64(st->min_key) * a.sum_scale, hi = okey_f64(st->max_key) * a.sum_scale;
+            fits = std::fabs(lo) < 0x1p62 && std::fabs(hi) < 0x1p62;   // (false for NaN)
+            flo = fits ? (__int128)std::llrint(lo) : 0; fhi = fits ? (__int128)std::llrint(hi) : 0;
+        } else {
+            flo = (__int128)okey_to_i64(st->min_key); fhi = (__int128)okey_to_i64(st->max_key);
+        }
+        const __int128 bias = flo < 0 ? flo : 0;
+        if (fits && fhi >= flo && fhi - bias < ((__int128)1 << 62)) { mode = 3; a.fx_bias = (long long)bias; }
+    }
     cudaStream_t s = db->stream;
     if (ring) {
         if (mode == 0) rc = moments ? sql_launch_ring<0, true>(db, ra, s) : sql_launch_ring<0, false>(db, ra, s);
         else if (mode == 1) rc = moments ? sql_launch_ring<1, true>(db, ra, s) : sql_launch_ring<1, false>(db, ra, s);
-        else rc = moments ? sql_launch_ring<2, true>(db, ra, s) : sql_launch_ring<2, false>(db, ra, s);
+        else if (mode == 2) rc = moments ? sql_launch_ring<2, true>(db, ra, s) : sql_launch_ring<2, false>(db, ra, s);
+        else rc = moments ? sql_launch_ring<3, true>(db, ra, s) : sql_launch_ring<3, false>(db, ra, s);
     } else {
         if (!strided && dense) {  // register kernel has no row-number filter: visit the progression
             a.first = (uint64_t)((step - phase) % step); a.stride = (uint64_t)step;
@@ -2254,7 +2274,8 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
         }
         if (mode == 0) rc = moments ? sql_launch_regs<0, true>(db, a, s) : sql_launch_regs<0, false>(db, a, s);
         else if (mode == 1) rc = moments ? sql_launch_regs<1, true>(db, a, s) : sql_launch_regs<1, false>(db, a, s);
-        else rc = moments ? sql_launch_regs<2, true>(db, a, s) : sql_launch_regs<2, false>(db, a, s);
+        else if (mode == 2) rc = moments ? sql_launch_regs<2, true>(db, a, s) : sql_launch_regs<2, false>(db, a, s);
+        else rc = moments ? sql_launch_regs<3, true>(db, a, s) : sql_launch_regs<3, false>(db, a, s);
     }
     if (rc) return rc;
     CU(cudaGetLastError());

@@ -16,8 +16,10 @@
 // fixed-point sum is the EXACT sum.  Three bin layouts, picked by the group count G:
 //   G == 1        registers, warp shuffles, one global update per CTA
 //   G <= 16       thread-private bins in shared memory ([bin][thread], conflict-free), no atomics in the loop
-//   G <= 4096     CTA-shared bins, 32-bit shared atomics with explicit carry propagation (64-bit shared
-//                 atomic adds are CAS loops on sm_100: SASS ATOMS.CAST.SPIN.64)
+//   G <= 4096     CTA-shared bins, 32-bit shared atomics (64-bit shared atomic adds are CAS loops on sm_100: SASS
+//                 ATOMS.CAST.SPIN.64).  Packed form (MODE 3, whenever the fixed-point values of the aggregate column span
+//                 fewer than 2^62 steps): THREE atomics per row carry the row count and the 62-bit value; general form
+//                 (MODE 2: COUNT-only queries, full-range int64 columns): a count word + four limbs with carry chains
 #pragma once
 
 #include "aqe_kernels.cuh"
@@ -75,6 +77,8 @@ constexpr int kSqlMaxCols = 5;          // the table has five columns; each is l
 constexpr int kSqlPrivateMaxGroups = 16;
 constexpr unsigned int kSqlPackedRows = 65535;   // rows a thread may add to one private bin between drains (16-bit packed counter)
 constexpr unsigned int kSqlPackedRowsMoments = 4095;   // ... with squares: three words per bin, 12 bits of headroom per field
+
+constexpr unsigned int kSqlSharedPackedLimit = 1024;   // MODE 3: a bin whose packed row counter reached this is emptied by the thread that saw it
 
 constexpr int kSqlMaxAlt = AQE_SQL_MAX_ALT;   // OR-ed conjunctions of a WHERE clause
 
@@ -136,6 +140,7 @@ struct SqlArgs {
     int member_used;
     unsigned int drain_rows;          // private bins (G <= 16) are drained before a thread has added this many rows to one (<= kSqlPackedRows)
     int pair_bins;                    // private bins: words 0 and 1 of a bin sit side by side and are updated with ONE 128-bit load / store
+    long long fx_bias;                // MODE 3: min(0, smallest fixed-point value of the aggregate column); bins hold sums of u = fx - fx_bias >= 0
     SqlExchange ex;
 };
 
@@ -209,8 +214,39 @@ __device__ __forceinline__ void shared_add128(unsigned int* limbs, unsigned int 
     limb_add(limbs + 3 * G + g, sign, c);
 }
 
+// MODE 3 of SqlBins (packed CTA-shared bins): the contents of one bin, taken out of shared memory by the caller -> global accumulators
+template <bool MOMENTS>
+__device__ __forceinline__ void sql_packed_to_global(unsigned long long* ga, long long bias, const unsigned int (&x)[4], const unsigned int (&y)[4]) {
+    // (no shortcut on "no rows": a bin emptied by two threads at once can hand the second one words of rows whose counter the
+    // first one took, or the other way round; every word is added for what it holds)
+    if ((x[0] | x[1] | x[2] | x[3] | y[0] | y[1] | y[2] | y[3]) == 0u) return;
+    const unsigned long long n = x[2] >> 20;
+    const unsigned __int128 u = (unsigned __int128)x[0] + ((unsigned __int128)x[1] << 32) + ((unsigned __int128)(x[2] & 0xfffffu) << 54) + ((unsigned __int128)x[3] << 64);
+    const __int128 v = (__int128)u + (__int128)(long long)n * (__int128)bias;
+    if (n) atomicAdd(ga + 0, n);
+    global_add128(ga + 1, (unsigned long long)v, (unsigned long long)((unsigned __int128)v >> 64));
+    if constexpr (MOMENTS) {
+        const unsigned __int128 q = (unsigned __int128)y[0] + ((unsigned __int128)y[1] << 32) + ((unsigned __int128)y[2] << 54) + ((unsigned __int128)y[3] << 64);
+        global_add128(ga + 3, (unsigned long long)q, (unsigned long long)(q >> 64));
+    }
+}
+// A bin whose row counter reached kSqlSharedPackedLimit, emptied by the thread that saw it (rare; out of line and with scalar arguments
+// only, so that the bins' bookkeeping stays in registers in the callers' loops).  See the layout note in SqlBins.
+template <bool MOMENTS>
+__device__ __noinline__ void sql_packed_spill(unsigned int* s_sum, unsigned int* s_sq, unsigned int G, unsigned int g, long long bias, unsigned long long* ga) {
+    unsigned int x[4], y[4] = {0u, 0u, 0u, 0u};
+    x[2] = atomicExch(s_sum + 2 * G + g, 0u);
+    x[0] = atomicExch(s_sum + g, 0u); x[1] = atomicExch(s_sum + G + g, 0u); x[3] = atomicExch(s_sum + 3 * G + g, 0u);
+    if constexpr (MOMENTS) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) y[l] = atomicExch(s_sq + l * G + g, 0u);
+    }
+    sql_packed_to_global<MOMENTS>(ga, bias, x, y);
+}
+
 // ---- bins: where a row's (count, value, value^2) lands ------------------------------------------------------
-// MODE 0: no GROUP BY (registers) | 1: thread-private shared bins | 2: CTA-shared bins with atomics.
+// MODE 0: no GROUP BY (registers) | 1: thread-private shared bins | 2: CTA-shared bins with atomics, general form |
+// 3: CTA-shared bins with atomics, packed form.
 // T = threads that add rows (the private bins are laid out [bin][T]); every thread of the CTA must call flush().
 template <int MODE, bool MOMENTS, int T> struct SqlBins {
     unsigned int G;
@@ -221,6 +257,16 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
     //         w0 = rows << 52 | sum of u[0:40)      w1 = sum of q[0:16) << 36 | sum of u[40:64)      w2 = sum of q[16:62)
     //         -- every field has 12 spare bits: fewer than kSqlPackedRowsMoments rows per bin between drains
     // MODE 2: cnt[G] u32 | sum limbs [4][G] u32 | (sq limbs [4][G])
+    // MODE 3: sum words [4][G] u32 | (sq words [4][G]), u = fx - bias in [0, 2^62), q = square in [0, 2^62):
+    //         w0 += u[0:32)             the return value tells the carry c0 out of the word
+    //         w1 += u[32:54) + c0       22-bit pieces: the word wraps at most once in 1023 rows; the return value tells, w3 counts the wraps
+    //         w2 += u[54:62) + 2^20     rows in the top 12 bits, the sum of the pieces below them: both stay inside their fields for 4095 rows
+    //         The ATOMS issue rate bounds these kernels, so what counts is atomics per row: 3 here (count included) against
+    //         1 + 3.15 in MODE 2 (count word, two limbs, and a third limb for the 15 % of the rows whose second limb carries -- some
+    //         lane of nearly every warp).  A thread that reads >= kSqlSharedPackedLimit rows out of w2's return value empties that bin
+    //         into the global accumulators on the spot, word by word with atomicExch: every word is a plain sum and every wrap is
+    //         counted by the add that caused it, so emptying a word between two adds loses nothing.  At most one add per thread is in
+    //         flight between seeing the limit and emptying, so a counter stays below 1024 + 288 whatever the key distribution.
     unsigned int* b_cnt;
     unsigned long long *p_slo, *p_shi, *p_qlo;
     unsigned int *s_sum, *s_sq;
@@ -229,16 +275,19 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
     bool with_sums;   // the query aggregates a column (false: COUNT only); uniform over the launch, set by the kernel after init()
     bool paired;      // MODE 1: words 0 and 1 interleaved as [bin][thread] 16-byte pairs (one LDS.128 + one STS.128 per row instead of
                       // two 64-bit chains); set by the kernel after init(), uniform over the launch.  p_slo then addresses the pairs.
+    long long bias;                 // MODE 3 (SqlArgs::fx_bias), set by the kernel after init()
+    unsigned long long* spill_acc;  // MODE 3: the global accumulators a full bin is emptied into, set by the kernel after init()
 
     static size_t smem_bytes(unsigned int G) {
         if (MODE == 1) return (size_t)G * T * (MOMENTS ? 24 : 16);
         if (MODE == 2) return (size_t)G * (4 + 16 + (MOMENTS ? 16 : 0));
+        if (MODE == 3) return (size_t)G * (16 + (MOMENTS ? 16 : 0));
         return 0;
     }
     // all threads of the CTA call init (it contains a barrier); tid < T owns a private column of bins
     __device__ __forceinline__ void init(unsigned char* smem, unsigned int groups, int tid, int nthreads) {
         G = groups;
-        with_sums = true; paired = false;
+        with_sums = true; paired = false; bias = 0; spill_acc = nullptr;
         b_cnt = reinterpret_cast<unsigned int*>(smem);
         r_cnt = 0; r_slo = 0; r_qlo = 0; r_shi = 0; r_qhi = 0;
         if constexpr (MODE == 1) {
@@ -251,8 +300,22 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
             s_sq = s_sum + (size_t)G * 4;
             for (unsigned int i = tid; i < G; i += nthreads) b_cnt[i] = 0;
             for (unsigned int i = tid; i < G * 4; i += nthreads) { s_sum[i] = 0; if constexpr (MOMENTS) s_sq[i] = 0; }
+        } else if constexpr (MODE == 3) {
+            s_sum = b_cnt;
+            s_sq = s_sum + (size_t)G * 4;
+            for (unsigned int i = tid; i < G * 4; i += nthreads) { s_sum[i] = 0; if constexpr (MOMENTS) s_sq[i] = 0; }
         }
         __syncthreads();
+    }
+    // one 62-bit value into words 0, 1 (and 3) of a packed bin
+    __device__ __forceinline__ void packed_add(unsigned int* w, unsigned int g, unsigned long long u) {
+        const unsigned int x0 = (unsigned int)u;
+        const unsigned int o0 = atomicAdd(w + g, x0);
+        const unsigned int a1 = ((unsigned int)(u >> 32) & 0x3fffffu) + ((o0 + x0 < o0) ? 1u : 0u);
+        if (a1) {   // (always, for floating-point columns; integer columns below 2^32 skip it)
+            const unsigned int o1 = atomicAdd(w + G + g, a1);
+            if (o1 + a1 < o1) atomicAdd(w + 3 * G + g, 1u);
+        }
     }
     __device__ __forceinline__ void add(unsigned int g, int tid, bool has_sum, long long fx, long long fq) {
         if constexpr (MODE == 0) {
@@ -284,12 +347,23 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
                 p_slo[s] += (1ull << 48) + ((unsigned long long)fx & 0xffffffffull);
                 if (has_sum) p_shi[s] += (unsigned long long)((fx >> 32) + 0x80000000ll);   // COUNT-only queries keep one chain
             }
-        } else {
+        } else if constexpr (MODE == 2) {
             atomicAdd(b_cnt + g, 1u);
             if (has_sum) {
                 shared_add128(s_sum, G, g, fx);
                 if constexpr (MOMENTS) shared_add128(s_sq, G, g, fq);
             }
+        } else {
+            const unsigned long long u = (unsigned long long)(fx - bias);
+            const unsigned int o2 = atomicAdd(s_sum + 2 * G + g, (unsigned int)(u >> 54) + (1u << 20));
+            packed_add(s_sum, g, u);
+            if constexpr (MOMENTS) {
+                const unsigned long long q = (unsigned long long)fq;
+                packed_add(s_sq, g, q);
+                const unsigned int q2 = (unsigned int)(q >> 54);
+                if (q2) atomicAdd(s_sq + 2 * G + g, q2);
+            }
+            if ((o2 >> 20) >= kSqlSharedPackedLimit) sql_packed_spill<MOMENTS>(s_sum, s_sq, G, g, bias, spill_acc + (size_t)g * 5);
         }
     }
     __device__ __forceinline__ void zero_private(int tid) {
@@ -362,6 +436,14 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
             }
         } else if constexpr (MODE == 1) {
             if (tid < T) drain(global_acc, tid);
+        } else if constexpr (MODE == 3) {
+            __syncthreads();
+            for (unsigned int g = tid; g < G; g += nthreads) {
+                unsigned int x[4], y[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int l = 0; l < 4; ++l) { x[l] = s_sum[l * G + g]; if constexpr (MOMENTS) y[l] = s_sq[l * G + g]; }
+                sql_packed_to_global<MOMENTS>(global_acc + (size_t)g * 5, bias, x, y);
+            }
         } else {
             __syncthreads();
             for (unsigned int g = tid; g < G; g += nthreads) {
@@ -512,6 +594,7 @@ __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
     bins.init(sql_smem, a.n_groups, tid, T);
     bins.with_sums = a.agg_slot >= 0;
     bins.paired = MODE == 1 && a.pair_bins != 0 && a.agg_slot >= 0;
+    bins.bias = a.fx_bias; bins.spill_acc = a.global_acc;
 
     // per-query facts, read from the parameter bank once
     const int agg_slot = a.agg_slot, group_slot = a.group_slot, n_alt = a.n_alt;
@@ -704,7 +787,31 @@ template <int T, int K> __device__ __forceinline__ uint32_t sql_mod_pass(const S
 
 // CTAs per SM the register allocation must leave room for (shared memory usually sets the real limit): 4 for the plain
 // ungrouped and the shared-atomic kernels (<= 56 registers), 3 for private bins and for moments, 2 for private bins with moments.
-constexpr int sql_ring_min_ctas(int mode, bool moments) { return mode == 1 ? (moments ? 2 : 3) : (moments ? 3 : 4); }
+// The packed shared bins always come with rows of >= 12 bytes (group column + aggregate column): shared memory holds three CTAs of them at K = 8 (with squares at K = 6).
+constexpr int sql_ring_min_ctas(int mode, bool moments) { return mode == 1 ? (moments ? 2 : 3) : (moments || mode == 3 ? 3 : 4); }
+
+// Packed shared-atomic bins, tiles few of whose rows pass: the ATOMS of a predicated-off row still costs its issue slot, so when no thread
+// of the warp kept more than half of its K rows the warp walks the set pass bits instead -- max over the lanes of popc(mask) rounds
+// in place of K, each reading its row's group key and value out of the stage again (two LDS, far cheaper than the atomics saved).
+template <int MODE, bool MOMENTS, int T>
+__device__ __forceinline__ void sql_sparse_adds(const SqlArgs& a, SqlBins<MODE, MOMENTS, T>& bins, int tid, uint32_t mask, unsigned int rounds,
+                                                const unsigned char* gb, int group_kind, const unsigned char* ab, int agg_kind) {
+    for (unsigned int i = 0; i < rounds; ++i) {
+        if (mask) {
+            const uint32_t row = (uint32_t)tid + (uint32_t)(__ffs(mask) - 1) * (uint32_t)T;
+            mask &= mask - 1u;
+            const unsigned int g = group_kind == 2 ? (unsigned int)(lds_row<int>(gb, row) - (int)a.key_min) : (unsigned int)(lds_row<long long>(gb, row) - a.key_min);
+            long long fx = 0, fq = 0;
+            if (agg_kind >= 0) {
+                double d;
+                if (agg_kind == 0) { d = lds_row<double>(ab, row); fx = __double2ll_rn(__dmul_rn(d, a.sum_scale)); }
+                else { fx = agg_kind == 2 ? (long long)lds_row<int>(ab, row) : lds_row<long long>(ab, row); d = (double)fx; }
+                if constexpr (MOMENTS) fq = __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale));
+            }
+            bins.add(g, tid, agg_kind >= 0, fx, fq);
+        }
+    }
+}
 
 template <int MODE, bool MOMENTS, int STAGES, int K>
 __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)) k_sql_ring(const SqlRingArgs ra) {
@@ -727,6 +834,7 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
     bins.init(bin_mem, a.n_groups, tid, kBulkThreads);  // ends with __syncthreads()
     bins.with_sums = a.agg_slot >= 0;
     bins.paired = MODE == 1 && a.pair_bins != 0 && a.agg_slot >= 0;
+    bins.bias = a.fx_bias; bins.spill_acc = a.global_acc;
 
     const uint64_t n_main = a.count & ~3ull;  // bulk copies move multiples of 16 bytes: 4 rows of a 4-byte column
     const uint64_t ntiles = (n_main + ra.tile_rows - 1) / ra.tile_rows;
@@ -839,9 +947,20 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
 #pragma unroll
                 for (int k = 0; k < K; ++k) if (g[k] >= bins.G) mask &= ~(1u << k);  // cannot happen for live rows with this table's own layout
             }
+            // shared-atomic bins: rounds of the sparse walk when it pays (sql_sparse_adds), else ~0u
+            auto sparse_rounds = [&](uint32_t m) -> unsigned int {
+                if constexpr (MODE == 3) {   // (MODE 2 runs under a 56-register cap that this second code path does not fit)
+                    const unsigned int r = __reduce_max_sync(0xffffffffu, (unsigned int)__popc(m));
+                    return 2u * r <= (unsigned int)K ? r : ~0u;
+                } else return ~0u;
+            };
             if (agg_kind < 0) {
+                const unsigned int sr = sparse_rounds(mask);
+                if (sr != ~0u) sql_sparse_adds(a, bins, tid, mask, sr, stage + group_off, group_kind, stage, -1);
+                else {
 #pragma unroll
-                for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, false, 0, 0);
+                    for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, false, 0, 0);
+                }
             } else if (agg_kind == 0) {
                 const unsigned char* ab = stage + agg_off;
                 long long fx[K], fq[K];
@@ -861,8 +980,12 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
                         fq[k] = MOMENTS ? __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale)) : 0;
                     }
                 }
+                const unsigned int sr = sparse_rounds(mask);
+                if (sr != ~0u) sql_sparse_adds(a, bins, tid, mask, sr, stage + group_off, group_kind, ab, agg_kind);
+                else {
 #pragma unroll
-                for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, true, fx[k], fq[k]);
+                    for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, true, fx[k], fq[k]);
+                }
             } else {
                 const unsigned char* ab = stage + agg_off;
                 long long fx[K], fq[K];
@@ -872,8 +995,12 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
                     const double d = (double)fx[k];
                     fq[k] = MOMENTS ? __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale)) : 0;
                 }
+                const unsigned int sr = sparse_rounds(mask);
+                if (sr != ~0u) sql_sparse_adds(a, bins, tid, mask, sr, stage + group_off, group_kind, ab, agg_kind);
+                else {
 #pragma unroll
-                for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, true, fx[k], fq[k]);
+                    for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, true, fx[k], fq[k]);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);

@@ -247,6 +247,23 @@ def test_sql_large_table_properties():
     by_pid = e.sql("SELECT COUNT(amount) FROM sales WHERE amount BETWEEN 100 AND 500 GROUP BY product_id")
     w = e.scan("amount", "amount", 100.0, 500.0)
     assert len(by_pid) == 1000 and sum(r.count for r in by_pid) == w.count
+    # 1000 groups (packed shared bins, three atomics per row): the groups' integer accumulators add up to the ungrouped scan's, word for
+    # word, and equal the general form's (AQE_SQL_PACKED=0)
+    q_pid = aqe.sql_parse("SELECT SUM(amount) FROM sales GROUP BY product_id", 0)
+    l_pid = aqe.sql_layout(q_pid, [e.sql_facts(q_pid)])
+    assert l_pid.n_groups == 1000 and l_pid.sum_shift == layout.sum_shift
+    pid = e.sql_scan(q_pid, l_pid, aqe.SQL_MOMENTS).reshape(-1, 5)
+    q_one = aqe.sql_parse("SELECT SUM(amount) FROM sales", 0)
+    one = e.sql_scan(q_one, aqe.sql_layout(q_one, [e.sql_facts(q_one)]), aqe.SQL_MOMENTS)
+    as_int = lambda lo, hi: int(lo) + (int(hi) << 64)
+    assert sum(int(c) for c in pid[:, 0]) == int(one[0]) == n
+    assert sum(as_int(r[1], r[2]) for r in pid) % (1 << 128) == as_int(one[1], one[2])
+    assert sum(as_int(r[3], r[4]) for r in pid) % (1 << 128) == as_int(one[3], one[4])
+    os.environ["AQE_SQL_PACKED"] = "0"
+    try:
+        assert (e.sql_scan(q_pid, l_pid, aqe.SQL_MOMENTS).reshape(-1, 5) == pid).all()
+    finally:
+        del os.environ["AQE_SQL_PACKED"]
     # 1-in-10 systematic sample through the strided visit: count is exact, estimate is close
     s = e.sql("SELECT SUM(amount) FROM sales", 10, "ci_correct")[0]
     half = (s.ci_upper - s.ci_lower) / 2
@@ -524,4 +541,79 @@ def test_sql_negative_values_and_keys_and_the_group_limit(oracle):
         for a, b in zip(got, want):     # one row per group: the reference divides by n - 1 = 0; whatever it reports (nan / inf), the engine reports too
             for u, v in zip(a[2:], b[2:]):
                 assert (math.isnan(u) and math.isnan(v)) or u == pytest.approx(v, rel=REL), (sql, a, b)
+    e.close()
+
+
+def _skewed_rows(oracle, n=120_000, seed=33):
+    """Nine rows in ten carry ONE product_id, the rest spread over 1000 keys: a CTA of the grouped scan adds far more than
+    kSqlSharedPackedLimit (1024) rows of a tile to one packed shared bin, so bins are emptied in mid-scan by the threads that see it."""
+    rng = np.random.default_rng(seed)
+    rows = oracle.synth(n, seed=seed)
+    rows["product_id"] = np.where(rng.random(n) < 0.9, 417, rng.integers(0, 1000, n))
+    rows["product_id"][:2] = (0, 999)
+    return rows
+
+
+PACKED_QUERIES = (("SELECT SUM(amount) FROM sales GROUP BY product_id", 0, 0),
+                  ("SELECT AVG(amount) FROM sales GROUP BY product_id", 0, aqe.SQL_MOMENTS),
+                  ("SELECT SUM(amount) FROM sales WHERE amount > 900 GROUP BY product_id", 0, 0),                 # few rows pass: the sparse walk
+                  ("SELECT SUM(amount) FROM sales WHERE region = 3 AND amount < 120.5 GROUP BY product_id", 0, aqe.SQL_MOMENTS),
+                  ("SELECT SUM(timestamp) FROM sales GROUP BY product_id", 0, 0),                                 # integer aggregate, values above 2^30
+                  ("SELECT AVG(id) FROM sales WHERE id > 500 GROUP BY product_id", 0, aqe.SQL_MOMENTS),
+                  ("SELECT SUM(region) FROM sales WHERE region >= 3 GROUP BY product_id", 0, 0),                  # pieces above bit 32 are all zero
+                  ("SELECT SUM(amount) FROM sales GROUP BY product_id", 50, aqe.SQL_MOMENTS),                      # strided visit (k_sql_agg)
+                  ("SELECT AVG(amount) FROM sales WHERE amount > 950 GROUP BY product_id", 10, 0),
+                  ("SELECT SUM(product_id) FROM sales GROUP BY product_id", 0, aqe.SQL_MOMENTS))
+
+
+def test_sql_packed_shared_bins_leave_the_words_of_the_general_form(tables, oracle, monkeypatch):
+    """Mid-sized GROUP BY (17..4096 keys): the packed shared bins (three atomics per row, SqlBins MODE 3 -- the default whenever the
+    aggregate column's fixed-point range allows) leave exactly the accumulator words of the general form (count word + limbs with
+    carry chains, AQE_SQL_PACKED=0), through both kernels: on the uniform table, on a table whose keys are skewed enough that bins
+    fill up and are emptied in mid-scan, and on signed data (bins hold value - column minimum)."""
+    from sql_helpers import signed_rows
+    uniform = [t for t in tables if t[0]["n"] == 100000][0][1]
+    signed = signed_rows(oracle, n=150_001)
+    signed["product_id"] = signed["product_id"] // 4          # 1024 keys, negative ones included
+    for name, rows in (("uniform", uniform), ("skewed", _skewed_rows(oracle)), ("signed", signed)):
+        e = aqe.Engine(0).from_rows(rows)
+        for sql, p, flags in PACKED_QUERIES:
+            q = aqe.sql_parse(sql, p)
+            layout = aqe.sql_layout(q, [e.sql_facts(q)])
+            assert 16 < layout.n_groups <= aqe.SQL_MAX_GROUPS
+            got = {}
+            for packed in ("1", "0"):
+                monkeypatch.setenv("AQE_SQL_PACKED", packed)
+                for variant in ("0", "1", "2"):
+                    monkeypatch.setenv("AQE_SQL_VARIANT", variant)
+                    got[packed, variant] = e.sql_scan(q, layout, flags)
+            monkeypatch.delenv("AQE_SQL_PACKED", raising=False)
+            monkeypatch.delenv("AQE_SQL_VARIANT", raising=False)
+            ref = got["0", "1"]
+            for k, v in got.items():
+                assert (v == ref).all(), (name, sql, p, k)
+            assert int(ref.reshape(-1, 5)[:, 0].sum()) > 0, (name, sql)
+        e.close()
+
+
+def test_sql_skewed_keys_against_oracle(oracle):
+    """The same skewed table end to end against the oracle's restatement of the reference executor."""
+    rows = _skewed_rows(oracle, n=60_000, seed=34)
+    e = aqe.Engine(0).from_rows(rows)
+    for sql, p, mode in (("SELECT SUM(amount) FROM sales GROUP BY product_id", 0, "run_query_groupby"),
+                         ("SELECT AVG(amount) FROM sales WHERE amount > 300 GROUP BY product_id", 0, "run_query_groupby_with_ci"),
+                         ("SELECT SUM(timestamp) FROM sales GROUP BY product_id", 0, "run_query_groupby"),
+                         ("SELECT AVG(amount) FROM sales WHERE product_id = 417 GROUP BY product_id", 50, "run_query_groupby_with_ci"),
+                         ("SELECT SUM(amount) FROM sales GROUP BY product_id", 50, "run_query_groupby_with_ci")):
+        try:
+            want = oracle.sql(rows, sql, p, mode)
+        except SqlError as ex:      # a key none of whose few rows was sampled: NULL -> stod in the reference (the last query)
+            assert ex.kind in ("stod", "terminate"), (sql, ex)
+            with pytest.raises(ValueError):
+                run_engine(e, sql, p, mode)
+            continue
+        assert rows_close(run_engine(e, sql, p, mode), want, REL) is None, (sql, p, rows_close(run_engine(e, sql, p, mode), want, REL))
+    x, k = rows["amount"], rows["product_id"]
+    r = {row.key: row.value for row in e.sql("SELECT SUM(amount) FROM sales GROUP BY product_id")}
+    assert r[417] == math.fsum(x[k == 417]) and r[999] == math.fsum(x[k == 999])      # exactly rounded, emptied bins included
     e.close()

@@ -4,9 +4,11 @@
 //            forms a gather kernel can use (ld.global.nc, ld.global.ca, ld.global.cg, L1::no_allocate) x loads in flight per
 //            thread x the device's L2 fetch-granularity limit (32 / 64 / 128 bytes).
 //   h2d      pinned host -> device cudaMemcpyAsync bandwidth, 1 GiB, per GPU and all GPUs at once (one thread per GPU).
+//   atoms    issue rate of 32-bit shared-memory atomics per SM (clocks per warp instruction) by address pattern, use of the return
+//            value, dependence between atomics and active lanes: the ceiling of the shared-bin GROUP BY kernels (k_sql_ring, G > 16).
 //
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo tools/microbench.cu -o tools/_bin/microbench
-//   tools/_bin/microbench gather [elems] | h2d [n_gpus]
+//   tools/_bin/microbench gather [elems] | h2d [n_gpus] | atoms [groups]
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -213,7 +215,110 @@ static int h2dnuma_main(int ngpu) {
     return 0;
 }
 
+
+// ---- atoms: shared-memory atomic issue rate ------------------------------------------------------------------------------
+// Every thread makes `iters` x 8 "rows"; a row is one of the shapes below on pseudo-random bins of a G-word table (limb-major
+// words w0 = s[g], w1 = s[G + g], ...).  Reported: SM clocks per warp-level ATOMS instruction and per row.
+//  0 one atomic, result unused            1 one atomic, result summed into a register     2 one atomic whose addend depends on the previous result
+//  3 like 0, bank = lane (no conflicts)   4 like 1, bank = lane                            5 atomicAdd(p, 1) (ATOMS.POPC.INC)
+//  6 like 0, 4 of 32 lanes active         7 like 0, 8 replicas of the table, replica = lane % 8
+//  8 two atomics, the second takes the first's carry (k_sql_ring packed bins, w0 -> w1), rows independent, no branch
+//  9 the packed row: w2 (result tested against a limit), w0 -> w1, branch on w1's wrap    10 three independent atomics, results unused
+// 11 like 9 with a fourth independent atomic (general form: count word + limbs)          12 like 10 plus a count word (four, results unused)
+template <int V> __global__ void __launch_bounds__(256) k_atoms(unsigned int G, int iters, int pattern, unsigned int* out, long long* clk) {
+    extern __shared__ unsigned int s[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (unsigned int i = tid; i < 8 * G; i += blockDim.x) s[i] = 0;
+    __syncthreads();
+    unsigned int x = (blockIdx.x * 256u + tid) * 2654435761u + 12345u, acc = 0, carry = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x = x * 1664525u + 1013904223u;
+            unsigned int h = x ^ (x >> 16);            // the LCG alone keeps the lanes of a warp in an arithmetic progression (a low-discrepancy,
+            h *= 0x7feb352du; h ^= h >> 15;            // nearly conflict-free set of bins): hash it so that the 32 bins of a warp row are independent
+            h *= 0x846ca68bu; h ^= h >> 16;
+            unsigned int g = pattern == 0 ? __umulhi(h, G) : __umulhi(x, G);
+            const unsigned int v = h | 0x80000000u;
+            if (V == 0) atomicAdd(s + g, v);
+            if (V == 1) acc += atomicAdd(s + g, v);
+            if (V == 2) { const unsigned int a = v + carry; const unsigned int o = atomicAdd(s + g, a); carry = (o + a < o) ? 1u : 0u; }
+            if (V == 3 || V == 4) { g = (g & ~31u) | lane; if (g >= G) g -= 32; if (V == 3) atomicAdd(s + g, v); else acc += atomicAdd(s + g, v); }
+            if (V == 5) atomicAdd(s + g, 1u);
+            if (V == 6) { if ((lane & 7) == 0) atomicAdd(s + g, v); }
+            if (V == 7) atomicAdd(s + g * 8 + (lane & 7), v);
+            if (V == 8) { const unsigned int o = atomicAdd(s + g, v); atomicAdd(s + G + g, (v >> 10) + ((o + v < o) ? 1u : 0u)); }
+            if (V == 9 || V == 11) {
+                const unsigned int o2 = atomicAdd(s + 2 * G + g, (v >> 24) + (1u << 20));
+                if (V == 11) atomicAdd(s + 4 * G + g, 1u);
+                const unsigned int o = atomicAdd(s + g, v);
+                const unsigned int a1 = (v >> 10) + ((o + v < o) ? 1u : 0u);
+                const unsigned int o1 = atomicAdd(s + G + g, a1);
+                if (o1 + a1 < o1) atomicAdd(s + 3 * G + g, 1u);
+                if ((o2 >> 20) >= 4000u) { atomicExch(s + 2 * G + g, 0u); acc += 1; }
+            }
+            if (V == 10 || V == 12) { atomicAdd(s + g, v >> 11); atomicAdd(s + G + g, (v >> 5) & 0x1fffffu); atomicAdd(s + 2 * G + g, v & 0xfffffu); if (V == 12) atomicAdd(s + 3 * G + g, 1u); }
+        }
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (tid == 0) clk[blockIdx.x] = t1 - t0;
+    if (acc == 0x12345678u || carry == 77u) out[0] = s[tid % G];   // keep the results alive
+}
+
+template <int V> static void run_atoms(unsigned int G, int ctas_per_sm, int pattern, int atoms_per_row, const char* what, unsigned int* out, long long* clk, int sms) {
+    const int iters = 2000;
+    const size_t smem = (size_t)8 * G * 4;
+    cudaFuncSetAttribute(k_atoms<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = sms * ctas_per_sm;
+    k_atoms<V><<<grid, 256, smem>>>(G, 10, pattern, out, clk);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    k_atoms<V><<<grid, 256, smem>>>(G, iters, pattern, out, clk);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    std::vector<long long> h(grid);
+    cudaMemcpy(h.data(), clk, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
+    double mean = 0;
+    for (long long c : h) mean += (double)c;
+    mean /= grid;
+    const double rows_per_sm_warp = (double)iters * 8 * ctas_per_sm * 8;   // warp-rows per SM
+    printf("{\"variant\": %d, \"what\": \"%s\", \"bins\": \"%s\", \"groups\": %u, \"ctas_per_sm\": %d, \"warps_per_sm\": %d, \"ms\": %.4f, \"clk_per_warp_row_per_sm\": %.2f, "
+           "\"clk_per_warp_atomic_per_sm\": %.2f, \"ms_per_1e9_rows_148_sms\": %.3f, \"err\": \"%s\"}\n",
+           V, what, pattern == 0 ? "independent per lane" : "arithmetic progression over the lanes (few bank conflicts)", G, ctas_per_sm, ctas_per_sm * 8, ms, mean / rows_per_sm_warp, mean / rows_per_sm_warp / atoms_per_row,
+           ms * 1e9 / ((double)iters * 8 * 256 * grid), cudaGetErrorString(cudaGetLastError()));
+}
+
+static int atoms_main(unsigned int G) {
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, 0);
+    unsigned int* out; long long* clk;
+    cudaMalloc(&out, 4096); cudaMalloc(&clk, sizeof(long long) * 4096);
+    for (int pattern : {0, 1})
+        for (int c : {3, 4}) {
+            const int n = prop.multiProcessorCount;
+            run_atoms<0>(G, c, pattern, 1, "one atomic, result unused", out, clk, n);
+            run_atoms<1>(G, c, pattern, 1, "one atomic, result summed", out, clk, n);
+            run_atoms<2>(G, c, pattern, 1, "one atomic, addend depends on the previous result", out, clk, n);
+            run_atoms<3>(G, c, pattern, 1, "result unused, bank = lane", out, clk, n);
+            run_atoms<5>(G, c, pattern, 1, "atomicAdd(p, 1): POPC.INC", out, clk, n);
+            run_atoms<6>(G, c, pattern, 1, "result unused, 4 of 32 lanes", out, clk, n);
+            run_atoms<7>(G, c, pattern, 1, "result unused, 8 replicas by lane", out, clk, n);
+            run_atoms<8>(G, c, pattern, 2, "two atomics, carry from the first into the second", out, clk, n);
+            run_atoms<9>(G, c, pattern, 3, "packed row: w2 / w0 -> w1, branch on the wrap", out, clk, n);
+            run_atoms<10>(G, c, pattern, 3, "three independent atomics, results unused", out, clk, n);
+            run_atoms<11>(G, c, pattern, 4, "packed row + a count word", out, clk, n);
+            run_atoms<12>(G, c, pattern, 4, "four independent atomics, results unused", out, clk, n);
+        }
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && !std::strcmp(argv[1], "atoms")) return atoms_main(argc >= 3 ? (unsigned int)std::atoi(argv[2]) : 1000u);
     if (argc >= 2 && !std::strcmp(argv[1], "h2dnuma")) return h2dnuma_main(argc >= 3 ? std::atoi(argv[2]) : 0);
     if (argc >= 2 && !std::strcmp(argv[1], "gather")) return gather_main(argc >= 3 ? std::strtoull(argv[2], nullptr, 10) : (1ull << 30));
     if (argc >= 2 && !std::strcmp(argv[1], "h2d")) return h2d_main(argc >= 3 ? std::atoi(argv[2]) : 0);

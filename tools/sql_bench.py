@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Timings of the SQL-string path (k_sql_agg) on a device-generated table: ms per query (median of reps, host wall clock
 around the synchronous C-ABI call aqe_sql_run), rows/s and achieved GB/s against the ALGORITHMIC bytes of the query (the widths of
-the distinct columns it reads x rows visited).  python tools/sql_bench.py [rows] [reps] [sampled|or] > out.json"""
+the distinct columns it reads x rows visited).  python tools/sql_bench.py [rows] [reps] [sampled|or|groups] > out.json"""
 import json
 import os
 import sys
@@ -52,6 +52,12 @@ def main():
                            "(region = 1 OR amount > 900)", "(region = 1 AND amount > 900 OR region = 3 AND amount < 100)", "product_id = 5", "product_id IN (1, 3, 5, 7)",
                            "product_id NOT IN (1, 3, 5, 7, 9, 11)", "amount NOT BETWEEN 100 AND 500", "(amount < 50 OR amount > 950 OR amount BETWEEN 400 AND 410)",
                            f"timestamp NOT BETWEEN {T0 + n // 4} AND {T0 + n // 2}")]
+    if len(sys.argv) > 3 and sys.argv[3] == "groups":   # mid-sized GROUP BY: the shared-atomic bins (A/B with AQE_SQL_PACKED=0)
+        cases = [(f"SELECT {agg} FROM sales{w} GROUP BY product_id", 0, mode, cols)
+                 for agg, mode, cols in (("SUM(amount)", "value", ["amount", "product_id"]), ("AVG(amount)", "value", ["amount", "product_id"]),
+                                         ("SUM(amount)", "ci_reference", ["amount", "product_id"]), ("SUM(timestamp)", "value", ["timestamp", "product_id"]),
+                                         ("COUNT(amount)", "value", ["product_id"]))
+                 for w in ("", " WHERE amount BETWEEN 100 AND 500", " WHERE amount > 900", " WHERE region = 3")]
     out = []
     import ctypes as C
     buf = (aqe.SqlRow * aqe.SQL_MAX_GROUPS)()

@@ -11,6 +11,8 @@ e = aqe.Engine(0).generate(n, seed=7)
 for sql, p, mode in (("SELECT SUM(amount) FROM sales", 0, "value"),
                      ("SELECT SUM(amount) FROM sales GROUP BY region", 0, "value"),
                      ("SELECT SUM(amount) FROM sales GROUP BY product_id", 0, "value"),
+                     ("SELECT SUM(amount) FROM sales WHERE amount > 900 GROUP BY product_id", 0, "value"),
+                     ("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 100 AND 500 GROUP BY region", 0, "ci_reference"),
                      ("SELECT SUM(amount) FROM sales GROUP BY region", 0, "ci_reference"),
                      ("SELECT SUM(amount) FROM sales WHERE product_id IN (1, 3, 5, 7)", 0, "value"),
                      ("SELECT AVG(amount) FROM sales GROUP BY region", 50, "ci_reference")):
