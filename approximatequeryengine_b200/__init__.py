@@ -185,6 +185,7 @@ def lib() -> C.CDLL:
         "aqe_shard": (vp, [vp, i32]),
         "aqe_shard_first_row": (u64, [vp, i32]),
         "aqe_shards_fused": (i32, [vp]),
+        "aqe_reference_order": (i32, [vp, u64, vp, vp, C.c_size_t, vp]),
         "aqe_count": (u64, [vp]),
         "aqe_node_count": (u64, [vp]),
         "aqe_tree_height": (u64, [vp]),
@@ -566,6 +567,19 @@ class Engine:
         acc = np.zeros(layout.n_groups * 5, dtype=np.uint64)
         check((self.L.aqe_sql_scan_exchange if exchange else self.L.aqe_sql_scan)(self.h, C.byref(q), C.byref(layout), flags, _ptr(acc)))
         return acc
+
+
+def reference_order(ids, ops=None) -> np.ndarray:
+    """Host only: the order in which the reference's B+ tree holds rows that arrived with these ids (aqe_reference_order; matters only
+    where ids repeat).  ops: [(rows, kind)] -- the calls that inserted them, kind 0 = insert_batch / load / insert_record, 1 = rows already
+    in table order; None = one insert_batch.  Returns perm with table[k] = arrival[perm[k]]."""
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    perm = np.empty(len(ids), dtype=np.uint64)
+    ops = list(ops or [])
+    op_rows = np.asarray([o[0] for o in ops], dtype=np.uint64)
+    op_kinds = np.asarray([o[1] for o in ops], dtype=np.int32)
+    check(lib().aqe_reference_order(_ptr(ids), len(ids), _ptr(op_rows) if ops else None, _ptr(op_kinds) if ops else None, len(ops), _ptr(perm)))
+    return perm
 
 
 def merge_stats(parts) -> Stats:

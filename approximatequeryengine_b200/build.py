@@ -63,7 +63,7 @@ def _run(cmd, verbose):
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> None:
     os.makedirs(LIBDIR, exist_ok=True)
     headers = [os.path.join(INCLUDE, "aqe_b200.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp", ".h"))]
-    lib_src = [os.path.join(CSRC, "aqe_engine.cu"), os.path.join(CSRC, "aqe_plan.cpp"), os.path.join(CSRC, "aqe_sql.cpp")]
+    lib_src = [os.path.join(CSRC, "aqe_engine.cu"), os.path.join(CSRC, "aqe_plan.cpp"), os.path.join(CSRC, "aqe_sql.cpp"), os.path.join(CSRC, "aqe_order.cpp")]
     cxx = _host_cxx()
     if force or not _newer(LIB, lib_src + headers):
         cmd = [_nvcc(), "-std=c++17", "-O3", *ARCH, "-lineinfo", "-ccbin", cxx, "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",

@@ -25,6 +25,7 @@
 
 #include "aqe_b200.h"
 #include "aqe_kernels.cuh"
+#include "aqe_order.hpp"
 #include "aqe_plan.hpp"
 #include "aqe_sql.hpp"
 #include "aqe_sql_kernels.cuh"
@@ -83,6 +84,7 @@ struct aqe_db {
 
     // host-side rows appended through insert_record / insert_batch and not yet on the device
     std::vector<aqe_record> host_rows;
+    std::vector<aqe::OrderOp> host_ops;  // how host_rows came about, call by call (aqe_order.hpp); empty: one insert_batch of all of them
     bool host_authoritative = false;  // host_rows is the whole table and the device copy is stale
 
     // scratch
@@ -271,7 +273,7 @@ struct IngestPool {
 };
 
 // Feeds `n` rows obtained chunk-wise from the thread-safe `fill(dst, first, count)` into the columns.
-// *unsorted_out is set if ids were found out of order.
+// *unsorted_out is set if ids were found out of order or repeated (not strictly ascending).
 // max_workers > 0 caps the reader threads (a sharded table loads its shards side by side and divides the readers among them).
 template <typename Fill>
 static int ingest_rows(aqe_db* db, uint64_t n, Fill fill, bool* unsorted_out, int max_workers = 0) {
@@ -338,23 +340,42 @@ static int ingest_rows(aqe_db* db, uint64_t n, Fill fill, bool* unsorted_out, in
     unsigned int flag = 0;
     CU(cudaMemcpy(&flag, unsorted, 4, cudaMemcpyDeviceToHost));
     cudaFree(unsorted);
-    bool bad = flag != 0;
-    for (uint64_t c = 1; c < nchunks && !bad; ++c) bad = first_id[c] < last_id[c - 1];
+    bool bad = flag != 0;   // an id below (bit 0) or equal to (bit 1) its predecessor: either way the host decides the order
+    for (uint64_t c = 1; c < nchunks && !bad; ++c) bad = first_id[c] <= last_id[c - 1];
     *unsorted_out = bad;
     return AQE_OK;
 }
 
-static int upload_host_rows(aqe_db* db, const aqe_record* rows, uint64_t n) {
+// rows[0, n) in arrival order -> `sorted` in the order the reference's table would hold them: ascending id (load_from_file ->
+// insert_batch orders rows by id, custom_bplus_db.cpp:198-200); rows that share an id sit where the reference's B+ tree puts them
+// after the same history of inserts (`ops`; none: one insert_batch of all rows) -- aqe_order.cpp.  Tables above
+// kReferenceOrderMaxRows keep equal ids in arrival order.
+static int order_like_reference(const aqe_record* rows, uint64_t n, const std::vector<aqe::OrderOp>& ops, std::vector<aqe_record>& sorted) {
+    try {
+        sorted.assign(rows, rows + n);
+        std::stable_sort(sorted.begin(), sorted.end(), [](const aqe_record& a, const aqe_record& b) { return a.id < b.id; });
+        bool dup = false;
+        for (uint64_t i = 1; i < n && !dup; ++i) dup = sorted[i].id == sorted[i - 1].id;
+        if (!dup || n > aqe::kReferenceOrderMaxRows) return AQE_OK;
+        std::vector<int64_t> ids(n);
+        for (uint64_t i = 0; i < n; ++i) ids[i] = rows[i].id;
+        std::vector<uint64_t> perm(n);
+        const aqe::OrderOp whole{n, aqe::ORDER_OP_BATCH};
+        const bool ok = ops.empty() ? aqe::reference_order(ids.data(), n, &whole, 1, perm.data())
+                                    : aqe::reference_order(ids.data(), n, ops.data(), ops.size(), perm.data());
+        if (!ok) return fail(AQE_ERR_STATE, "insert history does not cover the rows on the host");
+        for (uint64_t i = 0; i < n; ++i) sorted[i] = rows[perm[i]];
+    } catch (const std::bad_alloc&) { return fail(AQE_ERR_NOMEM, "out of host memory while ordering rows by id"); }
+    return AQE_OK;
+}
+
+static int upload_host_rows(aqe_db* db, const aqe_record* rows, uint64_t n, const std::vector<aqe::OrderOp>& ops = {}) {
     bool unsorted = false;
     int rc = ingest_rows(db, n, [&](aqe_record* dst, uint64_t first, uint64_t cnt) { std::memcpy(dst, rows + first, cnt * sizeof(aqe_record)); return true; }, &unsorted);
     if (rc) return rc;
     if (unsorted) {
-        // load_from_file -> insert_batch orders rows by id (custom_bplus_db.cpp:198-200); stable here
         std::vector<aqe_record> sorted;
-        try {
-            sorted.assign(rows, rows + n);
-            std::stable_sort(sorted.begin(), sorted.end(), [](const aqe_record& a, const aqe_record& b) { return a.id < b.id; });
-        } catch (const std::bad_alloc&) { return fail(AQE_ERR_NOMEM, "out of host memory while ordering rows by id"); }
+        if ((rc = order_like_reference(rows, n, ops, sorted))) return rc;
         rc = ingest_rows(db, n, [&](aqe_record* dst, uint64_t first, uint64_t cnt) { std::memcpy(dst, sorted.data() + first, cnt * sizeof(aqe_record)); return true; }, &unsorted);
     }
     return rc;
@@ -366,7 +387,7 @@ static int ensure_device(aqe_db* db) {
     int rc = db_init_cuda(db);
     if (rc) return rc;
     if (!db->host_authoritative) return AQE_OK;
-    rc = upload_host_rows(db, db->host_rows.data(), db->host_rows.size());
+    rc = upload_host_rows(db, db->host_rows.data(), db->host_rows.size(), db->host_ops);
     if (rc) return rc;
     db->host_authoritative = false;
     return AQE_OK;
@@ -479,7 +500,7 @@ int aqe_load_file(aqe_db* db, const char* path, uint64_t first_row, uint64_t n_r
     if (rc) return rc;
     if (first_row > f.total) first_row = f.total;
     const uint64_t n = std::min<uint64_t>(n_rows, f.total - first_row);
-    db->host_rows.clear(); db->host_authoritative = false;
+    db->host_rows.clear(); db->host_ops.clear(); db->host_authoritative = false;
     bool unsorted = false;
     rc = ingest_rows(db, n, [&](aqe_record* dst, uint64_t first, uint64_t cnt) { return f.read_rows(dst, first_row + first, cnt); }, &unsorted);
     if (rc == AQE_OK && unsorted) {
@@ -502,16 +523,20 @@ int aqe_open(const char* path, int device, aqe_db** out) {
 int aqe_append_records(aqe_db* db, const aqe_record* rows, size_t n) {
     if (!db || (!rows && n)) return fail(AQE_ERR_INVALID, "NULL argument");
     if (!db->host_authoritative) {
-        // first append after a load: pull the table back so that host_rows is the whole table
-        db->host_rows.clear();
-        if (db->n) {
-            db->host_rows.resize(db->n);
-            int rc = aqe_read_records(db, 0, db->n, db->host_rows.data());
-            if (rc) return rc;
-        }
+        // first append after a load: pull the table back so that host_rows is the whole table (rows that already are in table order)
+        if (db->host_rows.size() != db->n || db->host_ops.empty()) {
+            db->host_rows.clear(); db->host_ops.clear();
+            if (db->n) {
+                db->host_rows.resize(db->n);
+                int rc = aqe_read_records(db, 0, db->n, db->host_rows.data());
+                if (rc) return rc;
+                db->host_ops.push_back(aqe::OrderOp{db->n, aqe::ORDER_OP_RESTORE});
+            }
+        }   // else: host_rows still holds the rows of the device table in arrival order, host_ops their history
         db->host_authoritative = true;
     }
     db->host_rows.insert(db->host_rows.end(), rows, rows + n);
+    if (n) db->host_ops.push_back(aqe::OrderOp{(uint64_t)n, aqe::ORDER_OP_BATCH});   // one insert_batch, or one insert_record (a batch of one)
     return AQE_OK;
 }
 
@@ -520,7 +545,7 @@ int aqe_from_host_records(aqe_db* db, const aqe_record* rows, size_t n) {
     if (db->group) return group_from_host_records(db, rows, n);
     int rc = db_init_cuda(db);
     if (rc) return rc;
-    db->host_rows.clear(); db->host_authoritative = false;
+    db->host_rows.clear(); db->host_ops.clear(); db->host_authoritative = false;
     return upload_host_rows(db, rows, n);
 }
 
@@ -531,7 +556,7 @@ int aqe_attach_device_columns(aqe_db* db, const int64_t* id, const double* amoun
     int rc = db_init_cuda(db);
     if (rc) return rc;
     free_columns(db);
-    db->host_rows.clear(); db->host_authoritative = false;
+    db->host_rows.clear(); db->host_ops.clear(); db->host_authoritative = false;
     db->col = MutColumns{const_cast<int64_t*>(id), const_cast<double*>(amount), const_cast<int32_t*>(region),
                          const_cast<int32_t*>(product_id), const_cast<int64_t*>(timestamp)};
     db->owned = false;
@@ -544,7 +569,7 @@ int aqe_generate_synthetic(aqe_db* db, uint64_t seed, uint64_t first_row, uint64
     if (db->group) return group_generate(db, seed, first_row, n_rows, dist, columns_mask ? columns_mask : 0x1f);
     int rc = db_init_cuda(db);
     if (rc) return rc;
-    db->host_rows.clear(); db->host_authoritative = false;
+    db->host_rows.clear(); db->host_ops.clear(); db->host_authoritative = false;
     rc = alloc_columns(db, n_rows, columns_mask ? columns_mask : 0x1f);
     if (rc) return rc;
     if (n_rows == 0) return AQE_OK;
@@ -559,6 +584,20 @@ int aqe_generate_synthetic(aqe_db* db, uint64_t seed, uint64_t first_row, uint64
 int aqe_synth_rows_host(uint64_t seed, uint64_t first_row, uint64_t n_rows, int dist, aqe_record* rows) {
     if (!rows && n_rows) return fail(AQE_ERR_INVALID, "NULL rows");
     for (uint64_t i = 0; i < n_rows; ++i) synth_row(seed, first_row + i, dist, rows[i]);
+    return AQE_OK;
+}
+
+int aqe_reference_order(const int64_t* ids, uint64_t n, const uint64_t* op_rows, const int* op_kinds, size_t n_ops, uint64_t* perm) {
+    if ((!ids && n) || (!perm && n) || (n_ops && (!op_rows || !op_kinds))) return fail(AQE_ERR_INVALID, "NULL argument");
+    try {
+        std::vector<aqe::OrderOp> ops(n_ops);
+        for (size_t i = 0; i < n_ops; ++i) {
+            if (op_kinds[i] != aqe::ORDER_OP_BATCH && op_kinds[i] != aqe::ORDER_OP_RESTORE) return fail(AQE_ERR_INVALID, "bad op kind");
+            ops[i] = aqe::OrderOp{op_rows[i], op_kinds[i]};
+        }
+        if (ops.empty()) ops.push_back(aqe::OrderOp{n, aqe::ORDER_OP_BATCH});
+        if (!aqe::reference_order(ids, n, ops.data(), ops.size(), perm)) return fail(AQE_ERR_INVALID, "ops do not cover the rows, or too many rows to replay");
+    } catch (const std::bad_alloc&) { return fail(AQE_ERR_NOMEM, "out of host memory"); }
     return AQE_OK;
 }
 

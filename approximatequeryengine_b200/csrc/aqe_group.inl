@@ -169,7 +169,7 @@ static int group_set_layout(aqe_db* gdb, uint64_t n) {
     for (size_t g = (size_t)G->active; g < G->shards.size(); ++g) {   // shards left without rows give their memory back
         aqe_db* c = G->shards[g];
         if (c->cuda_ready) { CU(cudaSetDevice(c->device)); free_columns(c); }
-        c->host_rows.clear(); c->host_authoritative = false;
+        c->host_rows.clear(); c->host_ops.clear(); c->host_authoritative = false;
     }
     return group_reset_exchange(gdb);
 }
@@ -195,9 +195,9 @@ static int group_close(aqe_db* gdb) {
 }
 
 // ---- ingest ---------------------------------------------------------------------------------------------------------------
-// rows[0, n) are the whole table in host memory: every shard uploads its range; out-of-order ids anywhere (inside a shard: seen
-// on the device; across a boundary: seen here) send the table through one stable sort by id (custom_bplus_db.cpp:198-200).
-static int group_upload(aqe_db* gdb, const aqe_record* rows, uint64_t n) {
+// rows[0, n) are the whole table in host memory: every shard uploads its range; out-of-order or repeated ids anywhere (inside a
+// shard: seen on the device; across a boundary: seen here) send the table through order_like_reference (custom_bplus_db.cpp:198-200).
+static int group_upload(aqe_db* gdb, const aqe_record* rows, uint64_t n, const std::vector<aqe::OrderOp>& ops = {}) {
     Group* G = gdb->group;
     int rc = group_set_layout(gdb, n);
     if (rc) return rc;
@@ -208,7 +208,7 @@ static int group_upload(aqe_db* gdb, const aqe_record* rows, uint64_t n) {
             aqe_db* c = G->shards[g];
             int r = db_init_cuda(c);
             if (r) return r;
-            c->host_rows.clear(); c->host_authoritative = false;
+            c->host_rows.clear(); c->host_ops.clear(); c->host_authoritative = false;
             bool uns = false;
             const uint64_t lo = G->first[g];
             r = ingest_rows(c, G->rows_of(g), [&](aqe_record* dst, uint64_t f, uint64_t cnt) { std::memcpy(dst, src + lo + f, cnt * sizeof(aqe_record)); return true; }, &uns, per_shard);
@@ -220,24 +220,21 @@ static int group_upload(aqe_db* gdb, const aqe_record* rows, uint64_t n) {
     bool bad = false;
     for (int g = 0; g < G->active; ++g) bad = bad || unsorted[g];
     for (int g = 1; g < G->active && !bad; ++g)
-        if (G->rows_of(g) && G->first[g] > 0) bad = rows[G->first[g]].id < rows[G->first[g] - 1].id;
+        if (G->rows_of(g) && G->first[g] > 0) bad = rows[G->first[g]].id <= rows[G->first[g] - 1].id;
     if (!bad) return AQE_OK;
     std::vector<aqe_record> sorted;
-    try {
-        sorted.assign(rows, rows + n);
-        std::stable_sort(sorted.begin(), sorted.end(), [](const aqe_record& a, const aqe_record& b) { return a.id < b.id; });
-    } catch (const std::bad_alloc&) { return fail(AQE_ERR_NOMEM, "out of host memory while ordering rows by id"); }
+    if ((rc = order_like_reference(rows, n, ops, sorted))) return rc;
     return upload(sorted.data());
 }
 
 static int group_from_host_records(aqe_db* gdb, const aqe_record* rows, size_t n) {
-    gdb->host_rows.clear(); gdb->host_authoritative = false;
+    gdb->host_rows.clear(); gdb->host_ops.clear(); gdb->host_authoritative = false;
     return group_upload(gdb, rows, n);
 }
 
 static int group_ensure_device(aqe_db* gdb) {
     if (!gdb->host_authoritative) return group_prepare(gdb, gdb->group->active);
-    const int rc = group_upload(gdb, gdb->host_rows.data(), gdb->host_rows.size());
+    const int rc = group_upload(gdb, gdb->host_rows.data(), gdb->host_rows.size(), gdb->host_ops);
     if (rc) return rc;
     gdb->host_authoritative = false;
     return AQE_OK;
@@ -250,7 +247,7 @@ static int group_load_file(aqe_db* gdb, const char* path, uint64_t first_row, ui
     if (rc) return rc;
     if (first_row > f.total) first_row = f.total;
     const uint64_t n = std::min<uint64_t>(n_rows, f.total - first_row);
-    gdb->host_rows.clear(); gdb->host_authoritative = false;
+    gdb->host_rows.clear(); gdb->host_ops.clear(); gdb->host_authoritative = false;
     if ((rc = group_set_layout(gdb, n))) return rc;
     const int per_shard = std::max(1, 8 / G->active);
     std::vector<char> unsorted((size_t)G->active, 0);
@@ -258,7 +255,7 @@ static int group_load_file(aqe_db* gdb, const char* path, uint64_t first_row, ui
         aqe_db* c = G->shards[g];
         int r = db_init_cuda(c);
         if (r) return r;
-        c->host_rows.clear(); c->host_authoritative = false;
+        c->host_rows.clear(); c->host_ops.clear(); c->host_authoritative = false;
         bool uns = false;
         const uint64_t lo = first_row + G->first[g];
         r = ingest_rows(c, G->rows_of(g), [&](aqe_record* dst, uint64_t fr, uint64_t cnt) { return f.read_rows(dst, lo + fr, cnt); }, &uns, per_shard);
@@ -272,7 +269,7 @@ static int group_load_file(aqe_db* gdb, const char* path, uint64_t first_row, ui
         if (!G->rows_of(g) || G->first[g] == 0) continue;
         aqe_record edge[2];
         if (!f.read_rows(edge, first_row + G->first[g] - 1, 2)) return fail(AQE_ERR_IO, "short read while loading rows");
-        bad = edge[1].id < edge[0].id;
+        bad = edge[1].id <= edge[0].id;
     }
     if (!bad) return AQE_OK;
     std::vector<aqe_record> rows;
@@ -283,7 +280,7 @@ static int group_load_file(aqe_db* gdb, const char* path, uint64_t first_row, ui
 
 static int group_generate(aqe_db* gdb, uint64_t seed, uint64_t first_row, uint64_t n_rows, int dist, uint32_t mask) {
     Group* G = gdb->group;
-    gdb->host_rows.clear(); gdb->host_authoritative = false;
+    gdb->host_rows.clear(); gdb->host_ops.clear(); gdb->host_authoritative = false;
     int rc = group_set_layout(gdb, n_rows);
     if (rc) return rc;
     return group_run(gdb, [&](int g) { return aqe_generate_synthetic(G->shards[g], seed, first_row + G->first[g], G->rows_of(g), dist, mask); });

@@ -809,7 +809,9 @@ __global__ void __launch_bounds__(256) k_soa_to_aos(const Columns C, aqe_record*
 }
 
 // K7: ingest.  A warp reads 32 rows = 1 KiB contiguous; column stores are 256/128-byte coalesced.
-// `unsorted` is raised if ids are not ascending (then the host re-orders, custom_bplus_db.cpp:198-200).
+// `unsorted` is raised if ids are not strictly ascending: bit 0 for an id below its predecessor (the host re-orders,
+// custom_bplus_db.cpp:198-200), bit 1 for an id equal to it (duplicate ids: the host works out where the reference's tree
+// would have put them, aqe_order.cpp).
 struct MutColumns { int64_t* id; double* amount; int32_t* region; int32_t* product_id; int64_t* timestamp; };
 __global__ void __launch_bounds__(256) k_aos_to_soa(const aqe_record* __restrict__ rows, uint64_t n, MutColumns C, uint64_t dst,
                                                     int64_t prev_last_id, int has_prev, unsigned int* unsorted) {
@@ -821,8 +823,10 @@ __global__ void __launch_bounds__(256) k_aos_to_soa(const aqe_record* __restrict
         reinterpret_cast<uint4*>(&r)[0] = a; reinterpret_cast<uint4*>(&r)[1] = b;
         C.id[dst + k] = r.id; C.amount[dst + k] = r.amount; C.region[dst + k] = r.region;
         C.product_id[dst + k] = r.product_id; C.timestamp[dst + k] = r.timestamp;
-        const int64_t prev = k ? rows[k - 1].id : (has_prev ? prev_last_id : r.id);
-        if (r.id < prev) atomicOr(unsorted, 1u);
+        if (k || has_prev) {
+            const int64_t prev = k ? rows[k - 1].id : prev_last_id;
+            if (r.id <= prev) atomicOr(unsorted, r.id < prev ? 1u : 2u);
+        }
     }
 }
 

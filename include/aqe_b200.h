@@ -307,6 +307,13 @@ AQE_API aqe_db* aqe_shard(aqe_db* db, int g);                 /* borrowed handle
 AQE_API uint64_t aqe_shard_first_row(const aqe_db* db, int g);/* first table row of shard g; g = shard_count: N */
 AQE_API int aqe_shards_fused(const aqe_db* db);               /* 1: the shards exchange inside the kernels (distinct peer devices) */
 
+/* Host only: where the reference's B+ tree puts rows that SHARE an id.  ids[0, n) in arrival order; op_rows / op_kinds split them into the
+ * calls that inserted them (kind 0: one insert_batch / load_from_file / insert_record -- std::sort by id :198-200, then per row a leaf insert in
+ * front of equal keys :32-37, leaves splitting 127 / 128 :43-58; kind 1: rows already in table order; n_ops = 0: one batch of all rows).
+ * perm[k] = arrival number of the row at position k of the table (collect_all_records :660).  The engine orders tables with duplicate ids
+ * this way (up to 2^27 rows; larger ones keep equal ids in arrival order); tables without duplicates are simply ascending by id. */
+AQE_API int aqe_reference_order(const int64_t* ids, uint64_t n, const uint64_t* op_rows, const int* op_kinds, size_t n_ops, uint64_t* perm);
+
 AQE_API uint64_t aqe_count(const aqe_db* db);                 /* get_total_records :646 */
 AQE_API uint64_t aqe_node_count(const aqe_db* db);            /* get_node_count :654 (N/255+1) */
 AQE_API uint64_t aqe_tree_height(const aqe_db* db);           /* get_tree_height :650 (bulk-load shape) */

@@ -392,6 +392,12 @@ class Ref:
         if self.L.ref_insert_batch(self.h, _ptr(rows), len(rows)) != 0:
             raise RuntimeError("insert_batch failed")
 
+    def insert_record(self, row):
+        row = _rows(row)
+        assert len(row) == 1
+        if self.L.ref_insert_record(self.h, _ptr(row)) != 0:
+            raise RuntimeError("insert_record failed")
+
     def save(self, path: str):
         if self.L.ref_save(self.h, path.encode()) != 0:
             raise IOError(path)

@@ -161,7 +161,7 @@ def test_special_values(oracle):
 
 def test_duplicate_ids_and_all_equal_values(oracle):
     """Collisions: duplicate ids are allowed by the format (lower_bound insert, custom_bplus_db.cpp:32-37); aggregates do not
-    care, rows stay ordered by id (stably), and a constant column has zero variance."""
+    care, rows stay ordered by id, and a constant column has zero variance."""
     n = 30000
     rows = oracle.synth(n, seed=6)
     rows["id"][:] = np.repeat(np.arange(1, n // 3 + 1), 3)            # every id three times
@@ -557,3 +557,60 @@ def test_full_size_properties():
     assert ids.count == e.scan("amount", "amount", 100.0, 500.0).count
     r = e.approx("sum", error_percent=0.5, seed=1)
     assert r.status == 0 and abs(r.estimate - tot.sum) / tot.sum < 0.01
+
+
+def test_duplicate_ids_sit_where_the_reference_tree_puts_them(oracle, tmp_path, monkeypatch):
+    """Tables with duplicate ids: the engine's row order (reads, samplers, files) is the reference's leaf-chain order after the same
+    history of inserts -- golden orders minted from the unmodified reference (tests/golden/make_order_golden.py; csrc/aqe_order.cpp),
+    through from_rows, a record file, appended batches / single rows, a sharded handle and the drop-in module."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "order_cases.json")))
+    monkeypatch.setenv("AQE_MIN_SHARD_ROWS", "1")
+    for c in g["cases"]:
+        ids = np.asarray(c["ids"], dtype=np.int64)
+        rows = oracle.synth(len(ids), seed=3)
+        rows["id"] = ids
+        rows["timestamp"] = np.arange(len(ids))            # arrival number: tells rows with equal ids apart
+        want = np.asarray(c["order"], dtype=np.int64)
+        ops = c["ops"]
+        for devs in (None, [0, 0, 0]):
+            e = aqe.Engine(0) if devs is None else aqe.Engine(devices=devs)
+            at = 0
+            for cnt, _ in ops:                               # the history, call by call (one row = insert_record)
+                e.append(rows[at:at + cnt]); at += cnt
+            back = e.read_rows()
+            assert np.array_equal(back["timestamp"], want), (c["name"], devs)
+            assert np.array_equal(back["id"], ids[want])
+            if len(ops) == 1:
+                e2 = (aqe.Engine(0) if devs is None else aqe.Engine(devices=devs)).from_rows(rows)
+                assert np.array_equal(e2.read_rows()["timestamp"], want), (c["name"], "from_rows", devs)
+                e2.close()
+            # a query in between must not disturb the history: the rest of the rows appended after an upload
+            if len(ops) > 1:
+                e3 = aqe.Engine(0) if devs is None else aqe.Engine(devices=devs)
+                e3.append(rows[:ops[0][0]])
+                assert e3.count == ops[0][0] and e3.sum_int("timestamp") >= 0      # uploads
+                at = ops[0][0]
+                for cnt, _ in ops[1:]:
+                    e3.append(rows[at:at + cnt]); at += cnt
+                assert np.array_equal(e3.read_rows()["timestamp"], want), (c["name"], "query in between", devs)
+                e3.close()
+            # samplers read the table in that order
+            if len(ids) >= 1000:
+                prm = aqe.make_params("memory_stride", 10.0)
+                got = e.gather(e.plan("memory_stride", prm))
+                idx = oracle.indices(rows[want], "memory_stride", orc_params("memory_stride", 10.0))
+                assert np.array_equal(got["timestamp"], want[idx]), (c["name"], "memory_stride", devs)
+            # the file written from it holds the rows in table order; loading a file is one insert_batch of its rows in file order
+            path = str(tmp_path / "dups.aqe")
+            e.save_file(path)
+            assert np.array_equal(np.fromfile(path, dtype=rows.dtype, offset=24)["timestamp"], want)
+            e.close()
+        if len(ops) == 1:
+            path = str(tmp_path / "arrival.aqe")
+            with open(path, "wb") as f:                      # total | tree_height | count | rows in ARRIVAL order (custom_bplus_db.cpp:665-683)
+                np.asarray([len(rows), 1, len(rows)], dtype=np.uint64).tofile(f)
+                rows.tofile(f)
+            e = aqe.Engine(0).load_file(path)
+            assert np.array_equal(e.read_rows()["timestamp"], want), (c["name"], "load_file")
+            e.close()
