@@ -2073,7 +2073,9 @@ template <int MODE, bool MOMENTS> static int sql_launch_ring(const aqe_db* db, S
                       : sql_occupancy((const void*)k_sql_ring<MODE, MOMENTS, 2, 4>, kBulkThreads, smem_k);
     };
     int K = 4;
-    for (int want : {3, 2}) {
+    // (packed shared bins without squares: 56 registers, and at K = 6 the stages leave room for a FOURTH CTA -- 1000 groups over 1 B rows
+    // 2.56 ms against 2.77 ms at K = 8 / three CTAs; the kernel is bound by latency, not by a pipe: one / two / three CTAs 6.4 / 3.5 / 2.8 ms)
+    for (int want : {MODE == 3 && !MOMENTS ? 4 : 3, 3, 2}) {
         bool found = false;
         for (int k : {8, 6, 4}) if (!found && ctas_with(k) >= want) { K = k; found = true; }
         if (found) break;
@@ -2297,14 +2299,17 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
             flo = (__int128)okey_to_i64(st->min_key); fhi = (__int128)okey_to_i64(st->max_key);
         }
         const __int128 bias = flo < 0 ? flo : 0;
-        if (fits && fhi >= flo && fhi - bias < ((__int128)1 << 62)) { mode = 3; a.fx_bias = (long long)bias; }
+        // MODE 4 = MODE 3 + the ring kernel's walk over the pass bits of sparse tiles (72 registers, three CTAs per SM); without a WHERE
+        // clause or a sample filter every row passes and MODE 3 (56 registers, four CTAs per SM at K = 6) is the faster one
+        if (fits && fhi >= flo && fhi - bias < ((__int128)1 << 62)) { mode = (a.n_alt > 0 || step > 1) ? 4 : 3; a.fx_bias = (long long)bias; }
     }
     cudaStream_t s = db->stream;
     if (ring) {
         if (mode == 0) rc = moments ? sql_launch_ring<0, true>(db, ra, s) : sql_launch_ring<0, false>(db, ra, s);
         else if (mode == 1) rc = moments ? sql_launch_ring<1, true>(db, ra, s) : sql_launch_ring<1, false>(db, ra, s);
         else if (mode == 2) rc = moments ? sql_launch_ring<2, true>(db, ra, s) : sql_launch_ring<2, false>(db, ra, s);
-        else rc = moments ? sql_launch_ring<3, true>(db, ra, s) : sql_launch_ring<3, false>(db, ra, s);
+        else if (mode == 3) rc = moments ? sql_launch_ring<3, true>(db, ra, s) : sql_launch_ring<3, false>(db, ra, s);
+        else rc = moments ? sql_launch_ring<4, true>(db, ra, s) : sql_launch_ring<4, false>(db, ra, s);
     } else {
         if (!strided && dense) {  // register kernel has no row-number filter: visit the progression
             a.first = (uint64_t)((step - phase) % step); a.stride = (uint64_t)step;

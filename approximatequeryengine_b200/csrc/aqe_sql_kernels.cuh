@@ -140,7 +140,7 @@ struct SqlArgs {
     int member_used;
     unsigned int drain_rows;          // private bins (G <= 16) are drained before a thread has added this many rows to one (<= kSqlPackedRows)
     int pair_bins;                    // private bins: words 0 and 1 of a bin sit side by side and are updated with ONE 128-bit load / store
-    long long fx_bias;                // MODE 3: min(0, smallest fixed-point value of the aggregate column); bins hold sums of u = fx - fx_bias >= 0
+    long long fx_bias;                // MODE 3 / 4: min(0, smallest fixed-point value of the aggregate column); bins hold sums of u = fx - fx_bias >= 0
     SqlExchange ex;
 };
 
@@ -244,9 +244,35 @@ __device__ __noinline__ void sql_packed_spill(unsigned int* s_sum, unsigned int*
     sql_packed_to_global<MOMENTS>(ga, bias, x, y);
 }
 
+// one 62-bit value into words 0, 1 (and 3) of a packed bin
+__device__ __forceinline__ void sql_packed_add_value(unsigned int* w, unsigned int G, unsigned int g, unsigned long long u) {
+    const unsigned int x0 = (unsigned int)u;
+    const unsigned int o0 = atomicAdd(w + g, x0);
+    const unsigned int a1 = ((unsigned int)(u >> 32) & 0x3fffffu) + ((o0 + x0 < o0) ? 1u : 0u);
+    if (a1) {   // (always, for floating-point columns; integer columns below 2^32 skip it)
+        const unsigned int o1 = atomicAdd(w + G + g, a1);
+        if (o1 + a1 < o1) atomicAdd(w + 3 * G + g, 1u);
+    }
+}
+// one row into packed bin g: three shared atomics (six with squares), see the layout note in SqlBins
+template <bool MOMENTS>
+__device__ __forceinline__ void sql_packed_add_row(unsigned int* s_sum, unsigned int* s_sq, unsigned int G, unsigned int g, long long bias,
+                                                   unsigned long long* spill_acc, long long fx, long long fq) {
+    const unsigned long long u = (unsigned long long)(fx - bias);
+    const unsigned int o2 = atomicAdd(s_sum + 2 * G + g, (unsigned int)(u >> 54) + (1u << 20));
+    sql_packed_add_value(s_sum, G, g, u);
+    if constexpr (MOMENTS) {
+        const unsigned long long q = (unsigned long long)fq;
+        sql_packed_add_value(s_sq, G, g, q);
+        const unsigned int q2 = (unsigned int)(q >> 54);
+        if (q2) atomicAdd(s_sq + 2 * G + g, q2);
+    }
+    if ((o2 >> 20) >= kSqlSharedPackedLimit) sql_packed_spill<MOMENTS>(s_sum, s_sq, G, g, bias, spill_acc + (size_t)g * 5);
+}
+
 // ---- bins: where a row's (count, value, value^2) lands ------------------------------------------------------
 // MODE 0: no GROUP BY (registers) | 1: thread-private shared bins | 2: CTA-shared bins with atomics, general form |
-// 3: CTA-shared bins with atomics, packed form.
+// 3: CTA-shared bins with atomics, packed form | 4: the same + the sparse walk of the ring kernel (queries with a WHERE clause).
 // T = threads that add rows (the private bins are laid out [bin][T]); every thread of the CTA must call flush().
 template <int MODE, bool MOMENTS, int T> struct SqlBins {
     unsigned int G;
@@ -275,13 +301,13 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
     bool with_sums;   // the query aggregates a column (false: COUNT only); uniform over the launch, set by the kernel after init()
     bool paired;      // MODE 1: words 0 and 1 interleaved as [bin][thread] 16-byte pairs (one LDS.128 + one STS.128 per row instead of
                       // two 64-bit chains); set by the kernel after init(), uniform over the launch.  p_slo then addresses the pairs.
-    long long bias;                 // MODE 3 (SqlArgs::fx_bias), set by the kernel after init()
+    long long bias;                 // MODE 3 / 4 (SqlArgs::fx_bias), set by the kernel after init()
     unsigned long long* spill_acc;  // MODE 3: the global accumulators a full bin is emptied into, set by the kernel after init()
 
     static size_t smem_bytes(unsigned int G) {
         if (MODE == 1) return (size_t)G * T * (MOMENTS ? 24 : 16);
         if (MODE == 2) return (size_t)G * (4 + 16 + (MOMENTS ? 16 : 0));
-        if (MODE == 3) return (size_t)G * (16 + (MOMENTS ? 16 : 0));
+        if (MODE >= 3) return (size_t)G * (16 + (MOMENTS ? 16 : 0));
         return 0;
     }
     // all threads of the CTA call init (it contains a barrier); tid < T owns a private column of bins
@@ -300,22 +326,12 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
             s_sq = s_sum + (size_t)G * 4;
             for (unsigned int i = tid; i < G; i += nthreads) b_cnt[i] = 0;
             for (unsigned int i = tid; i < G * 4; i += nthreads) { s_sum[i] = 0; if constexpr (MOMENTS) s_sq[i] = 0; }
-        } else if constexpr (MODE == 3) {
+        } else if constexpr (MODE >= 3) {
             s_sum = b_cnt;
             s_sq = s_sum + (size_t)G * 4;
             for (unsigned int i = tid; i < G * 4; i += nthreads) { s_sum[i] = 0; if constexpr (MOMENTS) s_sq[i] = 0; }
         }
         __syncthreads();
-    }
-    // one 62-bit value into words 0, 1 (and 3) of a packed bin
-    __device__ __forceinline__ void packed_add(unsigned int* w, unsigned int g, unsigned long long u) {
-        const unsigned int x0 = (unsigned int)u;
-        const unsigned int o0 = atomicAdd(w + g, x0);
-        const unsigned int a1 = ((unsigned int)(u >> 32) & 0x3fffffu) + ((o0 + x0 < o0) ? 1u : 0u);
-        if (a1) {   // (always, for floating-point columns; integer columns below 2^32 skip it)
-            const unsigned int o1 = atomicAdd(w + G + g, a1);
-            if (o1 + a1 < o1) atomicAdd(w + 3 * G + g, 1u);
-        }
     }
     __device__ __forceinline__ void add(unsigned int g, int tid, bool has_sum, long long fx, long long fq) {
         if constexpr (MODE == 0) {
@@ -354,16 +370,7 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
                 if constexpr (MOMENTS) shared_add128(s_sq, G, g, fq);
             }
         } else {
-            const unsigned long long u = (unsigned long long)(fx - bias);
-            const unsigned int o2 = atomicAdd(s_sum + 2 * G + g, (unsigned int)(u >> 54) + (1u << 20));
-            packed_add(s_sum, g, u);
-            if constexpr (MOMENTS) {
-                const unsigned long long q = (unsigned long long)fq;
-                packed_add(s_sq, g, q);
-                const unsigned int q2 = (unsigned int)(q >> 54);
-                if (q2) atomicAdd(s_sq + 2 * G + g, q2);
-            }
-            if ((o2 >> 20) >= kSqlSharedPackedLimit) sql_packed_spill<MOMENTS>(s_sum, s_sq, G, g, bias, spill_acc + (size_t)g * 5);
+            sql_packed_add_row<MOMENTS>(s_sum, s_sq, G, g, bias, spill_acc, fx, fq);
         }
     }
     __device__ __forceinline__ void zero_private(int tid) {
@@ -436,7 +443,7 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
             }
         } else if constexpr (MODE == 1) {
             if (tid < T) drain(global_acc, tid);
-        } else if constexpr (MODE == 3) {
+        } else if constexpr (MODE >= 3) {
             __syncthreads();
             for (unsigned int g = tid; g < G; g += nthreads) {
                 unsigned int x[4], y[4] = {0u, 0u, 0u, 0u};
@@ -788,27 +795,32 @@ template <int T, int K> __device__ __forceinline__ uint32_t sql_mod_pass(const S
 // CTAs per SM the register allocation must leave room for (shared memory usually sets the real limit): 4 for the plain
 // ungrouped and the shared-atomic kernels (<= 56 registers), 3 for private bins and for moments, 2 for private bins with moments.
 // The packed shared bins always come with rows of >= 12 bytes (group column + aggregate column): shared memory holds three CTAs of them at K = 8 (with squares at K = 6).
-constexpr int sql_ring_min_ctas(int mode, bool moments) { return mode == 1 ? (moments ? 2 : 3) : (moments || mode == 3 ? 3 : 4); }
+constexpr int sql_ring_min_ctas(int mode, bool moments) { return mode == 1 ? (moments ? 2 : 3) : (moments || mode == 4 ? 3 : 4); }
 
-// Packed shared-atomic bins, tiles few of whose rows pass: the ATOMS of a predicated-off row still costs its issue slot, so when no thread
-// of the warp kept more than half of its K rows the warp walks the set pass bits instead -- max over the lanes of popc(mask) rounds
-// in place of K, each reading its row's group key and value out of the stage again (two LDS, far cheaper than the atomics saved).
-template <int MODE, bool MOMENTS, int T>
-__device__ __forceinline__ void sql_sparse_adds(const SqlArgs& a, SqlBins<MODE, MOMENTS, T>& bins, int tid, uint32_t mask, unsigned int rounds,
-                                                const unsigned char* gb, int group_kind, const unsigned char* ab, int agg_kind) {
+// Packed shared-atomic bins, tiles few of whose rows pass: the ATOMS of a predicated-off row still costs its issue slot, so when no
+// thread of the warp kept more than half of its K rows the warp walks the set pass bits instead -- max over the lanes of popc(mask)
+// rounds in place of K, each reading its row's group key and value out of the stage again (two LDS, far cheaper than the atomics
+// saved).  This second code path costs registers (72 against 56): it exists in MODE 4 only, which the host picks for queries
+// with a WHERE clause; queries without one run MODE 3, whose 56 registers leave room for a fourth CTA per SM.
+struct SqlSparseConsts {
+    unsigned int* s_sum; unsigned int* s_sq; unsigned long long* spill_acc;
+    long long bias, key_min;
+    double sum_scale, sq_scale;
+    unsigned int G; int group_kind, agg_kind;
+};
+template <bool MOMENTS, int T>
+__device__ __forceinline__ void sql_sparse_adds(const SqlSparseConsts& s, const unsigned char* gb, const unsigned char* ab, int tid, uint32_t mask, unsigned int rounds) {
     for (unsigned int i = 0; i < rounds; ++i) {
         if (mask) {
             const uint32_t row = (uint32_t)tid + (uint32_t)(__ffs(mask) - 1) * (uint32_t)T;
             mask &= mask - 1u;
-            const unsigned int g = group_kind == 2 ? (unsigned int)(lds_row<int>(gb, row) - (int)a.key_min) : (unsigned int)(lds_row<long long>(gb, row) - a.key_min);
-            long long fx = 0, fq = 0;
-            if (agg_kind >= 0) {
-                double d;
-                if (agg_kind == 0) { d = lds_row<double>(ab, row); fx = __double2ll_rn(__dmul_rn(d, a.sum_scale)); }
-                else { fx = agg_kind == 2 ? (long long)lds_row<int>(ab, row) : lds_row<long long>(ab, row); d = (double)fx; }
-                if constexpr (MOMENTS) fq = __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale));
-            }
-            bins.add(g, tid, agg_kind >= 0, fx, fq);
+            const unsigned int g = s.group_kind == 2 ? (unsigned int)(lds_row<int>(gb, row) - (int)s.key_min) : (unsigned int)(lds_row<long long>(gb, row) - s.key_min);
+            long long fx, fq = 0;
+            double d;
+            if (s.agg_kind == 0) { d = lds_row<double>(ab, row); fx = __double2ll_rn(__dmul_rn(d, s.sum_scale)); }
+            else { fx = s.agg_kind == 2 ? (long long)lds_row<int>(ab, row) : lds_row<long long>(ab, row); d = (double)fx; }
+            if constexpr (MOMENTS) fq = __double2ll_rn(__dmul_rn(__dmul_rn(d, d), s.sq_scale));
+            sql_packed_add_row<MOMENTS>(s.s_sum, s.s_sq, s.G, g, s.bias, s.spill_acc, fx, fq);
         }
     }
 }
@@ -949,18 +961,14 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
             }
             // shared-atomic bins: rounds of the sparse walk when it pays (sql_sparse_adds), else ~0u
             auto sparse_rounds = [&](uint32_t m) -> unsigned int {
-                if constexpr (MODE == 3) {   // (MODE 2 runs under a 56-register cap that this second code path does not fit)
+                if constexpr (MODE == 4) {   // (MODE 2 and 3 run under a 56-register cap that this second code path does not fit)
                     const unsigned int r = __reduce_max_sync(0xffffffffu, (unsigned int)__popc(m));
                     return 2u * r <= (unsigned int)K ? r : ~0u;
                 } else return ~0u;
             };
             if (agg_kind < 0) {
-                const unsigned int sr = sparse_rounds(mask);
-                if (sr != ~0u) sql_sparse_adds(a, bins, tid, mask, sr, stage + group_off, group_kind, stage, -1);
-                else {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, false, 0, 0);
-                }
+                for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, false, 0, 0);
             } else if (agg_kind == 0) {
                 const unsigned char* ab = stage + agg_off;
                 long long fx[K], fq[K];
@@ -981,8 +989,11 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
                     }
                 }
                 const unsigned int sr = sparse_rounds(mask);
-                if (sr != ~0u) sql_sparse_adds(a, bins, tid, mask, sr, stage + group_off, group_kind, ab, agg_kind);
-                else {
+                if (sr != ~0u) {
+                    if constexpr (MODE == 4)
+                        sql_sparse_adds<MOMENTS, T>(SqlSparseConsts{bins.s_sum, bins.s_sq, bins.spill_acc, bins.bias, a.key_min, a.sum_scale, a.sq_scale, bins.G, group_kind, agg_kind},
+                                                    stage + group_off, ab, tid, mask, sr);
+                } else {
 #pragma unroll
                     for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, true, fx[k], fq[k]);
                 }
@@ -996,8 +1007,11 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
                     fq[k] = MOMENTS ? __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale)) : 0;
                 }
                 const unsigned int sr = sparse_rounds(mask);
-                if (sr != ~0u) sql_sparse_adds(a, bins, tid, mask, sr, stage + group_off, group_kind, ab, agg_kind);
-                else {
+                if (sr != ~0u) {
+                    if constexpr (MODE == 4)
+                        sql_sparse_adds<MOMENTS, T>(SqlSparseConsts{bins.s_sum, bins.s_sq, bins.spill_acc, bins.bias, a.key_min, a.sum_scale, a.sq_scale, bins.G, group_kind, agg_kind},
+                                                    stage + group_off, ab, tid, mask, sr);
+                } else {
 #pragma unroll
                     for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, true, fx[k], fq[k]);
                 }
