@@ -666,7 +666,6 @@ def main():
     # ---- secondary: the SQL-string path (run_query*) -- grouped scans over the whole table (BASELINE configs[2]: 1 B rows) ----
     sql = None
     if rank == 0 and world == 1 and not args.skip_sql:
-        import ctypes as C
         n_sql = min(rows, 1_000_000_000)
         es = aqe.Engine(local).generate(n_sql, seed=SEED, columns=("id", "amount", "region", "product_id"))
         sql = {"rows": n_sql, "api": "aqe_sql_run (C-ABI, caller-owned row buffer) -> k_sql_ring, one launch per query; ms = median host wall clock of the synchronous call",
