@@ -617,3 +617,25 @@ def test_sql_skewed_keys_against_oracle(oracle):
     r = {row.key: row.value for row in e.sql("SELECT SUM(amount) FROM sales GROUP BY product_id")}
     assert r[417] == math.fsum(x[k == 417]) and r[999] == math.fsum(x[k == 999])      # exactly rounded, emptied bins included
     e.close()
+
+
+def test_sql_wide_int64_sums_over_many_groups_take_the_general_form(oracle):
+    """An int64 aggregate column whose values span more than 2^62 cannot use the packed shared bins (62-bit values): the general form
+    (four limbs with carries) answers, exactly -- checked against Python integers per group."""
+    n = 90_000
+    rows = oracle.synth(n, seed=21)
+    rng = np.random.default_rng(21)
+    rows["timestamp"] = rng.integers(-(2 ** 62) - 12345, 2 ** 62 + 999, n)
+    e = aqe.Engine(0).from_rows(rows)
+    got = e.sql("SELECT SUM(timestamp) FROM sales GROUP BY product_id")
+    want = {}
+    for k, v in zip(rows["product_id"].tolist(), rows["timestamp"].tolist()):
+        want[k] = want.get(k, 0) + v
+    assert len(got) == len(want)
+    for r in got:
+        assert (r.isum_hi << 64) + r.isum_lo == want[r.key] and r.count == int((rows["product_id"] == r.key).sum()), r.key
+    narrow = e.sql("SELECT SUM(id) FROM sales WHERE id > 1000 GROUP BY product_id")        # the packed form next to it, same table
+    for r in narrow:
+        m = (rows["product_id"] == r.key) & (rows["id"] > 1000)
+        assert (r.isum_hi << 64) + r.isum_lo == int(rows["id"][m].astype(object).sum())
+    e.close()
