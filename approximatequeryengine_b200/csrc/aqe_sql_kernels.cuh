@@ -17,7 +17,7 @@
 //   G == 1        registers, warp shuffles, one global update per CTA
 //   G <= 16       thread-private bins in shared memory ([bin][thread], conflict-free), no atomics in the loop
 //   G <= 4096     CTA-shared bins, 32-bit shared atomics (64-bit shared atomic adds are CAS loops on sm_100: SASS
-//                 ATOMS.CAST.SPIN.64).  Packed form (MODE 3, whenever the fixed-point values of the aggregate column span
+//                 ATOMS.CAST.SPIN.64).  Packed form (MODE 3 / 4, whenever the fixed-point values of the aggregate column span
 //                 fewer than 2^62 steps): THREE atomics per row carry the row count and the 62-bit value; general form
 //                 (MODE 2: COUNT-only queries, full-range int64 columns): a count word + four limbs with carry chains
 #pragma once
@@ -302,7 +302,7 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
     bool paired;      // MODE 1: words 0 and 1 interleaved as [bin][thread] 16-byte pairs (one LDS.128 + one STS.128 per row instead of
                       // two 64-bit chains); set by the kernel after init(), uniform over the launch.  p_slo then addresses the pairs.
     long long bias;                 // MODE 3 / 4 (SqlArgs::fx_bias), set by the kernel after init()
-    unsigned long long* spill_acc;  // MODE 3: the global accumulators a full bin is emptied into, set by the kernel after init()
+    unsigned long long* spill_acc;  // MODE 3 / 4: the global accumulators a full bin is emptied into, set by the kernel after init()
 
     static size_t smem_bytes(unsigned int G) {
         if (MODE == 1) return (size_t)G * T * (MOMENTS ? 24 : 16);
