@@ -267,7 +267,7 @@ __device__ __forceinline__ void sql_packed_add_row(unsigned int* s_sum, unsigned
         const unsigned int q2 = (unsigned int)(q >> 54);
         if (q2) atomicAdd(s_sq + 2 * G + g, q2);
     }
-    if ((o2 >> 20) >= kSqlSharedPackedLimit) sql_packed_spill<MOMENTS>(s_sum, s_sq, G, g, bias, spill_acc + (size_t)g * 5);
+    if (o2 >= (kSqlSharedPackedLimit << 20)) sql_packed_spill<MOMENTS>(s_sum, s_sq, G, g, bias, spill_acc + (size_t)g * 5);
 }
 
 // ---- bins: where a row's (count, value, value^2) lands ------------------------------------------------------
@@ -867,7 +867,7 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
             for (uint64_t c = blockIdx.x; c < ntiles; c += gridDim.x, ++it) {
                 const int s = it % STAGES;
                 const uint32_t round = it / STAGES;
-                if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+                if (round > 0) mbar_wait_long(&empty_bar[s], (round - 1) & 1, 20000u);
                 const uint64_t row0 = c * (uint64_t)ra.tile_rows;
                 const uint32_t rows = (uint32_t)((n_main - row0) < (uint64_t)ra.tile_rows ? (n_main - row0) : (uint64_t)ra.tile_rows);
                 unsigned char* stage = ring + (size_t)s * ra.stage_bytes;
@@ -907,7 +907,7 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
             }
             const int s = it % STAGES;
             const uint32_t round = it / STAGES;
-            mbar_wait(&full_bar[s], round & 1);
+            mbar_wait_long(&full_bar[s], round & 1, 20000u);
             const uint64_t row0 = c * (uint64_t)ra.tile_rows;
             const uint32_t rows = (uint32_t)((n_main - row0) < (uint64_t)ra.tile_rows ? (n_main - row0) : (uint64_t)ra.tile_rows);
             const unsigned char* stage = ring + (size_t)s * ra.stage_bytes;
@@ -993,6 +993,9 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
                     if constexpr (MODE == 4)
                         sql_sparse_adds<MOMENTS, T>(SqlSparseConsts{bins.s_sum, bins.s_sq, bins.spill_acc, bins.bias, a.key_min, a.sum_scale, a.sq_scale, bins.G, group_kind, agg_kind},
                                                     stage + group_off, ab, tid, mask, sr);
+                } else if (MODE == 3 && mask == (1u << K) - 1u) {   // no WHERE clause: every tile but the table's last is whole -- no test per row
+#pragma unroll
+                    for (int k = 0; k < K; ++k) bins.add(g[k], tid, true, fx[k], fq[k]);
                 } else {
 #pragma unroll
                     for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, true, fx[k], fq[k]);
@@ -1011,6 +1014,9 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
                     if constexpr (MODE == 4)
                         sql_sparse_adds<MOMENTS, T>(SqlSparseConsts{bins.s_sum, bins.s_sq, bins.spill_acc, bins.bias, a.key_min, a.sum_scale, a.sq_scale, bins.G, group_kind, agg_kind},
                                                     stage + group_off, ab, tid, mask, sr);
+                } else if (MODE == 3 && mask == (1u << K) - 1u) {   // no WHERE clause: every tile but the table's last is whole -- no test per row
+#pragma unroll
+                    for (int k = 0; k < K; ++k) bins.add(g[k], tid, true, fx[k], fq[k]);
                 } else {
 #pragma unroll
                     for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, true, fx[k], fq[k]);
