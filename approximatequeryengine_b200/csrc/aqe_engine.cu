@@ -2282,6 +2282,9 @@ static int sql_scan_impl(aqe_db* db, const aqe_sql_query* q, const aqe_sql_layou
     }
     const bool ring = !strided && aligned16 && variant != 1;
     int mode = a.group_slot < 0 ? 0 : (G <= (uint32_t)kSqlPrivateMaxGroups ? 1 : 2);
+    // COUNT-only queries over few groups: one ATOMS.POPC.INC per row on CTA-shared counters (the instruction adds up the lanes that name
+    // the same address, so 32 rows on 8 keys cost no more than on 32) instead of a read-modify-write of a private bin
+    if (mode == 1 && a.agg_slot < 0 && env_int("AQE_SQL_COUNT_SHARED", 1)) mode = 2;
     if (mode == 2 && a.agg_slot >= 0 && env_int("AQE_SQL_PACKED", 1)) {
         // Packed shared bins (SqlBins MODE 3, three atomics per row) hold sums of u = fx - bias with 0 <= u < 2^62: usable whenever the
         // fixed-point values of the aggregate column span fewer than 2^62 steps -- every floating-point column scaled for its own

@@ -967,8 +967,11 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
                 } else return ~0u;
             };
             if (agg_kind < 0) {
+                if constexpr (MODE == 0) bins.r_cnt += (unsigned long long)__popc(mask);   // COUNT without GROUP BY: the pass bits are the answer
+                else {
 #pragma unroll
-                for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, false, 0, 0);
+                    for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, false, 0, 0);
+                }
             } else if (agg_kind == 0) {
                 const unsigned char* ab = stage + agg_off;
                 long long fx[K], fq[K];
