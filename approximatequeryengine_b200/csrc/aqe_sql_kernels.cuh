@@ -720,17 +720,22 @@ template <typename T> __device__ __forceinline__ T lds_row(const unsigned char* 
     return *reinterpret_cast<const T*>(base + (size_t)row * sizeof(T));
 }
 
+// f64 range test of one row into its pass bit: three chained setp and one predicated and (the `? 0u : 1u) << k` form of the
+// same test compiles to a SEL per comparison: ~7.5 instructions per row against 4).  `ne` is NaN when the conjunct has no `!=`:
+// setp.neu of anything with NaN holds.  A NaN value fails the first comparison, as in `v >= lo && v <= hi && !(v == ne)`.
+__device__ __forceinline__ uint32_t sql_f64_range_bit(uint32_t mask, int bit, double v, double lo, double hi, double ne) {
+    asm("{\n .reg .pred p;\n setp.ge.f64 p, %1, %2;\n setp.le.and.f64 p, %1, %3, p;\n setp.neu.and.f64 p, %1, %4, p;\n @!p and.b32 %0, %0, %5;\n}"
+        : "+r"(mask) : "d"(v), "d"(lo), "d"(hi), "d"(ne), "r"(~(1u << bit)));   // (an immediate once the row loop is unrolled)
+    return mask;
+}
+
 // one conjunct of one column over this thread's row slots of the tile: clears the pass bit of every row that fails
 template <int T, int K> __device__ __forceinline__ uint32_t sql_pred_pass(const SqlCol& col, const SqlPred& p, const unsigned char* base, int tid, uint32_t mask) {
     if (col.kind == 0) {
-        const double lo = __longlong_as_double(p.lo), hi = __longlong_as_double(p.hi), ne = __longlong_as_double(p.ne);
-        const bool has_ne = p.has_ne != 0;
+        const double lo = __longlong_as_double(p.lo), hi = __longlong_as_double(p.hi);
+        const double ne = p.has_ne != 0 ? __longlong_as_double(p.ne) : __longlong_as_double(0x7ff8000000000000ll);
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const double v = lds_row<double>(base, tid + k * T);
-            const bool ok = v >= lo && v <= hi && !(has_ne && v == ne);
-            mask &= ~((ok ? 0u : 1u) << k);
-        }
+        for (int k = 0; k < K; ++k) mask = sql_f64_range_bit(mask, k, lds_row<double>(base, tid + k * T), lo, hi, ne);
     } else if (p.has_pred == 3) {   // membership bitmap in shared memory over [lo, lo + hi)
         const long long first = p.lo;
         const unsigned long long n = (unsigned long long)p.hi;
@@ -825,6 +830,37 @@ __device__ __forceinline__ void sql_sparse_adds(const SqlSparseConsts& s, const 
     }
 }
 
+// MODE 1 with squares over paired bins (the reference's run_query_groupby_with_ci over a handful of groups), one row, no branch:
+// the bin is read whether or not the row passes (the address is always a bin of this thread) and only the two stores carry the
+// pass bit.  The kernel is bound by its instruction count: this form costs 19 instructions per row against 25 for
+// `if (bit) bins.add(...)` (BSSY / BRA / BSYNC around every row, the runtime `paired` test, the row index).  Same words as
+// SqlBins<1, true, T>::add: w0 += 1 << 52 | u[0:40), w1 += q[0:16) << 36 | u[40:64), w2 += q >> 16 with u = fx ^ 2^63.
+// Loads and stores are volatile asm without a memory clobber, so that the compiler keeps them in order among themselves and
+// stays free to batch the stage reads of the K rows ahead of them; the mbarrier wait at the top of every tile and the
+// bar.sync at the start of a drain (both with memory clobbers) fence them against the C++ stores that empty the bins.
+__device__ __forceinline__ void sql_private_moments_row(uint32_t pair_addr, uint32_t q_addr, long long fx, long long fq, uint32_t pass_bit) {
+    asm volatile("{\n"
+        " .reg .pred p;\n"
+        " .reg .b64 w0, w1, w2, t, u;\n"
+        " ld.shared.v2.b64 {w0, w1}, [%0];\n"
+        " ld.shared.b64 w2, [%1];\n"
+        " setp.ne.u32 p, %4, 0;\n"
+        " and.b64 t, %2, 0x000000ffffffffff;\n"
+        " add.u64 w0, w0, t;\n"
+        " add.u64 w0, w0, 0x0010000000000000;\n"   // (a separate add: ptxas folds it into the IADD3.X of the high word)
+        " xor.b64 u, %2, 0x8000000000000000;\n"
+        " shr.u64 u, u, 40;\n"
+        " and.b64 t, %3, 0xffff;\n"
+        " shl.b64 t, t, 36;\n"
+        " or.b64 t, t, u;\n"
+        " add.u64 w1, w1, t;\n"
+        " shr.u64 t, %3, 16;\n"
+        " add.u64 w2, w2, t;\n"
+        " @p st.shared.v2.b64 [%0], {w0, w1};\n"
+        " @p st.shared.b64 [%1], w2;\n"
+        "}" ::"r"(pair_addr), "r"(q_addr), "l"(fx), "l"(fq), "r"(pass_bit));
+}
+
 template <int MODE, bool MOMENTS, int STAGES, int K>
 __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)) k_sql_ring(const SqlRingArgs ra) {
     extern __shared__ __align__(128) unsigned char sql_ring_smem[];
@@ -895,8 +931,12 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
         }
         for (int k = 0; k < a.ncols; ++k) if (a.cols[k].mod_step > 0) mod_slot = k;
         const SqlPred& ap = a.cols[agg_slot >= 0 ? agg_slot : 0].pred[0];
-        const bool agg_has_pred = fuse_agg_pred && ap.has_pred != 0, agg_has_ne = ap.has_ne != 0;
-        const double agg_lo = __longlong_as_double(ap.lo), agg_hi = __longlong_as_double(ap.hi), agg_ne = __longlong_as_double(ap.ne);
+        const bool agg_has_pred = fuse_agg_pred && ap.has_pred != 0;
+        const double agg_lo = __longlong_as_double(ap.lo), agg_hi = __longlong_as_double(ap.hi);
+        const double agg_ne = ap.has_ne != 0 ? __longlong_as_double(ap.ne) : __longlong_as_double(0x7ff8000000000000ll);   // NaN: no `!=` in the conjunct
+        // MODE 1 with squares, paired bins: this thread's column of bins as shared-memory addresses (sql_private_moments_row)
+        const uint32_t my_pair = smem_u32(bins.p_slo) + (uint32_t)tid * 16u, my_q = smem_u32(bins.p_qlo) + (uint32_t)tid * 8u;
+        const bool fast_moments = MODE == 1 && MOMENTS && bins.paired && a.pair_bins == 1;   // (AQE_SQL_PAIR_BINS=2: paired bins through SqlBins::add, the A/B)
         const int kmin32 = (int)a.key_min;
         uint32_t it = 0;
         unsigned int rows_since_drain = 0;
@@ -956,8 +996,13 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
 #pragma unroll
                     for (int k = 0; k < K; ++k) g[k] = (unsigned int)(lds_row<long long>(gb, tid + k * T) - a.key_min);
                 }
+                if constexpr (MODE == 1) {   // a key outside the layout cannot happen for live rows of this table; the clamp keeps every address a bin of this thread
 #pragma unroll
-                for (int k = 0; k < K; ++k) if (g[k] >= bins.G) mask &= ~(1u << k);  // cannot happen for live rows with this table's own layout
+                    for (int k = 0; k < K; ++k) g[k] = min(g[k], bins.G - 1u);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) if (g[k] >= bins.G) mask &= ~(1u << k);  // cannot happen for live rows with this table's own layout
+                }
             }
             // shared-atomic bins: rounds of the sparse walk when it pays (sql_sparse_adds), else ~0u
             auto sparse_rounds = [&](uint32_t m) -> unsigned int {
@@ -979,7 +1024,7 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const double d = lds_row<double>(ab, tid + k * T);
-                        mask &= ~(((d >= agg_lo && d <= agg_hi && !(agg_has_ne && d == agg_ne)) ? 0u : 1u) << k);
+                        mask = sql_f64_range_bit(mask, k, d, agg_lo, agg_hi, agg_ne);
                         fx[k] = __double2ll_rn(__dmul_rn(d, a.sum_scale));
                         fq[k] = MOMENTS ? __double2ll_rn(__dmul_rn(__dmul_rn(d, d), a.sq_scale)) : 0;
                     }
@@ -999,6 +1044,9 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
                 } else if (MODE == 3 && mask == (1u << K) - 1u) {   // no WHERE clause: every tile but the table's last is whole -- no test per row
 #pragma unroll
                     for (int k = 0; k < K; ++k) bins.add(g[k], tid, true, fx[k], fq[k]);
+                } else if (fast_moments) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) sql_private_moments_row(my_pair + g[k] * (uint32_t)(T * 16), my_q + g[k] * (uint32_t)(T * 8), fx[k], fq[k], mask & (1u << k));
                 } else {
 #pragma unroll
                     for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, true, fx[k], fq[k]);
@@ -1020,6 +1068,9 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
                 } else if (MODE == 3 && mask == (1u << K) - 1u) {   // no WHERE clause: every tile but the table's last is whole -- no test per row
 #pragma unroll
                     for (int k = 0; k < K; ++k) bins.add(g[k], tid, true, fx[k], fq[k]);
+                } else if (fast_moments) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) sql_private_moments_row(my_pair + g[k] * (uint32_t)(T * 16), my_q + g[k] * (uint32_t)(T * 8), fx[k], fq[k], mask & (1u << k));
                 } else {
 #pragma unroll
                     for (int k = 0; k < K; ++k) if ((mask >> k) & 1u) bins.add(g[k], tid, true, fx[k], fq[k]);
