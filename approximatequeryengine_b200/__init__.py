@@ -196,6 +196,7 @@ def lib() -> C.CDLL:
         "aqe_scan": (i32, [vp, C.POINTER(ScanSpec), C.POINTER(Partial)]),
         "aqe_scan_async": (i32, [vp, C.POINTER(ScanSpec), vp, vp]),
         "aqe_scan_host_column": (i32, [i32, vp, i32, u64, dbl, dbl, i32, C.POINTER(Partial)]),
+        "aqe_scan_host_column_multi": (i32, [C.POINTER(C.c_int), i32, vp, i32, u64, dbl, dbl, i32, C.POINTER(Partial)]),
         "aqe_merge_partials": (i32, [C.POINTER(Partial), i32, i32, C.POINTER(Partial)]),
         "aqe_exchange_init": (i32, [vp, i32, i32, vp]),
         "aqe_exchange_connect": (i32, [vp, vp]),
@@ -324,13 +325,17 @@ def build_plan(n_rows: int, method: str, params: SampleParams, engine: "Engine |
     return Plan(h)
 
 
-def host_scan_column(col: np.ndarray, lo: float = 0.0, hi: float = 0.0, use_pred: bool = False, device: int = 0,
+def host_scan_column(col: np.ndarray, lo: float = 0.0, hi: float = 0.0, use_pred: bool = False, device: "int | list[int]" = 0,
                      ptr: int | None = None, n: int | None = None, kind: int | None = None) -> Partial:
     """End-to-end form: a host-resident column in, a scalar partial out (chunked H2D overlapped with the scan)."""
     out = Partial()
     if ptr is None:
         kind = {np.dtype("float64"): 0, np.dtype("int64"): 1, np.dtype("int32"): 2}[col.dtype]
         ptr, n = col.ctypes.data, len(col)
+    if isinstance(device, (list, tuple)):   # several GPUs of this process: chunks handed out from one counter (aqe_scan_host_column_multi)
+        devs = (C.c_int * len(device))(*device)
+        check(lib().aqe_scan_host_column_multi(devs, len(device), C.c_void_p(ptr), kind, n, lo, hi, int(use_pred), C.byref(out)))
+        return out
     check(lib().aqe_scan_host_column(device, C.c_void_p(ptr), kind, n, lo, hi, int(use_pred), C.byref(out)))
     return out
 

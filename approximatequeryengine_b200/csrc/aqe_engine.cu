@@ -1037,7 +1037,7 @@ int aqe_scan_exchange(aqe_db* db, const aqe_scan_spec* spec, aqe_partial* out) {
 }
 
 int aqe_merge_partials(const aqe_partial* parts, int n, int is_integer, aqe_partial* out) {
-    if (!parts || !out || n < 0) return fail(AQE_ERR_INVALID, "bad argument");
+    if ((!parts && n > 0) || !out || n < 0) return fail(AQE_ERR_INVALID, "bad argument");   // (no partials: the empty result)
     aqe_partial r;
     std::memset(&r, 0, sizeof(r));
     r.minv = INFINITY; r.maxv = -INFINITY;
@@ -1151,29 +1151,26 @@ static int host_scan_ctx(int device, HostScanCtx** out) {
     return AQE_OK;
 }
 
-int aqe_scan_host_column(int device, const void* host_col, int col_kind_id, uint64_t n, double lo, double hi, int use_pred,
-                         aqe_partial* out) {
-    if (!out || (!host_col && n)) return fail(AQE_ERR_INVALID, "NULL argument");
-    if (col_kind_id < 0 || col_kind_id > 2) return fail(AQE_ERR_INVALID, "col_kind: 0 f64, 1 i64, 2 i32");
-    std::lock_guard<std::mutex> lock(g_hs_mu);
-    HostScanCtx* c = nullptr;
-    int rc = host_scan_ctx(device, &c);
-    if (rc) return rc;
+// Chunks of a host column through ONE device: copy in on two alternating streams, scan, 64-byte partial per chunk.  `next` hands out
+// chunk numbers (shared by the devices of aqe_scan_host_column_multi: a device whose link is slower simply takes fewer chunks);
+// parts[k] receives chunk k's partial whichever device scanned it -- every B200 runs the same grid over the same bytes, so the
+// partial of a chunk, and with it the merged result, does not depend on who took it.
+static int host_scan_chunks(HostScanCtx* c, const void* host_col, int col_kind_id, uint64_t n, uint64_t per_chunk, uint64_t nchunks, bool pinned,
+                            double lo, double hi, int use_pred, std::atomic<uint64_t>* next, aqe_partial* parts) {
+    CU(cudaSetDevice(c->device));
     const size_t esz = kind_size(col_kind_id);
-    const uint64_t per_chunk = c->chunk_bytes / esz;
-    const uint64_t nchunks = n ? (n + per_chunk - 1) / per_chunk : 0;
-    if (nchunks > c->max_chunks) return fail(AQE_ERR_UNSUPPORTED, "column too large for aqe_scan_host_column; raise AQE_E2E_CHUNK_MB");
-    cudaPointerAttributes attr;
-    const bool pinned = cudaPointerGetAttributes(&attr, host_col) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
     if (!pinned) {
         for (int i = 0; i < 2; ++i)
             if (!c->pinned[i]) CU(cudaHostAlloc(&c->pinned[i], c->chunk_bytes, cudaHostAllocDefault));
     }
     aqe_db* db = c->db;
-    // a fake one-column handle view per chunk
-    for (uint64_t k = 0; k < nchunks; ++k) {
-        const int b = (int)(k & 1);
+    std::vector<uint64_t> mine;
+    int rc = AQE_OK;
+    for (;;) {
+        const uint64_t k = next->fetch_add(1, std::memory_order_relaxed);
+        if (k >= nchunks) break;
+        const size_t slot = mine.size();
+        const int b = (int)(slot & 1);
         const uint64_t first = k * per_chunk, cnt = std::min<uint64_t>(per_chunk, n - first);
         const char* src = static_cast<const char*>(host_col) + first * esz;
         if (!pinned) {
@@ -1182,13 +1179,13 @@ int aqe_scan_host_column(int device, const void* host_col, int col_kind_id, uint
             src = static_cast<const char*>(c->pinned[b]);
         }
         CU(cudaMemcpyAsync(c->dev[b], src, cnt * esz, cudaMemcpyHostToDevice, c->streams[b]));
-        ScanArgs a;
+        ScanArgs a;   // a one-column view of the chunk
         std::memset(&a.ex, 0, sizeof(a.ex));
         a.agg = c->dev[b]; a.pred = nullptr; a.n = cnt; a.lo = lo; a.hi = hi; a.pdl_tail = 0;   // the chunk was just copied in on this stream
         integer_bounds(lo, hi, &a.ilo, &a.ihi);
         a.partials = b ? c->partials2 : db->scan_partials;
         a.ticket = b ? c->tickets2 : db->tickets + 1;
-        a.out = c->parts_dev + k;
+        a.out = c->parts_dev + slot;
         const int pm = use_pred ? 1 : 0;
         if (col_kind_id == K_F64) rc = launch_scan_pred<double, false>(db, a, pm, K_F64, true, c->streams[b]);
         else if (col_kind_id == K_I64) rc = launch_scan_pred<int64_t, false>(db, a, pm, K_I64, true, c->streams[b]);
@@ -1196,10 +1193,78 @@ int aqe_scan_host_column(int device, const void* host_col, int col_kind_id, uint
         if (rc) return rc;
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->freed[b], c->streams[b]));
+        mine.push_back(k);
     }
-    std::vector<aqe_partial> parts(nchunks);
     for (int i = 0; i < 2; ++i) CU(cudaStreamSynchronize(c->streams[i]));
-    if (nchunks) CU(cudaMemcpy(parts.data(), c->parts_dev, sizeof(aqe_partial) * nchunks, cudaMemcpyDeviceToHost));
+    if (mine.empty()) return AQE_OK;
+    std::vector<aqe_partial> got(mine.size());
+    CU(cudaMemcpy(got.data(), c->parts_dev, sizeof(aqe_partial) * mine.size(), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < mine.size(); ++i) parts[mine[i]] = got[i];
+    return AQE_OK;
+}
+
+static bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return pinned;
+}
+
+int aqe_scan_host_column(int device, const void* host_col, int col_kind_id, uint64_t n, double lo, double hi, int use_pred,
+                         aqe_partial* out) {
+    if (!out || (!host_col && n)) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (col_kind_id < 0 || col_kind_id > 2) return fail(AQE_ERR_INVALID, "col_kind: 0 f64, 1 i64, 2 i32");
+    std::lock_guard<std::mutex> lock(g_hs_mu);
+    HostScanCtx* c = nullptr;
+    int rc = host_scan_ctx(device, &c);
+    if (rc) return rc;
+    const uint64_t per_chunk = c->chunk_bytes / kind_size(col_kind_id);
+    const uint64_t nchunks = n ? (n + per_chunk - 1) / per_chunk : 0;
+    if (nchunks > c->max_chunks) return fail(AQE_ERR_UNSUPPORTED, "column too large for aqe_scan_host_column; raise AQE_E2E_CHUNK_MB");
+    std::vector<aqe_partial> parts(nchunks);
+    std::atomic<uint64_t> next{0};
+    rc = host_scan_chunks(c, host_col, col_kind_id, n, per_chunk, nchunks, n && host_pointer_is_pinned(host_col), lo, hi, use_pred, &next, parts.data());
+    if (rc) return rc;
+    return aqe_merge_partials(parts.data(), (int)nchunks, col_kind_id != K_F64, out);
+}
+
+// The same column through SEVERAL devices of this process: one host thread per device, chunks handed out from one counter, the
+// chunks' partials merged in chunk order.  Links that share a PCIe root or sit far from the column's NUMA node run slower (24-35 GB/s
+// per GPU with eight at once against 55 alone); with equal shards the step ends with the slowest of them, here every link
+// stays busy until the column is through.
+int aqe_scan_host_column_multi(const int* devices, int n_devices, const void* host_col, int col_kind_id, uint64_t n, double lo, double hi,
+                               int use_pred, aqe_partial* out) {
+    if (!out || !devices || (!host_col && n)) return fail(AQE_ERR_INVALID, "NULL argument");
+    if (n_devices < 1 || n_devices > 16) return fail(AQE_ERR_INVALID, "n_devices: 1 .. 16");
+    if (col_kind_id < 0 || col_kind_id > 2) return fail(AQE_ERR_INVALID, "col_kind: 0 f64, 1 i64, 2 i32");
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(AQE_ERR_INVALID, "devices: every device once");
+    std::lock_guard<std::mutex> lock(g_hs_mu);
+    std::vector<HostScanCtx*> ctx((size_t)n_devices, nullptr);
+    for (int i = 0; i < n_devices; ++i) {
+        const int rc = host_scan_ctx(devices[i], &ctx[i]);
+        if (rc) return rc;
+    }
+    const uint64_t per_chunk = ctx[0]->chunk_bytes / kind_size(col_kind_id);
+    const uint64_t nchunks = n ? (n + per_chunk - 1) / per_chunk : 0;
+    if (nchunks > ctx[0]->max_chunks) return fail(AQE_ERR_UNSUPPORTED, "column too large for aqe_scan_host_column_multi; raise AQE_E2E_CHUNK_MB");
+    std::vector<aqe_partial> parts(nchunks);
+    std::atomic<uint64_t> next{0};
+    const bool pinned = n && host_pointer_is_pinned(host_col);
+    std::vector<int> rcs((size_t)n_devices, AQE_OK);
+    std::vector<std::string> errs((size_t)n_devices);
+    std::vector<std::thread> th;
+    for (int i = 1; i < n_devices; ++i)
+        th.emplace_back([&, i] {
+            rcs[i] = host_scan_chunks(ctx[i], host_col, col_kind_id, n, per_chunk, nchunks, pinned, lo, hi, use_pred, &next, parts.data());
+            if (rcs[i]) errs[i] = g_err;   // (thread-local)
+        });
+    rcs[0] = host_scan_chunks(ctx[0], host_col, col_kind_id, n, per_chunk, nchunks, pinned, lo, hi, use_pred, &next, parts.data());
+    if (rcs[0]) errs[0] = g_err;
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n_devices; ++i)
+        if (rcs[i]) return fail(rcs[i], errs[i]);
     return aqe_merge_partials(parts.data(), (int)nchunks, col_kind_id != K_F64, out);
 }
 

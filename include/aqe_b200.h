@@ -339,6 +339,11 @@ AQE_API int aqe_scan_async(aqe_db* db, const aqe_scan_spec* spec, void* partial_
  * end-to-end (host buffers in, scalar out) form of sum_amount / sum_amount_where. */
 AQE_API int aqe_scan_host_column(int device, const void* host_col, int col_kind, uint64_t n, double lo, double hi,
                          int use_pred, aqe_partial* out);
+/* The same through several devices of this process (one host thread per device): chunks are handed out from one counter, so
+ * a device behind a slower link takes fewer of them, and merged in chunk order -- the result does not depend on which device
+ * took which chunk and equals aqe_scan_host_column's bit for bit.  `devices`: n_devices distinct CUDA device numbers. */
+AQE_API int aqe_scan_host_column_multi(const int* devices, int n_devices, const void* host_col, int col_kind, uint64_t n,
+                               double lo, double hi, int use_pred, aqe_partial* out);
 /* Fused cross-GPU exchange (one process per GPU on one NVLink/NVSwitch box).  aqe_exchange_init allocates this
  * rank's mailbox and returns its 64-byte CUDA IPC handle; after the ranks have all-gathered the handles
  * (any transport), aqe_exchange_connect maps every peer's mailbox.  aqe_scan_exchange[_async] then runs the

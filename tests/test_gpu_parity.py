@@ -520,6 +520,29 @@ def test_host_column_scan(oracle):
     assert aqe.host_scan_column(ts).isum == int(ts.astype(object).sum())
 
 
+def test_host_column_scan_over_several_devices(oracle):
+    """aqe_scan_host_column_multi: the chunks of one host column handed out to the GPUs of this process from one counter.  The
+    merged partial does not depend on which device took which chunk: bit-equal to the one-device call, every time."""
+    import ctypes as C
+    c = C.c_int(0)
+    aqe.lib().aqe_device_count(C.byref(c))
+    devices = list(range(min(c.value, 8)))
+    rows = oracle.synth(3_000_001, seed=23)
+    col = np.ascontiguousarray(rows["amount"])
+    os.environ.setdefault("AQE_E2E_CHUNK_MB", "8")
+    one = aqe.host_scan_column(col, 100.0, 500.0, use_pred=True)
+    wo, co = oracle.sum_amount_where(rows, 100.0, 500.0)
+    assert one.count == co and rel(one.sum, wo) <= REL
+    for _ in range(5):
+        many = aqe.host_scan_column(col, 100.0, 500.0, use_pred=True, device=devices)
+        assert many.count == one.count and many.sum == one.sum
+    ts = np.ascontiguousarray(rows["timestamp"])
+    assert aqe.host_scan_column(ts, device=devices).isum == int(ts.astype(object).sum())
+    assert aqe.host_scan_column(col[:0], device=devices).count == 0
+    with pytest.raises(aqe.AqeError):
+        aqe.host_scan_column(col, device=[0, 0])
+
+
 def test_shard_merge_equals_whole(oracle):
     """Contiguous shards merged in rank order give the single-GPU answer."""
     n = 1_000_003
