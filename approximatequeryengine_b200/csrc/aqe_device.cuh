@@ -248,6 +248,22 @@ __device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity, u
         "DONEL_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
 }
+// the same two on a barrier's shared-memory address (taken once outside a tile loop: the generic-to-shared conversion of a
+// __shared__ array element costs an S2UR / ULEA sequence per call)
+__device__ __forceinline__ void mbar_arrive_at(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_long_at(uint32_t bar_addr, uint32_t parity, uint32_t ns) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITA_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONEA_%=;\n"
+        "bra WAITA_%=;\n"
+        "DONEA_%=:\n"
+        "}\n" ::"r"(bar_addr), "r"(parity), "r"(ns) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // global -> shared bulk copy, completion signalled on `bar` as transaction bytes; L2 evict-first hint

@@ -938,6 +938,7 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
         const uint32_t my_pair = smem_u32(bins.p_slo) + (uint32_t)tid * 16u, my_q = smem_u32(bins.p_qlo) + (uint32_t)tid * 8u;
         const bool fast_moments = MODE == 1 && MOMENTS && bins.paired && a.pair_bins == 1;   // (AQE_SQL_PAIR_BINS=2: paired bins through SqlBins::add, the A/B)
         const int kmin32 = (int)a.key_min;
+        const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
         uint32_t it = 0;
         unsigned int rows_since_drain = 0;
         for (uint64_t c = blockIdx.x; c < ntiles; c += gridDim.x, ++it) {
@@ -947,13 +948,15 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
             }
             const int s = it % STAGES;
             const uint32_t round = it / STAGES;
-            mbar_wait_long(&full_bar[s], round & 1, 20000u);
-            const uint64_t row0 = c * (uint64_t)ra.tile_rows;
-            const uint32_t rows = (uint32_t)((n_main - row0) < (uint64_t)ra.tile_rows ? (n_main - row0) : (uint64_t)ra.tile_rows);
+            mbar_wait_long_at(full0 + 8u * (uint32_t)s, round & 1, 20000u);
             const unsigned char* stage = ring + (size_t)s * ra.stage_bytes;
-            // pass bits of rows tid, tid + T, ... of this tile
-            const uint32_t nk = rows > (uint32_t)tid ? (rows - (uint32_t)tid + T - 1) / T : 0u;
-            uint32_t mask = (1u << nk) - 1u;  // nk <= K
+            // pass bits of rows tid, tid + T, ... of this tile; every tile but the table's last is whole (tile_rows = T * K)
+            uint32_t mask = (1u << K) - 1u;
+            if (c + 1 == ntiles) {
+                const uint32_t rows = (uint32_t)(n_main - c * (uint64_t)ra.tile_rows);
+                const uint32_t nk = rows > (uint32_t)tid ? (rows - (uint32_t)tid + T - 1) / T : 0u;
+                mask = (1u << (nk < (uint32_t)K ? nk : (uint32_t)K)) - 1u;
+            }
             if (n_alt == 1) {
                 for (uint32_t pc = pred_cols[0]; pc; pc &= pc - 1) {
                     const int k = __ffs(pc) - 1;
@@ -975,7 +978,7 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
             }
             if (mod_slot >= 0) mask = sql_mod_pass<T, K>(a.cols[mod_slot], stage + ra.col_off[mod_slot], tid, mask);
             if (ra.samp_step > 1) {
-                uint32_t x = (uint32_t)((row0 + ra.samp_phase + (uint32_t)tid) % ra.samp_step);  // (row + phase) mod step
+                uint32_t x = (uint32_t)((c * (uint64_t)ra.tile_rows + ra.samp_phase + (uint32_t)tid) % ra.samp_step);  // (row + phase) mod step
                 const uint32_t dt = (uint32_t)T % ra.samp_step;                                  // advanced by T mod step per owned row
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
@@ -1077,7 +1080,7 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (lane == 0) mbar_arrive_at(empty0 + 8u * (uint32_t)s);
         }
         if (blockIdx.x == 0 && tid == 0) {  // the count % 4 tail
             for (uint64_t j = n_main; j < a.count; ++j) {
