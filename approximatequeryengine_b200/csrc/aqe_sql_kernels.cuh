@@ -305,7 +305,7 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
     unsigned long long* spill_acc;  // MODE 3 / 4: the global accumulators a full bin is emptied into, set by the kernel after init()
 
     static size_t smem_bytes(unsigned int G) {
-        if (MODE == 1) return (size_t)G * T * (MOMENTS ? 24 : 16);
+        if (MODE == 1) return (size_t)(G + 1) * T * (MOMENTS ? 24 : 16);   // + one bin per thread that is never drained: where the ring kernel sends keys outside the layout
         if (MODE == 2) return (size_t)G * (4 + 16 + (MOMENTS ? 16 : 0));
         if (MODE >= 3) return (size_t)G * (16 + (MOMENTS ? 16 : 0));
         return 0;
@@ -318,9 +318,10 @@ template <int MODE, bool MOMENTS, int T> struct SqlBins {
         r_cnt = 0; r_slo = 0; r_qlo = 0; r_shi = 0; r_qhi = 0;
         if constexpr (MODE == 1) {
             p_slo = reinterpret_cast<unsigned long long*>(smem);
-            p_shi = p_slo + (size_t)G * T;
-            p_qlo = p_shi + (size_t)G * T;
-            if (tid < T) zero_private(tid);
+            p_shi = p_slo + (size_t)(G + 1) * T;
+            p_qlo = p_shi + (size_t)(G + 1) * T;
+            // every word of the bins, whichever way the kernel addresses them afterwards (`paired` is set after init)
+            for (unsigned int i = tid; i < (G + 1) * T * (MOMENTS ? 3u : 2u); i += nthreads) p_slo[i] = 0;
         } else if constexpr (MODE == 2) {
             s_sum = b_cnt + G;
             s_sq = s_sum + (size_t)G * 4;
@@ -999,9 +1000,9 @@ __global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)
 #pragma unroll
                     for (int k = 0; k < K; ++k) g[k] = (unsigned int)(lds_row<long long>(gb, tid + k * T) - a.key_min);
                 }
-                if constexpr (MODE == 1) {   // a key outside the layout cannot happen for live rows of this table; the clamp keeps every address a bin of this thread
+                if constexpr (MODE == 1) {   // keys outside the layout (none among the live rows of a table the layout was taken from) land in bin G, which no drain reads
 #pragma unroll
-                    for (int k = 0; k < K; ++k) g[k] = min(g[k], bins.G - 1u);
+                    for (int k = 0; k < K; ++k) g[k] = min(g[k], bins.G);
                 } else {
 #pragma unroll
                     for (int k = 0; k < K; ++k) if (g[k] >= bins.G) mask &= ~(1u << k);  // cannot happen for live rows with this table's own layout

@@ -639,3 +639,33 @@ def test_sql_wide_int64_sums_over_many_groups_take_the_general_form(oracle):
         m = (rows["product_id"] == r.key) & (rows["id"] > 1000)
         assert (r.isum_hi << 64) + r.isum_lo == int(rows["id"][m].astype(object).sum())
     e.close()
+
+
+def test_sql_keys_outside_a_narrower_layout_are_dropped_by_every_bin_form(tables, monkeypatch):
+    """aqe_sql_scan with a caller-made layout that covers only part of the key range: rows whose key falls outside leave no trace, and
+    the groups inside hold exactly the words the full layout gives them -- thread-private bins (the branch-free row add sends such rows to
+    a bin of their own that no drain reads), the same bins through SqlBins::add (AQE_SQL_PAIR_BINS=2 / 0), CTA-shared bins, both kernels."""
+    g, rows, e = [t for t in tables if t[0]["n"] == 100000][0]
+    for sql, p, flags, lo, cnt in (("SELECT SUM(amount) FROM sales WHERE amount BETWEEN 100 AND 500 GROUP BY region", 0, aqe.SQL_MOMENTS, 2, 3),
+                                   ("SELECT SUM(amount) FROM sales GROUP BY region", 0, aqe.SQL_MOMENTS, 1, 6),
+                                   ("SELECT SUM(timestamp) FROM sales WHERE amount > 5 GROUP BY region", 0, aqe.SQL_MOMENTS, 5, 1),
+                                   ("SELECT AVG(amount) FROM sales GROUP BY region", 0, 0, 3, 4),
+                                   ("SELECT COUNT(amount) FROM sales GROUP BY region", 0, 0, 0, 2),
+                                   ("SELECT SUM(amount) FROM sales WHERE amount > 900 GROUP BY product_id", 0, 0, 100, 50),
+                                   ("SELECT AVG(amount) FROM sales GROUP BY product_id", 0, aqe.SQL_MOMENTS, 7, 300)):
+        q = aqe.sql_parse(sql, p)
+        full = aqe.sql_layout(q, [e.sql_facts(q)])
+        whole = e.sql_scan(q, full, flags).reshape(-1, 5)
+        part = aqe.SqlLayout.from_buffer_copy(bytes(full))
+        first = full.key_min + lo
+        part.key_min, part.n_groups = first, cnt
+        want = whole[lo:lo + cnt]
+        for pair_bins in ("1", "2", "0"):
+            monkeypatch.setenv("AQE_SQL_PAIR_BINS", pair_bins)
+            for variant in (None, "1"):
+                if variant:
+                    monkeypatch.setenv("AQE_SQL_VARIANT", variant)
+                got = e.sql_scan(q, part, flags).reshape(-1, 5)
+                monkeypatch.delenv("AQE_SQL_VARIANT", raising=False)
+                assert (got == want).all(), (sql, pair_bins, variant)
+        monkeypatch.delenv("AQE_SQL_PAIR_BINS", raising=False)
