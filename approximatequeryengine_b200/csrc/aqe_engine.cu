@@ -1165,6 +1165,8 @@ static int host_scan_chunks(HostScanCtx* c, const void* host_col, int col_kind_i
     }
     aqe_db* db = c->db;
     std::vector<uint64_t> mine;
+    // whatever goes wrong below, the copies and scans already queued on this device's two streams finish before the buffers are used again
+    struct Quiesce { HostScanCtx* c; bool armed = true; ~Quiesce() { if (armed) for (int i = 0; i < 2; ++i) cudaStreamSynchronize(c->streams[i]); } } quiesce{c};
     int rc = AQE_OK;
     for (;;) {
         const uint64_t k = next->fetch_add(1, std::memory_order_relaxed);
@@ -1196,6 +1198,7 @@ static int host_scan_chunks(HostScanCtx* c, const void* host_col, int col_kind_i
         mine.push_back(k);
     }
     for (int i = 0; i < 2; ++i) CU(cudaStreamSynchronize(c->streams[i]));
+    quiesce.armed = false;
     if (mine.empty()) return AQE_OK;
     std::vector<aqe_partial> got(mine.size());
     CU(cudaMemcpy(got.data(), c->parts_dev, sizeof(aqe_partial) * mine.size(), cudaMemcpyDeviceToHost));
