@@ -231,14 +231,16 @@ def total_rows(args) -> int:
 
 def workload_config(args, rows_per_gpu, cpu=False):
     tot = total_rows(args)
-    return {"workload": f"BASELINE.json configs[2]: {tot / 1e9:g}B-record synthetic sales table, exact SUM+COUNT(amount) WHERE amount BETWEEN 100 AND 500, "
-                        f"range-sharded across {args.gpus} GPU(s) ({scaling_of(args)} scaling: " +
-                        ("the table grows with the GPU count, 1B records per GPU)" if scaling_of(args) == "weak" and args.gpus > 1 else "ONE table split over the GPUs)"),
+    return {"workload": f"BASELINE.json configs[2]: {tot / 1e9:g}B-record synthetic sales table, exact SUM+COUNT(amount) WHERE amount BETWEEN 100 AND 500, " +
+                        ("the whole table resident on one GPU" if args.gpus == 1 else
+                         f"range-sharded across {args.gpus} GPU(s) ({scaling_of(args)} scaling: " +
+                         ("the table grows with the GPU count, 1B records per GPU)" if scaling_of(args) == "weak" else "ONE table split over the GPUs)")),
             "records_per_gpu": rows_per_gpu, "total_records": tot, "predicate": f"amount BETWEEN {LO:g} AND {HI:g}",
             "data_seed": SEED, "distribution": "amount ~ U(1,1000) fp64 (Philox4x32-10)",
             "l2": "inputs larger than L2: 8 bytes x records_per_gpu per pass vs 126 MB L2, no flush needed",
-            "parallelism": f"range-shard x{args.gpus}; 64-byte shard partials exchanged " +
-                           ("by an NCCL all-gather" if getattr(args, "no_fused", False) or args.gpus == 1 else "inside the scan kernel (NVLink peer stores, CUDA IPC mailboxes)")}
+            "parallelism": (f"range-shard x{args.gpus}; 64-byte shard partials exchanged " +
+                            ("by an NCCL all-gather" if getattr(args, "no_fused", False) else "inside the scan kernel (NVLink peer stores, CUDA IPC mailboxes)"))
+                           if args.gpus > 1 else "one shard, nothing to exchange: the kernel stores its 64-byte result straight into pinned host memory"}
 
 
 def expected_answers(total: int):
