@@ -31,6 +31,28 @@ def test_library_exports_every_declared_symbol():
     assert L.aqe_abi_version() == 5
 
 
+def test_host_only_entry_points_validate_their_arguments():
+    """What runs before any CUDA call: merging no partials is the empty result; the several-device host scan refuses a device named
+    twice, an empty device list and a NULL column without touching a GPU."""
+    import ctypes as C
+    L = aqe.lib()
+    out = aqe.Partial()
+    assert L.aqe_merge_partials(None, 0, 0, C.byref(out)) == 0 and out.count == 0 and out.sum == 0.0
+    assert L.aqe_merge_partials(None, 2, 0, C.byref(out)) != 0
+    two = (aqe.Partial * 2)()
+    two[0].count, two[0].sum, two[1].count, two[1].sum = 3, 1.5, 4, 2.25
+    assert L.aqe_merge_partials(two, 2, 0, C.byref(out)) == 0 and out.count == 7 and out.sum == 3.75
+    col = (C.c_double * 4)(1.0, 2.0, 3.0, 4.0)
+    for devs, n in (((0, 0), 2), ((0,), 0), ((0,) * 17, 17)):
+        arr = (C.c_int * max(len(devs), 1))(*devs)
+        assert L.aqe_scan_host_column_multi(arr, n, col, 0, 4, 0.0, 0.0, 0, C.byref(out)) != 0, devs
+        assert L.aqe_last_error()
+    one = (C.c_int * 1)(0)
+    assert L.aqe_scan_host_column_multi(one, 1, None, 0, 4, 0.0, 0.0, 0, C.byref(out)) != 0
+    assert L.aqe_scan_host_column_multi(one, 1, col, 7, 4, 0.0, 0.0, 0, C.byref(out)) != 0
+    assert L.aqe_scan_host_column_multi(None, 1, col, 0, 4, 0.0, 0.0, 0, C.byref(out)) != 0
+
+
 def test_struct_sizes_match_header():
     import ctypes as C
     assert C.sizeof(aqe.Partial) == 64
