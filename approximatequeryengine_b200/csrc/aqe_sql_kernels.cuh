@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
 //
 // The reference's `rowid % step = 0` over dense ids is a filter on the row number here (no id column read) -- used
 // while step is small enough that every 32-byte sector is touched anyway; larger steps take the strided visit.
-constexpr int kSqlMaxRowsPerThread = 8;  // K, rows per consumer thread and tile: 8 for rows of <= 8 bytes, 4 for wider rows (stage = 256 K rows)
+constexpr int kSqlMaxRowsPerThread = 16;  // K, rows per consumer thread and tile: 16 for 4-byte rows, 8 for rows of <= 8 bytes, 8 / 6 / 4 for wider rows (stage = 256 K rows)
 
 struct SqlRingArgs {
     SqlArgs q;

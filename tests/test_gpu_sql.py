@@ -669,3 +669,32 @@ def test_sql_keys_outside_a_narrower_layout_are_dropped_by_every_bin_form(tables
                 monkeypatch.delenv("AQE_SQL_VARIANT", raising=False)
                 assert (got == want).all(), (sql, pair_bins, variant)
         monkeypatch.delenv("AQE_SQL_PAIR_BINS", raising=False)
+
+
+def test_sql_four_byte_rows_take_sixteen_rows_per_thread_and_agree(oracle, monkeypatch):
+    """Ungrouped queries that read ONE int32 column run the ring with 16 rows per consumer thread and tile (K = 16; the grouped ones keep
+    K = 8).  Same accumulator words as K = 8 (AQE_SQL_K16=0) and as the register-staged kernel, on whole tiles, ragged last tiles and
+    tables smaller than a tile."""
+    for n in (1, 255, 4095, 4096, 4097, 12_289, 100_003):
+        rows = oracle.synth(n, seed=11 + n % 7)
+        e = aqe.Engine(0).from_rows(rows)
+        for sql, p in (("SELECT COUNT(*) FROM sales WHERE region = 1", 0), ("SELECT COUNT(*) FROM sales WHERE region IN (1, 3, 5, 7)", 0),
+                       ("SELECT COUNT(*) FROM sales WHERE (region = 1 OR region = 3)", 0), ("SELECT COUNT(amount) FROM sales GROUP BY region", 0),
+                       ("SELECT COUNT(amount) FROM sales GROUP BY product_id", 0), ("SELECT COUNT(*) FROM sales WHERE product_id NOT IN (1, 2, 3) GROUP BY product_id", 0),
+                       ("SELECT SUM(region) FROM sales GROUP BY region", 0), ("SELECT SUM(product_id) FROM sales WHERE product_id > 500", 0),
+                       ("SELECT COUNT(*) FROM sales WHERE region != 2 GROUP BY region", 3)):
+            q = aqe.sql_parse(sql, p)
+            layout = aqe.sql_layout(q, [e.sql_facts(q)])
+            monkeypatch.setenv("AQE_SQL_VARIANT", "2")
+            k16 = e.sql_scan(q, layout, 0)
+            monkeypatch.setenv("AQE_SQL_K16", "0")
+            k8 = e.sql_scan(q, layout, 0)
+            monkeypatch.delenv("AQE_SQL_K16", raising=False)
+            monkeypatch.setenv("AQE_SQL_DRAIN_ROWS", "16")
+            drained = e.sql_scan(q, layout, 0)
+            monkeypatch.delenv("AQE_SQL_DRAIN_ROWS", raising=False)
+            monkeypatch.setenv("AQE_SQL_VARIANT", "1")
+            regs = e.sql_scan(q, layout, 0)
+            monkeypatch.delenv("AQE_SQL_VARIANT", raising=False)
+            assert (k16 == regs).all() and (k8 == regs).all() and (drained == regs).all(), (n, sql)
+        e.close()
