@@ -2149,10 +2149,11 @@ template <int MODE, bool MOMENTS> static int sql_launch_ring(const aqe_db* db, S
         if (found) break;
     }
     if (row_bytes <= 8) K = 8;   // 16 KiB stages at most: always the largest tile
-    // One int32 column and nothing else, no GROUP BY (COUNT(*) WHERE region ...): 16 KiB stages hold 16 rows per thread.  These scans are bound by the
-    // consumers' instructions per row, a good half of which is per-tile bookkeeping: twice the rows per tile halves that share (1 B rows,
-    // `COUNT(*) WHERE region = 1` 1.08 -> 0.77 ms).  The grouped forms spill under their 56-register cap at K = 16 and lose (0.83 -> 0.95 ms): they keep K = 8.
-    constexpr bool kHasK16 = !MOMENTS && MODE == 0;
+    // One int32 column and nothing else (COUNT [WHERE region ...] [GROUP BY region | product_id]): 16 KiB stages hold 16 rows per thread.  These scans
+    // are bound by the consumers' instructions per row, a good half of which is per-tile bookkeeping: twice the rows per tile halves that share (1 B rows:
+    // `COUNT(*) WHERE region = 1` 1.08 -> 0.77 ms, `COUNT ... GROUP BY region` 0.78 -> 0.64, `... GROUP BY product_id` 0.96 -> 0.89).  The shared-bin kernel
+    // runs K = 16 under a three-CTA register budget (sql_ring_min_ctas): under the 56 registers of four CTAs it spills and loses (0.83 -> 0.95 ms).
+    constexpr bool kHasK16 = !MOMENTS && (MODE == 0 || MODE == 2);
     if (kHasK16 && row_bytes == 4 && env_int("AQE_SQL_K16", 1)) K = 16;
     { const int forced = env_int("AQE_SQL_K", 0); if (forced == 4 || forced == 6 || forced == 8) K = forced; }   // experiments (tools/sql_bench.py)
     const uint32_t tile = (uint32_t)(T * K);

@@ -801,7 +801,10 @@ template <int T, int K> __device__ __forceinline__ uint32_t sql_mod_pass(const S
 // CTAs per SM the register allocation must leave room for (shared memory usually sets the real limit): 4 for the plain
 // ungrouped and the shared-atomic kernels (<= 56 registers), 3 for private bins and for moments, 2 for private bins with moments.
 // The packed shared bins always come with rows of >= 12 bytes (group column + aggregate column): shared memory holds three CTAs of them at K = 8 (with squares at K = 6).
-constexpr int sql_ring_min_ctas(int mode, bool moments) { return mode == 1 ? (moments ? 2 : 3) : (moments || mode == 4 ? 3 : 4); }
+constexpr int sql_ring_min_ctas(int mode, bool moments, int k = 8) {
+    if (k == 16 && mode == 2) return 3;   // sixteen row slots per thread: under the 56 registers of four CTAs per SM they spill (0.83 -> 0.95 ms), under 72 they do not (0.78 -> 0.64)
+    return mode == 1 ? (moments ? 2 : 3) : (moments || mode == 4 ? 3 : 4);
+}
 
 // Packed shared-atomic bins, tiles few of whose rows pass: the ATOMS of a predicated-off row still costs its issue slot, so when no
 // thread of the warp kept more than half of its K rows the warp walks the set pass bits instead -- max over the lanes of popc(mask)
@@ -863,7 +866,7 @@ __device__ __forceinline__ void sql_private_moments_row(uint32_t pair_addr, uint
 }
 
 template <int MODE, bool MOMENTS, int STAGES, int K>
-__global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS)) k_sql_ring(const SqlRingArgs ra) {
+__global__ void __launch_bounds__(kBulkThreads, sql_ring_min_ctas(MODE, MOMENTS, K)) k_sql_ring(const SqlRingArgs ra) {
     extern __shared__ __align__(128) unsigned char sql_ring_smem[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
