@@ -730,6 +730,18 @@ __device__ __forceinline__ uint32_t sql_f64_range_bit(uint32_t mask, int bit, do
     return mask;
 }
 
+// the same for an int32 column (region, product_id): two (three with a `!=`) chained setp and one predicated and -- the 4-byte scans
+// spend 16 warp instructions per row (ncu, profiles/r2_sql_count_ncu_full_raw.csv) and the SEL form of this test was 7 of them
+__device__ __forceinline__ uint32_t sql_i32_range_bit(uint32_t mask, int bit, int v, int lo, int hi) {
+    asm("{\n .reg .pred p;\n setp.ge.s32 p, %1, %2;\n setp.le.and.s32 p, %1, %3, p;\n @!p and.b32 %0, %0, %4;\n}"
+        : "+r"(mask) : "r"(v), "r"(lo), "r"(hi), "r"(~(1u << bit)));
+    return mask;
+}
+__device__ __forceinline__ uint32_t sql_i32_range_ne_bit(uint32_t mask, int bit, int v, int lo, int hi, int ne) {
+    asm("{\n .reg .pred p;\n setp.ge.s32 p, %1, %2;\n setp.le.and.s32 p, %1, %3, p;\n setp.ne.and.s32 p, %1, %4, p;\n @!p and.b32 %0, %0, %5;\n}"
+        : "+r"(mask) : "r"(v), "r"(lo), "r"(hi), "r"(ne), "r"(~(1u << bit)));
+    return mask;
+}
 // one conjunct of one column over this thread's row slots of the tile: clears the pass bit of every row that fails
 template <int T, int K> __device__ __forceinline__ uint32_t sql_pred_pass(const SqlCol& col, const SqlPred& p, const unsigned char* base, int tid, uint32_t mask) {
     if (col.kind == 0) {
@@ -778,11 +790,12 @@ template <int T, int K> __device__ __forceinline__ uint32_t sql_pred_pass(const 
         const int lo = (int)lo64, hi = (int)hi64;
         const bool has_ne = p.has_ne != 0 && p.ne >= -2147483648ll && p.ne <= 2147483647ll;
         const int ne = (int)p.ne;
+        if (has_ne) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int v = lds_row<int>(base, tid + k * T);
-            const bool ok = v >= lo && v <= hi && !(has_ne && v == ne);
-            mask &= ~((ok ? 0u : 1u) << k);
+            for (int k = 0; k < K; ++k) mask = sql_i32_range_ne_bit(mask, k, lds_row<int>(base, tid + k * T), lo, hi, ne);
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) mask = sql_i32_range_bit(mask, k, lds_row<int>(base, tid + k * T), lo, hi);
         }
     }
     return mask;
