@@ -699,9 +699,10 @@ __global__ void __launch_bounds__(kSqlThreads) k_sql_agg(const SqlArgs a) {
 // type-specialised, fully unrolled pass over those rows (the type switch sits outside the row loop), then one pass
 // derives the group index, then one pass converts and accumulates the aggregate column.  A row-at-a-time interpreter
 // of the same query costs ~110 warp instructions per 32 rows (measured, ncu) and is issue/latency bound at 1.0 TB/s.
-// A tile holds exactly 256 K rows (K = 8 for rows of <= 8 bytes, 4 for wider rows, so a stage stays <= 32 KiB and every
-// row slot of a full tile is live); the passes are unconditional over the K slots, and slots beyond the rows of the table's
-// last tile read stale bytes of the same stage and stay masked off.
+// A tile holds exactly 256 K rows (K = 16 for a single int32 column, 8 for rows of <= 8 bytes, 8 / 6 / 4 for wider rows as the
+// occupancy allows -- sql_launch_ring -- so a stage stays <= 32 KiB and every row slot of a full tile is live); the passes are
+// unconditional over the K slots, and slots beyond the rows of the table's last tile read stale bytes of the same stage and
+// stay masked off.  Every tile but the table's last is whole: its pass bits start as the constant (1 << K) - 1.
 //
 // The reference's `rowid % step = 0` over dense ids is a filter on the row number here (no id column read) -- used
 // while step is small enough that every 32-byte sector is touched anyway; larger steps take the strided visit.
